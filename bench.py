@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the VQ-VAE latent-encoding hot path (BASELINE.json: "encoded patches/sec at 1/2/4/8
+B200; train step ms; % of HBM roofline").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path (model.enc + model.vq, i.e. the body of
+pipeline/patch_VAE.py:process_VAE) over one chunk of synthetic z-scored 2x128x128 patches per GPU.
+Prints ONE JSON line (rank 0).  See the module-level constants and DESIGN.md "Measurement"."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# algorithmic figures per patch, defaults (SURVEY.md section 8d / BASELINE.md section 4)
+ENC_BYTES = 131072 + 16384 + 16384          # x in, z_before out, z_after out
+ENC_FLOPS_ALGO = 22151168                    # 2 * (enc MACs + VQ MACs), reference layer structure
+CHUNK = 16384                                # patches per step per GPU (2.1 GB of input >> 126 MB L2)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        return world, rank, local, dist
+    return 1, 0, 0, None
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port; the Python reference
+# cannot travel to the GPU box), all host threads, bounded sample per step
+# ------------------------------------------------------------------------------------------
+def cpu_reference_rate(n_patches: int, batch: int, repeats: int, warmup: int = 1):
+    """Batched eval-mode enc+vq on the host (the fastest configuration of the reference's own code,
+    BASELINE.md section 2).  Returns patches/s and the thread count."""
+    from oracle import vqvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = O.calibrate_state(O.default_state("z16"), O.synthetic_patches(32, 1), seed=0)
+    x = O.synthetic_patches(n_patches, 2)
+    times = []
+    with torch.no_grad():
+        for r in range(warmup + repeats):
+            t0 = time.perf_counter()
+            for i in range(0, n_patches, batch):
+                zb = O.encoder(x[i:i + batch], st, O.EVAL)
+                O.vq_forward(zb, st["vq.w.weight"], 0.25)
+            dt = time.perf_counter() - t0
+            if r >= warmup:
+                times.append(dt)
+    return n_patches / min(times), torch.get_num_threads(), sum(times) / len(times)
+
+
+def run_reference(args):
+    world, rank, local, dist = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    sample, batch = 256, 256
+    from oracle import vqvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = O.calibrate_state(O.default_state("z16"), O.synthetic_patches(32, 1), seed=0)
+    x = O.synthetic_patches(sample, 2)
+
+    def step():
+        with torch.no_grad():
+            zb = O.encoder(x, st, O.EVAL)
+            O.vq_forward(zb, st["vq.w.weight"], 0.25)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "encoded patches/sec", "value": value, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "process_VAE bulk encode (enc+vq), VQ_VAE_z16 defaults, 2x128x128 patches, eval-BN batched "
+                               f"B={batch}; reference CPU path = oracle port on host cores (Python reference cannot travel)",
+                   "sample_patches_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample} patches per step x {args.steps} steps, batched eval enc+vq"},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def time_events(fn, reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def fp32_peak(dev):
+    import ctypes as C
+    from dynamorph_b200._lib import call, ptr
+    scratch = torch.zeros(16, device=dev)
+    flops = C.c_double()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    fn = lambda: call("dmb_bench_fp32_fma", 148 * 8, 256, 20000, ptr(scratch), C.byref(flops), st)
+    fn()
+    torch.cuda.synchronize()
+    ms = min(time_events(fn, 1) for _ in range(5))
+    return flops.value / (ms * 1e-3) / 1e12
+
+
+def layer_table(model, x, hbm_peak, fp32_tf):
+    """Per-launch device time of every kernel in one eval-mode encode step (each launched alone through
+    the layer-level C ABI on the same batch), with both roofs."""
+    import ctypes as C
+    from dynamorph_b200._lib import call, ptr
+    B = x.shape[0]
+    dev = x.device
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    h = model.num_hiddens
+    rh = model.num_residual_hiddens
+    K = model.num_embeddings
+    # (name, cin, H, cout, ks, stride)
+    layers = [("enc.0+enc.1 composite conv4x4s2", 2, 128, h // 2, 4, 2),
+              ("enc.4 conv4x4s2", h // 2, 64, h, 4, 2),
+              ("enc.7 conv4x4s2", h, 32, h, 4, 2),
+              ("enc.10 conv3x3", h, 16, h, 3, 1),
+              ("res conv3x3", h, 16, rh, 3, 1),
+              ("res conv1x1", rh, 16, h, 1, 1)]
+    rows = []
+    for name, cin, H, cout, ks, s in layers:
+        xin = torch.randn(B, cin, H, H, device=dev)
+        w = torch.randn(cin * ks * ks * cout, device=dev) * 0.05
+        b = torch.zeros(9 * cout, device=dev)
+        y = torch.empty(B, cout, H // s, H // s, device=dev)
+        fn = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
+                          None, None, 0, 0, None, 1, st)
+        fn(); torch.cuda.synchronize()
+        ms = time_events(fn, 5)
+        macs = (H // s) ** 2 * cout * cin * ks * ks
+        byts = (cin * H * H + cout * (H // s) ** 2) * 4
+        rows.append({"kernel": name, "launches_per_step": model.num_residual_layers if name.startswith("res") else 1,
+                     "ms": ms, "gbs": byts * B / ms / 1e6, "tflops": 2 * macs * B / ms / 1e9,
+                     "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "fp32_frac": 2 * macs * B / ms / 1e9 / fp32_tf})
+        del xin, y
+    z = torch.randn(B, h, 16, 16, device=dev)
+    cb = torch.randn(K, h, device=dev)
+    zst = torch.empty_like(z)
+    idx = torch.empty(B, 16, 16, dtype=torch.int32, device=dev)
+    fn = lambda: call("dmb_vq_forward", ptr(z), ptr(cb), B, h, 256, K, ptr(zst), ptr(idx), None, st)
+    fn(); torch.cuda.synchronize()
+    ms = time_events(fn, 5)
+    byts = (2 * h * 256 + 256) * 4
+    ops = 256 * K * h * 3
+    rows.append({"kernel": "vq fused", "launches_per_step": 1, "ms": ms, "gbs": byts * B / ms / 1e6,
+                 "tflops": ops * B / ms / 1e9, "hbm_frac": byts * B / ms / 1e6 / hbm_peak,
+                 "fp32_frac": ops * B / ms / 1e9 / (fp32_tf / 2)})
+    return rows
+
+
+def run_ours(args):
+    world, rank, local, dist = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if dist is not None:
+        dist.init_process_group("nccl", device_id=dev)
+    from dynamorph_b200 import _lib
+    from dynamorph_b200.HiddenStateExtractor.vae import VQ_VAE_z16
+    from dynamorph_b200.bulk import BulkEncoder
+    from dynamorph_b200.synthetic import calibrate, synthetic_patches
+    lib = _lib.load()
+
+    torch.manual_seed(0)
+    model = VQ_VAE_z16().to(dev)
+    calibrate(model, synthetic_patches(64, 1, dev))
+    model.eval()
+    chunk = args.chunk
+    # this rank's shard of the job: patch range [rank*chunk*steps, ...) -- independent, no collective
+    x = torch.cat([synthetic_patches(2048, 1234 + rank * 1000 + i, dev) for i in range(chunk // 2048)])
+    eng = model._engine
+    import ctypes as C
+    s = eng.spec(128, 128)
+    d = model.num_hiddens
+    zb = torch.empty(chunk, d, 16, 16, device=dev)
+    za = torch.empty_like(zb)
+    idx = torch.empty(chunk, 16, 16, dtype=torch.int32, device=dev)
+
+    def step(mode="eval"):
+        eng.encode(x, mode, out=(zb, za, idx))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.dmb_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.dmb_launch_count(0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t[0])
+    value = world * args.steps * chunk / (ms_total * 1e-3)
+
+    # secondary: as-written BN semantics (train-mode, batch 1 == per-patch statistics)
+    for _ in range(2):
+        step("per_sample")
+    torch.cuda.synchronize()
+    ms_ps = time_events(lambda: step("per_sample"), max(3, args.steps // 4))
+
+    # ---- end to end through the public host-buffer API (pinned host in, pinned host out)
+    enc = BulkEncoder(model, chunk=min(chunk, 4096), bn_mode="eval")
+    x_host = torch.empty(chunk, 2, 128, 128, dtype=torch.float32, pin_memory=True)
+    x_host.copy_(x)
+    out = enc.allocate_outputs(chunk)
+    enc.encode(x_host, out)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 8))
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        enc.encode(x_host, out)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * chunk / (float(t[0]) * 1e-3)
+    h2d = x_host.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in out.values())
+    # parity spot-check of what came back to the host against the device-resident run
+    same = bool(torch.equal(out["idx"].view(chunk, 16, 16), idx.cpu()))
+
+    line = {
+        "metric": "encoded patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "process_VAE bulk encode (model.enc + model.vq), VQ_VAE_z16 reference defaults "
+                               "(num_inputs=2,num_hiddens=16,num_residual_hiddens=32,num_embeddings=64), "
+                               f"{chunk} synthetic z-scored 2x128x128 patches per step per GPU, eval-mode BN, fp32; "
+                               "patch ranges sharded across ranks, no data-path collective",
+                   "chunk_patches": chunk, "bn_mode": "eval",
+                   "l2_policy": f"inputs larger than L2 ({chunk * 131072 / 1e9:.2f} GB per step vs 126 MB)"},
+        "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "dynamorph_b200.bulk.BulkEncoder.encode (pinned host -> HBM -> pinned host, 3-stream pipeline)",
+                "host_matches_device": same},
+        "gpu_launches": int(launches),
+        "per_sample_bn": {"value": world * chunk / (ms_ps * 1e-3), "unit": "patches/s", "ms_per_step": ms_ps,
+                          "note": "as-written process_VAE semantics (train-mode BN, batch 1) at batch speed"},
+    }
+    if rank == 0:
+        line["clocks"] = clocks
+        hbm_peak, peak_src = measured_peaks()
+        fp32_tf = fp32_peak(dev)
+        rows = layer_table(model, x[:min(chunk, 8192)], hbm_peak, fp32_tf)
+        total_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
+        dom = max(rows, key=lambda r: r["ms"] * r["launches_per_step"])
+        line["roofline"] = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                            "frac": dom["hbm_frac"], "traffic": None, "kernel": dom["kernel"],
+                            "peak_source": peak_src,
+                            "binding_roof": "fp32_fma (CUDA cores): the schema's bound is hbm|tensor, but this kernel "
+                                            "is FP32-FMA bound -- see fp32 fields",
+                            "fp32_achieved_tflops": dom["tflops"], "fp32_peak_tflops": fp32_tf,
+                            "fp32_frac": dom["fp32_frac"],
+                            "share_of_step": dom["ms"] * dom["launches_per_step"] / total_ms}
+        line["whole_step"] = {"hbm_frac_algorithmic": value / world * ENC_BYTES / 1e9 / hbm_peak,
+                              "fp32_frac_algorithmic_flops": value / world * ENC_FLOPS_ALGO / 1e12 / fp32_tf,
+                              "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
+        line["layers"] = rows
+        if world == 1 and not args.no_cpu:
+            v, cores, sec = cpu_reference_rate(1024, 256, 2)
+            line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
+                                    "sample": "1024 patches, batched eval enc+vq (B=256), best of 2 after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=CHUNK)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

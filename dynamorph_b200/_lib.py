@@ -1,0 +1,111 @@
+"""ctypes binding of libdynamorph_b200.so (the C ABI in include/dynamorph_b200.h).
+
+No CPU fallback: if the library is missing it is built in-tree with nvcc; if that fails the
+import of any op raises.  Signatures carry plain pointers and sizes only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+
+class DmbModel(C.Structure):
+    """struct dmb_model -- the constructor arguments of VQ_VAE that shape the computation."""
+    _fields_ = [
+        ("arch", C.c_int32), ("num_inputs", C.c_int32), ("num_hiddens", C.c_int32),
+        ("num_residual_hiddens", C.c_int32), ("num_residual_layers", C.c_int32),
+        ("num_embeddings", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("commitment_cost", C.c_float), ("weight_recon", C.c_float), ("weight_commitment", C.c_float),
+        ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+    ]
+
+
+ARCH_Z16, ARCH_Z32 = 0, 1
+BN_EVAL, BN_BATCH, BN_PER_SAMPLE = 0, 1, 2
+BN_MODES = {"eval": BN_EVAL, "batch": BN_BATCH, "per_sample": BN_PER_SAMPLE}
+
+_P = C.c_void_p
+_M = C.POINTER(DmbModel)
+_I64 = C.c_int64
+_I32 = C.c_int32
+_F = C.c_float
+
+# name -> argtypes; every function returns int (0 ok)
+SIGNATURES = {
+    "dmb_param_count": [_M, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)],
+    "dmb_param_lookup": [_M, C.c_char_p, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64)],
+    "dmb_latent_shape": [_M, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)],
+    "dmb_packed_floats": [_M, C.POINTER(_I64)],
+    "dmb_pack_weights": [_M, _P, _P, _I32, _P, _P],
+    "dmb_workspace_bytes": [_M, _I64, _I32, _I32, C.POINTER(C.c_size_t)],
+    "dmb_encoder_forward": [_M, _P, _P, _I64, _I32, _P, _P, _P, C.c_size_t, _P],
+    "dmb_vq_forward": [_P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],
+    "dmb_vq_reset": [_P, _I32, _P],
+    "dmb_vq_finalize": [_P, _I32, _I32, _F, _P, _P],
+    "dmb_vq_gather": [_P, _P, _I64, _I32, _I32, _I32, _P, _P],
+    "dmb_vq_backward": [_P, _P, _P, _P, _P, _F, _F, _I64, _I32, _I32, _I32, _P, _P, _P],
+    "dmb_encode": [_M, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, C.c_size_t, _P],
+    "dmb_decoder_forward": [_M, _P, _P, _I64, _I32, _P, _P, _P, C.c_size_t, _P],
+    "dmb_conv2d_forward": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, _I32, _P],
+    "dmb_conv_transpose2d_forward": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _P],
+    "dmb_bench_fp32_fma": [_I32, _I32, _I32, _P, C.POINTER(C.c_double), _P],
+    "dmb_recon_loss": [_P, _P, _P, _I32, _P, _I64, _I32, _I32, _P, _P],
+    "dmb_train_forward": [_M, _P, _P, _P, _P, _I32, _P, _I64, _P, _P, _P, _P, C.c_size_t, _P],
+    "dmb_train_backward": [_M, _P, _P, _P, _P, _I32, _P, _I64, _F, _P, _P, C.c_size_t, _P],
+    "dmb_adam_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P],
+    "dmb_zscore_patch": [_P, _I32, _I64, _I32, _P, _P],
+}
+
+_lib = None
+
+
+class DmbError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed) the shared library; raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.needs_build():
+        if os.path.isdir(_build.CSRC) and os.environ.get("DMB_NO_BUILD") != "1":
+            try:
+                _build.build()
+            except Exception as e:  # stale lib may still be usable; a missing one is fatal
+                if not os.path.exists(path):
+                    raise DmbError(f"libdynamorph_b200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(path):
+        raise DmbError("libdynamorph_b200.so not found (no CPU fallback exists); run "
+                       "`python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    lib.dmb_last_error.restype = C.c_char_p
+    lib.dmb_last_error.argtypes = []
+    lib.dmb_abi_version.restype = C.c_int
+    lib.dmb_abi_version.argtypes = []
+    lib.dmb_launch_count.restype = C.c_longlong
+    lib.dmb_launch_count.argtypes = [C.c_int]
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise DmbError(f"{name} failed ({rc}): {lib.dmb_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,124 @@
+"""Shared machinery of the drop-in module classes (see HiddenStateExtractor/vq_vae.py, vae.py).
+
+The classes own the same `nn.Conv2d / nn.BatchNorm2d / nn.ConvTranspose2d / nn.Embedding`
+containers, constructed in the reference's order, so `state_dict()` keys, default
+initialisation and RNG consumption are identical to the reference
+(/root/reference/HiddenStateExtractor/vq_vae.py:276-298, vae.py:273-294, :401-414) and a
+`model.pt` written by either side loads in the other.  Their `forward`s never touch
+`torch.nn.functional`: they call the engine, which calls the C ABI."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, engine as _engine
+
+CHANNEL_VAR = np.array([1., 1.])
+
+
+class VectorQuantizer(nn.Module):
+    """Drop-in for HiddenStateExtractor/vq_vae.py:25-116 (= vae.py:12-103)."""
+
+    def __init__(self, embedding_dim=128, num_embeddings=128, commitment_cost=0.25, device='cuda:0'):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.num_embeddings = num_embeddings
+        self.commitment_cost = commitment_cost
+        self.device = device
+        self.w = nn.Embedding(num_embeddings, embedding_dim)
+
+    def forward(self, inputs):
+        """-> (inputs + (quantized - inputs), loss, perplexity); one fused kernel."""
+        if torch.is_grad_enabled() and (inputs.requires_grad or self.w.weight.requires_grad):
+            from .autograd import VQFunction
+            return VQFunction.apply(inputs, self.w.weight, float(self.commitment_cost))
+        return _engine.vq_forward(inputs, self.w.weight.data, self.commitment_cost)
+
+    @property
+    def embeddings(self):
+        return self.w.weight
+
+    def encode_inputs(self, inputs):
+        """-> LongTensor (B, H, W) of nearest-code indices (first index on ties)."""
+        return _engine.vq_indices(inputs.detach(), self.w.weight.data).long()
+
+    def decode_inputs(self, encoding_indices):
+        """indices (B, H, W) -> quantized encodings (B, D, H, W)."""
+        return _engine.vq_gather(encoding_indices, self.w.weight.data)
+
+
+class ResidualBlock(nn.Module):
+    """Drop-in for HiddenStateExtractor/vq_vae.py:180-225: same `.layers` containers/keys."""
+
+    def __init__(self, num_hiddens=128, num_residual_hiddens=512, num_residual_layers=2):
+        super().__init__()
+        self.num_hiddens = num_hiddens
+        self.num_residual_layers = num_residual_layers
+        self.num_residual_hiddens = num_residual_hiddens
+        self.layers = []
+        for _ in range(self.num_residual_layers):
+            self.layers.append(nn.Sequential(
+                nn.ReLU(),
+                nn.Conv2d(self.num_hiddens, self.num_residual_hiddens, 3, padding=1),
+                nn.BatchNorm2d(self.num_residual_hiddens),
+                nn.ReLU(),
+                nn.Conv2d(self.num_residual_hiddens, self.num_hiddens, 1),
+                nn.BatchNorm2d(self.num_hiddens)))
+        self.layers = nn.ModuleList(self.layers)
+
+    def forward(self, x):
+        raise RuntimeError("dynamorph_b200.ResidualBlock is executed as part of the fused encoder/decoder "
+                           "schedule (model.enc / model.dec); it has no stand-alone kernel path")
+
+
+class _Stage(nn.Sequential):
+    """`model.enc` / `model.dec`: an nn.Sequential (for the state_dict keys) whose call runs the
+    fused CUDA schedule instead of the children."""
+
+    def _bind(self, owner, which):
+        object.__setattr__(self, "_owner", owner)
+        object.__setattr__(self, "_which", which)
+
+    def forward(self, x, bn_mode=None):
+        owner = self._owner
+        eng = owner._engine
+        needs_grad = torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad and owner.training and getattr(owner, "_stage_autograd", False):
+            from .autograd import stage_apply
+            return stage_apply(owner, self._which, x)
+        if self._which == "enc":
+            return eng.encoder_forward(x.detach(), bn_mode)
+        return eng.decoder_forward(x.detach(), bn_mode)
+
+
+class VQVAEBase(nn.Module):
+    """Common body of VQ_VAE / VQ_VAE_z16 / VQ_VAE_z32."""
+
+    _arch = _lib.ARCH_Z16
+
+    def _finish_init(self):
+        object.__setattr__(self, "_engine", _engine.Engine(self, self._arch))
+        self.enc._bind(self, "enc")
+        self.dec._bind(self, "dec")
+
+    # -- conveniences named by the north star (absent from the reference class) ---------------
+    def encode(self, inputs, bn_mode=None):
+        """inputs (B,C,H,W) -> LongTensor code indices (B,h,w): enc -> vq.encode_inputs."""
+        mode = bn_mode or ("eval" if not self.training else None)
+        if mode is None:
+            return self.vq.encode_inputs(self.enc(inputs))
+        return self._engine.encode(inputs, mode)[2].long()
+
+    def decode(self, encoding_indices, bn_mode=None):
+        """code indices -> reconstruction: vq.decode_inputs -> dec."""
+        return self.dec(self.vq.decode_inputs(encoding_indices), bn_mode)
+
+    def encode_latents(self, inputs, bn_mode="eval"):
+        """Batched process_VAE body: -> (z_before, z_after, idx int32)."""
+        return self._engine.encode(inputs, bn_mode)
+
+    def predict(self, inputs):
+        """Prediction fn, same as forward pass (vq_vae.py:340-342)."""
+        return self.forward(inputs)

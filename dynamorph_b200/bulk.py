@@ -1,0 +1,105 @@
+"""Bulk patch encoding from HOST buffers: the body of process_VAE
+(/root/reference/pipeline/patch_VAE.py:443-462) as a three-stream pipeline -- pinned-host -> HBM copy
+of chunk i+1, encode of chunk i, HBM -> pinned-host copy of chunk i-1 all overlap."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+
+class BulkEncoder:
+    def __init__(self, model, chunk: int = 8192, bn_mode: str = "eval", device=None,
+                 outputs=("z_before", "z_after", "idx")):
+        if bn_mode not in ("eval", "per_sample"):
+            raise ValueError("bulk encoding needs patch-independent statistics: bn_mode 'eval' or 'per_sample'")
+        self.model = model
+        self.engine = model._engine
+        self.chunk = int(chunk)
+        self.bn_mode = bn_mode
+        self.device = torch.device(device) if device is not None else self.engine.device
+        self.outputs = tuple(outputs)
+        self._bufs = None
+        self._streams = None
+
+    def _setup(self, C, H, W):
+        from . import _lib
+        import ctypes
+        s = self.engine.spec(H, W)
+        d, lh, lw = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.call("dmb_latent_shape", ctypes.byref(s), ctypes.byref(d), ctypes.byref(lh), ctypes.byref(lw))
+        key = (C, H, W)
+        if self._bufs is not None and self._bufs["key"] == key:
+            return
+        dev, n = self.device, self.chunk
+        self._bufs = {
+            "key": key, "lat": (d.value, lh.value, lw.value),
+            "x": [torch.empty(n, C, H, W, dtype=torch.float32, device=dev) for _ in range(2)],
+            "zb": [torch.empty(n, d.value, lh.value, lw.value, dtype=torch.float32, device=dev) for _ in range(2)],
+            "za": [torch.empty(n, d.value, lh.value, lw.value, dtype=torch.float32, device=dev) for _ in range(2)],
+            "idx": [torch.empty(n, lh.value, lw.value, dtype=torch.int32, device=dev) for _ in range(2)],
+        }
+        self._streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+
+    def allocate_outputs(self, n: int, C: int = 2, H: int = 128, W: int = 128, pin: bool = True) -> Dict[str, torch.Tensor]:
+        self._setup(C, H, W)
+        d, lh, lw = self._bufs["lat"]
+        out = {}
+        if "z_before" in self.outputs:
+            out["z_before"] = torch.empty(n, d * lh * lw, dtype=torch.float32, pin_memory=pin)
+        if "z_after" in self.outputs:
+            out["z_after"] = torch.empty(n, d * lh * lw, dtype=torch.float32, pin_memory=pin)
+        if "idx" in self.outputs:
+            out["idx"] = torch.empty(n, lh * lw, dtype=torch.int32, pin_memory=pin)
+        return out
+
+    @torch.no_grad()
+    def encode(self, x_host: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """x_host: (N, C, H, W) float32 on the host (pinned for full overlap).  Returns host tensors
+        'z_before' / 'z_after' (N, D*h*w) NCHW-flattened like patch_VAE.py:454-461, and 'idx'."""
+        if x_host.is_cuda:
+            raise ValueError("BulkEncoder.encode takes host tensors; use model.encode_latents for device data")
+        N, C, H, W = x_host.shape
+        self._setup(C, H, W)
+        if out is None:
+            out = self.allocate_outputs(N, C, H, W)
+        b = self._bufs
+        s_in, s_cmp, s_out = self._streams
+        cur = torch.cuda.current_stream(self.device)
+        for s in self._streams:
+            s.wait_stream(cur)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        used = [False, False]
+        self.engine.packed(0 if self.bn_mode == "eval" else 2, H, W)   # pack on the current stream first
+        for s in self._streams:
+            s.wait_stream(cur)
+        for i, a in enumerate(range(0, N, self.chunk)):
+            j = i & 1
+            e = min(N, a + self.chunk)
+            n = e - a
+            with torch.cuda.stream(s_in):
+                if used[j]:
+                    s_in.wait_event(ev_cmp[j])          # x[j] consumed by the encode two chunks ago
+                b["x"][j][:n].copy_(x_host[a:e], non_blocking=True)
+                ev_in[j].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[j])
+                if used[j]:
+                    s_cmp.wait_event(ev_out[j])         # outputs[j] drained to the host
+                self.engine.encode(b["x"][j][:n], self.bn_mode, out=(b["zb"][j], b["za"][j], b["idx"][j]))
+                ev_cmp[j].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[j])
+                if "z_before" in out:
+                    out["z_before"][a:e].copy_(b["zb"][j][:n].reshape(n, -1), non_blocking=True)
+                if "z_after" in out:
+                    out["z_after"][a:e].copy_(b["za"][j][:n].reshape(n, -1), non_blocking=True)
+                if "idx" in out:
+                    out["idx"][a:e].copy_(b["idx"][j][:n].reshape(n, -1), non_blocking=True)
+                ev_out[j].record(s_out)
+            used[j] = True
+        for s in self._streams:
+            cur.wait_stream(s)
+        return out

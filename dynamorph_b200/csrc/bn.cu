@@ -1,0 +1,91 @@
+// BatchNorm bookkeeping kernels: statistics finalisation and the residual merge.
+// Reference semantics: nn.BatchNorm2d (eps 1e-5, momentum 0.1, biased variance to normalise,
+// unbiased to track) as used at HiddenStateExtractor/vq_vae.py:205,208,279-288.
+#include "common.cuh"
+
+namespace dmb {
+namespace {
+
+// one warp per output (channel, or sample*channel): fixed-order sum of the per-CTA partials
+__global__ void bn_finalize_kernel(const BnFinalizeArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nout = a.per_sample ? a.B * a.C : a.C;
+    if (warp >= nout) return;
+    const int c = warp % a.C;
+    const int bs = a.per_sample ? warp / a.C : 0;
+    const int nb = a.per_sample ? 1 : a.B;
+    const int n = nb * a.nbands;
+    double s = 0.0, q = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const int bb = bs + i / a.nbands, band = i % a.nbands;
+        const double* p = a.partials + (((size_t)bb * a.nbands + band) * a.C + c) * 2;
+        s += p[0]; q += p[1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane) return;
+    const double cnt = (double)a.count_per_sample * nb;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float sc = a.gamma[c] * invstd;
+    a.scale[warp] = sc;
+    a.shift[warp] = a.beta[c] - (float)mean * sc;
+    if (a.save_mean) { a.save_mean[warp] = (float)mean; a.save_invstd[warp] = invstd; }
+    if (!a.per_sample && a.running_mean) {
+        const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+        a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)mean;
+        a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unbiased;
+    }
+}
+
+__global__ void affine_add_kernel(const AffineAddArgs a, int64_t total4) {
+    const int hw4 = a.HW >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t plane = i / hw4;            // b*C + c
+        const int c = (int)(plane % a.C);
+        const int64_t t = a.per_sample ? plane : c;
+        float4 va = __ldg(reinterpret_cast<const float4*>(a.a) + i);
+        float4 vb = a.b ? __ldg(reinterpret_cast<const float4*>(a.b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.sa) {
+            const float s = a.sa[t], sh = a.ta[t];
+            va.x = fmaf(va.x, s, sh); va.y = fmaf(va.y, s, sh); va.z = fmaf(va.z, s, sh); va.w = fmaf(va.w, s, sh);
+        }
+        if (a.b && a.sb) {
+            const float s = a.sb[t], sh = a.tb[t];
+            vb.x = fmaf(vb.x, s, sh); vb.y = fmaf(vb.y, s, sh); vb.z = fmaf(vb.z, s, sh); vb.w = fmaf(vb.w, s, sh);
+        }
+        reinterpret_cast<float4*>(a.out)[i] = make_float4(va.x + vb.x, va.y + vb.y, va.z + vb.z, va.w + vb.w);
+    }
+}
+
+}  // namespace
+
+int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
+    const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
+    const int threads = 128;
+    const int64_t blocks = (nout * 32 + threads - 1) / threads;
+    bn_finalize_kernel<<<(unsigned)blocks, threads, 0, st>>>(a);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int affine_add(const AffineAddArgs& a, cudaStream_t st) {
+    DMB_CHECK(a.HW % 4 == 0, "affine_add: HW must be a multiple of 4");
+    const int64_t total4 = a.B * a.C * (a.HW >> 2);
+    int64_t blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    affine_add_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, total4);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+}  // namespace dmb

@@ -1,0 +1,369 @@
+// Direct convolution forward on CUDA cores (fp32, exact), NCHW planar.
+//
+// Covers every Conv2d on the path: 1x1, 3x3 (pad 1) and 4x4 stride 2 (pad 1)
+// (reference layers: HiddenStateExtractor/vq_vae.py:203-209, :276-289, :298).
+//
+// Why CUDA cores and not tcgen05: the reduction is C*kh*kw = 32..256 with 8..32 output
+// channels and the parity bar is fp32 1e-4 / bit-exact indices (BASELINE.json north_star);
+// see DESIGN.md "Roofline".  The kernel is FP32-FMA bound, so the design goal is FFMA
+// issue share: each thread owns PW=8 consecutive output pixels x CO_T output channels
+// (64 accumulators), activations come from a shared-memory tile with conflict-free 128-bit
+// loads, weights from shared memory as warp-uniform 128-bit broadcasts.
+//
+// Shared-memory tile, per (local patch, input channel, input row):
+//   stride 2: the zero-padded row is split by column parity into two planes P0/P1, so the
+//             four taps of a 4x4/stride-2 window read P0[ox], P1[ox], P0[ox+1], P1[ox+1]:
+//             unit-stride in ox for both planes (space-to-depth done by the loader);
+//   stride 1: one plane holding the padded row.
+//   Inside a plane, 16-byte granules are dealt round-robin to NG = PW/4 sub-planes so that
+//   the i-th 128-bit load of neighbouring threads hits neighbouring granules (no bank
+//   conflicts although each thread walks PW contiguous floats).
+#include "common.cuh"
+
+namespace dmb {
+
+namespace {
+
+constexpr int PW = 8;        // output pixels per thread along x
+constexpr int NG = PW / 4;   // granules per strip
+
+struct ConvK {
+    ConvFwdArgs a;
+    int TR, NP, CIC, nbands, SPR, RIN, NPL, PLW, SUBW;
+    int row_stride, ci_stride, patch_stride, w_floats, tile_floats;
+    int threads;
+};
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int KS, int STRIDE, int CO_T>
+__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvK k) {
+    extern __shared__ __align__(16) float smem[];
+    const ConvFwdArgs& a = k.a;
+    constexpr int PAD = (KS == 1) ? 0 : 1;
+    constexpr int NPLANES = (STRIDE == 2) ? 2 : 1;
+    constexpr int NV = (KS == 1) ? NG : NG + 1;   // float4 loads per plane row
+
+    float* ws = smem;
+    float* tile = smem + ((k.w_floats + 3) & ~3);
+
+    const int tid = threadIdx.x;
+    const int band = blockIdx.x % k.nbands;
+    const int64_t b0 = (int64_t)(blockIdx.x / k.nbands) * k.NP;
+
+    // thread -> (channel group, local patch, row, strip)
+    const int strips_per_patch = k.TR * k.SPR;
+    const int strips = k.NP * strips_per_patch;
+    const int cg = tid / strips;
+    const int srem = tid - cg * strips;
+    const int pl = srem / strips_per_patch;
+    const int prem = srem - pl * strips_per_patch;
+    const int row = prem / k.SPR;
+    const int sx = prem - row * k.SPR;
+    const int oy = band * k.TR + row;
+    const int64_t b = b0 + pl;
+    const bool live = b < a.B;
+
+    float acc[CO_T][PW];
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c)
+#pragma unroll
+        for (int p = 0; p < PW; ++p) acc[c][p] = 0.f;
+
+    const int in_row0 = band * k.TR * STRIDE - PAD;   // input row held in tile row 0
+    const int W4 = a.W >> 2;
+
+    for (int c0 = 0; c0 < a.Cin; c0 += k.CIC) {
+        __syncthreads();
+        // ---- weights chunk: contiguous [CIC][KS][KS][Cout]
+        if constexpr (CO_T % 4 == 0) {
+            const float4* src = reinterpret_cast<const float4*>(a.w + (size_t)c0 * KS * KS * a.Cout);
+            float4* dst = reinterpret_cast<float4*>(ws);
+            for (int i = tid; i < (k.w_floats >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+        } else {
+            const float* src = a.w + (size_t)c0 * KS * KS * a.Cout;
+            for (int i = tid; i < k.w_floats; i += blockDim.x) ws[i] = __ldg(src + i);
+        }
+        // ---- activation tile with the producer's BN affine + ReLU applied on the fly
+        {
+            const int per_row = W4;
+            const int total = k.NP * k.CIC * k.RIN * per_row;
+            for (int e = tid; e < total; e += blockDim.x) {
+                int q = e % per_row;
+                int t = e / per_row;
+                int r = t % k.RIN; t /= k.RIN;
+                int cil = t % k.CIC;
+                int lp = t / k.CIC;
+                const int64_t bb = b0 + lp;
+                const int ci = c0 + cil;
+                const int iy = in_row0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bb < a.B && iy >= 0 && iy < a.H) {
+                    v = __ldg(reinterpret_cast<const float4*>(
+                            a.x + (((size_t)bb * a.Cin + ci) * a.H + iy) * a.W) + q);
+                    if (a.in_scale) {
+                        const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + ci;
+                        const float s = __ldg(a.in_scale + ai), sh = __ldg(a.in_shift + ai);
+                        v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh);
+                        v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
+                    }
+                    if (a.in_relu) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                        v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                }
+                float* rowp = tile + lp * k.patch_stride + cil * k.ci_stride + r * k.row_stride;
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int p = 4 * q + i + PAD;              // index in the padded row
+                    const int plane = (NPLANES == 2) ? (p & 1) : 0;
+                    const int j = (NPLANES == 2) ? (p >> 1) : p;
+                    const int g = j >> 2;
+                    rowp[plane * k.PLW + (g % NG) * k.SUBW + (g / NG) * 4 + (j & 3)] = vv[i];
+                }
+                if (PAD) {
+                    if (q == 0) rowp[0] = 0.f;                  // padded index 0 (plane 0, j 0)
+                    if (q == per_row - 1) {
+                        const int p = a.W + 1;                  // right halo
+                        const int plane = (NPLANES == 2) ? (p & 1) : 0;
+                        const int j = (NPLANES == 2) ? (p >> 1) : p;
+                        const int g = j >> 2;
+                        rowp[plane * k.PLW + (g % NG) * k.SUBW + (g / NG) * 4 + (j & 3)] = 0.f;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- FMA core
+        const float* tp = tile + pl * k.patch_stride + (row * STRIDE) * k.row_stride;
+        const float* wp = ws + cg * CO_T;
+        for (int cil = 0; cil < k.CIC; ++cil) {
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+                const float* rp = tp + cil * k.ci_stride + ky * k.row_stride;
+                float av[NPLANES][NV * 4];
+#pragma unroll
+                for (int pn = 0; pn < NPLANES; ++pn)
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        const float4 t4 = lds4(rp + pn * k.PLW + (i % NG) * k.SUBW + (sx + i / NG) * 4);
+                        av[pn][4 * i + 0] = t4.x; av[pn][4 * i + 1] = t4.y;
+                        av[pn][4 * i + 2] = t4.z; av[pn][4 * i + 3] = t4.w;
+                    }
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+                    float wv[CO_T];
+                    const float* wrow = wp + ((cil * KS + ky) * KS + kx) * a.Cout;
+                    if constexpr (CO_T % 4 == 0) {
+#pragma unroll
+                        for (int c = 0; c < CO_T; c += 4) {
+                            const float4 t4 = lds4(wrow + c);
+                            wv[c] = t4.x; wv[c + 1] = t4.y; wv[c + 2] = t4.z; wv[c + 3] = t4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CO_T; ++c) wv[c] = wrow[c];
+                    }
+                    const int pn = (STRIDE == 2) ? (kx & 1) : 0;
+                    const int off = (STRIDE == 2) ? (kx >> 1) : kx;
+#pragma unroll
+                    for (int c = 0; c < CO_T; ++c)
+#pragma unroll
+                        for (int p = 0; p < PW; ++p)
+                            acc[c][p] = fmaf(wv[c], av[pn][p + off], acc[c][p]);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: bias (+ border classes), skip, ReLU, store, statistics
+    const int rc = (oy == 0) ? 0 : ((oy == a.Ho - 1) ? 2 : 1);
+    float ssum[CO_T], ssq[CO_T];
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) {
+        const int co = cg * CO_T + c;
+        float bmid, bl, br;
+        if (a.bias_classes) {
+            bl = __ldg(a.bias + (rc * 3 + 0) * a.Cout + co);
+            bmid = __ldg(a.bias + (rc * 3 + 1) * a.Cout + co);
+            br = __ldg(a.bias + (rc * 3 + 2) * a.Cout + co);
+        } else {
+            bl = bmid = br = __ldg(a.bias + co);
+        }
+        float o[PW];
+#pragma unroll
+        for (int p = 0; p < PW; ++p) o[p] = acc[c][p] + bmid;
+        if (sx == 0) o[0] = acc[c][0] + bl;
+        if (sx == k.SPR - 1) o[PW - 1] = acc[c][PW - 1] + br;
+        const size_t off = (((size_t)b * a.Cout + co) * a.Ho + oy) * a.Wo + sx * PW;
+        if (a.skip && live) {
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.skip + off) + i);
+                o[4 * i] += s4.x; o[4 * i + 1] += s4.y; o[4 * i + 2] += s4.z; o[4 * i + 3] += s4.w;
+            }
+        }
+        if (a.out_relu) {
+#pragma unroll
+            for (int p = 0; p < PW; ++p) o[p] = fmaxf(o[p], 0.f);
+        }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < NG; ++i)
+                reinterpret_cast<float4*>(a.y + off)[i] =
+                    make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int p = 0; p < PW; ++p) { s += o[p]; q = fmaf(o[p], o[p], q); }
+        ssum[c] = s; ssq[c] = q;
+    }
+
+    if (a.stats) {
+        // deterministic two-level reduction: thread partials -> smem -> one warp per (patch, channel)
+        __syncthreads();
+        float2* sp = reinterpret_cast<float2*>(smem);   // [NP][Cout][strips_per_patch]
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c)
+            sp[((size_t)pl * a.Cout + cg * CO_T + c) * strips_per_patch + prem] = make_float2(ssum[c], ssq[c]);
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+        for (int pc = warp; pc < k.NP * a.Cout; pc += nwarps) {
+            const int lp = pc / a.Cout, co = pc - lp * a.Cout;
+            double s = 0.0, q = 0.0;
+            for (int i = lane; i < strips_per_patch; i += 32) {
+                const float2 v = sp[(size_t)pc * strips_per_patch + i];
+                s += (double)v.x; q += (double)v.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if (lane == 0 && b0 + lp < a.B) {
+                double* dst = a.stats + ((((size_t)(b0 + lp)) * k.nbands + band) * a.Cout + co) * 2;
+                dst[0] = s; dst[1] = q;
+            }
+        }
+    }
+}
+
+int plan(const ConvFwdArgs& a, int co_t, ConvK& k) {
+    k.a = a;
+    const int KS = a.ks, S = a.stride;
+    const int ncg = a.Cout / co_t;
+    k.SPR = a.Wo / PW;
+    const int strips_per_patch_full = a.Ho * k.SPR;
+    const int tpp = strips_per_patch_full * ncg;
+    const int target = 128;
+    if (tpp >= target) {
+        k.NP = 1;
+        k.TR = 1;
+        for (int tr = 1; tr <= a.Ho; ++tr)
+            if (a.Ho % tr == 0 && tr * k.SPR * ncg <= target) k.TR = tr;
+    } else {
+        k.TR = a.Ho;
+        k.NP = target / tpp;
+        if (k.NP > a.B) k.NP = (int)a.B;
+        if (k.NP < 1) k.NP = 1;
+    }
+    k.nbands = a.Ho / k.TR;
+    k.threads = k.NP * k.TR * k.SPR * ncg;
+    if (k.threads > 256 || k.threads < 1) return -1;
+    k.RIN = (k.TR - 1) * S + KS;
+    k.NPL = (S == 2) ? 2 : 1;
+    const int elems = (KS == 1) ? a.W : ((S == 2) ? a.Wo + 1 : a.W + 2);   // valid j per plane
+    const int granules = (elems + 3) / 4 + ((KS == 1) ? 0 : 1);             // + overrun granule
+    k.SUBW = ((granules + NG - 1) / NG) * 4;
+    k.PLW = NG * k.SUBW;
+    k.row_stride = k.NPL * k.PLW;
+    // Narrow maps put several output rows into one 8-lane shared-memory phase; pad the row so
+    // that consecutive output rows start SPR granules apart (mod 32 banks) -> conflict-free.
+    if (k.SPR < 8) {
+        const int want = (k.SPR * 4) % 32;
+        int rs = k.row_stride;
+        for (int i = 0; i < 8 && (S * rs) % 32 != want; ++i) rs += 4;
+        if ((S * rs) % 32 == want) k.row_stride = rs;
+    }
+    k.ci_stride = k.RIN * k.row_stride;
+    // input-channel chunk: keep (weights + tile) under 54 KB so 4 CTAs share an SM
+    const int budget = 54 * 1024 / 4;
+    k.CIC = 1;
+    for (int c = 1; c <= a.Cin; ++c) {
+        if (a.Cin % c) continue;
+        const int fl = c * KS * KS * a.Cout + k.NP * c * k.ci_stride;
+        if (fl <= budget) k.CIC = c;
+    }
+    k.patch_stride = k.CIC * k.ci_stride;
+    k.w_floats = k.CIC * KS * KS * a.Cout;
+    k.tile_floats = k.NP * k.patch_stride;
+    return 0;
+}
+
+template <int KS, int STRIDE, int CO_T>
+int launch(const ConvK& k, cudaStream_t st) {
+    const ConvFwdArgs& a = k.a;
+    size_t smem = (size_t)(((k.w_floats + 3) & ~3) + k.tile_floats) * sizeof(float);
+    const size_t stats_smem = a.stats ? (size_t)k.NP * a.Cout * k.TR * k.SPR * sizeof(float2) : 0;
+    if (stats_smem > smem) smem = stats_smem;
+    auto kern = conv_fwd_kernel<KS, STRIDE, CO_T>;
+    if (smem > 48 * 1024) {
+        static size_t configured[64] = {0};   // per instantiation, per device
+        int dev = 0;
+        DMB_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+            DMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) configured[dev] = smem;
+        }
+    }
+    const int64_t groups = (a.B + k.NP - 1) / k.NP;
+    const int64_t grid = groups * k.nbands;
+    DMB_CHECK(grid > 0 && grid < (1ll << 31), "conv_fwd: grid %lld out of range", (long long)grid);
+    kern<<<(unsigned)grid, k.threads, smem, st>>>(k);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int pick_co_t(int Cout) { return (Cout % 8 == 0) ? 8 : ((Cout % 4 == 0) ? 4 : ((Cout % 2 == 0) ? 2 : 0)); }
+
+}  // namespace
+
+int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo) {
+    ConvFwdArgs a{};
+    a.ks = ks; a.stride = stride; a.Cin = Cin; a.Cout = Cout; a.Ho = Ho; a.Wo = Wo;
+    a.H = (stride == 2) ? Ho * 2 : Ho; a.W = (stride == 2) ? Wo * 2 : Wo; a.B = 1 << 20;
+    ConvK k;
+    const int co_t = pick_co_t(Cout);
+    if (!co_t || Wo % PW || plan(a, co_t, k)) return -1;
+    return k.nbands;
+}
+
+int conv_fwd(const ConvFwdArgs& a, cudaStream_t st) {
+    DMB_CHECK(a.B > 0, "conv_fwd: empty batch");
+    DMB_CHECK((a.ks == 1 && a.stride == 1) || (a.ks == 3 && a.stride == 1) || (a.ks == 4 && a.stride == 2),
+              "conv_fwd: unsupported kernel %dx%d stride %d", a.ks, a.ks, a.stride);
+    DMB_CHECK(a.Ho * a.stride == a.H && a.Wo * a.stride == a.W, "conv_fwd: geometry mismatch");
+    DMB_CHECK(a.Wo % PW == 0, "conv_fwd: output width %d must be a multiple of %d", a.Wo, PW);
+    const int co_t = pick_co_t(a.Cout);
+    DMB_CHECK(co_t != 0, "conv_fwd: Cout=%d must be even", a.Cout);
+    ConvK k;
+    DMB_CHECK(plan(a, co_t, k) == 0, "conv_fwd: no launch plan for Cout=%d Ho=%d Wo=%d", a.Cout, a.Ho, a.Wo);
+    DMB_CHECK((size_t)(k.w_floats + k.tile_floats) * 4 <= 200 * 1024,
+              "conv_fwd: tile does not fit shared memory (Cin=%d Cout=%d W=%d)", a.Cin, a.Cout, a.W);
+#define DMB_DISPATCH(KS, S)                                         \
+    if (a.ks == KS && a.stride == S) {                              \
+        if (co_t == 8) return launch<KS, S, 8>(k, st);              \
+        if (co_t == 4) return launch<KS, S, 4>(k, st);              \
+        return launch<KS, S, 2>(k, st);                             \
+    }
+    DMB_DISPATCH(1, 1)
+    DMB_DISPATCH(3, 1)
+    DMB_DISPATCH(4, 2)
+#undef DMB_DISPATCH
+    return -1;
+}
+
+}  // namespace dmb

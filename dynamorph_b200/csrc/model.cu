@@ -1,0 +1,611 @@
+// Model-level host code: parameter layout, workspace carving, and the layer schedule of the
+// encoder / quantiser / decoder for both reference architectures, behind the C ABI.
+//   z16: HiddenStateExtractor/vq_vae.py:276-298 (== vae.py:273-294)
+//   z32: HiddenStateExtractor/vae.py:401-414
+#include <stdarg.h>
+#include <atomic>
+#include <string.h>
+
+#include "model.h"
+
+namespace dmb {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Builder {
+    Layout& L;
+    int64_t p = 0, bb = 0, pk = 0;
+    explicit Builder(Layout& l) : L(l) {}
+    int64_t take_param(const std::string& key, int64_t n) {
+        L.entries.push_back({key, 0, p, n});
+        const int64_t o = p; p += n; return o;
+    }
+    int64_t take_buf(const std::string& key, int64_t n) {
+        L.entries.push_back({key, 1, bb, n});
+        const int64_t o = bb; bb += n; return o;
+    }
+    int64_t take_packed(int64_t n) { const int64_t o = pk; pk += (n + 3) & ~3ll; return o; }
+
+    int conv(const std::string& key, int cin, int cout, int ks, int stride, bool transposed) {
+        ConvL c{};
+        c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.transposed = transposed; c.bn = -1;
+        c.w_off = take_param(key + ".weight", (int64_t)cin * cout * ks * ks);
+        c.b_off = take_param(key + ".bias", cout);
+        c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
+        c.pb_off = take_packed(cout);
+        L.convs.push_back(c);
+        return (int)L.convs.size() - 1;
+    }
+    // z16 head: conv1x1 (key0) + conv4x4 s2 (key1) -> one composite conv over `cin` channels
+    int composite(const std::string& key0, const std::string& key1, int cin, int cmid) {
+        ConvL c{};
+        c.cin = cin; c.cout = cmid; c.cmid = cmid; c.ks = 4; c.stride = 2; c.composite = 1; c.bn = -1;
+        c.bias_classes = 1;
+        c.w0_off = take_param(key0 + ".weight", (int64_t)cmid * cin);
+        c.b0_off = take_param(key0 + ".bias", cmid);
+        c.w_off = take_param(key1 + ".weight", (int64_t)cmid * cmid * 16);
+        c.b_off = take_param(key1 + ".bias", cmid);
+        c.pw_off = take_packed((int64_t)cin * 16 * cmid);
+        c.pb_off = take_packed(9 * cmid);
+        L.convs.push_back(c);
+        return (int)L.convs.size() - 1;
+    }
+    void bn(const std::string& key, int c, int conv_idx) {
+        BnL b{};
+        b.c = c;
+        b.g_off = take_param(key + ".weight", c);
+        b.b_off = take_param(key + ".bias", c);
+        b.rm_off = take_buf(key + ".running_mean", c);
+        b.rv_off = take_buf(key + ".running_var", c);
+        b.pg_off = take_packed(c);
+        b.pb_off = take_packed(c);
+        L.bns.push_back(b);
+        L.convs[conv_idx].bn = (int)L.bns.size() - 1;
+    }
+    void res(const std::string& prefix, int h, int rh, int n, std::vector<ResL>& out) {
+        for (int i = 0; i < n; ++i) {
+            const std::string p = prefix + ".layers." + std::to_string(i);
+            ResL r;
+            r.a = conv(p + ".1", h, rh, 3, 1, false);
+            bn(p + ".2", rh, r.a);
+            r.b = conv(p + ".4", rh, h, 1, 1, false);
+            bn(p + ".5", h, r.b);
+            out.push_back(r);
+        }
+    }
+};
+
+}  // namespace
+
+int build_layout(const dmb_model* m, Layout& L) {
+    DMB_CHECK(m != nullptr, "null model descriptor");
+    DMB_CHECK(m->arch == DMB_ARCH_Z16 || m->arch == DMB_ARCH_Z32, "unknown arch %d", m->arch);
+    DMB_CHECK(m->num_inputs >= 1 && m->num_hiddens >= 8 && m->num_hiddens % 8 == 0,
+              "num_hiddens=%d must be a positive multiple of 8", m->num_hiddens);
+    DMB_CHECK(m->num_residual_hiddens >= 2 && m->num_residual_hiddens % 2 == 0,
+              "num_residual_hiddens=%d must be even", m->num_residual_hiddens);
+    DMB_CHECK(m->num_residual_layers >= 0 && m->num_residual_layers <= 6, "num_residual_layers out of range");
+    DMB_CHECK(m->num_embeddings >= 1 && m->num_embeddings <= 1024, "num_embeddings=%d outside [1,1024]", m->num_embeddings);
+    const int down = (m->arch == DMB_ARCH_Z16) ? 8 : 4;
+    DMB_CHECK(m->height > 0 && m->width > 0 && m->height % down == 0 && m->width % (down * 8) == 0,
+              "patch %dx%d: height must be a multiple of %d and width of %d", m->height, m->width, down, down * 8);
+    DMB_CHECK(m->num_inputs % 2 == 0 || m->arch == DMB_ARCH_Z16 || true, "unused");
+    L = Layout();
+    L.m = *m;
+    Builder B(L);
+    const int ni = m->num_inputs, h = m->num_hiddens, h2 = h / 2, h4 = h / 4, rh = m->num_residual_hiddens;
+    const int nl = m->num_residual_layers;
+    if (m->arch == DMB_ARCH_Z16) {
+        L.e1 = B.composite("enc.0", "enc.1", ni, h2); B.bn("enc.2", h2, L.e1);
+        L.e2 = B.conv("enc.4", h2, h, 4, 2, false);   B.bn("enc.5", h, L.e2);
+        L.e3 = B.conv("enc.7", h, h, 4, 2, false);    B.bn("enc.8", h, L.e3);
+        L.e4 = B.conv("enc.10", h, h, 3, 1, false);   B.bn("enc.11", h, L.e4);
+        B.res("enc.12", h, rh, nl, L.enc_res);
+        L.codebook_off = B.take_param("vq.w.weight", (int64_t)m->num_embeddings * h);
+        L.d0 = B.conv("dec.0", h, h2, 4, 2, true);
+        L.d1 = B.conv("dec.2", h2, h4, 4, 2, true);
+        L.d2 = B.conv("dec.4", h4, h4, 4, 2, true);
+        L.d3 = B.conv("dec.6", h4, ni, 1, 1, false);
+        L.lh = m->height / 8; L.lw = m->width / 8;
+    } else {
+        L.e1 = B.conv("enc.0", ni, h2, 4, 2, false);  B.bn("enc.1", h2, L.e1);
+        L.e2 = B.conv("enc.3", h2, h, 4, 2, false);   B.bn("enc.4", h, L.e2);
+        B.res("enc.5", h, rh, nl, L.enc_res);
+        L.codebook_off = B.take_param("vq.w.weight", (int64_t)m->num_embeddings * h);
+        B.res("dec.0", h, rh, nl, L.dec_res);
+        L.d0 = B.conv("dec.1", h, h2, 4, 2, true);    B.bn("dec.2", h2, L.d0);
+        L.d1 = B.conv("dec.4", h2, ni, 4, 2, true);
+        L.lh = m->height / 4; L.lw = m->width / 4;
+    }
+    L.D = h;
+    L.n_params = B.p; L.n_bnbuf = B.bb; L.n_packed = B.pk;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------
+namespace {
+struct Bump {
+    char* base; size_t off = 0;
+    explicit Bump(void* b) : base((char*)b) {}
+    template <class T> T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+}  // namespace
+
+int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* base, Workspace& w) {
+    (void)keep;
+    const dmb_model& m = L.m;
+    Bump bp(base);
+    const int h = m.num_hiddens, h2 = h / 2, h4 = h / 4, rh = m.num_residual_hiddens;
+    const int64_t H = m.height, W = m.width;
+    const int64_t lat = (int64_t)L.lh * L.lw;
+    w = Workspace();
+    if (m.arch == DMB_ARCH_Z16) {
+        w.y1 = bp.take<float>(B * h2 * (H / 2) * (W / 2));
+        w.y2 = bp.take<float>(B * h * (H / 4) * (W / 4));
+        w.y3 = bp.take<float>(B * h * lat);
+        w.y4 = bp.take<float>(B * h * lat);
+    } else {
+        w.y1 = bp.take<float>(B * h2 * (H / 2) * (W / 2));
+        w.y2 = bp.take<float>(B * h * lat);
+    }
+    for (size_t i = 0; i < L.enc_res.size(); ++i) {
+        w.era.push_back(bp.take<float>(B * rh * lat));
+        w.erb.push_back(bp.take<float>(B * h * lat));
+        w.ehs.push_back(bp.take<float>(B * h * lat));
+    }
+    w.zb = bp.take<float>(B * h * lat);
+    w.za = bp.take<float>(B * h * lat);
+    w.idx = bp.take<int32_t>(B * lat);
+    for (size_t i = 0; i < L.dec_res.size(); ++i) {
+        w.dra.push_back(bp.take<float>(B * rh * lat));
+        w.drb.push_back(bp.take<float>(B * h * lat));
+        w.dhs.push_back(bp.take<float>(B * h * lat));
+    }
+    if (keep) {
+        if (m.arch == DMB_ARCH_Z16) {
+            w.t1 = bp.take<float>(B * h2 * 4 * lat);
+            w.t2 = bp.take<float>(B * h4 * 16 * lat);
+            w.t3 = bp.take<float>(B * h4 * 64 * lat);
+        } else {
+            w.t1 = bp.take<float>(B * h2 * 4 * lat);
+        }
+        w.dec = bp.take<float>(B * m.num_inputs * H * W);
+    }
+    // BatchNorm scratch, one per BN layer, in Layout::bns order (conv order)
+    w.bn.resize(L.bns.size());
+    if (bn_mode != DMB_BN_EVAL) {
+        for (size_t ci = 0; ci < L.convs.size(); ++ci) {
+            const ConvL& c = L.convs[ci];
+            if (c.bn < 0) continue;
+            int64_t Ho, Wo;
+            int nb;
+            const bool enc_side = (int)ci == L.e1 || (int)ci == L.e2 || (int)ci == L.e3 || (int)ci == L.e4;
+            if (c.transposed) {                      // z32 dec.1 (lat -> 2x)
+                Ho = 2 * L.lh; Wo = 2 * L.lw;
+                nb = convt_fwd_bands(c.cin, c.cout, L.lh, L.lw);
+            } else if ((int)ci == L.e1) {
+                Ho = H / 2; Wo = W / 2; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo);
+            } else if ((int)ci == L.e2) {
+                Ho = H / 4; Wo = W / 4; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo);
+            } else {
+                (void)enc_side;
+                Ho = L.lh; Wo = L.lw; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo);
+            }
+            DMB_CHECK(nb > 0, "no launch plan for conv %zu", ci);
+            BnWs& b = w.bn[c.bn];
+            const int64_t rows = (bn_mode == DMB_BN_PER_SAMPLE) ? B : 1;
+            b.nbands = nb;
+            b.count = Ho * Wo;
+            b.part = bp.take<double>(B * nb * c.cout * 2);
+            b.scale = bp.take<float>(rows * c.cout);
+            b.shift = bp.take<float>(rows * c.cout);
+            b.mean = bp.take<float>(rows * c.cout);
+            b.invstd = bp.take<float>(rows * c.cout);
+        }
+    }
+    w.vq_stats = bp.take<double>(2 + m.num_embeddings);
+    w.recon_sum = bp.take<double>(4);
+    w.scalars = bp.take<float>(8);
+    w.bytes = (bp.off + 255) & ~(size_t)255;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// schedules
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Act {             // an activation tensor plus the affine (BN) still to be applied to it
+    const float* p = nullptr;
+    const float* s = nullptr;
+    const float* t = nullptr;
+};
+
+struct Ctx {
+    const Layout& L;
+    const float* packed;
+    Workspace& w;
+    int64_t B;
+    int mode;
+    float* bnbuf;      // running stats to update in BATCH mode (may be null)
+    cudaStream_t st;
+    bool per_sample() const { return mode == DMB_BN_PER_SAMPLE; }
+};
+
+// conv (or convT) layer `ci`: in -> out, optional ReLU on load; in BN modes gathers statistics and
+// finalises them, returning the affine that the consumer must apply.
+int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* out,
+             const float* skip, bool out_relu, Act* result) {
+    const ConvL& l = c.L.convs[ci];
+    const bool bn_live = (l.bn >= 0 && c.mode != DMB_BN_EVAL);
+    BnWs* bw = bn_live ? &c.w.bn[l.bn] : nullptr;
+    int Ho, Wo;
+    if (l.transposed) {
+        ConvTFwdArgs a{};
+        a.x = in.p; a.y = out; a.w = c.packed + l.pw_off; a.bias = c.packed + l.pb_off;
+        a.in_scale = in.s; a.in_shift = in.t; a.in_per_sample = c.per_sample(); a.in_relu = in_relu;
+        a.out_relu = out_relu && !bn_live;
+        a.stats = bn_live ? bw->part : nullptr;
+        a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout;
+        DMB_TRY(convt_fwd(a, c.st));
+        Ho = 2 * H; Wo = 2 * W;
+    } else {
+        ConvFwdArgs a{};
+        a.x = in.p; a.y = out; a.w = c.packed + l.pw_off; a.bias = c.packed + l.pb_off;
+        a.bias_classes = l.bias_classes;
+        a.in_scale = in.s; a.in_shift = in.t; a.in_per_sample = c.per_sample(); a.in_relu = in_relu;
+        a.skip = bn_live ? nullptr : skip;
+        a.out_relu = out_relu && !bn_live;
+        a.stats = bn_live ? bw->part : nullptr;
+        a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout;
+        a.ks = l.ks; a.stride = l.stride;
+        a.Ho = H / l.stride; a.Wo = W / l.stride;
+        DMB_TRY(conv_fwd(a, c.st));
+        Ho = a.Ho; Wo = a.Wo;
+    }
+    if (result) { result->p = out; result->s = nullptr; result->t = nullptr; }
+    if (bn_live) {
+        const BnL& b = c.L.bns[l.bn];
+        BnFinalizeArgs f{};
+        f.partials = bw->part; f.B = (int)c.B; f.nbands = bw->nbands; f.C = l.cout;
+        f.count_per_sample = (int64_t)Ho * Wo;
+        f.per_sample = c.per_sample();
+        f.gamma = c.packed + b.pg_off; f.beta = c.packed + b.pb_off;
+        f.eps = c.L.m.bn_eps; f.momentum = c.L.m.bn_momentum;
+        f.scale = bw->scale; f.shift = bw->shift;
+        f.running_mean = (c.bnbuf && !c.per_sample()) ? c.bnbuf + b.rm_off : nullptr;
+        f.running_var = (c.bnbuf && !c.per_sample()) ? c.bnbuf + b.rv_off : nullptr;
+        f.save_mean = bw->mean; f.save_invstd = bw->invstd;
+        DMB_TRY(bn_finalize(f, c.st));
+        if (result) { result->s = bw->scale; result->t = bw->shift; }
+    }
+    return 0;
+}
+
+// ResidualBlock (vq_vae.py:203-225).  `h` enters possibly with a pending affine; returns the block
+// output.  If `fuse_last` is given, the last layer's merge is left to the consumer (VQ kernel).
+struct Pending { Act a, b; bool valid = false; };
+int run_res(Ctx& c, const std::vector<ResL>& res, std::vector<float*>& ra, std::vector<float*>& rb,
+            std::vector<float*>& hs, Act h, int H, int W, float* final_out, Pending* fuse_last, Act* out) {
+    const int64_t hw = (int64_t)H * W;
+    for (size_t i = 0; i < res.size(); ++i) {
+        const bool last = (i + 1 == res.size());
+        float* dst = (last && final_out) ? final_out : hs[i];
+        Act a1, b1;
+        if (c.mode == DMB_BN_EVAL) {
+            DMB_TRY(run_conv(c, res[i].a, h, true, H, W, ra[i], nullptr, true, &a1));
+            DMB_TRY(run_conv(c, res[i].b, a1, false, H, W, dst, h.p, false, &b1));
+            h = b1;
+        } else {
+            DMB_TRY(run_conv(c, res[i].a, h, true, H, W, ra[i], nullptr, false, &a1));
+            DMB_TRY(run_conv(c, res[i].b, a1, true, H, W, rb[i], nullptr, false, &b1));
+            if (last && fuse_last) {
+                fuse_last->a = h; fuse_last->b = b1; fuse_last->valid = true;
+                *out = Act();
+                return 0;
+            }
+            AffineAddArgs aa{};
+            aa.a = h.p; aa.sa = h.s; aa.ta = h.t; aa.b = b1.p; aa.sb = b1.s; aa.tb = b1.t;
+            aa.per_sample = c.per_sample(); aa.out = dst; aa.B = c.B; aa.C = c.L.m.num_hiddens; aa.HW = (int)hw;
+            DMB_TRY(affine_add(aa, c.st));
+            h = Act(); h.p = dst;
+        }
+    }
+    *out = h;
+    return 0;
+}
+
+// encoder: x -> z_before (written to zb_out unless the final merge is handed to `fuse`)
+int run_encoder(Ctx& c, const float* x, float* zb_out, Pending* fuse) {
+    const Layout& L = c.L;
+    const dmb_model& m = L.m;
+    const int H = m.height, W = m.width;
+    const bool ev = c.mode == DMB_BN_EVAL;
+    Act in; in.p = x;
+    Act a1, a2, a3, a4, out;
+    if (m.arch == DMB_ARCH_Z16) {
+        DMB_TRY(run_conv(c, L.e1, in, false, H, W, c.w.y1, nullptr, ev, &a1));
+        DMB_TRY(run_conv(c, L.e2, a1, !ev, H / 2, W / 2, c.w.y2, nullptr, ev, &a2));
+        DMB_TRY(run_conv(c, L.e3, a2, !ev, H / 4, W / 4, c.w.y3, nullptr, ev, &a3));
+        float* y4 = (L.enc_res.empty() && zb_out && ev) ? zb_out : c.w.y4;
+        DMB_TRY(run_conv(c, L.e4, a3, !ev, H / 8, W / 8, y4, nullptr, false, &a4));
+    } else {
+        DMB_TRY(run_conv(c, L.e1, in, false, H, W, c.w.y1, nullptr, ev, &a1));
+        float* y2 = (L.enc_res.empty() && zb_out && ev) ? zb_out : c.w.y2;
+        DMB_TRY(run_conv(c, L.e2, a1, !ev, H / 2, W / 2, y2, nullptr, false, &a4));
+    }
+    if (L.enc_res.empty()) {
+        if (a4.s) {                       // materialise the pending BN affine (no residual block)
+            AffineAddArgs aa{};
+            aa.a = a4.p; aa.sa = a4.s; aa.ta = a4.t; aa.b = nullptr;
+            aa.per_sample = c.per_sample(); aa.out = zb_out; aa.B = c.B; aa.C = m.num_hiddens;
+            aa.HW = L.lh * L.lw;
+            DMB_TRY(affine_add(aa, c.st));
+        }
+        return 0;
+    }
+    DMB_TRY(run_res(c, L.enc_res, c.w.era, c.w.erb, c.w.ehs, a4, L.lh, L.lw, zb_out, fuse, &out));
+    return 0;
+}
+
+int run_vq(Ctx& c, const float* codebook, const float* z, const Pending* pre, float* zb_out,
+           float* z_after, int32_t* idx, double* stats) {
+    VqArgs a{};
+    a.codebook = codebook; a.B = c.B; a.D = c.L.D; a.P = c.L.lh * c.L.lw; a.K = c.L.m.num_embeddings;
+    a.z_st = z_after; a.idx = idx; a.stats = stats;
+    if (pre && pre->valid) {
+        a.pre_a = pre->a.p; a.pre_sa = pre->a.s; a.pre_ta = pre->a.t;
+        a.pre_b = pre->b.p; a.pre_sb = pre->b.s; a.pre_tb = pre->b.t;
+        a.pre_per_sample = c.per_sample();
+        a.z_before_out = zb_out;
+    } else {
+        a.z = z;
+    }
+    return vq_forward(a, c.st);
+}
+
+int run_decoder(Ctx& c, const float* za, float* decoded) {
+    const Layout& L = c.L;
+    const dmb_model& m = L.m;
+    const bool ev = c.mode == DMB_BN_EVAL;
+    Act in; in.p = za;
+    Act a1, a2, a3, o;
+    if (m.arch == DMB_ARCH_Z16) {
+        DMB_CHECK(c.w.t1 && c.w.t2 && c.w.t3, "decoder needs a workspace carved with keep_activations=1");
+        DMB_TRY(run_conv(c, L.d0, in, false, L.lh, L.lw, c.w.t1, nullptr, true, &a1));
+        DMB_TRY(run_conv(c, L.d1, a1, false, 2 * L.lh, 2 * L.lw, c.w.t2, nullptr, true, &a2));
+        DMB_TRY(run_conv(c, L.d2, a2, false, 4 * L.lh, 4 * L.lw, c.w.t3, nullptr, true, &a3));
+        DMB_TRY(run_conv(c, L.d3, a3, false, 8 * L.lh, 8 * L.lw, decoded, nullptr, false, &o));
+    } else {
+        DMB_CHECK(c.w.t1, "decoder needs a workspace carved with keep_activations=1");
+        Act h;
+        DMB_TRY(run_res(c, L.dec_res, c.w.dra, c.w.drb, c.w.dhs, in, L.lh, L.lw, nullptr, nullptr, &h));
+        DMB_TRY(run_conv(c, L.d0, h, false, L.lh, L.lw, c.w.t1, nullptr, ev, &a1));
+        DMB_TRY(run_conv(c, L.d1, a1, !ev, 2 * L.lh, 2 * L.lw, decoded, nullptr, false, &o));
+    }
+    return 0;
+}
+
+__global__ void recon_loss_kernel(const float* __restrict__ dec, const float* __restrict__ x,
+                                  const float* __restrict__ mask, int mask_c, const float* __restrict__ cvar,
+                                  int64_t total4, int C, int hw4, double* out) {
+    __shared__ double red[8];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t plane = i / hw4;
+        const int c = (int)(plane % C);
+        const int64_t b = plane / C;
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dec) + i);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (mask) {
+            const int64_t mi = (mask_c == 1) ? (b * hw4 + (i - plane * hw4)) : i;
+            mk = __ldg(reinterpret_cast<const float4*>(mask) + mi);
+        }
+        const float cv = __ldg(cvar + c);
+        // mse_loss(decoded*mask, inputs*mask, 'none') / channel_var  (vq_vae.py:322)
+        float e0 = d.x * mk.x - v.x * mk.x, e1 = d.y * mk.y - v.y * mk.y;
+        float e2 = d.z * mk.z - v.z * mk.z, e3 = d.w * mk.w - v.w * mk.w;
+        acc += (double)((e0 * e0) / cv) + (double)((e1 * e1) / cv) + (double)((e2 * e2) / cv) + (double)((e3 * e3) / cv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+        atomicAdd(out, s);
+    }
+}
+
+}  // namespace
+}  // namespace dmb
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+using namespace dmb;
+
+extern "C" {
+
+int dmb_abi_version(void) { return DMB_ABI_VERSION; }
+const char* dmb_last_error(void) { return dmb::g_err; }
+
+int dmb_param_count(const dmb_model* m, int64_t* n_params, int64_t* n_bnbuf, int32_t* n_bn) {
+    Layout L;
+    DMB_TRY(build_layout(m, L));
+    if (n_params) *n_params = L.n_params;
+    if (n_bnbuf) *n_bnbuf = L.n_bnbuf;
+    if (n_bn) *n_bn = (int32_t)L.bns.size();
+    return 0;
+}
+
+int dmb_param_lookup(const dmb_model* m, const char* key_host, int32_t* which, int64_t* offset, int64_t* numel) {
+    Layout L;
+    DMB_TRY(build_layout(m, L));
+    DMB_CHECK(key_host != nullptr, "null key");
+    for (const Entry& e : L.entries)
+        if (e.key == key_host) {
+            if (which) *which = e.which;
+            if (offset) *offset = e.off;
+            if (numel) *numel = e.numel;
+            return 0;
+        }
+    DMB_CHECK(false, "no such state_dict key: %s", key_host);
+}
+
+int dmb_latent_shape(const dmb_model* m, int32_t* d, int32_t* lh, int32_t* lw) {
+    Layout L;
+    DMB_TRY(build_layout(m, L));
+    if (d) *d = L.D;
+    if (lh) *lh = L.lh;
+    if (lw) *lw = L.lw;
+    return 0;
+}
+
+int dmb_packed_floats(const dmb_model* m, int64_t* n) {
+    Layout L;
+    DMB_TRY(build_layout(m, L));
+    DMB_CHECK(n != nullptr, "null output");
+    *n = L.n_packed;
+    return 0;
+}
+
+int dmb_pack_weights(const dmb_model* m, const float* params, const float* bnbuf, int32_t bn_mode,
+                     float* packed, void* stream) {
+    Layout L;
+    DMB_TRY(build_layout(m, L));
+    DMB_CHECK(params && bnbuf && packed, "dmb_pack_weights: null pointer");
+    DMB_CHECK(bn_mode >= 0 && bn_mode <= 2, "bad bn_mode %d", bn_mode);
+    return pack_weights(L, params, bnbuf, bn_mode, packed, (cudaStream_t)stream);
+}
+
+int dmb_workspace_bytes(const dmb_model* m, int64_t batch, int32_t bn_mode, int32_t keep, size_t* bytes) {
+    Layout L;
+    DMB_TRY(build_layout(m, L));
+    DMB_CHECK(batch > 0 && bytes, "dmb_workspace_bytes: bad arguments");
+    Workspace w;
+    DMB_TRY(carve_workspace(L, batch, bn_mode, keep, nullptr, w));
+    *bytes = w.bytes;
+    return 0;
+}
+
+static int prep(const dmb_model* m, int64_t batch, int32_t bn_mode, int keep, void* workspace,
+                size_t workspace_bytes, Layout& L, Workspace& w) {
+    DMB_TRY(build_layout(m, L));
+    DMB_CHECK(batch > 0 && batch < (1 << 24), "batch %lld out of range", (long long)batch);
+    DMB_CHECK(bn_mode >= 0 && bn_mode <= 2, "bad bn_mode %d", bn_mode);
+    DMB_CHECK(workspace != nullptr, "null workspace");
+    DMB_TRY(carve_workspace(L, batch, bn_mode, keep, workspace, w));
+    DMB_CHECK(w.bytes <= workspace_bytes, "workspace too small: need %zu bytes, have %zu", w.bytes, workspace_bytes);
+    return 0;
+}
+
+int dmb_encoder_forward(const dmb_model* m, const float* packed, const float* x, int64_t batch,
+                        int32_t bn_mode, float* z_before, float* bnbuf_inout, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    Layout L; Workspace w;
+    DMB_CHECK(packed && x && z_before, "dmb_encoder_forward: null pointer");
+    // keep flag only affects the tail of the carve; probe which one the caller sized for
+    DMB_TRY(prep(m, batch, bn_mode, 0, workspace, workspace_bytes, L, w));
+    Ctx c{L, packed, w, batch, bn_mode, bnbuf_inout, (cudaStream_t)stream};
+    return run_encoder(c, x, z_before, nullptr);
+}
+
+int dmb_encode(const dmb_model* m, const float* packed, const float* codebook, const float* x,
+               int64_t batch, int32_t bn_mode, float* z_before, float* z_after, int32_t* idx,
+               double* vq_stats, void* workspace, size_t workspace_bytes, void* stream) {
+    Layout L; Workspace w;
+    DMB_CHECK(packed && codebook && x, "dmb_encode: null pointer");
+    DMB_CHECK(bn_mode != DMB_BN_BATCH, "dmb_encode: BATCH statistics make patches interdependent; "
+              "use EVAL or PER_SAMPLE for bulk encoding");
+    DMB_TRY(prep(m, batch, bn_mode, 0, workspace, workspace_bytes, L, w));
+    Ctx c{L, packed, w, batch, bn_mode, nullptr, (cudaStream_t)stream};
+    float* zb = z_before ? z_before : w.zb;
+    Pending pend;
+    DMB_TRY(run_encoder(c, x, zb, bn_mode == DMB_BN_EVAL ? nullptr : &pend));
+    return run_vq(c, codebook, zb, &pend, zb, z_after, idx, vq_stats);
+}
+
+int dmb_decoder_forward(const dmb_model* m, const float* packed, const float* z_after, int64_t batch,
+                        int32_t bn_mode, float* decoded, float* bnbuf_inout, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    Layout L; Workspace w;
+    DMB_CHECK(packed && z_after && decoded, "dmb_decoder_forward: null pointer");
+    DMB_TRY(prep(m, batch, bn_mode, 1, workspace, workspace_bytes, L, w));
+    Ctx c{L, packed, w, batch, bn_mode, bnbuf_inout, (cudaStream_t)stream};
+    return run_decoder(c, z_after, decoded);
+}
+
+int dmb_conv2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
+                       int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout, int32_t ksize,
+                       int32_t stride, const float* in_scale, const float* in_shift,
+                       int32_t in_per_sample, int32_t in_relu, const float* skip, int32_t out_relu,
+                       void* stream) {
+    DMB_CHECK(x && w_packed && bias && y, "dmb_conv2d_forward: null pointer");
+    DMB_CHECK((in_scale == nullptr) == (in_shift == nullptr), "dmb_conv2d_forward: scale/shift must come together");
+    DMB_CHECK(stride >= 1 && h % stride == 0 && w % stride == 0, "dmb_conv2d_forward: bad geometry");
+    ConvFwdArgs a{};
+    a.x = x; a.y = y; a.w = w_packed; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift;
+    a.in_per_sample = in_per_sample; a.in_relu = in_relu; a.skip = skip; a.out_relu = out_relu;
+    a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
+    a.Ho = h / stride; a.Wo = w / stride;
+    return conv_fwd(a, (cudaStream_t)stream);
+}
+
+int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
+                                 int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,
+                                 const float* in_scale, const float* in_shift, int32_t in_per_sample,
+                                 int32_t in_relu, int32_t out_relu, void* stream) {
+    DMB_CHECK(x && w_packed && bias && y, "dmb_conv_transpose2d_forward: null pointer");
+    ConvTFwdArgs a{};
+    a.x = x; a.y = y; a.w = w_packed; a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift;
+    a.in_per_sample = in_per_sample; a.in_relu = in_relu; a.out_relu = out_relu;
+    a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout;
+    return convt_fwd(a, (cudaStream_t)stream);
+}
+
+long long dmb_launch_count(int reset) {
+    const long long v = dmb::g_launches.load();
+    if (reset) dmb::g_launches.store(0);
+    return v;
+}
+
+int dmb_recon_loss(const float* decoded, const float* x, const float* mask, int32_t mask_channels,
+                   const float* channel_var, int64_t batch, int32_t channels, int32_t hw,
+                   double* sum_out, void* stream) {
+    DMB_CHECK(decoded && x && channel_var && sum_out, "dmb_recon_loss: null pointer");
+    DMB_CHECK(hw % 4 == 0, "dmb_recon_loss: H*W must be a multiple of 4");
+    DMB_CHECK(!mask || mask_channels == 1 || mask_channels == channels, "dmb_recon_loss: mask channels %d", mask_channels);
+    const int64_t total4 = batch * channels * (hw / 4);
+    int64_t blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    recon_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        decoded, x, mask, mask_channels, channel_var, total4, channels, hw / 4, sum_out);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+}  // extern "C"

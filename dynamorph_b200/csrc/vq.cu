@@ -1,0 +1,309 @@
+// Fused VectorQuantizer forward (HiddenStateExtractor/vq_vae.py:52-84, :90-116).
+//
+// One thread per latent position.  The codebook lives in shared memory, the position's D
+// channel values in registers; squared distances use the reference's direct-difference
+// form and reproduce torch's CPU summation order for the channel reduction (cascade sum:
+// 16-element sequential runs folded level by level, no FMA contraction), so that on
+// identical inputs the argmin is bit-identical to torch.argmax(-distances) -- first index
+// wins ties.  The same pass gathers the code vector, forms z + (q - z), accumulates
+// sum (q - z)^2 and the code histogram: the reference's (B,K,D,H,W) broadcast is never
+// materialised.  HBM traffic is the algorithmic minimum: read z once, write z_st + idx.
+#include "common.cuh"
+
+namespace dmb {
+namespace {
+
+constexpr int VQ_THREADS = 128;
+constexpr int KU = 4;   // codes processed together (independent add chains)
+
+// torch's multi_row_sum (aten/src/ATen/native/cpu/SumKernel.cpp) for one output element:
+// level_step = 16 for every size < 2^20.
+template <int D>
+__device__ __forceinline__ void dist_cascade(const float (&z)[D], const float* __restrict__ e, float& out) {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int i = 0;
+#pragma unroll
+    for (int c0 = 0; c0 + 16 <= D; c0 += 16) {
+#pragma unroll
+        for (int c = c0; c < c0 + 16; c += 4) {
+            const float4 ev = *reinterpret_cast<const float4*>(e + c);
+            float d;
+            d = __fsub_rn(z[c], ev.x);     acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+            d = __fsub_rn(z[c + 1], ev.y); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+            d = __fsub_rn(z[c + 2], ev.z); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+            d = __fsub_rn(z[c + 3], ev.w); acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+        }
+        i = c0 + 16;
+        acc1 = __fadd_rn(acc1, acc0); acc0 = 0.f;
+        if ((i & (15 << 4)) == 0) {
+            acc2 = __fadd_rn(acc2, acc1); acc1 = 0.f;
+            if ((i & (15 << 8)) == 0) { acc3 = __fadd_rn(acc3, acc2); acc2 = 0.f; }
+        }
+    }
+#pragma unroll
+    for (int c = (D / 16) * 16; c < D; ++c) {
+        const float d = __fsub_rn(z[c], e[c]);
+        acc0 = __fadd_rn(acc0, __fmul_rn(d, d));
+    }
+    acc0 = __fadd_rn(acc0, acc1);
+    acc0 = __fadd_rn(acc0, acc2);
+    acc0 = __fadd_rn(acc0, acc3);
+    out = acc0;
+}
+
+template <int D>
+__global__ void __launch_bounds__(VQ_THREADS) vq_kernel(const VqArgs a, int kchunk) {
+    extern __shared__ __align__(16) float cb[];          // [kchunk][D]
+    __shared__ int hist[1024];
+    __shared__ double red[VQ_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int64_t n = (int64_t)blockIdx.x * VQ_THREADS + tid;
+    const int64_t total = a.B * a.P;
+    const bool live = n < total;
+    const int64_t b = live ? n / a.P : 0;
+    const int pos = live ? (int)(n - b * a.P) : 0;
+
+    float z[D];
+    if (live) {
+        const size_t base = (size_t)b * D * a.P + pos;
+        if (a.pre_b) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const size_t t = (a.pre_per_sample ? (size_t)b * D : 0) + c;
+                float va = __ldg(a.pre_a + base + (size_t)c * a.P);
+                float vb = __ldg(a.pre_b + base + (size_t)c * a.P);
+                if (a.pre_sa) va = fmaf(va, a.pre_sa[t], a.pre_ta[t]);
+                if (a.pre_sb) vb = fmaf(vb, a.pre_sb[t], a.pre_tb[t]);
+                z[c] = va + vb;
+                if (a.z_before_out) a.z_before_out[base + (size_t)c * a.P] = z[c];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; ++c) z[c] = __ldg(a.z + base + (size_t)c * a.P);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) z[c] = 0.f;
+    }
+
+    float best = 0.f;
+    int bi = -1;
+    for (int k0 = 0; k0 < a.K; k0 += kchunk) {
+        const int kc = min(kchunk, a.K - k0);
+        __syncthreads();
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.codebook + (size_t)k0 * D);
+            float4* dst = reinterpret_cast<float4*>(cb);
+            for (int i = tid; i < kc * D / 4; i += VQ_THREADS) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        int k = 0;
+        for (; k + KU <= kc; k += KU) {
+            float d[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) dist_cascade<D>(z, cb + (k + u) * D, d[u]);
+#pragma unroll
+            for (int u = 0; u < KU; ++u)
+                if (bi < 0 || d[u] < best) { best = d[u]; bi = k0 + k + u; }
+        }
+        for (; k < kc; ++k) {
+            float d;
+            dist_cascade<D>(z, cb + k * D, d);
+            if (bi < 0 || d < best) { best = d; bi = k0 + k; }
+        }
+    }
+
+    // gather + straight-through value + loss partial
+    double lsum = 0.0;
+    if (live) {
+        const float* e = a.codebook + (size_t)bi * D;
+        const size_t base = (size_t)b * D * a.P + pos;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const float q = __ldg(e + c);
+            const float diff = __fsub_rn(q, z[c]);
+            if (a.z_st) a.z_st[base + (size_t)c * a.P] = __fadd_rn(z[c], diff);
+            lsum += (double)diff * (double)diff;
+        }
+        if (a.idx) a.idx[n] = bi;
+    }
+    if (a.stats) {
+        for (int i = tid; i < a.K; i += VQ_THREADS) hist[i] = 0;
+        __syncthreads();
+        if (live) atomicAdd(&hist[bi], 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        if ((tid & 31) == 0) red[tid >> 5] = lsum;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < VQ_THREADS / 32; ++w) s += red[w];
+            atomicAdd(a.stats + 0, s);
+            const int64_t rem = total - (int64_t)blockIdx.x * VQ_THREADS;
+            atomicAdd(a.stats + 1, (double)(rem < VQ_THREADS ? rem : VQ_THREADS));
+        }
+        for (int i = tid; i < a.K; i += VQ_THREADS)
+            if (hist[i]) atomicAdd(a.stats + 2 + i, (double)hist[i]);   // integer-valued: order-free
+    }
+}
+
+__global__ void vq_finalize_kernel(const double* stats, int d, int k, float beta, float* out2) {
+    // loss = mse(q, z.detach()) + beta * mse(q.detach(), z) (vq_vae.py:74-76); perplexity :79-82
+    __shared__ double red[32];
+    const double npos = stats[1];
+    double ent = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const float p = (float)(stats[2 + i] / npos);
+        ent += (double)(p * logf(p + 1e-10f));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ent;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+        const float mse = (float)(stats[0] / (npos * d));
+        out2[0] = mse + beta * mse;
+        out2[1] = expf(-(float)s);
+    }
+}
+
+__global__ void vq_gather_kernel(const int32_t* idx, const float* cb, int64_t total, int d, int p, int k, float* q) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= total) return;
+    const int64_t b = n / p;
+    const int pos = (int)(n - b * p);
+    int i = idx[n];
+    i = i < 0 ? 0 : (i >= k ? k - 1 : i);
+    for (int c = 0; c < d; ++c) q[((size_t)b * d + c) * p + pos] = __ldg(cb + (size_t)i * d + c);
+}
+
+template <int D>
+int launch_vq(const VqArgs& a, cudaStream_t st) {
+    const int64_t total = a.B * a.P;
+    const int64_t blocks = (total + VQ_THREADS - 1) / VQ_THREADS;
+    DMB_CHECK(blocks < (1ll << 31), "vq: too many positions");
+    int kchunk = a.K;
+    const int max_codes = (96 * 1024) / (D * 4);
+    if (kchunk > max_codes) kchunk = max_codes;
+    const size_t smem = (size_t)kchunk * D * 4;
+    auto kern = vq_kernel<D>;
+    if (smem > 40 * 1024) DMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, VQ_THREADS, smem, st>>>(a, kchunk);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+}  // namespace
+
+int vq_forward(const VqArgs& a, cudaStream_t st) {
+    DMB_CHECK(a.B > 0 && a.P > 0, "vq: empty input");
+    DMB_CHECK(a.K >= 1 && a.K <= 1024, "vq: num_embeddings %d outside [1, 1024]", a.K);
+    switch (a.D) {
+        case 8: return launch_vq<8>(a, st);
+        case 16: return launch_vq<16>(a, st);
+        case 32: return launch_vq<32>(a, st);
+        case 64: return launch_vq<64>(a, st);
+        case 128: return launch_vq<128>(a, st);
+        default: break;
+    }
+    DMB_CHECK(false, "vq: embedding_dim %d not in {8,16,32,64,128}", a.D);
+}
+
+}  // namespace dmb
+
+// ---------------------------------------------------------------------------------------
+// C ABI (include/dynamorph_b200.h)
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int dmb_vq_reset(double* stats, int32_t k, void* stream) {
+    DMB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (2 + (size_t)k), (cudaStream_t)stream));
+    return 0;
+}
+
+int dmb_vq_forward(const float* z, const float* codebook, int64_t batch, int32_t d,
+                   int32_t positions_per_patch, int32_t k, float* z_st, int32_t* idx,
+                   double* stats, void* stream) {
+    DMB_CHECK(z && codebook, "dmb_vq_forward: null input");
+    dmb::VqArgs a{};
+    a.z = z; a.codebook = codebook; a.B = batch; a.D = d; a.P = positions_per_patch; a.K = k;
+    a.z_st = z_st; a.idx = idx; a.stats = stats;
+    return dmb::vq_forward(a, (cudaStream_t)stream);
+}
+
+int dmb_vq_finalize(const double* stats, int32_t d, int32_t k, float commitment_cost,
+                    float* out2, void* stream) {
+    DMB_CHECK(stats && out2, "dmb_vq_finalize: null pointer");
+    dmb::vq_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(stats, d, k, commitment_cost, out2);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int dmb_vq_gather(const int32_t* idx, const float* codebook, int64_t batch, int32_t d,
+                  int32_t positions_per_patch, int32_t k, float* q, void* stream) {
+    DMB_CHECK(idx && codebook && q, "dmb_vq_gather: null pointer");
+    const int64_t total = batch * positions_per_patch;
+    if (total == 0) return 0;
+    dmb::vq_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        idx, codebook, total, d, positions_per_patch, k, q);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// VectorQuantizer backward (autograd of vq_vae.py:65-76):
+//   dL/dz      = g_zst + g_loss * beta * 2 (z - q) / N            (commitment term + straight-through)
+//   dL/dE[k]   = g_loss * sum_{p: idx[p]=k} 2 (q[p] - z[p]) / N   (codebook term; N = B*D*P)
+// ---------------------------------------------------------------------------------------
+namespace dmb {
+namespace {
+
+__global__ void vq_backward_kernel(const float* __restrict__ z, const float* __restrict__ cb,
+                                   const int32_t* __restrict__ idx, const float* __restrict__ g_zst,
+                                   const float* __restrict__ g_loss, float g_loss_scale, float beta,
+                                   int64_t total, int d, int p, float* __restrict__ grad_z,
+                                   float* __restrict__ grad_cb) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= total) return;
+    const float gl = (g_loss ? __ldg(g_loss) : 1.f) * g_loss_scale;
+    const float coef = gl * 2.f / (float)((double)total * d);
+    const int64_t b = n / p;
+    const int pos = (int)(n - b * p);
+    const int k = idx[n];
+    const size_t base = (size_t)b * d * p + pos;
+    for (int c = 0; c < d; ++c) {
+        const float zv = __ldg(z + base + (size_t)c * p);
+        const float q = __ldg(cb + (size_t)k * d + c);
+        const float g = g_zst ? __ldg(g_zst + base + (size_t)c * p) : 0.f;
+        if (grad_z) grad_z[base + (size_t)c * p] = g + coef * beta * (zv - q);
+        if (grad_cb) atomicAdd(grad_cb + (size_t)k * d + c, coef * (q - zv));
+    }
+}
+
+}  // namespace
+}  // namespace dmb
+
+extern "C" int dmb_vq_backward(const float* z, const float* codebook, const int32_t* idx,
+                               const float* g_zst, const float* g_loss_dev, float g_loss_scale,
+                               float commitment_cost, int64_t batch, int32_t d,
+                               int32_t positions_per_patch, int32_t k, float* grad_z,
+                               float* grad_codebook, void* stream) {
+    DMB_CHECK(z && codebook && idx, "dmb_vq_backward: null pointer");
+    const int64_t total = batch * positions_per_patch;
+    if (grad_codebook)
+        DMB_CUDA(cudaMemsetAsync(grad_codebook, 0, sizeof(float) * (size_t)k * d, (cudaStream_t)stream));
+    if (total == 0) return 0;
+    dmb::vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        z, codebook, idx, g_zst, g_loss_dev, g_loss_scale, commitment_cost, total, d,
+        positions_per_patch, grad_z, grad_codebook);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}

@@ -1,0 +1,184 @@
+/*
+ * dynamorph_b200 -- C ABI of the B200-native VQ-VAE latent-encoding path.
+ *
+ * The reference (mehta-lab/dynamorph) has no FFI: its boundary for this path is the
+ * Python class API (HiddenStateExtractor/vq_vae.py, HiddenStateExtractor/vae.py,
+ * pipeline/patch_VAE.py:process_VAE, run_training.py:run_one_batch).  This header is the
+ * C-ABI a maintainer binds underneath that API (ctypes stub in INTEGRATION.md); the Python
+ * mirror in dynamorph_b200/ is exactly such a binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; dmb_last_error() gives the text
+ *     (thread-local).  No exceptions cross the ABI, nothing is allocated, no implicit sync.
+ *   - every pointer is a caller-owned DEVICE pointer unless its name ends in _host;
+ *     every launch goes to the caller's `stream` (a cudaStream_t passed as void*).
+ *   - tensors are float32, dense NCHW (the reference's layout); indices are int32.
+ *   - `params`  : all trainable tensors, concatenated in reference state_dict order, each
+ *                 in its torch layout (Conv2d (Cout,Cin,kh,kw); ConvTranspose2d
+ *                 (Cin,Cout,kh,kw); BatchNorm weight/bias (C); Embedding (K,D)).
+ *     `bnbuf`   : for every BatchNorm in state_dict order: running_mean[C], running_var[C].
+ *     dmb_param_lookup() exposes the offsets by state_dict key.
+ */
+#ifndef DYNAMORPH_B200_H
+#define DYNAMORPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMB_ABI_VERSION 1
+
+/* architecture: HiddenStateExtractor/vq_vae.py:276-298 == vae.py:273-294 (z16); vae.py:401-414 (z32) */
+enum { DMB_ARCH_Z16 = 0, DMB_ARCH_Z32 = 1 };
+
+/* BatchNorm statistics mode:
+ *   EVAL       running statistics (model.eval()); folded into the conv weights at pack time
+ *   BATCH      statistics of the current call's batch (train mode; run_training.py:404)
+ *   PER_SAMPLE train-mode statistics with batch 1, i.e. per patch -- what
+ *              pipeline/patch_VAE.py:445-449 computes as written                              */
+enum { DMB_BN_EVAL = 0, DMB_BN_BATCH = 1, DMB_BN_PER_SAMPLE = 2 };
+
+/* Constructor arguments of VQ_VAE (vq_vae.py:232-245) that shape the computation. */
+typedef struct dmb_model {
+    int32_t arch;
+    int32_t num_inputs;
+    int32_t num_hiddens;
+    int32_t num_residual_hiddens;
+    int32_t num_residual_layers;
+    int32_t num_embeddings;
+    int32_t height;            /* input patch height (128 in the reference pipeline) */
+    int32_t width;
+    float   commitment_cost;
+    float   weight_recon;      /* ignored (1) for z32: vae.py:440 */
+    float   weight_commitment; /* ignored (1) for z32 */
+    float   bn_eps;            /* 1e-5 */
+    float   bn_momentum;       /* 0.1  */
+} dmb_model;
+
+int         dmb_abi_version(void);
+const char* dmb_last_error(void);
+
+/* ---- parameter layout -------------------------------------------------------------- */
+/* Totals: trainable floats in `params`, floats in `bnbuf`, number of BatchNorm layers.  */
+int dmb_param_count(const dmb_model* m, int64_t* n_params, int64_t* n_bnbuf, int32_t* n_bn);
+/* Offset/numel of one state_dict entry (e.g. "enc.4.weight", "enc.5.running_var",
+ * "vq.w.weight").  *which = 0 if it lives in `params`, 1 if in `bnbuf`.                  */
+int dmb_param_lookup(const dmb_model* m, const char* key_host, int32_t* which,
+                     int64_t* offset, int64_t* numel);
+/* Latent geometry: D = num_hiddens, (lh, lw) = 16x16 (z16) or 32x32 (z32) for 128x128.  */
+int dmb_latent_shape(const dmb_model* m, int32_t* d, int32_t* lh, int32_t* lw);
+
+/* ---- weight packing ---------------------------------------------------------------- */
+/* Kernel-layout copy of the weights ([Cin][kh][kw][Cout], conv1x1(2->h/2) composed into
+ * the first 4x4 conv, BN folded in for DMB_BN_EVAL).  Re-run whenever params change.     */
+int dmb_packed_floats(const dmb_model* m, int64_t* n);
+int dmb_pack_weights(const dmb_model* m, const float* params, const float* bnbuf,
+                     int32_t bn_mode, float* packed, void* stream);
+
+/* ---- encode path: model.enc + model.vq (pipeline/patch_VAE.py:448-449) ------------- */
+/* Bytes of scratch for a batch of B patches.  keep_activations != 0 reserves room for
+ * everything the backward pass re-reads.                                                 */
+int dmb_workspace_bytes(const dmb_model* m, int64_t batch, int32_t bn_mode,
+                        int32_t keep_activations, size_t* bytes);
+
+/* z_before = enc(x).  x: (B, num_inputs, H, W); z_before: (B, D, lh, lw).
+ * BATCH mode also updates running_mean / running_var in `bnbuf_inout` (may be NULL).     */
+int dmb_encoder_forward(const dmb_model* m, const float* packed, const float* x, int64_t batch,
+                        int32_t bn_mode, float* z_before, float* bnbuf_inout,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* VectorQuantizer.forward (vq_vae.py:52-84) on z: (B, D, lh, lw), codebook (K, D).
+ *   z_st      : z + (q - z)                       (may be NULL)
+ *   idx       : int32 (B, lh, lw) first-argmin    (may be NULL)
+ *   stats     : double[2+K] accumulators, zeroed by the caller's previous dmb_vq_reset():
+ *               [0] = sum (q - z)^2, [1] = positions, [2..] = code histogram (may be NULL) */
+int dmb_vq_forward(const float* z, const float* codebook, int64_t batch, int32_t d,
+                   int32_t positions_per_patch, int32_t k, float* z_st, int32_t* idx,
+                   double* stats, void* stream);
+int dmb_vq_reset(double* stats, int32_t k, void* stream);
+/* loss = (1 + commitment_cost) * mean((q - z)^2); perplexity = exp(-sum p log(p + 1e-10)).
+ * out2: float[2] = {loss, perplexity}.                                                   */
+int dmb_vq_finalize(const double* stats, int32_t d, int32_t k, float commitment_cost,
+                    float* out2, void* stream);
+/* VectorQuantizer.decode_inputs (vq_vae.py:105-116): idx (B, lh, lw) -> (B, D, lh, lw).  */
+int dmb_vq_gather(const int32_t* idx, const float* codebook, int64_t batch, int32_t d,
+                  int32_t positions_per_patch, int32_t k, float* q, void* stream);
+
+/* Gradient of VectorQuantizer.forward (autograd of vq_vae.py:65-76).  g_zst: gradient w.r.t. the
+ * straight-through output (may be NULL = 0); g_loss_dev: device scalar gradient of the loss output
+ * (NULL = 1), multiplied by g_loss_scale.  grad_z / grad_codebook (zeroed inside) may be NULL.   */
+int dmb_vq_backward(const float* z, const float* codebook, const int32_t* idx, const float* g_zst,
+                    const float* g_loss_dev, float g_loss_scale, float commitment_cost, int64_t batch,
+                    int32_t d, int32_t positions_per_patch, int32_t k, float* grad_z,
+                    float* grad_codebook, void* stream);
+
+/* enc + vq in one call: the process_VAE hot path.  Any of z_before / z_after / idx /
+ * vq_stats may be NULL.                                                                  */
+int dmb_encode(const dmb_model* m, const float* packed, const float* codebook, const float* x,
+               int64_t batch, int32_t bn_mode, float* z_before, float* z_after, int32_t* idx,
+               double* vq_stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- decoder + losses: model.dec and the loss of VQ_VAE.forward (vq_vae.py:319-323) -- */
+int dmb_decoder_forward(const dmb_model* m, const float* packed, const float* z_after,
+                        int64_t batch, int32_t bn_mode, float* decoded, float* bnbuf_inout,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* sum over all elements of ((decoded*mask - x*mask)^2 / channel_var[c]) -> *sum_out (double,
+ * accumulated; zero it first).  mask: (B,1,H,W) or (B,C,H,W) or NULL (ones).             */
+int dmb_recon_loss(const float* decoded, const float* x, const float* mask, int32_t mask_channels,
+                   const float* channel_var, int64_t batch, int32_t channels, int32_t hw,
+                   double* sum_out, void* stream);
+
+/* ---- single layers (unit tests, micro-benchmarks) --------------------------------------- */
+/* nn.Conv2d forward, kernel/stride in {(1,1), (3,1) pad 1, (4,2) pad 1}; w_packed is
+ * [Cin][k][k][Cout].  Optional on-load transform relu?(x*in_scale[c]+in_shift[c]) (tables [Cin] or
+ * [B][Cin]), optional skip tensor added to the output, optional ReLU on the output.            */
+int dmb_conv2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
+                       int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout, int32_t ksize,
+                       int32_t stride, const float* in_scale, const float* in_shift,
+                       int32_t in_per_sample, int32_t in_relu, const float* skip, int32_t out_relu,
+                       void* stream);
+/* nn.ConvTranspose2d(k=4, stride=2, padding=1) forward; w_packed is [Cin][4][4][Cout].        */
+int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
+                                 int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,
+                                 const float* in_scale, const float* in_shift, int32_t in_per_sample,
+                                 int32_t in_relu, int32_t out_relu, void* stream);
+/* Launch a register-resident FMA loop (16 chains x iters per thread) and report the FLOPs it
+ * performs in *flops_out_host; the caller times it with CUDA events to get the FP32 roof.    */
+int dmb_bench_fp32_fma(int32_t blocks, int32_t threads, int32_t iters, float* scratch,
+                       double* flops_out_host, void* stream);
+/* Number of kernels this library has launched in the process (reset != 0 zeroes it).        */
+long long dmb_launch_count(int reset);
+
+/* ---- training step (run_training.py:404-408) ---------------------------------------- */
+/* Full forward in BATCH mode keeping activations, producing decoded and
+ * losses_out float[4] = {recon_loss, commitment_loss, total_loss, perplexity}.           */
+int dmb_train_forward(const dmb_model* m, const float* packed, const float* params,
+                      const float* x, const float* mask, int32_t mask_channels,
+                      const float* channel_var, int64_t batch, float* decoded,
+                      float* losses_out, float* bnbuf_inout, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* Gradient of total_loss w.r.t. every trainable tensor, written (not accumulated) to
+ * `grads` in the layout of `params`.  Uses the workspace left by dmb_train_forward.       */
+int dmb_train_backward(const dmb_model* m, const float* packed, const float* params,
+                       const float* x, const float* mask, int32_t mask_channels,
+                       const float* channel_var, int64_t batch, float grad_scale,
+                       float* grads, void* workspace, size_t workspace_bytes, void* stream);
+/* torch.optim.Adam (betas, eps, no weight decay), bias-corrected, step is 1-based.
+ * grad_scale multiplies the gradient first (1/world_size after an allreduce-sum).        */
+int dmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  int64_t n, float lr, float beta1, float beta2, float eps, int32_t step,
+                  float grad_scale, void* stream);
+
+/* ---- input staging (pipeline/train_utils.py:252-274) -------------------------------- */
+/* zscore_patch: per patch and channel (x - mean) / (std + DBL_EPSILON), float64 or
+ * float32 or uint16 input, float32 output.  in_dtype: 0 = f32, 1 = f64, 2 = u16.         */
+int dmb_zscore_patch(const void* raw, int32_t in_dtype, int64_t planes, int32_t hw,
+                     float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNAMORPH_B200_H */

@@ -313,6 +313,8 @@ def run_ours(args):
     h2d = x_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out.values())
     # parity spot-check of what came back to the host against the device-resident run
+    step("eval")
+    torch.cuda.synchronize()
     same = bool(torch.equal(out["idx"].view(chunk, 16, 16), idx.cpu()))
 
     line = {

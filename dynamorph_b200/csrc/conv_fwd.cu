@@ -10,14 +10,15 @@
 // (64 accumulators), activations come from a shared-memory tile with conflict-free 128-bit
 // loads, weights from shared memory as warp-uniform 128-bit broadcasts.
 //
-// Shared-memory tile, per (local patch, input channel, input row):
-//   stride 2: the zero-padded row is split by column parity into two planes P0/P1, so the
-//             four taps of a 4x4/stride-2 window read P0[ox], P1[ox], P0[ox+1], P1[ox+1]:
-//             unit-stride in ox for both planes (space-to-depth done by the loader);
-//   stride 1: one plane holding the padded row.
-//   Inside a plane, 16-byte granules are dealt round-robin to NG = PW/4 sub-planes so that
-//   the i-th 128-bit load of neighbouring threads hits neighbouring granules (no bank
-//   conflicts although each thread walks PW contiguous floats).
+// Shared-memory tile, per (local patch, input channel, input row): the RAW input row, shifted right by
+// one 16-byte granule (4 floats) so that the left zero-padding column sits in a granule of its own and
+// every data granule keeps its 16-byte alignment.  Rows are fetched global->shared with cp.async
+// (16 B each, zero-fill for rows outside the image): no register staging, all copies of a chunk in
+// flight at once.  Inside a row, granules are dealt round-robin to NGS sub-planes (NGS = granules a
+// thread advances per strip: 4 for stride 2, 2 for stride 1) so the i-th 128-bit load of neighbouring
+// threads hits neighbouring granules -> no bank conflicts although each thread walks 16-24 contiguous
+// floats.  The producer's BatchNorm affine + ReLU (BATCH / PER_SAMPLE modes) is applied by an in-place
+// pass over the landed tile; zero padding is untouched by it, as torch pads after the activation.
 #include "common.cuh"
 
 namespace dmb {
@@ -29,20 +30,30 @@ constexpr int NG = PW / 4;   // granules per strip
 
 struct ConvK {
     ConvFwdArgs a;
-    int TR, NP, CIC, nbands, SPR, RIN, NPL, PLW, SUBW;
+    int TR, NP, CIC, nbands, SPR, RIN, SUBW;
     int row_stride, ci_stride, patch_stride, w_floats, tile_floats;
     int threads;
 };
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// 16-byte global->shared async copy (LDGSTS); src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 template <int KS, int STRIDE, int CO_T>
-__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvK k) {
+__global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
     extern __shared__ __align__(16) float smem[];
     const ConvFwdArgs& a = k.a;
     constexpr int PAD = (KS == 1) ? 0 : 1;
-    constexpr int NPLANES = (STRIDE == 2) ? 2 : 1;
-    constexpr int NV = (KS == 1) ? NG : NG + 1;   // float4 loads per plane row
+    constexpr int PADL = PAD ? 4 : 0;                       // floats of left shift inside a tile row
+    constexpr int NGS = (STRIDE == 2) ? 4 : 2;               // sub-planes == granules per strip
+    constexpr int NV = (KS == 1) ? 2 : ((STRIDE == 2) ? 6 : 4);   // float4 loads per tile row per thread
 
     float* ws = smem;
     float* tile = smem + ((k.w_floats + 3) & ~3);
@@ -72,69 +83,84 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvK k) {
 
     const int in_row0 = band * k.TR * STRIDE - PAD;   // input row held in tile row 0
     const int W4 = a.W >> 2;
+    // loader role of this thread: column slot ld_q (one 16-byte granule of the input row), first tile
+    // row ld_r0, row step ld_rstep; the granule's place inside a tile row is loop-invariant.
+    const int ld_q = tid % W4;
+    const int ld_r0 = tid / W4;
+    const int ld_rstep = (int)blockDim.x / W4;
+    auto gslot = [&](int g) { return (g % NGS) * k.SUBW + (g / NGS) * 4; };
+    const int so_dst = gslot(ld_q + PADL / 4);
+    const int so_left = gslot(0), so_right = gslot(W4 + 1);
+    const int nrows = k.NP * k.CIC * k.RIN;
+    const bool transform = (a.in_scale != nullptr) || a.in_relu;
 
     for (int c0 = 0; c0 < a.Cin; c0 += k.CIC) {
         __syncthreads();
         // ---- weights chunk: contiguous [CIC][KS][KS][Cout]
         if constexpr (CO_T % 4 == 0) {
-            const float4* src = reinterpret_cast<const float4*>(a.w + (size_t)c0 * KS * KS * a.Cout);
-            float4* dst = reinterpret_cast<float4*>(ws);
-            for (int i = tid; i < (k.w_floats >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+            const float* src = a.w + (size_t)c0 * KS * KS * a.Cout;
+            for (int i = tid; i < (k.w_floats >> 2); i += blockDim.x) cp_async16(ws + 4 * i, src + 4 * i, 16);
         } else {
             const float* src = a.w + (size_t)c0 * KS * KS * a.Cout;
             for (int i = tid; i < k.w_floats; i += blockDim.x) ws[i] = __ldg(src + i);
         }
-        // ---- activation tile with the producer's BN affine + ReLU applied on the fly
-        {
-            const int per_row = W4;
-            const int total = k.NP * k.CIC * k.RIN * per_row;
-            for (int e = tid; e < total; e += blockDim.x) {
-                int q = e % per_row;
-                int t = e / per_row;
-                int r = t % k.RIN; t /= k.RIN;
-                int cil = t % k.CIC;
-                int lp = t / k.CIC;
+        // ---- activation tile: one cp.async per (row, granule); rows walked with carries, no divisions
+        if (ld_r0 < ld_rstep) {
+            int r = ld_r0, cil = 0, lp = 0;
+            while (r >= k.RIN) { r -= k.RIN; ++cil; }
+            while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
+            for (int rr = ld_r0; rr < nrows; rr += ld_rstep) {
                 const int64_t bb = b0 + lp;
-                const int ci = c0 + cil;
                 const int iy = in_row0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bb < a.B && iy >= 0 && iy < a.H) {
-                    v = __ldg(reinterpret_cast<const float4*>(
-                            a.x + (((size_t)bb * a.Cin + ci) * a.H + iy) * a.W) + q);
-                    if (a.in_scale) {
-                        const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + ci;
-                        const float s = __ldg(a.in_scale + ai), sh = __ldg(a.in_shift + ai);
-                        v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh);
-                        v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
-                    }
-                    if (a.in_relu) {
-                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
-                        v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                    }
-                }
                 float* rowp = tile + lp * k.patch_stride + cil * k.ci_stride + r * k.row_stride;
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int p = 4 * q + i + PAD;              // index in the padded row
-                    const int plane = (NPLANES == 2) ? (p & 1) : 0;
-                    const int j = (NPLANES == 2) ? (p >> 1) : p;
-                    const int g = j >> 2;
-                    rowp[plane * k.PLW + (g % NG) * k.SUBW + (g / NG) * 4 + (j & 3)] = vv[i];
-                }
-                if (PAD) {
-                    if (q == 0) rowp[0] = 0.f;                  // padded index 0 (plane 0, j 0)
-                    if (q == per_row - 1) {
-                        const int p = a.W + 1;                  // right halo
-                        const int plane = (NPLANES == 2) ? (p & 1) : 0;
-                        const int j = (NPLANES == 2) ? (p >> 1) : p;
-                        const int g = j >> 2;
-                        rowp[plane * k.PLW + (g % NG) * k.SUBW + (g / NG) * 4 + (j & 3)] = 0.f;
+                const bool valid = bb < a.B && iy >= 0 && iy < a.H;
+                const float* src = valid ? a.x + (((size_t)bb * a.Cin + (c0 + cil)) * a.H + iy) * a.W + 4 * ld_q : a.x;
+                cp_async16(rowp + so_dst, src, valid ? 16 : 0);
+                if constexpr (PAD == 1) {
+                    if (ld_q == 0) {
+                        *reinterpret_cast<float4*>(rowp + so_left) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(rowp + so_right) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+                r += ld_rstep;
+                while (r >= k.RIN) { r -= k.RIN; ++cil; }
+                while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
             }
         }
+        cp_async_wait_all();
         __syncthreads();
+        if (transform) {
+            // in-place BN affine + ReLU over the granules this thread copied (valid rows only)
+            if (ld_r0 < ld_rstep) {
+                int r = ld_r0, cil = 0, lp = 0;
+                while (r >= k.RIN) { r -= k.RIN; ++cil; }
+                while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
+                for (int rr = ld_r0; rr < nrows; rr += ld_rstep) {
+                    const int64_t bb = b0 + lp;
+                    const int iy = in_row0 + r;
+                    if (bb < a.B && iy >= 0 && iy < a.H) {
+                        float4* gp = reinterpret_cast<float4*>(
+                            tile + lp * k.patch_stride + cil * k.ci_stride + r * k.row_stride + so_dst);
+                        float4 v = *gp;
+                        if (a.in_scale) {
+                            const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + c0 + cil;
+                            const float sc = __ldg(a.in_scale + ai), sh = __ldg(a.in_shift + ai);
+                            v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh);
+                            v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+                        }
+                        if (a.in_relu) {
+                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                            v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        }
+                        *gp = v;
+                    }
+                    r += ld_rstep;
+                    while (r >= k.RIN) { r -= k.RIN; ++cil; }
+                    while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- FMA core
         const float* tp = tile + pl * k.patch_stride + (row * STRIDE) * k.row_stride;
@@ -143,15 +169,13 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvK k) {
 #pragma unroll
             for (int ky = 0; ky < KS; ++ky) {
                 const float* rp = tp + cil * k.ci_stride + ky * k.row_stride;
-                float av[NPLANES][NV * 4];
+                float av[NV * 4];
 #pragma unroll
-                for (int pn = 0; pn < NPLANES; ++pn)
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        const float4 t4 = lds4(rp + pn * k.PLW + (i % NG) * k.SUBW + (sx + i / NG) * 4);
-                        av[pn][4 * i + 0] = t4.x; av[pn][4 * i + 1] = t4.y;
-                        av[pn][4 * i + 2] = t4.z; av[pn][4 * i + 3] = t4.w;
-                    }
+                for (int i = 0; i < NV; ++i) {
+                    const float4 t4 = lds4(rp + (i % NGS) * k.SUBW + (sx + i / NGS) * 4);
+                    av[4 * i + 0] = t4.x; av[4 * i + 1] = t4.y;
+                    av[4 * i + 2] = t4.z; av[4 * i + 3] = t4.w;
+                }
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx) {
                     float wv[CO_T];
@@ -166,13 +190,13 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvK k) {
 #pragma unroll
                         for (int c = 0; c < CO_T; ++c) wv[c] = wrow[c];
                     }
-                    const int pn = (STRIDE == 2) ? (kx & 1) : 0;
-                    const int off = (STRIDE == 2) ? (kx >> 1) : kx;
+                    // window index of tap kx for output pixel p (window starts at tile position STRIDE*ox0;
+                    // input column c lives at position c + PADL, and c = STRIDE*ox + kx - PAD)
 #pragma unroll
                     for (int c = 0; c < CO_T; ++c)
 #pragma unroll
                         for (int p = 0; p < PW; ++p)
-                            acc[c][p] = fmaf(wv[c], av[pn][p + off], acc[c][p]);
+                            acc[c][p] = fmaf(wv[c], av[STRIDE * p + kx + PADL - PAD], acc[c][p]);
                 }
             }
         }
@@ -271,14 +295,12 @@ int plan(const ConvFwdArgs& a, int co_t, ConvK& k) {
     }
     k.nbands = a.Ho / k.TR;
     k.threads = k.NP * k.TR * k.SPR * ncg;
-    if (k.threads > 256 || k.threads < 1) return -1;
+    if (k.threads > 128 || k.threads < 1) return -1;
     k.RIN = (k.TR - 1) * S + KS;
-    k.NPL = (S == 2) ? 2 : 1;
-    const int elems = (KS == 1) ? a.W : ((S == 2) ? a.Wo + 1 : a.W + 2);   // valid j per plane
-    const int granules = (elems + 3) / 4 + ((KS == 1) ? 0 : 1);             // + overrun granule
-    k.SUBW = ((granules + NG - 1) / NG) * 4;
-    k.PLW = NG * k.SUBW;
-    k.row_stride = k.NPL * k.PLW;
+    const int ngs = (S == 2) ? 4 : 2;
+    const int granules = a.W / 4 + ((KS == 1) ? 0 : 2);     // data granules + one zero granule per side
+    k.SUBW = ((granules + ngs - 1) / ngs) * 4;
+    k.row_stride = ngs * k.SUBW;
     // Narrow maps put several output rows into one 8-lane shared-memory phase; pad the row so
     // that consecutive output rows start SPR granules apart (mod 32 banks) -> conflict-free.
     if (k.SPR < 8) {
@@ -353,6 +375,7 @@ int conv_fwd(const ConvFwdArgs& a, cudaStream_t st) {
     DMB_CHECK(plan(a, co_t, k) == 0, "conv_fwd: no launch plan for Cout=%d Ho=%d Wo=%d", a.Cout, a.Ho, a.Wo);
     DMB_CHECK((size_t)(k.w_floats + k.tile_floats) * 4 <= 200 * 1024,
               "conv_fwd: tile does not fit shared memory (Cin=%d Cout=%d W=%d)", a.Cin, a.Cout, a.W);
+    DMB_CHECK(a.W / 4 <= k.threads, "conv_fwd: input width %d too large for a %d-thread CTA", a.W, k.threads);
 #define DMB_DISPATCH(KS, S)                                         \
     if (a.ks == KS && a.stride == S) {                              \
         if (co_t == 8) return launch<KS, S, 8>(k, st);              \

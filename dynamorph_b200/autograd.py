@@ -44,3 +44,84 @@ class VQFunction(torch.autograd.Function):
         call("dmb_vq_backward", ptr(z), ptr(cb), ptr(idx), ptr(gzst), ptr(gl), scale, ctx.beta,
              B, D, H * W, K, ptr(gz), ptr(gcb), _stream())
         return gz, gcb, None
+
+
+class TrainStepFunction(torch.autograd.Function):
+    """Whole-model forward (train-mode BatchNorm) with the gradient of `total_loss` w.r.t. every
+    trainable tensor computed by the fused backward schedule (dmb_train_forward / dmb_train_backward)."""
+
+    @staticmethod
+    def forward(ctx, model, inputs, batch_mask, *params):
+        import ctypes as C
+        from ._lib import BN_BATCH
+        eng = model._engine
+        x = _require_cuda(inputs.detach(), "inputs")
+        B, Cin, H, W = x.shape
+        s = eng.spec(H, W)
+        packed = eng.packed(BN_BATCH, H, W)
+        ws, n = eng.workspace(s, B, BN_BATCH, 1)
+        mask, mc = None, 0
+        if batch_mask is not None:
+            mask = _require_cuda(batch_mask.detach(), "batch_mask")
+            mc = mask.shape[1]
+            if mask.shape[0] != B or tuple(mask.shape[2:]) != (H, W) or mc not in (1, Cin):
+                mask = mask.expand(B, Cin, H, W).contiguous()
+                mc = Cin
+        cv = model.channel_var.data.reshape(-1).contiguous()
+        decoded = torch.empty_like(x)
+        losses = torch.empty(4, dtype=torch.float32, device=x.device)
+        call("dmb_train_forward", C.byref(s), ptr(packed), ptr(eng.flat_params), ptr(x), ptr(mask), mc, ptr(cv), B,
+             ptr(decoded), ptr(losses), ptr(eng.flat_bn), ptr(ws), n, _stream())
+        eng._bump_num_batches_tracked()
+        ctx.model, ctx.spec, ctx.mc, ctx.nws = model, s, mc, n
+        ctx.save_for_backward(x, mask if mask is not None else torch.empty(0, device=x.device), cv, decoded, packed)
+        ctx.ws_token = eng.workspace_token()
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(decoded)
+        recon, commit, total, ppl = losses[0], losses[1], losses[2], losses[3]
+        ctx.mark_non_differentiable(ppl)
+        return decoded, recon, commit, total, ppl
+
+    @staticmethod
+    def backward(ctx, g_dec, g_recon, g_commit, g_total, g_ppl):
+        import ctypes as C
+        model = ctx.model
+        eng = model._engine
+        if g_recon is not None or g_commit is not None:
+            raise NotImplementedError("dynamorph_b200: back-propagate through `total_loss` (recon_loss / "
+                                      "commitment_loss are reported values of the fused step)")
+        if g_total is None:
+            return (None,) * (3 + len(eng.trainable()))
+        if eng.workspace_token() != ctx.ws_token:
+            raise RuntimeError("dynamorph_b200: the activation workspace was reused by another call before "
+                               "backward(); call backward() right after the forward of the same batch")
+        x, mask, cv, decoded, packed = ctx.saved_tensors
+        mask_t = mask if mask.numel() else None
+        B = x.shape[0]
+        flat_g = torch.empty_like(eng.flat_params)
+        ws = eng._ws
+        call("dmb_train_backward", C.byref(ctx.spec), ptr(packed), ptr(eng.flat_params), ptr(x), ptr(mask_t), ctx.mc,
+             ptr(cv), ptr(decoded), B, 1.0, ptr(flat_g), ptr(ws), ctx.nws, _stream())
+        flat_g.mul_(g_total)
+        eng.last_flat_grad = flat_g
+        grads = tuple(flat_g[off:off + n].view(p.shape) if p.requires_grad else None for p, off, n in eng._views)
+        return (None, None, None) + grads
+
+
+def train_forward(model, inputs, time_matching_mat=None, batch_mask=None):
+    """VQ_VAE.forward in training mode with autograd attached (reference: vq_vae.py:300-338)."""
+    if time_matching_mat is not None:
+        raise NotImplementedError("time_matching_mat is not part of the fused training step yet "
+                                  "(SURVEY.md section 8f, row N3)")
+    eng = model._engine
+    eng.flatten()
+    params = [p for p, _, _ in eng._views]
+    decoded, recon, commit, total, ppl = TrainStepFunction.apply(model, inputs, batch_mask, *params)
+    out = {'recon_loss': recon, 'commitment_loss': commit, 'time_matching_loss': 0.}
+    if getattr(model, "_total_last", False):
+        out['perplexity'] = ppl
+        out['total_loss'] = total
+    else:
+        out['total_loss'] = total
+        out['perplexity'] = ppl
+    return decoded, out

@@ -89,3 +89,78 @@ int affine_add(const AffineAddArgs& a, cudaStream_t st) {
 }
 
 }  // namespace dmb
+
+// ---------------------------------------------------------------------------------------
+// backward bookkeeping
+// ---------------------------------------------------------------------------------------
+namespace dmb {
+namespace {
+
+__global__ void bn_bwd_finalize_kernel(const BnBwdArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nout = a.per_sample ? a.B * a.C : a.C;
+    if (warp >= nout) return;
+    const int c = warp % a.C;
+    const int bs = a.per_sample ? warp / a.C : 0;
+    const int nb = a.per_sample ? 1 : a.B;
+    const int n = nb * a.nbands;
+    double sg = 0.0, sgy = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const int bb = bs + i / a.nbands, band = i % a.nbands;
+        const double* p = a.partials + (((size_t)bb * a.nbands + band) * a.C + c) * 2;
+        sg += p[0]; sgy += p[1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sgy += __shfl_xor_sync(0xffffffffu, sgy, o);
+    }
+    if (lane) return;
+    const double N = (double)a.count_per_sample * nb;
+    const double mu = a.mean[warp], is = a.invstd[warp], g = a.gamma[c];
+    const double dbeta = sg;
+    const double dgamma = is * (sgy - mu * sg);          // sum g * xhat
+    // dL/dy = g*is*[ gr - dbeta/N - xhat*dgamma/N ],  xhat = (y - mu)*is
+    a.A[warp] = (float)(g * is);
+    a.Bc[warp] = (float)(-g * is * is * dgamma / N);
+    a.Cc[warp] = (float)(-g * is * dbeta / N + g * is * is * mu * dgamma / N);
+    if (a.per_sample) {
+        atomicAdd(a.dgamma + c, (float)dgamma);
+        atomicAdd(a.dbeta + c, (float)dbeta);
+    } else {
+        a.dgamma[c] = (float)dgamma;
+        a.dbeta[c] = (float)dbeta;
+    }
+}
+
+__global__ void sum_partials_kernel(const double* partials, int n, int C, float* out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += partials[((size_t)i * C + warp) * 2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[warp] = (float)s;
+}
+
+}  // namespace
+
+int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st) {
+    const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
+    const int threads = 128;
+    bn_bwd_finalize_kernel<<<(unsigned)((nout * 32 + threads - 1) / threads), threads, 0, st>>>(a);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int sum_partials(const double* partials, int B, int nbands, int C, float* out, cudaStream_t st) {
+    sum_partials_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(partials, B * nbands, C, out);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+}  // namespace dmb

@@ -50,15 +50,22 @@ struct ConvFwdArgs {
     const float* w;         // packed [Cin][KS][KS][Cout]
     const float* bias;      // [Cout] or [9][Cout] when bias_classes (row class*3 + col class)
     int bias_classes;       // 0 / 1
-    // transform applied to x on load:  v = relu?(v * in_scale[c] + in_shift[c])
+    // transform applied to x on load:  v = relu?(v * in_scale[c] + x2 * in_b[c] + in_shift[c])
     const float* in_scale;  // nullptr = identity; [Cin] or [B][Cin]
     const float* in_shift;
     int in_per_sample;      // stride B over the affine table
     int in_relu;
-    // epilogue
+    const float* x2;        // optional second input tensor (BatchNorm backward: the raw activation)
+    const float* in_b;      // its per-channel coefficient table (same indexing as in_scale)
+    // epilogue:  o = acc + bias;  o *= [mask_src*mask_s+mask_t > 0];  o += skip;  o = relu?(o)
+    const float* mask_src;  // (B, Cout, Ho, Wo) or nullptr: ReLU gate of the layer back-propagated into
+    const float* mask_s;    // its affine (nullptr = identity), [Cout] or [B][Cout] (mask_per_sample)
+    const float* mask_t;
+    int mask_per_sample;
     const float* skip;      // (B, Cout, Ho, Wo) added to the output, or nullptr
     int out_relu;
-    double* stats;          // [B][nbands][Cout][2] per-CTA (sum, sum of squares) or nullptr
+    double* stats;          // [B][nbands][Cout][2] per-CTA partial sums or nullptr
+    const float* stat_src;  // nullptr: (sum o, sum o^2); else (sum o, sum o*stat_src)  (BatchNorm backward)
     int B, Cin, H, W, Cout, Ho, Wo;
     int ks, stride;         // (1,1) (3,1) (4,2)
 };
@@ -76,12 +83,40 @@ struct ConvTFwdArgs {
     const float* in_shift;
     int in_per_sample;
     int in_relu;
+    const float* x2;
+    const float* in_b;
+    const float* mask_src;  // (B, Cout, 2H, 2W)
+    const float* mask_s;
+    const float* mask_t;
+    int mask_per_sample;
     int out_relu;
     double* stats;          // [B][nbands][Cout][2] or nullptr
+    const float* stat_src;
     int B, Cin, H, W, Cout;
 };
 int convt_fwd(const ConvTFwdArgs& a, cudaStream_t st);
 int convt_fwd_bands(int Cin, int Cout, int H, int W);
+
+// ------------------------------------------------------------------------------------
+// weight gradients (wgrad.cu)
+// ------------------------------------------------------------------------------------
+struct WgradArgs {
+    const float* g;         // (B, Cout, Ho, Wo) gradient tensor;  gy = g*ga[c] + y*gb[c] + gc[c]
+    const float* y;         // optional raw conv output (BatchNorm backward) or nullptr
+    const float* ga; const float* gb; const float* gc;   // nullptr = identity
+    int g_per_sample;
+    const float* x;         // (B, Cin, H, W) conv input before the producer's BN/ReLU
+    const float* xs; const float* xt;                    // act = relu?(x*xs[c] + xt[c]); nullptr = identity
+    int x_per_sample;
+    int x_relu;
+    int ones_channel;       // append a constant-one input channel (composite head bias chain)
+    int B, Cin, H, W, Cout, Ho, Wo, ks, stride;
+    float* partials;        // scratch: wgrad_partial_floats() floats per CTA x *ncta
+};
+int wgrad_partial_floats(const WgradArgs& a, int* ncta);
+int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStream_t st);
+int composite_chain(const float* dweff, const float* w0, const float* b0, const float* w1, int ni, int cm,
+                    float* dw0, float* db0, float* dw1, float* db1, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------
 // batch-norm bookkeeping (bn.cu)
@@ -105,6 +140,23 @@ struct BnFinalizeArgs {
     float* save_invstd;
 };
 int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st);
+
+// BatchNorm backward bookkeeping: from per-CTA partial (sum g, sum g*y) build dgamma, dbeta and the
+// coefficients of  dL/dy = A*g + Bc*y + Cc  that the dgrad / wgrad kernels apply on load.
+struct BnBwdArgs {
+    const double* partials;  // [B][nbands][C][2]
+    int B, nbands, C;
+    int64_t count_per_sample;
+    int per_sample;
+    const float* gamma;
+    const float* mean;       // saved by the forward finalize ([C] or [B][C])
+    const float* invstd;
+    float* A; float* Bc; float* Cc;     // [C] or [B][C]
+    float* dgamma; float* dbeta;        // [C]; written (BATCH) or accumulated over samples (PER_SAMPLE)
+};
+int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st);
+// out[c] = sum over (b, band) of partials[b][band][c][0]   (bias gradient of a layer without BatchNorm)
+int sum_partials(const double* partials, int B, int nbands, int C, float* out, cudaStream_t st);
 
 // out = (a*sa+ta) + (b*sb+tb), all (B, C, HW); the affine tables follow the per_sample flag.
 struct AffineAddArgs {
@@ -132,5 +184,9 @@ struct VqArgs {
     double* stats;           // [2+K] or nullptr
 };
 int vq_forward(const VqArgs& a, cudaStream_t st);
+// gradient of the quantiser; optional per-CTA BatchNorm-backward sums [B*p/128][d][2] against stat_src
+int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx, const float* g_zst,
+                      float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
+                      float* grad_codebook, double* stats, const float* stat_src, cudaStream_t st);
 
 }  // namespace dmb

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
     const int so_dst = gslot(ld_q + PADL / 4);
     const int so_left = gslot(0), so_right = gslot(W4 + 1);
     const int nrows = k.NP * k.CIC * k.RIN;
-    const bool transform = (a.in_scale != nullptr) || a.in_relu;
+    const bool transform = (a.in_scale != nullptr) || a.in_relu || (a.x2 != nullptr);
 
     for (int c0 = 0; c0 < a.Cin; c0 += k.CIC) {
         __syncthreads();
@@ -142,8 +142,14 @@ __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
                         float4* gp = reinterpret_cast<float4*>(
                             tile + lp * k.patch_stride + cil * k.ci_stride + r * k.row_stride + so_dst);
                         float4 v = *gp;
-                        if (a.in_scale) {
-                            const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + c0 + cil;
+                        const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + c0 + cil;
+                        if (a.x2) {
+                            const float4 u = __ldg(reinterpret_cast<const float4*>(
+                                a.x2 + (((size_t)bb * a.Cin + (c0 + cil)) * a.H + iy) * a.W) + ld_q);
+                            const float sc = __ldg(a.in_scale + ai), bc = __ldg(a.in_b + ai), sh = __ldg(a.in_shift + ai);
+                            v.x = fmaf(v.x, sc, fmaf(u.x, bc, sh)); v.y = fmaf(v.y, sc, fmaf(u.y, bc, sh));
+                            v.z = fmaf(v.z, sc, fmaf(u.z, bc, sh)); v.w = fmaf(v.w, sc, fmaf(u.w, bc, sh));
+                        } else if (a.in_scale) {
                             const float sc = __ldg(a.in_scale + ai), sh = __ldg(a.in_shift + ai);
                             v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh);
                             v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
@@ -222,6 +228,21 @@ __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
         if (sx == 0) o[0] = acc[c][0] + bl;
         if (sx == k.SPR - 1) o[PW - 1] = acc[c][PW - 1] + br;
         const size_t off = (((size_t)b * a.Cout + co) * a.Ho + oy) * a.Wo + sx * PW;
+        if (a.mask_src && live) {
+            float ms = 1.f, mt = 0.f;
+            if (a.mask_s) {
+                const size_t mi = (a.mask_per_sample ? (size_t)b * a.Cout : 0) + co;
+                ms = __ldg(a.mask_s + mi); mt = __ldg(a.mask_t + mi);
+            }
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.mask_src + off) + i);
+                if (!(fmaf(m4.x, ms, mt) > 0.f)) o[4 * i] = 0.f;
+                if (!(fmaf(m4.y, ms, mt) > 0.f)) o[4 * i + 1] = 0.f;
+                if (!(fmaf(m4.z, ms, mt) > 0.f)) o[4 * i + 2] = 0.f;
+                if (!(fmaf(m4.w, ms, mt) > 0.f)) o[4 * i + 3] = 0.f;
+            }
+        }
         if (a.skip && live) {
 #pragma unroll
             for (int i = 0; i < NG; ++i) {
@@ -240,8 +261,22 @@ __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
                     make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
         }
         float s = 0.f, q = 0.f;
+        if (a.stats) {
+            if (a.stat_src) {
+                if (live) {
 #pragma unroll
-        for (int p = 0; p < PW; ++p) { s += o[p]; q = fmaf(o[p], o[p], q); }
+                    for (int i = 0; i < NG; ++i) {
+                        const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.stat_src + off) + i);
+                        s += o[4 * i] + o[4 * i + 1] + o[4 * i + 2] + o[4 * i + 3];
+                        q = fmaf(o[4 * i], y4.x, q); q = fmaf(o[4 * i + 1], y4.y, q);
+                        q = fmaf(o[4 * i + 2], y4.z, q); q = fmaf(o[4 * i + 3], y4.w, q);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < PW; ++p) { s += o[p]; q = fmaf(o[p], o[p], q); }
+            }
+        }
         ssum[c] = s; ssq[c] = q;
     }
 

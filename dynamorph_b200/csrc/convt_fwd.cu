@@ -72,8 +72,14 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTK k) {
                 if (bb < a.B && iy >= 0 && iy < a.H) {
                     v = __ldg(reinterpret_cast<const float4*>(
                             a.x + (((size_t)bb * a.Cin + ci) * a.H + iy) * a.W) + q);
-                    if (a.in_scale) {
-                        const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + ci;
+                    const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + ci;
+                    if (a.x2) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(
+                            a.x2 + (((size_t)bb * a.Cin + ci) * a.H + iy) * a.W) + q);
+                        const float s = __ldg(a.in_scale + ai), bc = __ldg(a.in_b + ai), sh = __ldg(a.in_shift + ai);
+                        v.x = fmaf(v.x, s, fmaf(u.x, bc, sh)); v.y = fmaf(v.y, s, fmaf(u.y, bc, sh));
+                        v.z = fmaf(v.z, s, fmaf(u.z, bc, sh)); v.w = fmaf(v.w, s, fmaf(u.w, bc, sh));
+                    } else if (a.in_scale) {
                         const float s = __ldg(a.in_scale + ai), sh = __ldg(a.in_shift + ai);
                         v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh);
                         v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
@@ -136,18 +142,48 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTK k) {
         const int co = cg * CO_T + c;
         const float bv = __ldg(a.bias + co);
         float s = 0.f, q = 0.f;
+        float ms = 1.f, mt = 0.f;
+        if (a.mask_src && a.mask_s) {
+            const size_t mi = (a.mask_per_sample ? (size_t)b * a.Cout : 0) + co;
+            if (live) { ms = __ldg(a.mask_s + mi); mt = __ldg(a.mask_t + mi); }
+        }
 #pragma unroll
         for (int py = 0; py < 2; ++py) {
             float o[2 * PWI];
+            const size_t off = (((size_t)b * a.Cout + co) * Ho + 2 * m + py) * Wo + sx * 2 * PWI;
 #pragma unroll
-            for (int p = 0; p < 2 * PWI; ++p) {
-                o[p] = acc[c][py][p] + bv;
+            for (int p = 0; p < 2 * PWI; ++p) o[p] = acc[c][py][p] + bv;
+            if (a.mask_src && live) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.mask_src + off) + i);
+                    if (!(fmaf(m4.x, ms, mt) > 0.f)) o[4 * i] = 0.f;
+                    if (!(fmaf(m4.y, ms, mt) > 0.f)) o[4 * i + 1] = 0.f;
+                    if (!(fmaf(m4.z, ms, mt) > 0.f)) o[4 * i + 2] = 0.f;
+                    if (!(fmaf(m4.w, ms, mt) > 0.f)) o[4 * i + 3] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2 * PWI; ++p)
                 if (a.out_relu) o[p] = fmaxf(o[p], 0.f);
-                s += o[p]; q = fmaf(o[p], o[p], q);
+            if (a.stats) {
+                if (a.stat_src) {
+                    if (live) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.stat_src + off) + i);
+                            s += o[4 * i] + o[4 * i + 1] + o[4 * i + 2] + o[4 * i + 3];
+                            q = fmaf(o[4 * i], y4.x, q); q = fmaf(o[4 * i + 1], y4.y, q);
+                            q = fmaf(o[4 * i + 2], y4.z, q); q = fmaf(o[4 * i + 3], y4.w, q);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < 2 * PWI; ++p) { s += o[p]; q = fmaf(o[p], o[p], q); }
+                }
             }
             if (live) {
-                float4* dst = reinterpret_cast<float4*>(
-                    a.y + (((size_t)b * a.Cout + co) * Ho + 2 * m + py) * Wo + sx * 2 * PWI);
+                float4* dst = reinterpret_cast<float4*>(a.y + off);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
                 dst[1] = make_float4(o[4], o[5], o[6], o[7]);
             }

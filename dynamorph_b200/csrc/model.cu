@@ -45,6 +45,9 @@ struct Builder {
         c.b_off = take_param(key + ".bias", cout);
         c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
         c.pb_off = take_packed(cout);
+        c.pdw_off = take_packed((int64_t)cin * cout * ks * ks);
+        if (cin > L.max_c) L.max_c = cin;
+        if (cout > L.max_c) L.max_c = cout;
         L.convs.push_back(c);
         return (int)L.convs.size() - 1;
     }
@@ -59,6 +62,7 @@ struct Builder {
         c.b_off = take_param(key1 + ".bias", cmid);
         c.pw_off = take_packed((int64_t)cin * 16 * cmid);
         c.pb_off = take_packed(9 * cmid);
+        c.pdw_off = -1;
         L.convs.push_back(c);
         return (int)L.convs.size() - 1;
     }
@@ -130,6 +134,7 @@ int build_layout(const dmb_model* m, Layout& L) {
         L.lh = m->height / 4; L.lw = m->width / 4;
     }
     L.D = h;
+    L.pzero_off = B.take_packed(L.max_c);
     L.n_params = B.p; L.n_bnbuf = B.bb; L.n_packed = B.pk;
     return 0;
 }
@@ -221,6 +226,55 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             b.mean = bp.take<float>(rows * c.cout);
             b.invstd = bp.take<float>(rows * c.cout);
         }
+    }
+    if (keep && bn_mode != DMB_BN_EVAL) {
+        // ---- backward scratch
+        const int64_t rows = (bn_mode == DMB_BN_PER_SAMPLE) ? B : 1;
+        w.bnb.resize(L.bns.size());
+        for (size_t ci = 0; ci < L.convs.size(); ++ci) {
+            const ConvL& c = L.convs[ci];
+            if (c.bn < 0) continue;
+            Workspace::BnB& b = w.bnb[c.bn];
+            // the gradient that feeds this BN comes from a kernel whose band count is at most the map height
+            const int64_t hmax = (m.arch == DMB_ARCH_Z16 && (int)ci == L.e1) ? H / 2 :
+                                 (((int)ci == L.e2 && m.arch == DMB_ARCH_Z16) ? H / 4 :
+                                 ((m.arch == DMB_ARCH_Z32 && ((int)ci == L.e1 || (int)ci == L.d0)) ? H / 2 : L.lh));
+            b.part = bp.take<double>(B * hmax * c.cout * 2);
+            b.A = bp.take<float>(rows * c.cout);
+            b.Bc = bp.take<float>(rows * c.cout);
+            b.Cc = bp.take<float>(rows * c.cout);
+        }
+        w.gd = bp.take<float>(B * m.num_inputs * H * W);
+        if (m.arch == DMB_ARCH_Z16) {
+            w.g_t3 = bp.take<float>(B * h4 * 64 * lat);
+            w.g_t2 = bp.take<float>(B * h4 * 16 * lat);
+            w.g_t1 = bp.take<float>(B * h2 * 4 * lat);
+            w.g_y3 = bp.take<float>(B * h * lat);
+            w.g_y2 = bp.take<float>(B * h * (H / 4) * (W / 4));
+            w.g_y1 = bp.take<float>(B * h2 * (H / 2) * (W / 2));
+        } else {
+            w.g_t1 = bp.take<float>(B * h2 * 4 * lat);
+            w.g_y1 = bp.take<float>(B * h2 * (H / 2) * (W / 2));
+        }
+        w.g_za = bp.take<float>(B * h * lat);
+        w.g_zb = bp.take<float>(B * h * lat);
+        for (size_t i = 0; i < L.enc_res.size(); ++i) {
+            w.g_era.push_back(bp.take<float>(B * rh * lat));
+            w.g_eh.push_back(bp.take<float>(B * h * lat));
+        }
+        for (size_t i = 0; i < L.dec_res.size(); ++i) {
+            w.g_dra.push_back(bp.take<float>(B * rh * lat));
+            w.g_dh.push_back(bp.take<float>(B * h * lat));
+        }
+        w.bias_part = bp.take<double>(B * (H / 2) * (size_t)(L.max_c > 2 ? L.max_c : 2) * 2);
+        size_t maxw = 0;
+        for (const ConvL& c : L.convs) {
+            const size_t f = (size_t)(c.cin + 1) * c.ks * c.ks * c.cout + c.cout + (size_t)c.cin;
+            if (f > maxw) maxw = f;
+        }
+        w.wg_part_floats = maxw * 148 * 2;
+        w.wg_part = bp.take<float>(w.wg_part_floats);
+        w.dweff = bp.take<float>((size_t)(m.num_inputs + 1) * 16 * h2 + h2 + 16);
     }
     w.vq_stats = bp.take<double>(2 + m.num_embeddings);
     w.recon_sum = bp.take<double>(4);
@@ -439,6 +493,236 @@ __global__ void recon_loss_kernel(const float* __restrict__ dec, const float* __
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// training step: backward schedule
+// ---------------------------------------------------------------------------------------
+__global__ void recon_grad_kernel(const float* __restrict__ dec, const float* __restrict__ x,
+                                  const float* __restrict__ mask, int mask_c, const float* __restrict__ cvar,
+                                  int64_t total4, int C, int hw4, float scale, float* __restrict__ gd) {
+    // d/d dec of  scale * sum ((dec*m - x*m)^2 / cv)  =  scale * 2 (dec*m - x*m) m / cv
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t plane = i / hw4;
+        const int c = (int)(plane % C);
+        const int64_t b = plane / C;
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dec) + i);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (mask) {
+            const int64_t mi = (mask_c == 1) ? (b * hw4 + (i - plane * hw4)) : i;
+            mk = __ldg(reinterpret_cast<const float4*>(mask) + mi);
+        }
+        const float k2 = 2.f * scale / __ldg(cvar + c);
+        float4 o;
+        o.x = k2 * (d.x * mk.x - v.x * mk.x) * mk.x; o.y = k2 * (d.y * mk.y - v.y * mk.y) * mk.y;
+        o.z = k2 * (d.z * mk.z - v.z * mk.z) * mk.z; o.w = k2 * (d.w * mk.w - v.w * mk.w) * mk.w;
+        reinterpret_cast<float4*>(gd)[i] = o;
+    }
+}
+
+__global__ void train_losses_kernel(const float* vq2, const double* recon_sum, double n_recon, float w_r, float w_c,
+                                    float* out4) {
+    const float recon = (float)(recon_sum[0] / n_recon);
+    out4[0] = recon;
+    out4[1] = vq2[0];
+    out4[2] = w_r * recon + w_c * vq2[0];
+    out4[3] = vq2[1];
+}
+
+struct GradT {            // dL/d(conv output) = A*g + Bc*y + Cc  (A == nullptr: just g)
+    const float* g = nullptr; const float* y = nullptr;
+    const float* A = nullptr; const float* Bc = nullptr; const float* Cc = nullptr;
+};
+
+struct Bwd {
+    Ctx& c;
+    const float* params;
+    float* grads;
+    cudaStream_t st;
+    bool ps() const { return c.per_sample(); }
+
+    // weight / bias gradient of conv layer li (input activation xin, H x W).  For ConvTranspose2d the roles
+    // are swapped: `G` must be a plain tensor (no BN after the decoder's ConvT in z16) of shape (Cout,2H,2W).
+    int wgrad_layer(int li, const GradT& G, const Act& xin, bool x_relu, int H, int W, bool with_bias) {
+        const ConvL& l = c.L.convs[li];
+        WgradArgs a{};
+        a.B = (int)c.B; a.ks = l.ks; a.stride = l.stride; a.partials = c.w.wg_part;
+        if (l.transposed) {
+            DMB_CHECK(G.A == nullptr, "ConvTranspose2d followed by BatchNorm: backward not scheduled");
+            a.g = xin.p; a.ga = xin.s; a.gc = xin.t; a.gb = nullptr; a.y = nullptr; a.g_per_sample = ps();
+            DMB_CHECK(!(xin.s && x_relu) , "ConvTranspose2d after BN+ReLU: backward not scheduled");
+            a.Cout = l.cin; a.Ho = H; a.Wo = W;
+            a.x = G.g; a.Cin = l.cout; a.H = 2 * H; a.W = 2 * W;
+        } else {
+            a.g = G.g; a.y = G.y; a.ga = G.A; a.gb = G.Bc; a.gc = G.Cc; a.g_per_sample = ps();
+            a.x = xin.p; a.xs = xin.s; a.xt = xin.t; a.x_per_sample = ps(); a.x_relu = x_relu;
+            a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.Ho = H / l.stride; a.Wo = W / l.stride;
+        }
+        int ncta = 0;
+        const int pf = wgrad_partial_floats(a, &ncta);
+        DMB_CHECK(pf > 0 && (size_t)pf * ncta <= c.w.wg_part_floats, "wgrad scratch too small for layer %d", li);
+        float* db = (with_bias && !l.transposed) ? grads + l.b_off : nullptr;
+        return wgrad(a, grads + l.w_off, db, nullptr, st);
+    }
+
+    // data gradient of conv layer li: G (at the layer's output, Ho x Wo) -> gout (at its input, H x W), gated by
+    // the ReLU of the tensor that fed the layer, plus optional skip and BatchNorm-backward sums.
+    int dgrad_layer(int li, const GradT& G, int H, int W, float* gout, const Act* gate, const float* skip,
+                    double* stats, const float* stat_src, int* nbands) {
+        const ConvL& l = c.L.convs[li];
+        DMB_CHECK(l.pdw_off >= 0, "layer %d has no data-gradient weights", li);
+        const float* wd = c.packed + l.pdw_off;
+        const float* zero = c.packed + c.L.pzero_off;
+        const bool up = (!l.transposed && l.stride == 2);      // conv stride 2 -> transposed-conv kernel
+        if (up) {
+            ConvTFwdArgs a{};
+            a.x = G.g; a.x2 = G.y; a.in_scale = G.A; a.in_b = G.Bc; a.in_shift = G.Cc; a.in_per_sample = ps();
+            a.y = gout; a.w = wd; a.bias = zero;
+            if (gate) { a.mask_src = gate->p; a.mask_s = gate->s; a.mask_t = gate->t; a.mask_per_sample = ps(); }
+            a.stats = stats; a.stat_src = stat_src;
+            a.B = (int)c.B; a.Cin = l.cout; a.H = H / 2; a.W = W / 2; a.Cout = l.cin;
+            DMB_CHECK(skip == nullptr, "skip not supported on the transposed data-gradient path");
+            if (nbands) *nbands = convt_fwd_bands(a.Cin, a.Cout, a.H, a.W);
+            return convt_fwd(a, st);
+        }
+        ConvFwdArgs a{};
+        a.x = G.g; a.x2 = G.y; a.in_scale = G.A; a.in_b = G.Bc; a.in_shift = G.Cc; a.in_per_sample = ps();
+        a.y = gout; a.w = wd; a.bias = zero;
+        if (gate) { a.mask_src = gate->p; a.mask_s = gate->s; a.mask_t = gate->t; a.mask_per_sample = ps(); }
+        a.skip = skip; a.stats = stats; a.stat_src = stat_src;
+        a.B = (int)c.B; a.Cin = l.cout; a.Cout = l.cin;
+        if (l.transposed) {      // ConvTranspose2d -> stride-2 conv over the (2H x 2W) output gradient
+            a.ks = 4; a.stride = 2; a.H = 2 * H; a.W = 2 * W; a.Ho = H; a.Wo = W;
+        } else {
+            a.ks = l.ks; a.stride = 1; a.H = H; a.W = W; a.Ho = H; a.Wo = W;
+        }
+        if (nbands) *nbands = conv_fwd_bands(a.ks, a.stride, a.Cin, a.Cout, a.Ho, a.Wo);
+        return conv_fwd(a, st);
+    }
+
+    // BatchNorm backward of layer li's BN from the partial sums the gradient producer left in bnb[].part
+    int bn_bwd(int li, int nbands, int64_t count, GradT* G, const float* g, const float* y) {
+        const ConvL& l = c.L.convs[li];
+        const BnL& b = c.L.bns[l.bn];
+        Workspace::BnB& bb = c.w.bnb[l.bn];
+        BnWs& bw = c.w.bn[l.bn];
+        BnBwdArgs a{};
+        a.partials = bb.part; a.B = (int)c.B; a.nbands = nbands; a.C = l.cout; a.count_per_sample = count;
+        a.per_sample = ps(); a.gamma = c.packed + b.pg_off; a.mean = bw.mean; a.invstd = bw.invstd;
+        a.A = bb.A; a.Bc = bb.Bc; a.Cc = bb.Cc; a.dgamma = grads + b.g_off; a.dbeta = grads + b.b_off;
+        DMB_TRY(bn_backward_finalize(a, st));
+        G->g = g; G->y = y; G->A = bb.A; G->Bc = bb.Bc; G->Cc = bb.Cc;
+        return 0;
+    }
+};
+
+int run_backward_z16(Ctx& c, const float* params, const float* x, const float* mask, int mask_c,
+                     const float* cvar, const float* decoded, float grad_scale, float* grads) {
+    const Layout& L = c.L;
+    const dmb_model& m = L.m;
+    Workspace& w = c.w;
+    cudaStream_t st = c.st;
+    Bwd B{c, params, grads, st};
+    const int H = m.height, W = m.width, lh = L.lh, lw = L.lw;
+    const int h = m.num_hiddens, h2 = h / 2, h4 = h / 4;
+    const int64_t nrec = c.B * (int64_t)m.num_inputs * H * W;
+    int nb = 0;
+
+    // 0. reconstruction-loss gradient
+    {
+        const int64_t total4 = nrec / 4;
+        int64_t blocks = (total4 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        recon_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(decoded, x, mask, mask_c, cvar, total4, m.num_inputs,
+                                                            H * W / 4, grad_scale * m.weight_recon / (float)nrec, w.gd);
+        DMB_CUDA(cudaGetLastError());
+        DMB_LAUNCHED(1);
+    }
+    // 1-4. decoder (no BatchNorm): dec.6 conv1x1, dec.4 / dec.2 / dec.0 ConvT
+    Act t3; t3.p = w.t3; Act t2; t2.p = w.t2; Act t1; t1.p = w.t1; Act za; za.p = w.za;
+    GradT G; G.g = w.gd;
+    DMB_TRY(B.wgrad_layer(L.d3, G, t3, false, H, W, true));
+    DMB_TRY(B.dgrad_layer(L.d3, G, H, W, w.g_t3, &t3, nullptr, w.bias_part, nullptr, &nb));
+    DMB_TRY(sum_partials(w.bias_part, (int)c.B, nb, h4, grads + L.convs[L.d2].b_off, st));
+    G = GradT(); G.g = w.g_t3;
+    DMB_TRY(B.wgrad_layer(L.d2, G, t2, false, H / 2, W / 2, false));
+    DMB_TRY(B.dgrad_layer(L.d2, G, H / 2, W / 2, w.g_t2, &t2, nullptr, w.bias_part, nullptr, &nb));
+    DMB_TRY(sum_partials(w.bias_part, (int)c.B, nb, h4, grads + L.convs[L.d1].b_off, st));
+    G = GradT(); G.g = w.g_t2;
+    DMB_TRY(B.wgrad_layer(L.d1, G, t1, false, H / 4, W / 4, false));
+    DMB_TRY(B.dgrad_layer(L.d1, G, H / 4, W / 4, w.g_t1, &t1, nullptr, w.bias_part, nullptr, &nb));
+    DMB_TRY(sum_partials(w.bias_part, (int)c.B, nb, h2, grads + L.convs[L.d0].b_off, st));
+    G = GradT(); G.g = w.g_t1;
+    DMB_TRY(B.wgrad_layer(L.d0, G, za, false, lh, lw, false));
+    DMB_TRY(B.dgrad_layer(L.d0, G, lh, lw, w.g_za, nullptr, nullptr, nullptr, nullptr, nullptr));
+
+    // 5. quantiser: straight-through + commitment term; codebook gradient; BN sums for the last residual layer
+    const int nres = (int)L.enc_res.size();
+    DMB_CHECK(nres >= 1, "training needs num_residual_layers >= 1");
+    const int P = lh * lw;
+    {
+        const ConvL& lb = L.convs[L.enc_res[nres - 1].b];
+        DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, w.g_za, grad_scale * m.weight_commitment,
+                                  m.commitment_cost, c.B, h, P, m.num_embeddings, w.g_zb, grads + L.codebook_off,
+                                  w.bnb[lb.bn].part, w.erb[nres - 1], st));
+    }
+    // 6. residual layers, last to first
+    const float* g_cur = w.g_zb;
+    int nb_cur = P / 128;
+    Act y4a; y4a.p = w.y4; y4a.s = w.bn[L.convs[L.e4].bn].scale; y4a.t = w.bn[L.convs[L.e4].bn].shift;
+    for (int i = nres - 1; i >= 0; --i) {
+        const int la = L.enc_res[i].a, lb = L.enc_res[i].b;
+        GradT Gb, Ga;
+        DMB_TRY(B.bn_bwd(lb, nb_cur, P, &Gb, g_cur, w.erb[i]));
+        Act ra; ra.p = w.era[i]; ra.s = w.bn[L.convs[la].bn].scale; ra.t = w.bn[L.convs[la].bn].shift;
+        DMB_TRY(B.wgrad_layer(lb, Gb, ra, true, lh, lw, true));
+        DMB_TRY(B.dgrad_layer(lb, Gb, lh, lw, w.g_era[i], &ra, nullptr, w.bnb[L.convs[la].bn].part, w.era[i], &nb));
+        DMB_TRY(B.bn_bwd(la, nb, P, &Ga, w.g_era[i], w.era[i]));
+        Act hin;                      // the layer's input h_i (pending affine for i == 0)
+        if (i == 0) hin = y4a; else hin.p = w.ehs[i - 1];
+        DMB_TRY(B.wgrad_layer(la, Ga, hin, true, lh, lw, true));
+        const int prev_bn = (i == 0) ? L.convs[L.e4].bn : L.convs[L.enc_res[i - 1].b].bn;
+        const float* stat_src = (i == 0) ? w.y4 : w.erb[i - 1];
+        DMB_TRY(B.dgrad_layer(la, Ga, lh, lw, w.g_eh[i], &hin, g_cur, w.bnb[prev_bn].part, stat_src, &nb));
+        g_cur = w.g_eh[i];
+        nb_cur = nb;
+    }
+    // 7. enc.10 (3x3) behind enc.11 BN
+    GradT G4, G3, G2, G1;
+    DMB_TRY(B.bn_bwd(L.e4, nb_cur, P, &G4, g_cur, w.y4));
+    Act y3a; y3a.p = w.y3; y3a.s = w.bn[L.convs[L.e3].bn].scale; y3a.t = w.bn[L.convs[L.e3].bn].shift;
+    DMB_TRY(B.wgrad_layer(L.e4, G4, y3a, true, lh, lw, true));
+    DMB_TRY(B.dgrad_layer(L.e4, G4, lh, lw, w.g_y3, &y3a, nullptr, w.bnb[L.convs[L.e3].bn].part, w.y3, &nb));
+    // 8. enc.7 (4x4 s2) behind enc.8 BN
+    DMB_TRY(B.bn_bwd(L.e3, nb, P, &G3, w.g_y3, w.y3));
+    Act y2a; y2a.p = w.y2; y2a.s = w.bn[L.convs[L.e2].bn].scale; y2a.t = w.bn[L.convs[L.e2].bn].shift;
+    DMB_TRY(B.wgrad_layer(L.e3, G3, y2a, true, H / 4, W / 4, true));
+    DMB_TRY(B.dgrad_layer(L.e3, G3, H / 4, W / 4, w.g_y2, &y2a, nullptr, w.bnb[L.convs[L.e2].bn].part, w.y2, &nb));
+    // 9. enc.4 (4x4 s2) behind enc.5 BN
+    DMB_TRY(B.bn_bwd(L.e2, nb, (int64_t)(H / 4) * (W / 4), &G2, w.g_y2, w.y2));
+    Act y1a; y1a.p = w.y1; y1a.s = w.bn[L.convs[L.e1].bn].scale; y1a.t = w.bn[L.convs[L.e1].bn].shift;
+    DMB_TRY(B.wgrad_layer(L.e2, G2, y1a, true, H / 2, W / 2, true));
+    DMB_TRY(B.dgrad_layer(L.e2, G2, H / 2, W / 2, w.g_y1, &y1a, nullptr, w.bnb[L.convs[L.e1].bn].part, w.y1, &nb));
+    // 10. composite head (enc.0 1x1 + enc.1 4x4 s2) behind enc.2 BN: gradient of the effective conv, then chain rule
+    DMB_TRY(B.bn_bwd(L.e1, nb, (int64_t)(H / 2) * (W / 2), &G1, w.g_y1, w.y1));
+    {
+        const ConvL& l = L.convs[L.e1];
+        WgradArgs a{};
+        a.B = (int)c.B; a.ks = 4; a.stride = 2; a.partials = w.wg_part;
+        a.g = G1.g; a.y = G1.y; a.ga = G1.A; a.gb = G1.Bc; a.gc = G1.Cc; a.g_per_sample = c.per_sample();
+        a.x = x; a.ones_channel = 1;
+        a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.Ho = H / 2; a.Wo = W / 2;
+        int ncta = 0;
+        const int pf = wgrad_partial_floats(a, &ncta);
+        DMB_CHECK(pf > 0 && (size_t)pf * ncta <= w.wg_part_floats, "wgrad scratch too small for the head");
+        DMB_TRY(wgrad(a, nullptr, nullptr, w.dweff, st));
+        DMB_TRY(composite_chain(w.dweff, params + l.w0_off, params + l.b0_off, params + l.w_off, l.cin, l.cmid,
+                                grads + l.w0_off, grads + l.b0_off, grads + l.w_off, grads + l.b_off, st));
+    }
+    return 0;
+}
+
 }  // namespace
 }  // namespace dmb
 
@@ -584,6 +868,45 @@ int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const fl
     a.in_per_sample = in_per_sample; a.in_relu = in_relu; a.out_relu = out_relu;
     a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout;
     return convt_fwd(a, (cudaStream_t)stream);
+}
+
+int dmb_train_forward(const dmb_model* m, const float* packed, const float* params, const float* x,
+                      const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
+                      float* decoded, float* losses_out, float* bnbuf_inout, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    Layout L; Workspace w;
+    DMB_CHECK(packed && params && x && channel_var && decoded && losses_out, "dmb_train_forward: null pointer");
+    DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
+    cudaStream_t st = (cudaStream_t)stream;
+    Ctx c{L, packed, w, batch, DMB_BN_BATCH, bnbuf_inout, st};
+    Pending pend;
+    DMB_TRY(run_encoder(c, x, w.zb, &pend));
+    DMB_CUDA(cudaMemsetAsync(w.vq_stats, 0, sizeof(double) * (2 + m->num_embeddings), st));
+    DMB_CUDA(cudaMemsetAsync(w.recon_sum, 0, sizeof(double) * 4, st));
+    DMB_TRY(run_vq(c, params + L.codebook_off, w.zb, &pend, w.zb, w.za, w.idx, w.vq_stats));
+    DMB_TRY(dmb_vq_finalize(w.vq_stats, L.D, m->num_embeddings, m->commitment_cost, w.scalars, stream));
+    DMB_TRY(run_decoder(c, w.za, decoded));
+    DMB_TRY(dmb_recon_loss(decoded, x, mask, mask_channels, channel_var, batch, m->num_inputs,
+                           m->height * m->width, w.recon_sum, stream));
+    const bool z32 = m->arch == DMB_ARCH_Z32;
+    train_losses_kernel<<<1, 1, 0, st>>>(w.scalars, w.recon_sum, (double)batch * m->num_inputs * m->height * m->width,
+                                         z32 ? 1.f : m->weight_recon, z32 ? 1.f : m->weight_commitment, losses_out);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int dmb_train_backward(const dmb_model* m, const float* packed, const float* params, const float* x,
+                       const float* mask, int32_t mask_channels, const float* channel_var,
+                       const float* decoded, int64_t batch, float grad_scale, float* grads, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    Layout L; Workspace w;
+    DMB_CHECK(packed && params && x && channel_var && decoded && grads, "dmb_train_backward: null pointer");
+    DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
+    DMB_CHECK(m->arch == DMB_ARCH_Z16, "dmb_train_backward: only the z16 architecture (vq_vae.VQ_VAE / vae.VQ_VAE_z16) "
+              "has a backward schedule so far");
+    Ctx c{L, packed, w, batch, DMB_BN_BATCH, nullptr, (cudaStream_t)stream};
+    return run_backward_z16(c, params, x, mask, mask_channels, channel_var, decoded, grad_scale, grads);
 }
 
 long long dmb_launch_count(int reset) {

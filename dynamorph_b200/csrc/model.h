@@ -22,6 +22,7 @@ struct ConvL {
     int64_t w0_off, b0_off;      // composite: the 1x1 conv's weight / bias in params
     int bn;                      // BatchNorm that follows (index into bns) or -1
     int64_t pw_off, pb_off;      // packed weight [cin][ks][ks][cout], bias [cout] or [9][cout]
+    int64_t pdw_off;             // packed weight of the data-gradient conv [cout][ks][ks][cin] (-1: none)
     int bias_classes;
 };
 
@@ -36,6 +37,8 @@ struct Layout {
     std::vector<BnL> bns;
     int64_t n_params = 0, n_bnbuf = 0, n_packed = 0;
     int64_t codebook_off = 0;
+    int64_t pzero_off = 0;       // zeros[max channels] in packed (bias of the data-gradient convs)
+    int max_c = 0;
     // encoder
     int e1 = -1, e2 = -1, e3 = -1, e4 = -1;   // z32 uses e1, e2 only
     std::vector<ResL> enc_res, dec_res;
@@ -58,6 +61,17 @@ struct Workspace {
     float *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;   // decoder activations
     float* dec = nullptr;
     std::vector<BnWs> bn;                  // one per BatchNorm, same order as Layout::bns
+    // ---- backward (keep != 0)
+    struct BnB { double* part; float *A, *Bc, *Cc; };
+    std::vector<BnB> bnb;
+    float *gd = nullptr, *g_t3 = nullptr, *g_t2 = nullptr, *g_t1 = nullptr, *g_za = nullptr, *g_zb = nullptr;
+    std::vector<float*> g_era, g_eh;       // encoder residual: grad at BN_a output (masked), grad at layer input
+    std::vector<float*> g_dra, g_dh;       // decoder residual (z32)
+    float *g_y3 = nullptr, *g_y2 = nullptr, *g_y1 = nullptr;
+    double* bias_part = nullptr;           // stats partials for bias grads of BN-less layers
+    float* wg_part = nullptr;              // wgrad per-CTA partials
+    float* dweff = nullptr;                // composite head: packed effective-weight gradient
+    size_t wg_part_floats = 0;
     double* vq_stats = nullptr;            // [2+K]
     double* recon_sum = nullptr;           // [1]
     float* scalars = nullptr;              // [8] vq loss, perplexity, ...

@@ -18,10 +18,11 @@ struct PackL {
     int cin, cout, ks, transposed, composite, cmid, bias_classes, fold;
     int64_t w_off, b_off, w0_off, b0_off, pw_off, pb_off;
     int64_t g_off, beta_off, rm_off, rv_off;
-    int64_t start;     // first packed-element id of this layer (weights then bias)
-    int64_t nw, nb;
+    int64_t start;     // first packed-element id of this layer (weights, bias, data-gradient weights)
+    int64_t nw, nb, nd, pdw_off;
+    int stride;
 };
-struct PackPlan { int n; int64_t total; float eps; PackL l[MAX_PACK]; int nbn; int64_t bn_start;
+struct PackPlan { int n; int64_t total; float eps; PackL l[MAX_PACK]; int nbn; int64_t bn_start; int64_t zero_off; int nzero;
                   int64_t bg_off[MAX_PACK], bb_off[MAX_PACK], bpg_off[MAX_PACK], bpb_off[MAX_PACK]; int bc[MAX_PACK]; };
 
 __device__ double bn_scale(const PackL& l, const float* params, const float* bnbuf, int co, float eps, double* shift_mean) {
@@ -35,8 +36,11 @@ __global__ void pack_kernel(const PackPlan p, const float* __restrict__ params,
                             const float* __restrict__ bnbuf, float* __restrict__ packed) {
     for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < p.total;
          id += (int64_t)gridDim.x * blockDim.x) {
-        if (id >= p.bn_start) {      // gamma / beta copies
+        if (id >= p.bn_start) {      // gamma / beta copies, then the zero vector
             int64_t r = id - p.bn_start;
+            int64_t nbn_el = 0;
+            for (int i = 0; i < p.nbn; ++i) nbn_el += 2 * p.bc[i];
+            if (r >= nbn_el) { packed[p.zero_off + (r - nbn_el)] = 0.f; continue; }
             for (int i = 0; i < p.nbn; ++i) {
                 if (r < 2 * p.bc[i]) {
                     if (r < p.bc[i]) packed[p.bpg_off[i] + r] = params[p.bg_off[i] + r];
@@ -72,6 +76,19 @@ __global__ void pack_kernel(const PackPlan p, const float* __restrict__ params,
                 w = params[l.w_off + ((int64_t)(co * l.cin + ci) * K + ky) * K + kx];
             }
             packed[l.pw_off + e] = (float)(w * s);
+        } else if (e >= l.nw + l.nb) {
+            // data-gradient weights [cout][k][k][cin]: conv stride 1 flips the taps (correlation ->
+            // convolution); stride-2 conv / ConvTranspose2d keep them (they swap kernels instead)
+            const int64_t ed = e - l.nw - l.nb;
+            const int ci = (int)(ed % l.cin);
+            int64_t t = ed / l.cin;
+            int kx = (int)(t % K); t /= K;
+            int ky = (int)(t % K);
+            const int co = (int)(t / K);
+            if (!l.transposed && l.stride == 1) { ky = K - 1 - ky; kx = K - 1 - kx; }
+            const float w = l.transposed ? params[l.w_off + ((int64_t)(ci * l.cout + co) * K + ky) * K + kx]
+                                         : params[l.w_off + ((int64_t)(co * l.cin + ci) * K + ky) * K + kx];
+            packed[l.pdw_off + ed] = w;
         } else {
             const int64_t eb = e - l.nw;
             const int co = (int)(eb % l.cout);
@@ -120,7 +137,10 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
         l.start = start;
         l.nw = (int64_t)c.cin * c.ks * c.ks * c.cout;
         l.nb = (int64_t)(c.bias_classes ? 9 : 1) * c.cout;
-        start += l.nw + l.nb;
+        l.nd = (c.pdw_off >= 0) ? l.nw : 0;
+        l.pdw_off = c.pdw_off;
+        l.stride = c.stride;
+        start += l.nw + l.nb + l.nd;
     }
     p.bn_start = start;
     p.nbn = (int)L.bns.size();
@@ -129,6 +149,9 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
         p.bpg_off[i] = L.bns[i].pg_off; p.bpb_off[i] = L.bns[i].pb_off; p.bc[i] = L.bns[i].c;
         start += 2 * L.bns[i].c;
     }
+    p.zero_off = L.pzero_off;
+    p.nzero = L.max_c;
+    start += L.max_c;
     p.total = start;
     const int threads = 256;
     int blocks = (int)((p.total + threads - 1) / threads);

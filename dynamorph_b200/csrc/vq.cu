@@ -265,29 +265,68 @@ int dmb_vq_gather(const int32_t* idx, const float* codebook, int64_t batch, int3
 namespace dmb {
 namespace {
 
-__global__ void vq_backward_kernel(const float* __restrict__ z, const float* __restrict__ cb,
-                                   const int32_t* __restrict__ idx, const float* __restrict__ g_zst,
-                                   const float* __restrict__ g_loss, float g_loss_scale, float beta,
-                                   int64_t total, int d, int p, float* __restrict__ grad_z,
-                                   float* __restrict__ grad_cb) {
+__global__ void __launch_bounds__(128) vq_backward_kernel(
+        const float* __restrict__ z, const float* __restrict__ cb, const int32_t* __restrict__ idx,
+        const float* __restrict__ g_zst, const float* __restrict__ g_loss, float g_loss_scale, float beta,
+        int64_t total, int d, int p, float* __restrict__ grad_z, float* __restrict__ grad_cb,
+        double* __restrict__ stats, const float* __restrict__ stat_src) {
+    // stats (optional): per-CTA (sum g, sum g*stat_src) per channel, layout [block][d][2] -- the BatchNorm
+    // backward sums of the residual layer that produced z.  Needs p % 128 == 0 (a CTA stays in one patch).
+    __shared__ float red[4][2];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= total) return;
+    const bool live = n < total;
     const float gl = (g_loss ? __ldg(g_loss) : 1.f) * g_loss_scale;
     const float coef = gl * 2.f / (float)((double)total * d);
-    const int64_t b = n / p;
-    const int pos = (int)(n - b * p);
-    const int k = idx[n];
+    const int64_t b = live ? n / p : 0;
+    const int pos = live ? (int)(n - b * p) : 0;
+    const int k = live ? idx[n] : 0;
     const size_t base = (size_t)b * d * p + pos;
     for (int c = 0; c < d; ++c) {
-        const float zv = __ldg(z + base + (size_t)c * p);
-        const float q = __ldg(cb + (size_t)k * d + c);
-        const float g = g_zst ? __ldg(g_zst + base + (size_t)c * p) : 0.f;
-        if (grad_z) grad_z[base + (size_t)c * p] = g + coef * beta * (zv - q);
-        if (grad_cb) atomicAdd(grad_cb + (size_t)k * d + c, coef * (q - zv));
+        float gz = 0.f, sy = 0.f;
+        if (live) {
+            const float zv = __ldg(z + base + (size_t)c * p);
+            const float q = __ldg(cb + (size_t)k * d + c);
+            const float g = g_zst ? __ldg(g_zst + base + (size_t)c * p) : 0.f;
+            gz = g + coef * beta * (zv - q);
+            if (grad_z) grad_z[base + (size_t)c * p] = gz;
+            if (grad_cb) atomicAdd(grad_cb + (size_t)k * d + c, coef * (q - zv));
+            if (stats) sy = gz * __ldg(stat_src + base + (size_t)c * p);
+        }
+        if (stats) {
+            float s = gz;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s; red[threadIdx.x >> 5][1] = sy; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double* dst = stats + ((size_t)blockIdx.x * d + c) * 2;
+                dst[0] = (double)red[0][0] + (double)red[1][0] + (double)red[2][0] + (double)red[3][0];
+                dst[1] = (double)red[0][1] + (double)red[1][1] + (double)red[2][1] + (double)red[3][1];
+            }
+        }
     }
 }
 
 }  // namespace
+}  // namespace dmb
+
+namespace dmb {
+int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx, const float* g_zst,
+                      float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
+                      float* grad_codebook, double* stats, const float* stat_src, cudaStream_t st) {
+    const int64_t total = batch * p;
+    DMB_CHECK(!stats || p % 128 == 0, "vq backward: positions per patch (%d) must be a multiple of 128", p);
+    DMB_CUDA(cudaMemsetAsync(grad_codebook, 0, sizeof(float) * (size_t)k * d, st));
+    vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+        z, codebook, idx, g_zst, nullptr, g_loss_scale, beta, total, d, p, grad_z, grad_codebook, stats, stat_src);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
 }  // namespace dmb
 
 extern "C" int dmb_vq_backward(const float* z, const float* codebook, const int32_t* idx,
@@ -302,7 +341,7 @@ extern "C" int dmb_vq_backward(const float* z, const float* codebook, const int3
     if (total == 0) return 0;
     dmb::vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         z, codebook, idx, g_zst, g_loss_dev, g_loss_scale, commitment_cost, total, d,
-        positions_per_patch, grad_z, grad_codebook);
+        positions_per_patch, grad_z, grad_codebook, nullptr, nullptr);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -40,6 +40,8 @@ class Engine:
         self._packed: Dict[int, Tuple[tuple, torch.Tensor]] = {}
         self._ws: Optional[torch.Tensor] = None
         self._flat_dirty = 0                              # bumped when the flat buffer is written directly
+        self._ws_uses = 0
+        self.last_flat_grad = None
         self._bn_dirty = 0                                # bumped when the library updates running stats
         self._spec_cache: Dict[Tuple[int, int], DmbModel] = {}
 
@@ -176,7 +178,12 @@ class Engine:
         return buf
 
     # ---------------------------------------------------------------- workspace
+    def workspace_token(self) -> int:
+        """Changes whenever a call may have overwritten the activation workspace."""
+        return self._ws_uses
+
     def workspace(self, s: DmbModel, batch: int, mode: int, keep: int) -> Tuple[torch.Tensor, int]:
+        self._ws_uses += 1
         nbytes = C.c_size_t()
         call("dmb_workspace_bytes", C.byref(s), batch, mode, keep, C.byref(nbytes))
         need = nbytes.value

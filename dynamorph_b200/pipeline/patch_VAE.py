@@ -1,0 +1,123 @@
+"""Drop-in for `process_VAE` of /root/reference/pipeline/patch_VAE.py:343-509 (VAE branch).
+
+Same inputs (`<raw>/<well>_file_paths.pkl`, `<well>_static_patches.pkl`, the `latent_encoding` config
+section) and the same outputs (`<raw>/<basename(weights)>/<well>_latent_space.pkl` and
+`_latent_space_after.pkl`: float32 (N, D*h*w), NCHW-flattened, pickle protocol 4), but the per-patch
+python loop (batch 1, two blocking D2H copies per patch, autograd on) is replaced by the pipelined bulk
+encoder: z-score on the GPU, chunked H2D / encode / D2H on three streams.
+
+BatchNorm semantics: the reference never calls `model.eval()`, so as written it normalises every patch
+with that patch's own statistics (train-mode BN, batch 1).  `bn_mode="per_sample"` (default) reproduces
+exactly that; `bn_mode="eval"` uses the trained running statistics."""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from ..HiddenStateExtractor import vae
+from ..bulk import BulkEncoder
+from .train_utils import zscore_patch_device
+
+
+def encode_patches(model, dataset: np.ndarray, device, bn_mode: str = "per_sample", chunk: int = 4096,
+                   zscore: bool = True):
+    """(N, C, H, W) raw patches on the host -> (z_before, z_after) float32 (N, D*h*w) on the host."""
+    n = dataset.shape[0]
+    enc = BulkEncoder(model, chunk=chunk, bn_mode=bn_mode, device=device, outputs=("z_before", "z_after"))
+    out = enc.allocate_outputs(n, dataset.shape[1], dataset.shape[2], dataset.shape[3], pin=True)
+    if not zscore:
+        x = torch.from_numpy(np.ascontiguousarray(dataset, dtype=np.float32))
+        enc.encode(x, out)
+    else:
+        # z-score needs the raw (float64 / uint16) values: stage chunk-wise, normalise on the device and
+        # feed the device tensor straight into the encoder (no float32 host copy)
+        eng = model._engine
+        zb_dev = za_dev = idx_dev = None
+        for a in range(0, n, chunk):
+            part = np.ascontiguousarray(dataset[a:a + chunk])
+            if part.dtype not in (np.float32, np.float64, np.uint16):
+                part = part.astype(np.float64)
+            xd = zscore_patch_device(torch.from_numpy(part).to(device, non_blocking=True))
+            zb, za, _ = eng.encode(xd, bn_mode)
+            out["z_before"][a:a + xd.shape[0]].copy_(zb.reshape(xd.shape[0], -1), non_blocking=True)
+            out["z_after"][a:a + xd.shape[0]].copy_(za.reshape(xd.shape[0], -1), non_blocking=True)
+    torch.cuda.synchronize(device)
+    return out["z_before"].numpy(), out["z_after"].numpy()
+
+
+def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: int = 0, bn_mode: str = "per_sample",
+                **kwargs):
+    """Wrapper method for VAE encoding: loads the prepared dataset of one well and encodes its static
+    patches with the trained VQ-VAE; writes the two latent-space pickles (reference: patch_VAE.py:343-462)."""
+    cfg = config_.latent_encoding
+    channels = cfg.channels
+    network = cfg.network
+    weights_dir = cfg.weights
+    save_output = getattr(cfg, "save_output", False)
+    assert len(channels) > 0, "At least one channel must be specified"
+
+    model_path = os.path.join(weights_dir, 'model.pt')
+    model_name = os.path.basename(weights_dir)
+    output_dir = os.path.join(raw_folder, model_name)
+    os.makedirs(output_dir, exist_ok=True)
+
+    assert len(set(site[:2] for site in sites)) == 1, "Sites should be from a single well/condition"
+    well = sites[0][:2]
+
+    print(f"\tloading file paths {os.path.join(raw_folder, '%s_file_paths.pkl' % well)}")
+    with open(os.path.join(raw_folder, '%s_file_paths.pkl' % well), 'rb') as f:
+        fs = pickle.load(f)
+    print(f"\tloading static patches {os.path.join(raw_folder, '%s_static_patches.pkl' % well)}")
+    with open(os.path.join(raw_folder, '%s_static_patches.pkl' % well), 'rb') as f:
+        dataset = pickle.load(f)
+    dataset = np.squeeze(dataset)
+    assert dataset.ndim == 4, "dataset tensor dimension can only be 4, not {}".format(dataset.ndim)
+    assert len(fs) == dataset.shape[0], "file paths and patches disagree"
+    device = torch.device('cuda:%d' % gpu)
+    print('Encoding images using gpu {}...'.format(gpu))
+    if 'VAE' not in network:
+        raise ValueError('Network {} is not available'.format(network))
+    network_cls = getattr(vae, network)
+    model = network_cls(num_inputs=dataset.shape[1],
+                        num_hiddens=cfg.num_hiddens,
+                        num_residual_hiddens=cfg.num_residual_hiddens,
+                        num_residual_layers=2,
+                        num_embeddings=cfg.num_embeddings,
+                        commitment_cost=getattr(cfg, "commitment_cost", 0.25),
+                        gpu=True)
+    model = model.to(device)
+    try:
+        model.load_state_dict(torch.load(model_path, map_location=device))
+    except Exception as ex:
+        print(ex)
+        raise ValueError("Error in loading model weights for VQ-VAE")
+
+    # the reference keys results by file name and re-stacks them in `fs` order (patch_VAE.py:450-455);
+    # encoding in dataset order is the same thing as long as names are unique
+    z_b, z_a = encode_patches(model, dataset, device, bn_mode=bn_mode)
+    order = {f: i for i, f in enumerate(fs)}
+    take = np.asarray([order[f] for f in fs])
+    dats = np.ascontiguousarray(z_b[take]).reshape((len(fs), -1))
+    print(f"\tsaving {os.path.join(output_dir, '%s_latent_space.pkl' % well)}")
+    with open(os.path.join(output_dir, '%s_latent_space.pkl' % well), 'wb') as f:
+        pickle.dump(dats, f, protocol=4)
+    dats = np.ascontiguousarray(z_a[take]).reshape((len(fs), -1))
+    print(f"\tsaving {os.path.join(output_dir, '%s_latent_space_after.pkl' % well)}")
+    with open(os.path.join(output_dir, '%s_latent_space_after.pkl' % well), 'wb') as f:
+        pickle.dump(dats, f, protocol=4)
+    if save_output:
+        # 20 reconstructions as .npy (the reference renders them to JPG with matplotlib, which is a
+        # plotting concern outside this path)
+        np.random.seed(0)
+        random_inds = np.random.randint(0, dataset.shape[0], (20,))
+        model.train()
+        with torch.no_grad():
+            for i in random_inds:
+                sample = zscore_patch_device(torch.from_numpy(np.ascontiguousarray(dataset[i:i + 1])).to(device))
+                output = model(sample)[0]
+                np.save(os.path.join(output_dir, 'recon_%d.npy' % i),
+                        np.stack([sample[0].cpu().numpy(), output[0].cpu().numpy()]))
+    return output_dir

@@ -164,7 +164,7 @@ int dmb_train_forward(const dmb_model* m, const float* packed, const float* para
  * `grads` in the layout of `params`.  Uses the workspace left by dmb_train_forward.       */
 int dmb_train_backward(const dmb_model* m, const float* packed, const float* params,
                        const float* x, const float* mask, int32_t mask_channels,
-                       const float* channel_var, int64_t batch, float grad_scale,
+                       const float* channel_var, const float* decoded, int64_t batch, float grad_scale,
                        float* grads, void* workspace, size_t workspace_bytes, void* stream);
 /* torch.optim.Adam (betas, eps, no weight decay), bias-corrected, step is 1-based.
  * grad_scale multiplies the gradient first (1/world_size after an allreduce-sum).        */

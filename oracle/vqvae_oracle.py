@@ -55,6 +55,30 @@ def num_residual_layers(state: State, prefix: str) -> int:
 # --------------------------------------------------------------------------
 # building blocks
 # --------------------------------------------------------------------------
+_RELU_TAPS = None   # when a list: every ReLU input of the forward pass is appended (near-tie analysis)
+
+
+def _relu(t: Tensor) -> Tensor:
+    if _RELU_TAPS is not None:
+        _RELU_TAPS.append(t.detach())
+    return F.relu(t)
+
+
+def relu_near_ties(x: Tensor, state: State, mode: str, tol: float = 2e-6) -> int:
+    """Number of ReLU inputs of one forward pass with |pre-activation| < tol.  A different fp32
+    summation order can flip the gate of such an element, which changes gradients by O(one term):
+    the ReLU analogue of a VQ near-tie.  Tests relax the gradient tolerance when this is non-zero."""
+    global _RELU_TAPS
+    _RELU_TAPS = []
+    try:
+        with torch.no_grad():
+            zb = encoder(x, state, mode)
+            za = vq_forward(zb, state["vq.w.weight"], 0.25)[0]
+            decoder(za, state, mode)
+        return int(sum(int(((t.abs() < tol) & (t != 0)).sum()) for t in _RELU_TAPS))
+    finally:
+        _RELU_TAPS = None
+
 def batchnorm(x: Tensor, state: State, key: str, mode: str,
               new_running: Optional[State] = None) -> Tensor:
     """nn.BatchNorm2d in one of the three modes the reference's callers produce
@@ -81,10 +105,10 @@ def residual_block(x: Tensor, state: State, prefix: str, mode: str,
     out = x
     for i in range(num_residual_layers(state, prefix)):
         p = f"{prefix}.layers.{i}"
-        h = F.relu(out)
+        h = _relu(out)
         h = F.conv2d(h, state[p + ".1.weight"], state[p + ".1.bias"], padding=1)
         h = batchnorm(h, state, p + ".2", mode, new_running)
-        h = F.relu(h)
+        h = _relu(h)
         h = F.conv2d(h, state[p + ".4.weight"], state[p + ".4.bias"])
         h = batchnorm(h, state, p + ".5", mode, new_running)
         out = out + h
@@ -102,16 +126,16 @@ def encoder(x: Tensor, state: State, mode: str,
     if arch_of(s) == "z16":
         h = F.conv2d(x, s["enc.0.weight"], s["enc.0.bias"])
         h = F.conv2d(h, s["enc.1.weight"], s["enc.1.bias"], stride=2, padding=1)
-        h = F.relu(batchnorm(h, s, "enc.2", mode, new_running))
+        h = _relu(batchnorm(h, s, "enc.2", mode, new_running))
         h = F.conv2d(h, s["enc.4.weight"], s["enc.4.bias"], stride=2, padding=1)
-        h = F.relu(batchnorm(h, s, "enc.5", mode, new_running))
+        h = _relu(batchnorm(h, s, "enc.5", mode, new_running))
         h = F.conv2d(h, s["enc.7.weight"], s["enc.7.bias"], stride=2, padding=1)
-        h = F.relu(batchnorm(h, s, "enc.8", mode, new_running))
+        h = _relu(batchnorm(h, s, "enc.8", mode, new_running))
         h = F.conv2d(h, s["enc.10.weight"], s["enc.10.bias"], padding=1)
         h = batchnorm(h, s, "enc.11", mode, new_running)
         return residual_block(h, s, "enc.12", mode, new_running)
     h = F.conv2d(x, s["enc.0.weight"], s["enc.0.bias"], stride=2, padding=1)
-    h = F.relu(batchnorm(h, s, "enc.1", mode, new_running))
+    h = _relu(batchnorm(h, s, "enc.1", mode, new_running))
     h = F.conv2d(h, s["enc.3.weight"], s["enc.3.bias"], stride=2, padding=1)
     h = batchnorm(h, s, "enc.4", mode, new_running)
     return residual_block(h, s, "enc.5", mode, new_running)
@@ -124,13 +148,13 @@ def decoder(zq: Tensor, state: State, mode: str,
     if mode == PER_SAMPLE:
         return torch.cat([decoder(zq[i:i + 1], s, BATCH) for i in range(zq.shape[0])], 0)
     if arch_of(s) == "z16":
-        h = F.relu(F.conv_transpose2d(zq, s["dec.0.weight"], s["dec.0.bias"], stride=2, padding=1))
-        h = F.relu(F.conv_transpose2d(h, s["dec.2.weight"], s["dec.2.bias"], stride=2, padding=1))
-        h = F.relu(F.conv_transpose2d(h, s["dec.4.weight"], s["dec.4.bias"], stride=2, padding=1))
+        h = _relu(F.conv_transpose2d(zq, s["dec.0.weight"], s["dec.0.bias"], stride=2, padding=1))
+        h = _relu(F.conv_transpose2d(h, s["dec.2.weight"], s["dec.2.bias"], stride=2, padding=1))
+        h = _relu(F.conv_transpose2d(h, s["dec.4.weight"], s["dec.4.bias"], stride=2, padding=1))
         return F.conv2d(h, s["dec.6.weight"], s["dec.6.bias"])
     h = residual_block(zq, s, "dec.0", mode, new_running)
     h = F.conv_transpose2d(h, s["dec.1.weight"], s["dec.1.bias"], stride=2, padding=1)
-    h = F.relu(batchnorm(h, s, "dec.2", mode, new_running))
+    h = _relu(batchnorm(h, s, "dec.2", mode, new_running))
     return F.conv_transpose2d(h, s["dec.4.weight"], s["dec.4.bias"], stride=2, padding=1)
 
 

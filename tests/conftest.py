@@ -40,7 +40,8 @@ class Golden:
         a = self.z[k]
         if a.dtype == np.float16:
             a = a.astype(np.float32)
-        return torch.from_numpy(np.ascontiguousarray(a))
+        a = np.array(a, copy=True, order='C')            # keeps 0-dim scalars 0-dim
+        return torch.from_numpy(a)
 
     def group(self, prefix):
         p = prefix.rstrip("/") + "/"

@@ -54,6 +54,7 @@ SIGNATURES = {
     "dmb_train_forward": [_M, _P, _P, _P, _P, _I32, _P, _I64, _P, _P, _P, _P, C.c_size_t, _P],
     "dmb_train_backward": [_M, _P, _P, _P, _P, _I32, _P, _P, _I64, _F, _P, _P, C.c_size_t, _P],
     "dmb_adam_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P],
+    "dmb_adam_step_dev": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _F, _P],
     "dmb_zscore_patch": [_P, _I32, _I64, _I32, _P, _P],
 }
 

@@ -187,6 +187,7 @@ int vq_forward(const VqArgs& a, cudaStream_t st);
 // gradient of the quantiser; optional per-CTA BatchNorm-backward sums [B*p/128][d][2] against stat_src
 int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx, const float* g_zst,
                       float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
-                      float* grad_codebook, double* stats, const float* stat_src, cudaStream_t st);
+                      float* grad_codebook, double* stats, const float* stat_src, float* scratch, int scratch_rows,
+                      cudaStream_t st);
 
 }  // namespace dmb

@@ -275,6 +275,9 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
         w.wg_part_floats = maxw * 148 * 2;
         w.wg_part = bp.take<float>(w.wg_part_floats);
         w.dweff = bp.take<float>((size_t)(m.num_inputs + 1) * 16 * h2 + h2 + 16);
+        w.vq_part_rows = (int)((B * lat + 255) / 256 < 296 ? (B * lat + 255) / 256 : 296);
+        if (w.vq_part_rows < 2) w.vq_part_rows = 2;
+        w.vq_part = bp.take<float>((size_t)w.vq_part_rows * m.num_embeddings * h);
     }
     w.vq_stats = bp.take<double>(2 + m.num_embeddings);
     w.recon_sum = bp.take<double>(4);
@@ -665,7 +668,7 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
         const ConvL& lb = L.convs[L.enc_res[nres - 1].b];
         DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, w.g_za, grad_scale * m.weight_commitment,
                                   m.commitment_cost, c.B, h, P, m.num_embeddings, w.g_zb, grads + L.codebook_off,
-                                  w.bnb[lb.bn].part, w.erb[nres - 1], st));
+                                  w.bnb[lb.bn].part, w.erb[nres - 1], w.vq_part, w.vq_part_rows, st));
     }
     // 6. residual layers, last to first
     const float* g_cur = w.g_zb;

@@ -71,6 +71,8 @@ struct Workspace {
     double* bias_part = nullptr;           // stats partials for bias grads of BN-less layers
     float* wg_part = nullptr;              // wgrad per-CTA partials
     float* dweff = nullptr;                // composite head: packed effective-weight gradient
+    float* vq_part = nullptr;              // codebook-gradient partials [vq_part_rows][K][D]
+    int vq_part_rows = 0;
     size_t wg_part_floats = 0;
     double* vq_stats = nullptr;            // [2+K]
     double* recon_sum = nullptr;           // [1]

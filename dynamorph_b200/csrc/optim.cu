@@ -24,6 +24,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// device-resident step counter variant (CUDA-graph replay: nothing in the launch changes between steps)
+__global__ void adam_tick_kernel(int* step, float* bc, float b1, float b2) {
+    const int t = ++step[0];
+    bc[0] = (float)(1.0 - pow((double)b1, (double)t));
+    bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                const float* __restrict__ bc, float gscale) {
+    const float step_size = lr / bc[0];
+    const float bc2_sqrt = bc[1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = m[i] + (1.f - b1) * (gi - m[i]);
+        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+}
+
 // one CTA per (patch, channel) plane: mean / population std in double, output float32
 template <typename T>
 __global__ void zscore_kernel(const T* __restrict__ raw, int hw, float* __restrict__ out) {
@@ -65,6 +85,24 @@ int dmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
     if (blocks > 148 * 8) blocks = 148 * 8;
     dmb::adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int dmb_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, int32_t* step_dev, float* bc_dev,
+                      float grad_scale, void* stream) {
+    DMB_CHECK(params && grads && exp_avg && exp_avg_sq && step_dev && bc_dev, "dmb_adam_step_dev: null pointer");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dmb::adam_tick_kernel<<<1, 1, 0, st>>>(step_dev, bc_dev, beta1, beta2);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dmb::adam_dev_kernel<<<(unsigned)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                          eps, bc_dev, grad_scale);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -265,14 +265,17 @@ int dmb_vq_gather(const int32_t* idx, const float* codebook, int64_t batch, int3
 namespace dmb {
 namespace {
 
+constexpr int VQB_MAXD = 128;
+
+// grad_z (+ optional BatchNorm-backward sums).  No atomics: the codebook gradient has its own kernel.
 __global__ void __launch_bounds__(128) vq_backward_kernel(
         const float* __restrict__ z, const float* __restrict__ cb, const int32_t* __restrict__ idx,
         const float* __restrict__ g_zst, const float* __restrict__ g_loss, float g_loss_scale, float beta,
-        int64_t total, int d, int p, float* __restrict__ grad_z, float* __restrict__ grad_cb,
+        int64_t total, int d, int p, float* __restrict__ grad_z,
         double* __restrict__ stats, const float* __restrict__ stat_src) {
     // stats (optional): per-CTA (sum g, sum g*stat_src) per channel, layout [block][d][2] -- the BatchNorm
     // backward sums of the residual layer that produced z.  Needs p % 128 == 0 (a CTA stays in one patch).
-    __shared__ float red[4][2];
+    __shared__ float red[VQB_MAXD][4][2];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = n < total;
     const float gl = (g_loss ? __ldg(g_loss) : 1.f) * g_loss_scale;
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
     const int pos = live ? (int)(n - b * p) : 0;
     const int k = live ? idx[n] : 0;
     const size_t base = (size_t)b * d * p + pos;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = 0; c < d; ++c) {
         float gz = 0.f, sy = 0.f;
         if (live) {
@@ -289,7 +293,6 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
             const float g = g_zst ? __ldg(g_zst + base + (size_t)c * p) : 0.f;
             gz = g + coef * beta * (zv - q);
             if (grad_z) grad_z[base + (size_t)c * p] = gz;
-            if (grad_cb) atomicAdd(grad_cb + (size_t)k * d + c, coef * (q - zv));
             if (stats) sy = gz * __ldg(stat_src + base + (size_t)c * p);
         }
         if (stats) {
@@ -299,16 +302,103 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
                 s += __shfl_xor_sync(0xffffffffu, s, o);
                 sy += __shfl_xor_sync(0xffffffffu, sy, o);
             }
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s; red[threadIdx.x >> 5][1] = sy; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double* dst = stats + ((size_t)blockIdx.x * d + c) * 2;
-                dst[0] = (double)red[0][0] + (double)red[1][0] + (double)red[2][0] + (double)red[3][0];
-                dst[1] = (double)red[0][1] + (double)red[1][1] + (double)red[2][1] + (double)red[3][1];
+            if (lane == 0) { red[c][warp][0] = s; red[c][warp][1] = sy; }
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < d; c += blockDim.x) {
+            double* dst = stats + ((size_t)blockIdx.x * d + c) * 2;
+            dst[0] = (double)red[c][0][0] + (double)red[c][1][0] + (double)red[c][2][0] + (double)red[c][3][0];
+            dst[1] = (double)red[c][0][1] + (double)red[c][1][1] + (double)red[c][2][1] + (double)red[c][3][1];
+        }
+    }
+}
+
+// Codebook gradient  dL/dE[k] = coef * sum_{p: idx[p]=k} (E[k] - z[p])   (embedding scatter-add).
+// Persistent CTAs walk tiles of 256 positions: coef*(q - z) is formed with coalesced reads into shared
+// memory, then (position, channel) pairs are added into a per-CTA [K][D] accumulator (lanes = channels, so a
+// warp touches distinct addresses).
+//   partial != nullptr : each CTA writes its accumulator to partial[blockIdx.x]; vq_codebook_fold_kernel sums the
+//                        rows in a fixed order
+//   partial == nullptr : accumulators are pushed into grad_cb (pre-zeroed) with global atomics (stand-alone op)
+__global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
+        const float* __restrict__ z, const float* __restrict__ cb, const int32_t* __restrict__ idx,
+        const float* __restrict__ g_loss, float g_loss_scale, int64_t total, int d, int p, int k,
+        float* __restrict__ partial, float* __restrict__ grad_cb) {
+    extern __shared__ float sm[];
+    float* acc = sm;                         // [k][d]
+    float* zt = sm + (size_t)k * d;          // [d][256]
+    int* it = reinterpret_cast<int*>(zt + (size_t)d * 256);   // [256]
+    const int tid = threadIdx.x;
+    const float gl = (g_loss ? __ldg(g_loss) : 1.f) * g_loss_scale;
+    const float coef = gl * 2.f / (float)((double)total * d);
+    for (int i = tid; i < k * d; i += 256) acc[i] = 0.f;
+    const int64_t ntiles = (total + 255) / 256;
+    const int pg = 256 / d;                  // positions handled per pass in the scatter phase (d <= 128)
+    const int c = tid % d, j = tid / d;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        __syncthreads();
+        const int64_t n = t * 256 + tid;
+        if (n < total) {
+            const int64_t b = n / p;
+            const size_t base = (size_t)b * d * p + (n - b * p);
+            const int kk = __ldg(idx + n);
+            for (int cc = 0; cc < d; ++cc)
+                zt[cc * 256 + tid] = coef * (__ldg(cb + (size_t)kk * d + cc) - __ldg(z + base + (size_t)cc * p));
+            it[tid] = kk;
+        } else {
+            it[tid] = -1;
+        }
+        __syncthreads();
+        if (j < pg) {
+            for (int pos = j; pos < 256; pos += pg) {
+                const int kk = it[pos];
+                if (kk >= 0) atomicAdd(&acc[kk * d + c], zt[c * 256 + pos]);
             }
         }
     }
+    __syncthreads();
+    if (partial) {
+        float* dst = partial + (size_t)blockIdx.x * k * d;
+        for (int i = tid; i < k * d; i += 256) dst[i] = acc[i];
+    } else {
+        for (int i = tid; i < k * d; i += 256)
+            if (acc[i] != 0.f) atomicAdd(grad_cb + i, acc[i]);
+    }
+}
+
+__global__ void vq_codebook_fold_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ grad_cb) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float s = 0.f;
+    for (int i = 0; i < nparts; ++i) s += partial[(size_t)i * n + e];
+    grad_cb[e] = s;
+}
+
+int vq_codebook_grad(const float* z, const float* cb, const int32_t* idx, const float* g_loss, float g_loss_scale,
+                     int64_t total, int d, int p, int k, float* grad_cb, float* scratch, int scratch_rows,
+                     cudaStream_t st) {
+    // scratch: scratch_rows x k x d floats, or nullptr -> global atomics straight into grad_cb
+    const size_t smem = ((size_t)k * d + (size_t)d * 256 + 256) * sizeof(float);
+    DMB_CHECK(smem <= 220 * 1024, "vq codebook gradient: K=%d D=%d does not fit shared memory", k, d);
+    if (smem > 48 * 1024)
+        DMB_CUDA(cudaFuncSetAttribute(vq_codebook_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (total + 255) / 256;
+    int grid = (int)(ntiles < 296 ? ntiles : 296);
+    if (scratch && scratch_rows > 0) {
+        if (grid > scratch_rows) grid = scratch_rows;
+        vq_codebook_scatter_kernel<<<grid, 256, smem, st>>>(z, cb, idx, g_loss, g_loss_scale, total, d, p, k, scratch, nullptr);
+        DMB_CUDA(cudaGetLastError());
+        DMB_LAUNCHED(1);
+        vq_codebook_fold_kernel<<<(k * d + 127) / 128, 128, 0, st>>>(scratch, grid, k * d, grad_cb);
+    } else {
+        DMB_CUDA(cudaMemsetAsync(grad_cb, 0, sizeof(float) * (size_t)k * d, st));
+        vq_codebook_scatter_kernel<<<grid, 256, smem, st>>>(z, cb, idx, g_loss, g_loss_scale, total, d, p, k, nullptr, grad_cb);
+    }
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
 }
 
 }  // namespace
@@ -317,14 +407,18 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
 namespace dmb {
 int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx, const float* g_zst,
                       float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
-                      float* grad_codebook, double* stats, const float* stat_src, cudaStream_t st) {
+                      float* grad_codebook, double* stats, const float* stat_src, float* scratch, int scratch_rows,
+                      cudaStream_t st) {
     const int64_t total = batch * p;
     DMB_CHECK(!stats || p % 128 == 0, "vq backward: positions per patch (%d) must be a multiple of 128", p);
-    DMB_CUDA(cudaMemsetAsync(grad_codebook, 0, sizeof(float) * (size_t)k * d, st));
+    DMB_CHECK(d <= VQB_MAXD, "vq backward: embedding_dim %d > %d", d, VQB_MAXD);
     vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-        z, codebook, idx, g_zst, nullptr, g_loss_scale, beta, total, d, p, grad_z, grad_codebook, stats, stat_src);
+        z, codebook, idx, g_zst, nullptr, g_loss_scale, beta, total, d, p, grad_z, stats, stat_src);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
+    if (grad_codebook)
+        DMB_TRY(vq_codebook_grad(z, codebook, idx, nullptr, g_loss_scale, total, d, p, k, grad_codebook, scratch,
+                                 scratch_rows, st));
     return 0;
 }
 }  // namespace dmb
@@ -336,13 +430,21 @@ extern "C" int dmb_vq_backward(const float* z, const float* codebook, const int3
                                float* grad_codebook, void* stream) {
     DMB_CHECK(z && codebook && idx, "dmb_vq_backward: null pointer");
     const int64_t total = batch * positions_per_patch;
+    DMB_CHECK(d <= dmb::VQB_MAXD, "dmb_vq_backward: embedding_dim %d > %d", d, dmb::VQB_MAXD);
+    if (total == 0) {
+        if (grad_codebook)
+            DMB_CUDA(cudaMemsetAsync(grad_codebook, 0, sizeof(float) * (size_t)k * d, (cudaStream_t)stream));
+        return 0;
+    }
+    if (grad_z) {
+        dmb::vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            z, codebook, idx, g_zst, g_loss_dev, g_loss_scale, commitment_cost, total, d,
+            positions_per_patch, grad_z, nullptr, nullptr);
+        DMB_CUDA(cudaGetLastError());
+        DMB_LAUNCHED(1);
+    }
     if (grad_codebook)
-        DMB_CUDA(cudaMemsetAsync(grad_codebook, 0, sizeof(float) * (size_t)k * d, (cudaStream_t)stream));
-    if (total == 0) return 0;
-    dmb::vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        z, codebook, idx, g_zst, g_loss_dev, g_loss_scale, commitment_cost, total, d,
-        positions_per_patch, grad_z, grad_codebook, nullptr, nullptr);
-    DMB_CUDA(cudaGetLastError());
-    DMB_LAUNCHED(1);
+        DMB_TRY(dmb::vq_codebook_grad(z, codebook, idx, g_loss_dev, g_loss_scale, total, d, positions_per_patch, k,
+                                      grad_codebook, nullptr, 0, (cudaStream_t)stream));
     return 0;
 }

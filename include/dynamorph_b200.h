@@ -172,6 +172,13 @@ int dmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   int64_t n, float lr, float beta1, float beta2, float eps, int32_t step,
                   float grad_scale, void* stream);
 
+/* Same update with the step counter on the device: step_dev (int32, starts at 0) is incremented and the
+ * bias corrections written to bc_dev (float[2]) by a one-thread kernel first, so a captured CUDA graph
+ * can be replayed unchanged every step.                                                          */
+int dmb_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, int32_t* step_dev, float* bc_dev,
+                      float grad_scale, void* stream);
+
 /* ---- input staging (pipeline/train_utils.py:252-274) -------------------------------- */
 /* zscore_patch: per patch and channel (x - mean) / (std + DBL_EPSILON), float64 or
  * float32 or uint16 input, float32 output.  in_dtype: 0 = f32, 1 = f64, 2 = u16.         */

@@ -317,6 +317,30 @@ def run_ours(args):
     torch.cuda.synchronize()
     same = bool(torch.equal(out["idx"].view(chunk, 16, 16), idx.cpu()))
 
+    # ---- train step (BASELINE.json configs[1] / [4]): forward + backward + (allreduce) + Adam, fp32, BATCH-mode BN
+    from dynamorph_b200.trainer import FusedTrainer
+    tb = 256 if world == 1 else 512
+    torch.manual_seed(0)
+    tmodel = VQ_VAE_z16().to(dev)
+    calibrate(tmodel, synthetic_patches(64, 1, dev))
+    tmodel.train()
+    trainer = FusedTrainer(tmodel, lr=1e-4, use_graph=True)
+    xt = synthetic_patches(tb, 4321 + rank, dev)
+    for _ in range(5):
+        trainer.step(xt)
+    barrier()
+    tsteps = max(10, args.steps)
+    e0.record()
+    for _ in range(tsteps):
+        tl = trainer.step(xt)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / tsteps], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    train_ms = float(t[0])
+    train_losses = [float(v) for v in tl.tolist()]
+
     line = {
         "metric": "encoded patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
@@ -331,6 +355,10 @@ def run_ours(args):
                 "api": "dynamorph_b200.bulk.BulkEncoder.encode (pinned host -> HBM -> pinned host, 3-stream pipeline)",
                 "host_matches_device": same},
         "gpu_launches": int(launches),
+        "train_step": {"ms": train_ms, "batch_per_gpu": tb, "global_batch": tb * world,
+                       "patches_per_s": tb * world / (train_ms * 1e-3), "dtype": "f32",
+                       "what": "forward + backward + one flat-gradient NCCL allreduce (N>1) + fused Adam, CUDA-graph replay; "
+                               "per-rank BatchNorm statistics", "total_loss_after": train_losses[2]},
         "per_sample_bn": {"value": world * chunk / (ms_ps * 1e-3), "unit": "patches/s", "ms_per_step": ms_ps,
                           "note": "as-written process_VAE semantics (train-mode BN, batch 1) at batch speed"},
     }

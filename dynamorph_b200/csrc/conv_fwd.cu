@@ -31,7 +31,7 @@ constexpr int NG = PW / 4;   // granules per strip
 struct ConvK {
     ConvFwdArgs a;
     int TR, NP, CIC, nbands, SPR, RIN, SUBW;
-    int row_stride, ci_stride, patch_stride, w_floats, tile_floats;
+    int row_stride, ci_stride, patch_stride, w_floats, tile_floats, stage_floats;
     int threads;
 };
 
@@ -42,9 +42,9 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, i
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <int KS, int STRIDE, int CO_T>
 __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
@@ -54,9 +54,6 @@ __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
     constexpr int PADL = PAD ? 4 : 0;                       // floats of left shift inside a tile row
     constexpr int NGS = (STRIDE == 2) ? 4 : 2;               // sub-planes == granules per strip
     constexpr int NV = (KS == 1) ? 2 : ((STRIDE == 2) ? 6 : 4);   // float4 loads per tile row per thread
-
-    float* ws = smem;
-    float* tile = smem + ((k.w_floats + 3) & ~3);
 
     const int tid = threadIdx.x;
     const int band = blockIdx.x % k.nbands;
@@ -91,78 +88,94 @@ __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
     auto gslot = [&](int g) { return (g % NGS) * k.SUBW + (g / NGS) * 4; };
     const int so_dst = gslot(ld_q + PADL / 4);
     const int so_left = gslot(0), so_right = gslot(W4 + 1);
-    const int nrows = k.NP * k.CIC * k.RIN;
     const bool transform = (a.in_scale != nullptr) || a.in_relu || (a.x2 != nullptr);
 
-    for (int c0 = 0; c0 < a.Cin; c0 += k.CIC) {
-        __syncthreads();
-        // ---- weights chunk: contiguous [CIC][KS][KS][Cout]
-        if constexpr (CO_T % 4 == 0) {
-            const float* src = a.w + (size_t)c0 * KS * KS * a.Cout;
-            for (int i = tid; i < (k.w_floats >> 2); i += blockDim.x) cp_async16(ws + 4 * i, src + 4 * i, 16);
-        } else {
-            const float* src = a.w + (size_t)c0 * KS * KS * a.Cout;
-            for (int i = tid; i < k.w_floats; i += blockDim.x) ws[i] = __ldg(src + i);
-        }
-        // ---- activation tile: one cp.async per (row, granule); rows walked with carries, no divisions
-        if (ld_r0 < ld_rstep) {
-            int r = ld_r0, cil = 0, lp = 0;
-            while (r >= k.RIN) { r -= k.RIN; ++cil; }
-            while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
-            for (int rr = ld_r0; rr < nrows; rr += ld_rstep) {
-                const int64_t bb = b0 + lp;
-                const int iy = in_row0 + r;
-                float* rowp = tile + lp * k.patch_stride + cil * k.ci_stride + r * k.row_stride;
-                const bool valid = bb < a.B && iy >= 0 && iy < a.H;
-                const float* src = valid ? a.x + (((size_t)bb * a.Cin + (c0 + cil)) * a.H + iy) * a.W + 4 * ld_q : a.x;
-                cp_async16(rowp + so_dst, src, valid ? 16 : 0);
-                if constexpr (PAD == 1) {
-                    if (ld_q == 0) {
-                        *reinterpret_cast<float4*>(rowp + so_left) = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4*>(rowp + so_right) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Two-stage software pipeline over input-channel chunks: the cp.async copies of chunk c+1 are in flight
+    // while chunk c is being multiplied (shared memory holds two {weights, tile} stages).
+    auto issue_loads = [&](int c0, int stage) {
+        float* wsS = smem + stage * k.stage_floats;
+        float* tileS = wsS + ((k.w_floats + 3) & ~3);
+            // ---- weights chunk: contiguous [CIC][KS][KS][Cout]
+            if constexpr (CO_T % 4 == 0) {
+                const float* src = a.w + (size_t)c0 * KS * KS * a.Cout;
+                for (int i = tid; i < (k.w_floats >> 2); i += blockDim.x) cp_async16(wsS + 4 * i, src + 4 * i, 16);
+            } else {
+                const float* src = a.w + (size_t)c0 * KS * KS * a.Cout;
+                for (int i = tid; i < k.w_floats; i += blockDim.x) wsS[i] = __ldg(src + i);
+            }
+            // ---- activation tile: one cp.async per (row, granule).  A thread keeps its granule column and walks
+            // the rows of each (patch, channel) plane with strength-reduced pointers.
+            if (ld_r0 < ld_rstep) {
+                for (int lp = 0; lp < k.NP; ++lp) {
+                    const int64_t bb = b0 + lp;
+                    const bool pvalid = bb < a.B;
+                    for (int cil = 0; cil < k.CIC; ++cil) {
+                        const float* plane = a.x + ((size_t)(pvalid ? bb : 0) * a.Cin + (c0 + cil)) * a.H * a.W + 4 * ld_q;
+                        float* dplane = tileS + lp * k.patch_stride + cil * k.ci_stride;
+                        for (int r = ld_r0; r < k.RIN; r += ld_rstep) {
+                            const int iy = in_row0 + r;
+                            const bool valid = pvalid && iy >= 0 && iy < a.H;
+                            float* rowp = dplane + r * k.row_stride;
+                            cp_async16(rowp + so_dst, valid ? plane + (size_t)iy * a.W : a.x, valid ? 16 : 0);
+                            if constexpr (PAD == 1) {
+                                if (ld_q == 0) {
+                                    *reinterpret_cast<float4*>(rowp + so_left) = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    *reinterpret_cast<float4*>(rowp + so_right) = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+                        }
                     }
                 }
-                r += ld_rstep;
-                while (r >= k.RIN) { r -= k.RIN; ++cil; }
-                while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
             }
+        cp_async_commit();
+    };
+
+    const int nchunks = a.Cin / k.CIC;
+    issue_loads(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * k.CIC;
+        float* ws = smem + (ch & 1) * k.stage_floats;
+        float* tile = ws + ((k.w_floats + 3) & ~3);
+        if (ch + 1 < nchunks) {
+            issue_loads(c0 + k.CIC, (ch + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        cp_async_wait_all();
         __syncthreads();
         if (transform) {
             // in-place BN affine + ReLU over the granules this thread copied (valid rows only)
             if (ld_r0 < ld_rstep) {
-                int r = ld_r0, cil = 0, lp = 0;
-                while (r >= k.RIN) { r -= k.RIN; ++cil; }
-                while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
-                for (int rr = ld_r0; rr < nrows; rr += ld_rstep) {
+                for (int lp = 0; lp < k.NP; ++lp) {
                     const int64_t bb = b0 + lp;
-                    const int iy = in_row0 + r;
-                    if (bb < a.B && iy >= 0 && iy < a.H) {
-                        float4* gp = reinterpret_cast<float4*>(
-                            tile + lp * k.patch_stride + cil * k.ci_stride + r * k.row_stride + so_dst);
-                        float4 v = *gp;
+                    if (bb >= a.B) break;
+                    for (int cil = 0; cil < k.CIC; ++cil) {
                         const size_t ai = (a.in_per_sample ? (size_t)bb * a.Cin : 0) + c0 + cil;
-                        if (a.x2) {
-                            const float4 u = __ldg(reinterpret_cast<const float4*>(
-                                a.x2 + (((size_t)bb * a.Cin + (c0 + cil)) * a.H + iy) * a.W) + ld_q);
-                            const float sc = __ldg(a.in_scale + ai), bc = __ldg(a.in_b + ai), sh = __ldg(a.in_shift + ai);
-                            v.x = fmaf(v.x, sc, fmaf(u.x, bc, sh)); v.y = fmaf(v.y, sc, fmaf(u.y, bc, sh));
-                            v.z = fmaf(v.z, sc, fmaf(u.z, bc, sh)); v.w = fmaf(v.w, sc, fmaf(u.w, bc, sh));
-                        } else if (a.in_scale) {
-                            const float sc = __ldg(a.in_scale + ai), sh = __ldg(a.in_shift + ai);
-                            v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh);
-                            v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+                        float sc = 1.f, bc = 0.f, sh = 0.f;
+                        if (a.in_scale) { sc = __ldg(a.in_scale + ai); sh = __ldg(a.in_shift + ai); }
+                        if (a.x2) bc = __ldg(a.in_b + ai);
+                        const float* plane2 = a.x2 ? a.x2 + ((size_t)bb * a.Cin + (c0 + cil)) * a.H * a.W + 4 * ld_q : nullptr;
+                        float* dplane = tile + lp * k.patch_stride + cil * k.ci_stride + so_dst;
+                        for (int r = ld_r0; r < k.RIN; r += ld_rstep) {
+                            const int iy = in_row0 + r;
+                            if (iy < 0 || iy >= a.H) continue;
+                            float4* gp = reinterpret_cast<float4*>(dplane + r * k.row_stride);
+                            float4 v = *gp;
+                            if (plane2) {
+                                const float4 u = __ldg(reinterpret_cast<const float4*>(plane2 + (size_t)iy * a.W));
+                                v.x = fmaf(v.x, sc, fmaf(u.x, bc, sh)); v.y = fmaf(v.y, sc, fmaf(u.y, bc, sh));
+                                v.z = fmaf(v.z, sc, fmaf(u.z, bc, sh)); v.w = fmaf(v.w, sc, fmaf(u.w, bc, sh));
+                            } else if (a.in_scale) {
+                                v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh);
+                                v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+                            }
+                            if (a.in_relu) {
+                                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                                v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                            }
+                            *gp = v;
                         }
-                        if (a.in_relu) {
-                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
-                            v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                        }
-                        *gp = v;
                     }
-                    r += ld_rstep;
-                    while (r >= k.RIN) { r -= k.RIN; ++cil; }
-                    while (cil >= k.CIC) { cil -= k.CIC; ++lp; }
                 }
             }
             __syncthreads();
@@ -206,6 +219,7 @@ __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
                 }
             }
         }
+        __syncthreads();     // everyone is done with this stage before chunk ch+2 overwrites it
     }
 
     // ---- epilogue: bias (+ border classes), skip, ReLU, store, statistics
@@ -345,24 +359,27 @@ int plan(const ConvFwdArgs& a, int co_t, ConvK& k) {
         if ((S * rs) % 32 == want) k.row_stride = rs;
     }
     k.ci_stride = k.RIN * k.row_stride;
-    // input-channel chunk: keep (weights + tile) under 54 KB so 4 CTAs share an SM
+    // input-channel chunk: two pipeline stages of (weights + tile) under 54 KB so 4 CTAs share an SM;
+    // prefer at least two chunks so that loads overlap the FMA core
     const int budget = 54 * 1024 / 4;
     k.CIC = 1;
     for (int c = 1; c <= a.Cin; ++c) {
         if (a.Cin % c) continue;
-        const int fl = c * KS * KS * a.Cout + k.NP * c * k.ci_stride;
-        if (fl <= budget) k.CIC = c;
+        if (a.Cin >= 2 && c > a.Cin / 2) break;
+        const int fl = ((c * KS * KS * a.Cout + 3) & ~3) + k.NP * c * k.ci_stride;
+        if (2 * fl <= budget) k.CIC = c;
     }
     k.patch_stride = k.CIC * k.ci_stride;
     k.w_floats = k.CIC * KS * KS * a.Cout;
     k.tile_floats = k.NP * k.patch_stride;
+    k.stage_floats = ((k.w_floats + 3) & ~3) + k.tile_floats;
     return 0;
 }
 
 template <int KS, int STRIDE, int CO_T>
 int launch(const ConvK& k, cudaStream_t st) {
     const ConvFwdArgs& a = k.a;
-    size_t smem = (size_t)(((k.w_floats + 3) & ~3) + k.tile_floats) * sizeof(float);
+    size_t smem = (size_t)2 * k.stage_floats * sizeof(float);
     const size_t stats_smem = a.stats ? (size_t)k.NP * a.Cout * k.TR * k.SPR * sizeof(float2) : 0;
     if (stats_smem > smem) smem = stats_smem;
     auto kern = conv_fwd_kernel<KS, STRIDE, CO_T>;
@@ -408,7 +425,7 @@ int conv_fwd(const ConvFwdArgs& a, cudaStream_t st) {
     DMB_CHECK(co_t != 0, "conv_fwd: Cout=%d must be even", a.Cout);
     ConvK k;
     DMB_CHECK(plan(a, co_t, k) == 0, "conv_fwd: no launch plan for Cout=%d Ho=%d Wo=%d", a.Cout, a.Ho, a.Wo);
-    DMB_CHECK((size_t)(k.w_floats + k.tile_floats) * 4 <= 200 * 1024,
+    DMB_CHECK((size_t)2 * k.stage_floats * 4 <= 200 * 1024,
               "conv_fwd: tile does not fit shared memory (Cin=%d Cout=%d W=%d)", a.Cin, a.Cout, a.W);
     DMB_CHECK(a.W / 4 <= k.threads, "conv_fwd: input width %d too large for a %d-thread CTA", a.W, k.threads);
 #define DMB_DISPATCH(KS, S)                                         \

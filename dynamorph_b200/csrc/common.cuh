@@ -105,8 +105,10 @@ struct WgradArgs {
     const float* y;         // optional raw conv output (BatchNorm backward) or nullptr
     const float* ga; const float* gb; const float* gc;   // nullptr = identity
     int g_per_sample;
+    int g_relu;             // relu(gy) after the affine (ConvTranspose2d whose input is relu(bn(.)))
     const float* x;         // (B, Cin, H, W) conv input before the producer's BN/ReLU
-    const float* xs; const float* xt;                    // act = relu?(x*xs[c] + xt[c]); nullptr = identity
+    const float* xs; const float* xt;                    // act = relu?(x*xs[c] + x2*xb[c] + xt[c]); nullptr = identity
+    const float* x2; const float* xb;                    // optional second tensor (ConvTranspose2d followed by BN)
     int x_per_sample;
     int x_relu;
     int ones_channel;       // append a constant-one input channel (composite head bias chain)

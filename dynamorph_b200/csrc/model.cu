@@ -552,11 +552,12 @@ struct Bwd {
         WgradArgs a{};
         a.B = (int)c.B; a.ks = l.ks; a.stride = l.stride; a.partials = c.w.wg_part;
         if (l.transposed) {
-            DMB_CHECK(G.A == nullptr, "ConvTranspose2d followed by BatchNorm: backward not scheduled");
+            // roles swapped: "gy" := the ConvTranspose input activation relu?(xin*s+t), "act" := dL/d(output)
             a.g = xin.p; a.ga = xin.s; a.gc = xin.t; a.gb = nullptr; a.y = nullptr; a.g_per_sample = ps();
-            DMB_CHECK(!(xin.s && x_relu) , "ConvTranspose2d after BN+ReLU: backward not scheduled");
+            a.g_relu = x_relu;
             a.Cout = l.cin; a.Ho = H; a.Wo = W;
-            a.x = G.g; a.Cin = l.cout; a.H = 2 * H; a.W = 2 * W;
+            a.x = G.g; a.xs = G.A; a.xt = G.Cc; a.x2 = G.A ? G.y : nullptr; a.xb = G.Bc; a.x_per_sample = ps();
+            a.Cin = l.cout; a.H = 2 * H; a.W = 2 * W;
         } else {
             a.g = G.g; a.y = G.y; a.ga = G.A; a.gb = G.Bc; a.gc = G.Cc; a.g_per_sample = ps();
             a.x = xin.p; a.xs = xin.s; a.xt = xin.t; a.x_per_sample = ps(); a.x_relu = x_relu;
@@ -620,6 +621,78 @@ struct Bwd {
     }
 };
 
+__global__ void channel_sum_kernel(const float* __restrict__ g, int64_t B, int C, int hw, float* __restrict__ out) {
+    // out[c] = sum over (b, pixel) of g[b][c][pixel]; one CTA per channel, fixed order
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int64_t b = 0; b < B; ++b) {
+        const float* p = g + ((size_t)b * C + c) * hw;
+        float part = 0.f;
+        for (int i = threadIdx.x; i < hw; i += blockDim.x) part += p[i];
+        s += (double)part;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+        out[c] = (float)t;
+    }
+}
+
+// ResidualBlock backward (vq_vae.py:203-225), last layer first.  On entry `g_cur` is the gradient at the
+// block output and the BatchNorm-backward sums of the LAST layer's second BN are already in bnb[].part
+// (nb_cur bands).  h0 = the block input (with a pending affine if it is a BN output); prev_bn / stat0 name the
+// BatchNorm that produced h0 (-1: none) so that its sums are gathered while the input gradient is written.
+int res_backward(Bwd& B, const std::vector<ResL>& res, std::vector<float*>& ra, std::vector<float*>& rb,
+                 std::vector<float*>& hs, std::vector<float*>& g_ra, std::vector<float*>& g_h, const Act& h0,
+                 int prev_bn0, const float* stat0, const float* g_cur, int nb_cur, int lh, int lw,
+                 const float** g_out, int* nb_out) {
+    Ctx& c = B.c;
+    const Layout& L = c.L;
+    Workspace& w = c.w;
+    const int P = lh * lw;
+    int nb = nb_cur;
+    for (int i = (int)res.size() - 1; i >= 0; --i) {
+        const int la = res[i].a, lb = res[i].b;
+        GradT Gb, Ga;
+        DMB_TRY(B.bn_bwd(lb, nb_cur, P, &Gb, g_cur, rb[i]));
+        Act a_in; a_in.p = ra[i]; a_in.s = w.bn[L.convs[la].bn].scale; a_in.t = w.bn[L.convs[la].bn].shift;
+        DMB_TRY(B.wgrad_layer(lb, Gb, a_in, true, lh, lw, true));
+        DMB_TRY(B.dgrad_layer(lb, Gb, lh, lw, g_ra[i], &a_in, nullptr, w.bnb[L.convs[la].bn].part, ra[i], &nb));
+        DMB_TRY(B.bn_bwd(la, nb, P, &Ga, g_ra[i], ra[i]));
+        Act hin;
+        if (i == 0) hin = h0; else hin.p = hs[i - 1];
+        DMB_TRY(B.wgrad_layer(la, Ga, hin, true, lh, lw, true));
+        const int prev_bn = (i == 0) ? prev_bn0 : L.convs[res[i - 1].b].bn;
+        const float* stat_src = (i == 0) ? stat0 : rb[i - 1];
+        double* part = prev_bn >= 0 ? w.bnb[prev_bn].part : nullptr;
+        DMB_TRY(B.dgrad_layer(la, Ga, lh, lw, g_h[i], &hin, g_cur, part, prev_bn >= 0 ? stat_src : nullptr, &nb));
+        g_cur = g_h[i];
+        nb_cur = nb;
+    }
+    *g_out = g_cur;
+    *nb_out = nb_cur;
+    return 0;
+}
+
+int recon_grad(Ctx& c, const float* x, const float* mask, int mask_c, const float* cvar, const float* decoded,
+               float scale) {
+    const dmb_model& m = c.L.m;
+    const int64_t nrec = c.B * (int64_t)m.num_inputs * m.height * m.width;
+    const int64_t total4 = nrec / 4;
+    int64_t blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    recon_grad_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(decoded, x, mask, mask_c, cvar, total4, m.num_inputs,
+                                                          m.height * m.width / 4, scale / (float)nrec, c.w.gd);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
 int run_backward_z16(Ctx& c, const float* params, const float* x, const float* mask, int mask_c,
                      const float* cvar, const float* decoded, float grad_scale, float* grads) {
     const Layout& L = c.L;
@@ -629,19 +702,10 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
     Bwd B{c, params, grads, st};
     const int H = m.height, W = m.width, lh = L.lh, lw = L.lw;
     const int h = m.num_hiddens, h2 = h / 2, h4 = h / 4;
-    const int64_t nrec = c.B * (int64_t)m.num_inputs * H * W;
     int nb = 0;
 
     // 0. reconstruction-loss gradient
-    {
-        const int64_t total4 = nrec / 4;
-        int64_t blocks = (total4 + 255) / 256;
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        recon_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(decoded, x, mask, mask_c, cvar, total4, m.num_inputs,
-                                                            H * W / 4, grad_scale * m.weight_recon / (float)nrec, w.gd);
-        DMB_CUDA(cudaGetLastError());
-        DMB_LAUNCHED(1);
-    }
+    DMB_TRY(recon_grad(c, x, mask, mask_c, cvar, decoded, grad_scale * m.weight_recon));
     // 1-4. decoder (no BatchNorm): dec.6 conv1x1, dec.4 / dec.2 / dec.0 ConvT
     Act t3; t3.p = w.t3; Act t2; t2.p = w.t2; Act t1; t1.p = w.t1; Act za; za.p = w.za;
     GradT G; G.g = w.gd;
@@ -671,26 +735,11 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
                                   w.bnb[lb.bn].part, w.erb[nres - 1], w.vq_part, w.vq_part_rows, st));
     }
     // 6. residual layers, last to first
-    const float* g_cur = w.g_zb;
-    int nb_cur = P / 128;
+    const float* g_cur = nullptr;
+    int nb_cur = 0;
     Act y4a; y4a.p = w.y4; y4a.s = w.bn[L.convs[L.e4].bn].scale; y4a.t = w.bn[L.convs[L.e4].bn].shift;
-    for (int i = nres - 1; i >= 0; --i) {
-        const int la = L.enc_res[i].a, lb = L.enc_res[i].b;
-        GradT Gb, Ga;
-        DMB_TRY(B.bn_bwd(lb, nb_cur, P, &Gb, g_cur, w.erb[i]));
-        Act ra; ra.p = w.era[i]; ra.s = w.bn[L.convs[la].bn].scale; ra.t = w.bn[L.convs[la].bn].shift;
-        DMB_TRY(B.wgrad_layer(lb, Gb, ra, true, lh, lw, true));
-        DMB_TRY(B.dgrad_layer(lb, Gb, lh, lw, w.g_era[i], &ra, nullptr, w.bnb[L.convs[la].bn].part, w.era[i], &nb));
-        DMB_TRY(B.bn_bwd(la, nb, P, &Ga, w.g_era[i], w.era[i]));
-        Act hin;                      // the layer's input h_i (pending affine for i == 0)
-        if (i == 0) hin = y4a; else hin.p = w.ehs[i - 1];
-        DMB_TRY(B.wgrad_layer(la, Ga, hin, true, lh, lw, true));
-        const int prev_bn = (i == 0) ? L.convs[L.e4].bn : L.convs[L.enc_res[i - 1].b].bn;
-        const float* stat_src = (i == 0) ? w.y4 : w.erb[i - 1];
-        DMB_TRY(B.dgrad_layer(la, Ga, lh, lw, w.g_eh[i], &hin, g_cur, w.bnb[prev_bn].part, stat_src, &nb));
-        g_cur = w.g_eh[i];
-        nb_cur = nb;
-    }
+    DMB_TRY(res_backward(B, L.enc_res, w.era, w.erb, w.ehs, w.g_era, w.g_eh, y4a, L.convs[L.e4].bn, w.y4,
+                         w.g_zb, P / 128, lh, lw, &g_cur, &nb_cur));
     // 7. enc.10 (3x3) behind enc.11 BN
     GradT G4, G3, G2, G1;
     DMB_TRY(B.bn_bwd(L.e4, nb_cur, P, &G4, g_cur, w.y4));
@@ -723,6 +772,73 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
         DMB_TRY(composite_chain(w.dweff, params + l.w0_off, params + l.b0_off, params + l.w_off, l.cin, l.cmid,
                                 grads + l.w0_off, grads + l.b0_off, grads + l.w_off, grads + l.b_off, st));
     }
+    return 0;
+}
+
+// vae.py:401-414.  enc: conv4s2 -> BN -> ReLU -> conv4s2 -> BN -> ResidualBlock;  dec: ResidualBlock -> ConvT ->
+// BN -> ReLU -> ConvT.  total = recon + commitment (vae.py:440).
+int run_backward_z32(Ctx& c, const float* params, const float* x, const float* mask, int mask_c,
+                     const float* cvar, const float* decoded, float grad_scale, float* grads) {
+    const Layout& L = c.L;
+    const dmb_model& m = L.m;
+    Workspace& w = c.w;
+    cudaStream_t st = c.st;
+    Bwd B{c, params, grads, st};
+    const int H = m.height, W = m.width, lh = L.lh, lw = L.lw;
+    const int h = m.num_hiddens;
+    const int P = lh * lw;
+    const int nres_e = (int)L.enc_res.size(), nres_d = (int)L.dec_res.size();
+    DMB_CHECK(nres_e >= 1 && nres_d >= 1, "training needs num_residual_layers >= 1");
+    int nb = 0;
+
+    DMB_TRY(recon_grad(c, x, mask, mask_c, cvar, decoded, grad_scale));
+    // dec.4 ConvT (h/2 -> ni), input relu(bn(t1)); its bias gradient is the per-channel sum of the loss gradient
+    channel_sum_kernel<<<m.num_inputs, 256, 0, st>>>(w.gd, c.B, m.num_inputs, H * W, grads + L.convs[L.d1].b_off);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    const int bn_d = L.convs[L.d0].bn;
+    Act t1a; t1a.p = w.t1; t1a.s = w.bn[bn_d].scale; t1a.t = w.bn[bn_d].shift;
+    GradT G; G.g = w.gd;
+    DMB_TRY(B.wgrad_layer(L.d1, G, t1a, true, H / 2, W / 2, false));
+    DMB_TRY(B.dgrad_layer(L.d1, G, H / 2, W / 2, w.g_t1, &t1a, nullptr, w.bnb[bn_d].part, w.t1, &nb));
+    // dec.1 ConvT (h -> h/2) behind dec.2 BN; input = decoder residual block output
+    GradT Gd;
+    DMB_TRY(B.bn_bwd(L.d0, nb, (int64_t)(H / 2) * (W / 2), &Gd, w.g_t1, w.t1));
+    Act hD; hD.p = w.dhs[nres_d - 1];
+    DMB_TRY(B.wgrad_layer(L.d0, Gd, hD, false, lh, lw, false));
+    DMB_CUDA(cudaMemsetAsync(grads + L.convs[L.d0].b_off, 0, sizeof(float) * L.convs[L.d0].cout, st));   // exactly 0: BN follows
+    {
+        const ConvL& lb = L.convs[L.dec_res[nres_d - 1].b];
+        DMB_TRY(B.dgrad_layer(L.d0, Gd, lh, lw, w.g_za, nullptr, nullptr, w.bnb[lb.bn].part, w.drb[nres_d - 1], &nb));
+    }
+    // decoder residual block (input: the quantised latent, no BN before it)
+    Act zaA; zaA.p = w.za;
+    const float* g_cur = nullptr;
+    int nb_cur = 0;
+    DMB_TRY(res_backward(B, L.dec_res, w.dra, w.drb, w.dhs, w.g_dra, w.g_dh, zaA, -1, nullptr, w.g_za, nb, lh, lw,
+                         &g_cur, &nb_cur));
+    // quantiser
+    {
+        const ConvL& lb = L.convs[L.enc_res[nres_e - 1].b];
+        DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, g_cur, grad_scale, m.commitment_cost, c.B, h, P,
+                                  m.num_embeddings, w.g_zb, grads + L.codebook_off, w.bnb[lb.bn].part,
+                                  w.erb[nres_e - 1], w.vq_part, w.vq_part_rows, st));
+    }
+    // encoder residual block (input: bn(y2), pending affine)
+    const int bn2 = L.convs[L.e2].bn, bn1 = L.convs[L.e1].bn;
+    Act y2a; y2a.p = w.y2; y2a.s = w.bn[bn2].scale; y2a.t = w.bn[bn2].shift;
+    DMB_TRY(res_backward(B, L.enc_res, w.era, w.erb, w.ehs, w.g_era, w.g_eh, y2a, bn2, w.y2, w.g_zb, P / 128, lh, lw,
+                         &g_cur, &nb_cur));
+    // enc.3 conv4x4s2 (h/2 -> h) behind enc.4 BN; input relu(bn(y1))
+    GradT G2, G1;
+    DMB_TRY(B.bn_bwd(L.e2, nb_cur, P, &G2, g_cur, w.y2));
+    Act y1a; y1a.p = w.y1; y1a.s = w.bn[bn1].scale; y1a.t = w.bn[bn1].shift;
+    DMB_TRY(B.wgrad_layer(L.e2, G2, y1a, true, H / 2, W / 2, true));
+    DMB_TRY(B.dgrad_layer(L.e2, G2, H / 2, W / 2, w.g_y1, &y1a, nullptr, w.bnb[bn1].part, w.y1, &nb));
+    // enc.0 conv4x4s2 (ni -> h/2) behind enc.1 BN; input x
+    DMB_TRY(B.bn_bwd(L.e1, nb, (int64_t)(H / 2) * (W / 2), &G1, w.g_y1, w.y1));
+    Act xin; xin.p = x;
+    DMB_TRY(B.wgrad_layer(L.e1, G1, xin, false, H, W, true));
     return 0;
 }
 
@@ -906,9 +1022,9 @@ int dmb_train_backward(const dmb_model* m, const float* packed, const float* par
     Layout L; Workspace w;
     DMB_CHECK(packed && params && x && channel_var && decoded && grads, "dmb_train_backward: null pointer");
     DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
-    DMB_CHECK(m->arch == DMB_ARCH_Z16, "dmb_train_backward: only the z16 architecture (vq_vae.VQ_VAE / vae.VQ_VAE_z16) "
-              "has a backward schedule so far");
     Ctx c{L, packed, w, batch, DMB_BN_BATCH, nullptr, (cudaStream_t)stream};
+    if (m->arch == DMB_ARCH_Z32)
+        return run_backward_z32(c, params, x, mask, mask_channels, channel_var, decoded, grad_scale, grads);
     return run_backward_z16(c, params, x, mask, mask_channels, channel_var, decoded, grad_scale, grads);
 }
 

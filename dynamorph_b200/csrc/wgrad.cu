@@ -78,7 +78,14 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgK k) {
                         if (a.xs) {
                             const size_t ai = (a.x_per_sample ? (size_t)b * a.Cin : 0) + c;
                             const float s = __ldg(a.xs + ai), sh = __ldg(a.xt + ai);
-                            v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh); v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
+                            if (a.x2) {
+                                const float bc = __ldg(a.xb + ai);
+                                const float4 u = __ldg(reinterpret_cast<const float4*>(a.x2 + (((size_t)b * a.Cin + c) * a.H + iy) * a.W) + q);
+                                v.x = fmaf(v.x, s, fmaf(u.x, bc, sh)); v.y = fmaf(v.y, s, fmaf(u.y, bc, sh));
+                                v.z = fmaf(v.z, s, fmaf(u.z, bc, sh)); v.w = fmaf(v.w, s, fmaf(u.w, bc, sh));
+                            } else {
+                                v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh); v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
+                            }
                         }
                         if (a.x_relu) {
                             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
@@ -116,6 +123,9 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgK k) {
                     } else {
                         v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh); v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
                     }
+                }
+                if (a.g_relu) {
+                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                 }
                 *reinterpret_cast<float4*>(gs + c * k.g_stride + r * a.Wo + 4 * q) = v;
             }

@@ -9,7 +9,7 @@ from oracle import vqvae_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-Z16_CASES = ["vqvae_default", "z16_masked", "vqvae_heavy"]
+Z16_CASES = ["vqvae_default", "z16_masked", "vqvae_heavy", "z32_default"]
 
 
 @pytest.fixture(scope="module")
@@ -120,7 +120,7 @@ def _check_after_steps(g, st, model, steps, lr):
             assert float(diff.max()) <= 2.01 * steps * lr, k
 
 
-@pytest.mark.parametrize("name", ["vqvae_default", "z16_masked"])
+@pytest.mark.parametrize("name", ["vqvae_default", "z16_masked", "z32_default"])
 @pytest.mark.parametrize("opt_kind", ["torch_adam", "fused_adam"])
 def test_first_adam_step_elementwise(name, opt_kind, U):
     """One step from the fixture's state: expected parameters = torch.optim.Adam applied (on the CPU) to the
@@ -153,7 +153,7 @@ def test_first_adam_step_elementwise(name, opt_kind, U):
     assert all(p.grad is None for p in m.parameters())       # model.zero_grad() after the step
 
 
-@pytest.mark.parametrize("name", ["vqvae_default", "z16_masked"])
+@pytest.mark.parametrize("name", ["vqvae_default", "z16_masked", "z32_default"])
 @pytest.mark.parametrize("opt_kind", ["torch_adam", "fused_adam"])
 def test_run_one_batch_adam_steps(name, opt_kind, U):
     from dynamorph_b200.run_training import run_one_batch
@@ -215,3 +215,33 @@ def test_zscore_patch_device():
     o2 = zscore_patch_device(u16).cpu().numpy()
     r2 = O.zscore_patch(raw.astype(np.uint16).astype(np.float64)).astype(np.float32)
     assert np.allclose(o2, r2, atol=2e-6 * np.abs(r2).max())
+
+
+@pytest.mark.parametrize("name", ["vqvae_default", "z32_default"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_trainer_matches_run_one_batch(name, use_graph, U):
+    """The CUDA-graph trainer and the autograd path are the same arithmetic: identical losses and parameters."""
+    from dynamorph_b200.run_training import run_one_batch
+    from dynamorph_b200.optim import FusedAdam
+    from dynamorph_b200.trainer import FusedTrainer
+    g = Golden(name)
+    st = g.state()
+    x = g.t("x_train").cuda()
+    lr = 1e-3
+    m1 = U.model_from_state(st).train()
+    opt = FusedAdam(m1, lr=lr)
+    tl = {}
+    for _ in range(3):
+        m1, tl = run_one_batch(m1, x.clone(), tl, model_kwargs={}, optimizer=opt, transform=None, training=True)
+    m2 = U.model_from_state(st).train()
+    tr = FusedTrainer(m2, lr=lr, use_graph=use_graph)
+    curve = []
+    for _ in range(3):
+        curve.append(tr.step(x).tolist()[2])
+    assert np.allclose(curve, tl["total_loss"], rtol=1e-5)
+    sd1, sd2 = m1.state_dict(), m2.state_dict()
+    for k in sd1:
+        if sd1[k].dtype.is_floating_point:
+            assert float((sd1[k] - sd2[k]).abs().max()) <= 1e-6 + 1e-5 * float(sd1[k].abs().max()), k
+        else:
+            assert int(sd1[k]) == int(sd2[k]), k

@@ -149,6 +149,13 @@ int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const fl
  * performs in *flops_out_host; the caller times it with CUDA events to get the FP32 roof.    */
 int dmb_bench_fp32_fma(int32_t blocks, int32_t threads, int32_t iters, float* scratch,
                        double* flops_out_host, void* stream);
+/* Same for the conv kernels' register-tile shape (8x8 accumulators, acc[c][p] += w[c]*a[p+kx]; order 0 = pixel
+ * loop innermost, 1 = channel loop innermost): the practical FFMA ceiling of that inner loop.     */
+int dmb_bench_fma_tile(int32_t order, int32_t blocks, int32_t iters, float* scratch,
+                       double* flops_out_host, void* stream);
+/* ... and with the packed FFMA2 (fma.rn.f32x2, new on sm_100) form of the same tile.             */
+int dmb_bench_fma2_tile(int32_t order, int32_t blocks, int32_t iters, float* scratch,
+                        double* flops_out_host, void* stream);
 /* Number of kernels this library has launched in the process (reset != 0 zeroes it).        */
 long long dmb_launch_count(int reset);
 

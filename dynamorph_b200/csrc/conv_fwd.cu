@@ -405,7 +405,11 @@ int pick_co_t(int Cout) { return (Cout % 8 == 0) ? 8 : ((Cout % 4 == 0) ? 4 : ((
 
 }  // namespace
 
-int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo) {
+int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool plain) {
+    if (plain) {       // plain forward calls go to the TMA kernel when the geometry has an instantiation
+        const int nb = conv_tma_bands(ks, stride, Cin, Cout, Ho * stride, Wo * stride);
+        if (nb > 0) return nb;
+    }
     ConvFwdArgs a{};
     a.ks = ks; a.stride = stride; a.Cin = Cin; a.Cout = Cout; a.Ho = Ho; a.Wo = Wo;
     a.H = (stride == 2) ? Ho * 2 : Ho; a.W = (stride == 2) ? Wo * 2 : Wo; a.B = 1 << 20;
@@ -420,6 +424,10 @@ int conv_fwd(const ConvFwdArgs& a, cudaStream_t st) {
     DMB_CHECK((a.ks == 1 && a.stride == 1) || (a.ks == 3 && a.stride == 1) || (a.ks == 4 && a.stride == 2),
               "conv_fwd: unsupported kernel %dx%d stride %d", a.ks, a.ks, a.stride);
     DMB_CHECK(a.Ho * a.stride == a.H && a.Wo * a.stride == a.W, "conv_fwd: geometry mismatch");
+    {
+        const int r = conv_tma(a, st);      // 1 = not taken (unsupported shape or a data-gradient call)
+        if (r <= 0) return r;
+    }
     DMB_CHECK(a.Wo % PW == 0, "conv_fwd: output width %d must be a multiple of %d", a.Wo, PW);
     const int co_t = pick_co_t(a.Cout);
     DMB_CHECK(co_t != 0, "conv_fwd: Cout=%d must be even", a.Cout);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "dmb_bench_fp32_fma": [_I32, _I32, _I32, _P, C.POINTER(C.c_double), _P],
     "dmb_bench_fma_tile": [_I32, _I32, _I32, _P, C.POINTER(C.c_double), _P],
     "dmb_bench_fma2_tile": [_I32, _I32, _I32, _P, C.POINTER(C.c_double), _P],
+    "dmb_bench_fma_conv": [_I32, _I32, _I32, _P, C.POINTER(C.c_double), _P],
     "dmb_recon_loss": [_P, _P, _P, _I32, _P, _I64, _I32, _I32, _P, _P],
     "dmb_train_forward": [_M, _P, _P, _P, _P, _I32, _P, _I64, _P, _P, _P, _P, C.c_size_t, _P],
     "dmb_train_backward": [_M, _P, _P, _P, _P, _I32, _P, _P, _I64, _F, _P, _P, C.c_size_t, _P],

@@ -156,6 +156,10 @@ int dmb_bench_fma_tile(int32_t order, int32_t blocks, int32_t iters, float* scra
 /* ... and with the packed FFMA2 (fma.rn.f32x2, new on sm_100) form of the same tile.             */
 int dmb_bench_fma2_tile(int32_t order, int32_t blocks, int32_t iters, float* scratch,
                         double* flops_out_host, void* stream);
+/* The conv inner loop with its weight operand in shared memory (0), __constant__ memory (1) or the kernel
+ * parameter block (2): measures what the register-bank conflicts of the shared-memory form cost.   */
+int dmb_bench_fma_conv(int32_t variant, int32_t blocks, int32_t iters, float* scratch,
+                       double* flops_out_host, void* stream);
 /* Number of kernels this library has launched in the process (reset != 0 zeroes it).        */
 long long dmb_launch_count(int reset);
 

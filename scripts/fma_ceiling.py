@@ -24,3 +24,6 @@ for order in (0, 1):
 for order in (0, 1):
     ms = t(lambda: call("dmb_bench_fma2_tile", order, 148 * 4, 4000, ptr(scratch), C.byref(fl), st))
     print(f"8x8 tile FFMA2 order={order}: {fl.value/ms/1e9:.1f} TFLOP/s")
+for variant, name in ((0, "weights in shared memory"), (1, "weights in __constant__"), (2, "weights in kernel params")):
+    ms = t(lambda: call("dmb_bench_fma_conv", variant, 148 * 4, 40, ptr(scratch), C.byref(fl), st))
+    print(f"conv core, {name}: {fl.value/ms/1e9:.1f} TFLOP/s")

@@ -3,6 +3,7 @@ C ABI (dmb_conv2d_forward), against torch's CPU float64 conv2d on the same seede
 reference's nn.Conv2d performs, HiddenStateExtractor/vq_vae.py:203-209, :276-289).  Tolerance 1e-5 of max|y|
 (fp32 accumulation-order noise is ~1e-6; the path-level bar in BASELINE.json is 1e-4)."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -50,7 +51,10 @@ def reference(x, w, bias, ks, stride, in_scale=None, in_shift=None, per_sample=F
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "k%ds%d_%dto%d_w%d" % s)
 @pytest.mark.parametrize("B", [1, 5])
-def test_conv_layer_matches_torch(shape, B):
+@pytest.mark.parametrize("weights", ["smem", "const"])
+def test_conv_layer_matches_torch(shape, B, weights, monkeypatch):
+    # "const" forces the constant-pool weight form of csrc/conv_tma.cu (taken by default only for large launches)
+    monkeypatch.setenv("DMB_CONV_WEIGHTS", weights)
     ks, stride, cin, cout, W = shape
     g = torch.Generator(device="cuda").manual_seed(ks * 1000 + cin * 10 + cout + B)
     x = torch.randn(B, cin, W, W, device="cuda", generator=g)

@@ -51,10 +51,13 @@ __constant__ float c_pool[POOL_FLOATS];
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
-template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_>
+template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, bool RELU_REG_ = false>
 struct TC {
     static constexpr int KS = KS_, S = STRIDE_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
     static constexpr bool WCONST = WCONST_;
+    // ReLU of the input applied in registers right after the tile loads (eval-mode residual block: relu on load, no
+    // BatchNorm affine; zero padding is a fixed point of ReLU) instead of by the in-place pass over the tile
+    static constexpr bool RELU_REG = RELU_REG_;
     static constexpr int PAD = (KS == 1) ? 0 : 1;
     static constexpr int WO = W / S, HO = H / S;
     static constexpr int NCG = COUT / CO_T;
@@ -238,7 +241,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
 #pragma unroll
         for (int p = 0; p < PW; ++p) acc[c][p] = 0.f;
 
-    const bool transform = (a.in_scale != nullptr) || a.in_relu;
+    const bool transform = (a.in_scale != nullptr) || (a.in_relu && !C::RELU_REG);
 
     issue(0, 0);
 #pragma unroll 1
@@ -279,6 +282,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
                 if (col + 3 < 0 || col + 3 >= C::W) v.w = 0.f;
                 *gp = v;
             }
+            fence_proxy_async();     // these generic-proxy writes precede the TMA refill of this stage
             __syncthreads();
         }
 
@@ -299,6 +303,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
                     for (int i = 0; i < C::NV; ++i) {
                         const float4 t4 = lds4(rp + 4 * i);
                         av[4 * i + 0] = t4.x; av[4 * i + 1] = t4.y; av[4 * i + 2] = t4.z; av[4 * i + 3] = t4.w;
+                    }
+                    if constexpr (C::RELU_REG) {
+#pragma unroll
+                        for (int i = 0; i < C::NV * 4; ++i) av[i] = fmaxf(av[i], 0.f);
                     }
 #pragma unroll
                     for (int kx = 0; kx < KS; ++kx) {
@@ -514,6 +522,7 @@ bool use_pool(const ConvFwdArgs& a, cudaStream_t st, int w_floats) {
 
 // Band count (BatchNorm partial rows per sample) of the TMA kernel for this geometry, or 0 if it has no instantiation.
 int conv_tma_bands(int ks, int stride, int Cin, int Cout, int H, int W) {
+    { const char* e = getenv("DMB_CONV_TMA"); if (e && e[0] == '0') return 0; }
 #define X(KS, S, CI, CO, WIN) \
     if (ks == KS && stride == S && Cin == CI && Cout == CO && W == WIN && H == WIN) return TC<KS, S, CI, CO, WIN, false>::NBANDS;
     DMB_TMA_SHAPES(X)
@@ -524,10 +533,20 @@ int conv_tma_bands(int ks, int stride, int Cin, int Cout, int H, int W) {
 // Returns 1 if the call was not taken (caller falls back to conv_fwd's generic kernel), 0 on success, <0 on error.
 int conv_tma(const ConvFwdArgs& a, cudaStream_t st) {
     if (!tma_plain(a)) return 1;
+    { const char* e = getenv("DMB_CONV_TMA"); if (e && e[0] == '0') return 1; }      // A/B switch: generic kernel only
 #define X(KS, S, CI, CO, WIN)                                                                        \
     if (a.ks == KS && a.stride == S && a.Cin == CI && a.Cout == CO && a.W == WIN && a.H == WIN) {   \
-        if constexpr (CI * KS * KS * CO <= POOL_FLOATS) {                                            \
-            if (use_pool(a, st, CI * KS * KS * CO)) return launch_tma<TC<KS, S, CI, CO, WIN, true>>(a, st); \
+        /* the 1x1 layers are HBM-bound: the shared-memory form (one tile read serves all channel groups) wins */ \
+        if constexpr (CI * KS * KS * CO <= POOL_FLOATS && KS > 1) {                                  \
+            if (use_pool(a, st, CI * KS * KS * CO)) {                                                \
+                if constexpr (KS == 3) {          /* residual-block 3x3: eval-mode ReLU on load in registers */ \
+                    if (a.in_relu && !a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, true, true>>(a, st); \
+                }                                                                                    \
+                return launch_tma<TC<KS, S, CI, CO, WIN, true>>(a, st);                              \
+            }                                                                                        \
+        }                                                                                            \
+        if constexpr (KS == 3) {                                                                     \
+            if (a.in_relu && !a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, false, true>>(a, st); \
         }                                                                                            \
         return launch_tma<TC<KS, S, CI, CO, WIN, false>>(a, st);                                     \
     }

@@ -317,25 +317,28 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
 
 // Codebook gradient  dL/dE[k] = coef * sum_{p: idx[p]=k} (E[k] - z[p])   (embedding scatter-add).
 // Persistent CTAs walk tiles of 256 positions: coef*(q - z) is formed with coalesced reads into shared
-// memory, then (position, channel) pairs are added into a per-CTA [K][D] accumulator (lanes = channels, so a
-// warp touches distinct addresses).
+// memory, then added into a per-CTA [K][D] accumulator.  Deterministic, no atomics inside the CTA: thread (c, j) OWNS
+// the accumulators (k, c) with k % pg == j, scans the tile's codes in ascending position order and adds the
+// positions that are its own -- run-to-run bit-identical sums (an earlier shared-memory atomicAdd version made the
+// codebook gradient differ in the last bit between runs, which Adam amplifies on zero-mean gradients).
 //   partial != nullptr : each CTA writes its accumulator to partial[blockIdx.x]; vq_codebook_fold_kernel sums the
 //                        rows in a fixed order
 //   partial == nullptr : accumulators are pushed into grad_cb (pre-zeroed) with global atomics (stand-alone op)
+constexpr int ZT_PITCH = 257;                // [d][257]: lanes over channels hit distinct banks
 __global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
         const float* __restrict__ z, const float* __restrict__ cb, const int32_t* __restrict__ idx,
         const float* __restrict__ g_loss, float g_loss_scale, int64_t total, int d, int p, int k,
         float* __restrict__ partial, float* __restrict__ grad_cb) {
     extern __shared__ float sm[];
     float* acc = sm;                         // [k][d]
-    float* zt = sm + (size_t)k * d;          // [d][256]
-    int* it = reinterpret_cast<int*>(zt + (size_t)d * 256);   // [256]
+    float* zt = sm + (size_t)k * d;          // [d][ZT_PITCH]
+    int* it = reinterpret_cast<int*>(zt + (((size_t)d * ZT_PITCH + 3) & ~(size_t)3));   // [256], 16-byte aligned
     const int tid = threadIdx.x;
     const float gl = (g_loss ? __ldg(g_loss) : 1.f) * g_loss_scale;
     const float coef = gl * 2.f / (float)((double)total * d);
     for (int i = tid; i < k * d; i += 256) acc[i] = 0.f;
     const int64_t ntiles = (total + 255) / 256;
-    const int pg = 256 / d;                  // positions handled per pass in the scatter phase (d <= 128)
+    const int pg = 256 / d;                  // code classes (k % pg) handled in parallel (d <= 128)
     const int c = tid % d, j = tid / d;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         __syncthreads();
@@ -345,16 +348,21 @@ __global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
             const size_t base = (size_t)b * d * p + (n - b * p);
             const int kk = __ldg(idx + n);
             for (int cc = 0; cc < d; ++cc)
-                zt[cc * 256 + tid] = coef * (__ldg(cb + (size_t)kk * d + cc) - __ldg(z + base + (size_t)cc * p));
+                zt[cc * ZT_PITCH + tid] = coef * (__ldg(cb + (size_t)kk * d + cc) - __ldg(z + base + (size_t)cc * p));
             it[tid] = kk;
         } else {
             it[tid] = -1;
         }
         __syncthreads();
         if (j < pg) {
-            for (int pos = j; pos < 256; pos += pg) {
-                const int kk = it[pos];
-                if (kk >= 0) atomicAdd(&acc[kk * d + c], zt[c * 256 + pos]);
+            for (int pos4 = 0; pos4 < 256; pos4 += 4) {
+                const int4 k4 = *reinterpret_cast<const int4*>(it + pos4);
+                const int kks[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = kks[u];
+                    if (kk >= 0 && (kk % pg) == j) acc[kk * d + c] += zt[c * ZT_PITCH + pos4 + u];
+                }
             }
         }
     }
@@ -380,7 +388,7 @@ int vq_codebook_grad(const float* z, const float* cb, const int32_t* idx, const 
                      int64_t total, int d, int p, int k, float* grad_cb, float* scratch, int scratch_rows,
                      cudaStream_t st) {
     // scratch: scratch_rows x k x d floats, or nullptr -> global atomics straight into grad_cb
-    const size_t smem = ((size_t)k * d + (size_t)d * 256 + 256) * sizeof(float);
+    const size_t smem = ((size_t)k * d + (size_t)d * ZT_PITCH + 256 + 4) * sizeof(float);
     DMB_CHECK(smem <= 220 * 1024, "vq codebook gradient: K=%d D=%d does not fit shared memory", k, d);
     if (smem > 48 * 1024)
         DMB_CUDA(cudaFuncSetAttribute(vq_codebook_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,558 +1,33 @@
-// Direct convolution forward, TMA-fed (sm_100a), fp32 exact, NCHW planar.
-//
-// Same arithmetic and register tile as conv_fwd.cu (thread = 8 consecutive output pixels x 8 output channels,
-// 64 FFMA accumulators), but every geometric quantity is a compile-time constant and the shared-memory tile is
-// written by the TMA unit instead of per-thread cp.async code:
-//
-//   * the activation tile of one input-channel chunk is ONE cp.async.bulk.tensor.4d (UTMALDG) over the tensor
-//     viewed as (W, H, B, C): box = (W+12, rows, NP, CIC) starting at column -4 / row band*TR*S-PAD.  Zero
-//     padding (left/right columns, rows above/below the image, patches past the end of the batch) is the TMA
-//     out-of-bounds fill -- no padding stores, no per-row predicates, no address arithmetic in the SM.
-//   * both complete on one mbarrier per stage (expect_tx); two stages, chunk c+1 in flight while chunk c is
-//     multiplied; one elected thread issues, everybody waits with mbarrier.try_wait.
-//
-// Weight operand.  ncu showed the shared-memory-weight form of the inner loop capped by register-bank conflicts
-// (dispatch stalls; ~55 % of the FFMAs read two fresh same-parity registers because a stride-2 activation window
-// puts all eight pixels of a tap in registers of one parity).  When the layer's weights fit the 60 KB constant pool
-// (WCONST variant) they are copied device-to-device into __constant__ memory ahead of the launch and reach the FFMA
-// through uniform registers (LDCU + FFMA R, R, UR, R): one vector-register read less per FFMA, no weight LDS at all.
-// Measured on the isolated inner loop (dmb_bench_fma_conv): 49.7 -> 60.6 TFLOP/s.  The channel group is therefore
-// warp-uniform (it comes from the warp index).  Otherwise (graph capture, weights too large, tiny launches) the
-// weight chunk is one cp.async.bulk (UBLKCP) into shared memory on the same mbarrier.
-//
-// Bank conflicts without re-laying the tile out: a thread walks S*8+KS-S contiguous floats of a tile row with
-// 128-bit loads, so neighbouring strips start 2*S granules (16 B units) apart.  The eight lanes of a quarter-warp are
-// (strip bit 0, output-row bit 0, z), z = second strip bit for wide stride-1 maps, else the patch bit.  The row pitch is
-// an odd number of granules and the per-patch plane has an odd (stride 2) or 4-mod-8 (stride 1) number of granules, so
-// the eight lanes always hit eight different bank groups: conflict-free on the natural row-major layout.
-//
-// Reference layers served: HiddenStateExtractor/vq_vae.py:203-209 (ResidualBlock convs), :276-289 (encoder),
-// vae.py:401-407 (VQ_VAE_z32 encoder).  conv_fwd.cu remains the generic fallback (and the data-gradient kernel).
+// Entry points of the TMA-fed convolution: tries the per-family dispatch units (conv_tma_default.cu, conv_tma_heavy.cu;
+// the kernel itself is conv_tma.cuh).  Split so that the two families compile in parallel.
 #include "common.cuh"
 
-#include <mutex>
-#include <type_traits>
 #include <stdlib.h>
-
-#include <cuda.h>
-#include <cudaTypedefs.h>
 
 namespace dmb {
 
-namespace {
+int conv_tma_default(const ConvFwdArgs& a, cudaStream_t st);
+int conv_tma_heavy(const ConvFwdArgs& a, cudaStream_t st);
+int conv_tma_bands_default(int ks, int stride, int Cin, int Cout, int H, int W);
+int conv_tma_bands_heavy(int ks, int stride, int Cin, int Cout, int H, int W);
 
-constexpr int PW = 8;      // output pixels per thread along x
-constexpr int CO_T = 8;    // output channels per thread
-constexpr int NTHREADS = 128;
-constexpr int NSTAGE = 2;
-constexpr int POOL_FLOATS = 15360;     // 60 KB of the 64 KB constant bank
-
-__constant__ float c_pool[POOL_FLOATS];
-
-constexpr int cmin(int a, int b) { return a < b ? a : b; }
-
-template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, bool RELU_REG_ = false>
-struct TC {
-    static constexpr int KS = KS_, S = STRIDE_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
-    static constexpr bool WCONST = WCONST_;
-    // ReLU of the input applied in registers right after the tile loads (eval-mode residual block: relu on load, no
-    // BatchNorm affine; zero padding is a fixed point of ReLU) instead of by the in-place pass over the tile
-    static constexpr bool RELU_REG = RELU_REG_;
-    static constexpr int PAD = (KS == 1) ? 0 : 1;
-    static constexpr int WO = W / S, HO = H / S;
-    static constexpr int NCG = COUT / CO_T;
-    // Channel groups per CTA.  Shared-memory weights: up to four, one per warp-aligned slice of the CTA.  Constant-pool
-    // weights: ONE, taken from blockIdx.x -- the weight address must be built from values ptxas can prove uniform
-    // (blockIdx, loop counters), a warp index is not; the NCG CTAs of a tile re-read it through L2.
-    static constexpr int NCG_CTA = WCONST ? 1 : cmin(NCG, 4);
-    static constexpr int CG_SPLIT = NCG / NCG_CTA;            // CTAs per tile
-    static constexpr int SPR = WO / PW;                       // strips per output row
-    static constexpr bool ZS1 = (S == 1 && SPR >= 4);         // lane bit 2 = second strip bit (else patch bit)
-    static constexpr int SR = ZS1 ? SPR / 4 : SPR / 2;
-    static constexpr int REM = 16 / (SR * NCG_CTA);
-    static constexpr int RH = cmin(HO / 2, 16 / (SR * cmin(NCG, 4)));   // same rows per CTA in both weight forms
-    static constexpr int PH = REM / RH;
-    static constexpr int NP = (ZS1 ? 1 : 2) * PH;             // patches per CTA
-    static constexpr int TR = 2 * RH;                         // output rows per CTA
-    static constexpr int NBANDS = HO / TR;
-    static constexpr int RIN = (TR - 1) * S + KS;
-    // rows per patch plane: odd for stride 2, = 4 (mod 8) for stride 1 when the patch bit is a lane bit
-    static constexpr int RINP = ZS1 ? RIN : (S == 2 ? (RIN | 1) : ((RIN + 3) / 8 * 8 + 4));
-    // The TMA unit wants the innermost start coordinate 16-byte aligned (a box starting at column -1 faults), so a
-    // padded tile row starts at column -4: column c sits at position c + PADL and the left zero column at position 3.
-    static constexpr int PADL = PAD ? 4 : 0;
-    static constexpr int P = W + (PAD ? 12 : 4);              // tile row pitch (floats); odd number of granules
-    static constexpr int Q = P / 4;                           // ... in granules
-    static constexpr int PLANE = RINP * P;
-    static constexpr int NV = (S * (PW - 1) + KS + (PADL - PAD) + 3) / 4;    // float4 loads per tile row per thread
-    // input-channel chunk: two stages of (weights + tile) within ~54 KB so that four CTAs share an SM
-    static constexpr int stage_floats(int cic) {
-        return (WCONST ? 0 : ((cic * KS * KS * COUT + 31) & ~31)) + ((NP * cic * PLANE + 31) & ~31);
-    }
-    static constexpr int pick_cic() {
-        int best = 1;
-        for (int c = 1; c <= CIN; ++c) {
-            if (CIN % c) continue;
-            if (CIN >= 2 && c > CIN / 2) break;
-            if (NSTAGE * stage_floats(c) * 4 <= 54 * 1024) best = c;
-        }
-        return best;
-    }
-    static constexpr int CIC = pick_cic();
-    static constexpr int NCHUNK = CIN / CIC;
-    // Unroll of the in-chunk channel loop.  With an un-unrolled loop ptxas strength-reduces the constant-pool weight
-    // index into a vector register and falls back to LDC + 3-register FFMAs (seen for the 3x3 and 1x1 shapes).
-    static constexpr int CIL_UNROLL = !WCONST ? 1 : ((CIC * KS * KS <= 36) ? CIC : (KS == 4 ? 1 : (KS == 3 ? 2 : 8)));
-    static constexpr int WCHUNK = CIC * KS * KS * COUT;       // floats
-    static constexpr int WPAD = WCONST ? 0 : ((WCHUNK + 31) & ~31);
-    static constexpr int CI_STRIDE = NP * PLANE;
-    static constexpr int TILE = CIC * CI_STRIDE;
-    static constexpr int STAGE = stage_floats(CIC);
-    static constexpr int STATS_FLOATS = NP * NCG_CTA * CO_T * TR * SPR * 2;
-    static constexpr int SMEM_FLOATS = (NSTAGE * STAGE > STATS_FLOATS) ? NSTAGE * STAGE : STATS_FLOATS;
-    static constexpr size_t SMEM_BYTES = (size_t)SMEM_FLOATS * 4 + 128 /*alignment slack*/ + 64 /*barriers*/;
-    static constexpr uint32_t TX_BYTES = (uint32_t)((WCONST ? 0 : WCHUNK) + TILE) * 4u;
-    static constexpr int MIN_CTAS = (SMEM_BYTES + 1024) * 4 <= 227 * 1024 ? 4 : ((SMEM_BYTES + 1024) * 3 <= 227 * 1024 ? 3 : 2);
-    static constexpr int W_FLOATS = CIN * KS * KS * COUT;
-
-    static_assert(COUT % CO_T == 0 && NCG % NCG_CTA == 0, "Cout must be a multiple of 8 (and of 32 beyond 32)");
-    static_assert(WO % PW == 0 && SPR >= 2 && (SPR & (SPR - 1)) == 0, "output width must be 16, 32, 64, ...");
-    static_assert(SR >= 1 && 16 % (SR * NCG_CTA) == 0 && REM >= 1, "thread decomposition does not fit 128 threads");
-    static_assert(SR * RH * PH * NCG_CTA == 16 && SR * RH * PH >= 4, "channel group must be warp-uniform");
-    static_assert(HO % TR == 0, "rows per CTA must divide the output height");
-    static_assert(Q % 2 == 1, "row pitch must be an odd number of 16-byte granules");
-    static_assert(ZS1 || (S == 2 ? (RINP % 2 == 1) : (RINP % 8 == 4)), "patch plane granule count");
-    static_assert(P <= 256 && RINP <= 256 && CIC <= 256 && NP <= 256, "TMA box limits");
-    static_assert((KS == 1 && S == 1) || (KS == 3 && S == 1) || (KS == 4 && S == 2), "unsupported kernel");
-    static_assert(SMEM_BYTES <= 200 * 1024, "tile does not fit");
-    static_assert(!WCONST || W_FLOATS <= POOL_FLOATS, "weights do not fit the constant pool");
-};
-
-// ---- PTX wrappers (mbarrier + bulk copies) ----------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+static bool tma_disabled() {          // A/B switch: DMB_CONV_TMA=0 -> generic kernel only
+    const char* e = getenv("DMB_CONV_TMA");
+    return e && e[0] == '0';
 }
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-// The exit test is a warp vote so that the loop is a *uniform* loop for ptxas: a per-thread exit would make every
-// value computed after it look divergent and keep the constant-pool weights out of the uniform datapath.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!__all_sync(0xffffffffu, done != 0));
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-
-struct TmaConvArgs {
-    float* y;
-    const float* w;
-    const float* bias;
-    int bias_classes;
-    const float* in_scale;
-    const float* in_shift;
-    int in_per_sample;
-    int in_relu;
-    const float* skip;
-    int out_relu;
-    double* stats;
-    int B;
-};
-
-template <class C>
-__global__ void __launch_bounds__(NTHREADS, C::MIN_CTAS)
-conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
-    constexpr int KS = C::KS, S = C::S, P = C::P;
-    extern __shared__ uint8_t smem_raw[];
-    // 128-byte aligned carve-up: [stage 0 | stage 1 | barriers]
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t pad = (128u - (raw & 127u)) & 127u;
-    float* smem = reinterpret_cast<float*>(smem_raw + pad);
-    const uint32_t bar0 = smem_u32(smem) + (uint32_t)C::SMEM_FLOATS * 4u;   // NSTAGE x 8 bytes
-
-    const int tid = threadIdx.x;
-    // blockIdx.x = ((patch group * NBANDS) + band) * CG_SPLIT + channel-group slice.  (All from blockIdx.x: ptxas keeps
-    // values derived from it in uniform registers, which the constant-pool weight addressing below relies on.)
-    const int cgz = blockIdx.x % C::CG_SPLIT;
-    const int tile_id = blockIdx.x / C::CG_SPLIT;
-    const int band = tile_id % C::NBANDS;
-    const int b0 = (tile_id / C::NBANDS) * C::NP;
-
-    // thread -> (strip, row, local patch, channel group); see the header comment for the low three bits.  The channel
-    // group is constant inside a warp (the shuffle tells the compiler so: uniform-register weight addressing).
-    const int s0 = tid & 1, r0 = (tid >> 1) & 1, z = (tid >> 2) & 1;
-    int hi = tid >> 3;
-    const int sr = hi % C::SR; hi /= C::SR;
-    const int rh = hi % C::RH; hi /= C::RH;
-    const int ph = hi % C::PH;
-    const int cgl = __shfl_sync(0xffffffffu, hi / C::PH, 0);
-    const int sx = C::ZS1 ? (sr * 4 + z * 2 + s0) : (sr * 2 + s0);
-    const int row = rh * 2 + r0;
-    const int pl = C::ZS1 ? ph : (ph * 2 + z);
-    const int oy = band * C::TR + row;
-    const int b = b0 + pl;
-    const bool live = b < a.B;
-    const int in_row0 = band * C::TR * S - C::PAD;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(bar0 + 8u * s, 1u);
-        fence_barrier_init();
-        fence_proxy_async();
-        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](int ch, int stage) {
-        if (tid == 0) {
-            const uint32_t bar = bar0 + 8u * stage;
-            const uint32_t ws = smem_u32(smem + stage * C::STAGE);
-            fence_proxy_async();      // earlier generic-proxy accesses of this stage are ordered before the bulk writes
-            mbar_expect_tx(bar, C::TX_BYTES);
-            if constexpr (!C::WCONST) bulk_load_1d(ws, a.w + (size_t)ch * C::WCHUNK, (uint32_t)C::WCHUNK * 4u, bar);
-            tma_load_4d(ws + (uint32_t)C::WPAD * 4u, &tmap, bar, -C::PADL, in_row0, b0, ch * C::CIC);
-        }
-    };
-
-    float acc[CO_T][PW];
-#pragma unroll
-    for (int c = 0; c < CO_T; ++c)
-#pragma unroll
-        for (int p = 0; p < PW; ++p) acc[c][p] = 0.f;
-
-    const bool transform = (a.in_scale != nullptr) || (a.in_relu && !C::RELU_REG);
-
-    issue(0, 0);
-#pragma unroll 1
-    for (int ch = 0; ch < C::NCHUNK; ++ch) {
-        const int stage = ch & 1;
-        if (ch + 1 < C::NCHUNK) issue(ch + 1, stage ^ 1);
-        mbar_wait(bar0 + 8u * stage, (uint32_t)((ch >> 1) & 1));
-        const float* ws = smem + stage * C::STAGE;
-        float* tile = smem + stage * C::STAGE + C::WPAD;
-
-        if (transform) {
-            // in-place BatchNorm affine + ReLU of the producer over the landed tile; padding stays zero
-            constexpr int TOTG = C::CIC * C::NP * C::RINP * C::Q;
-            for (int g = tid; g < TOTG; g += NTHREADS) {
-                const int gq = g % C::Q;
-                int t = g / C::Q;
-                const int r = t % C::RINP; t /= C::RINP;
-                const int lp = t % C::NP;
-                const int cil = t / C::NP;
-                const int iy = in_row0 + r;
-                const int bb = b0 + lp;
-                if (iy < 0 || iy >= C::H || bb >= a.B) continue;
-                float sc = 1.f, sf = 0.f;
-                if (a.in_scale) {
-                    const size_t ai = (a.in_per_sample ? (size_t)bb * C::CIN : 0) + ch * C::CIC + cil;
-                    sc = __ldg(a.in_scale + ai); sf = __ldg(a.in_shift + ai);
-                }
-                float4* gp = reinterpret_cast<float4*>(tile + g * 4);
-                float4 v = *gp;
-                v.x = fmaf(v.x, sc, sf); v.y = fmaf(v.y, sc, sf); v.z = fmaf(v.z, sc, sf); v.w = fmaf(v.w, sc, sf);
-                if (a.in_relu) {
-                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                }
-                const int col = 4 * gq - C::PADL;      // image column of v.x
-                if (col < 0 || col >= C::W) v.x = 0.f;
-                if (col + 1 < 0 || col + 1 >= C::W) v.y = 0.f;
-                if (col + 2 < 0 || col + 2 >= C::W) v.z = 0.f;
-                if (col + 3 < 0 || col + 3 >= C::W) v.w = 0.f;
-                *gp = v;
-            }
-            fence_proxy_async();     // these generic-proxy writes precede the TMA refill of this stage
-            __syncthreads();
-        }
-
-        // ---- FMA core.  In the constant-pool form every weight address is built from uniform values only (blockIdx.z,
-        // loop counters), so ptxas emits LDCU + FFMA-with-UR-operand.
-        const float* tp = tile + pl * C::PLANE + (row * S) * P + S * PW * sx;
-        auto core = [&](auto cgc) {
-            constexpr int CGC = decltype(cgc)::value;                                  // >= 0: constant-pool weights
-            const float* wp = ws + cgz * (C::NCG_CTA * CO_T) + cgl * CO_T;             // shared-memory weights
-            const int wbase = ch * C::WCHUNK + cgz * CO_T;
-#pragma unroll(C::CIL_UNROLL)
-            for (int cil = 0; cil < C::CIC; ++cil) {
-#pragma unroll
-                for (int ky = 0; ky < KS; ++ky) {
-                    const float* rp = tp + cil * C::CI_STRIDE + ky * P;
-                    float av[C::NV * 4];
-#pragma unroll
-                    for (int i = 0; i < C::NV; ++i) {
-                        const float4 t4 = lds4(rp + 4 * i);
-                        av[4 * i + 0] = t4.x; av[4 * i + 1] = t4.y; av[4 * i + 2] = t4.z; av[4 * i + 3] = t4.w;
-                    }
-                    if constexpr (C::RELU_REG) {
-#pragma unroll
-                        for (int i = 0; i < C::NV * 4; ++i) av[i] = fmaxf(av[i], 0.f);
-                    }
-#pragma unroll
-                    for (int kx = 0; kx < KS; ++kx) {
-                        float wv[CO_T];
-                        if constexpr (CGC >= 0) {
-#pragma unroll
-                            for (int c = 0; c < CO_T; ++c)
-                                wv[c] = c_pool[wbase + ((cil * KS + ky) * KS + kx) * C::COUT + c];
-                        } else {
-                            const float* wrow = wp + ((cil * KS + ky) * KS + kx) * C::COUT;
-#pragma unroll
-                            for (int c = 0; c < CO_T; c += 4) {
-                                const float4 t4 = lds4(wrow + c);
-                                wv[c] = t4.x; wv[c + 1] = t4.y; wv[c + 2] = t4.z; wv[c + 3] = t4.w;
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < CO_T; ++c)
-#pragma unroll
-                            for (int p = 0; p < PW; ++p)
-                                acc[c][p] = fmaf(wv[c], av[S * p + kx + (C::PADL - C::PAD)], acc[c][p]);
-                    }
-                }
-            }
-        };
-        if constexpr (C::WCONST) core(std::integral_constant<int, 0>{});
-        else core(std::integral_constant<int, -1>{});
-        __syncthreads();     // this stage may be refilled (chunk ch+2) / reused by the statistics reduction
-    }
-
-    // ---- epilogue: bias (+ border classes of the composite head), skip, ReLU, store, statistics.
-    // cgz only ever meets uniform values (base pointers), see the note at its definition.
-    constexpr int CC = C::NCG_CTA * CO_T;           // channels this CTA produces
-    const float* bias_u = a.bias + cgz * CC;
-    float* y_u = a.y + (size_t)(cgz * CC) * (C::HO * C::WO);
-    const float* skip_u = a.skip ? a.skip + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
-    const int rc = (oy == 0) ? 0 : ((oy == C::HO - 1) ? 2 : 1);
-    float ssum[CO_T], ssq[CO_T];
-#pragma unroll
-    for (int c = 0; c < CO_T; ++c) {
-        const int co = cgl * CO_T + c;              // channel inside this CTA's slice
-        float bmid, bl, br;
-        if (a.bias_classes) {
-            bl = __ldg(bias_u + (rc * 3 + 0) * C::COUT + co);
-            bmid = __ldg(bias_u + (rc * 3 + 1) * C::COUT + co);
-            br = __ldg(bias_u + (rc * 3 + 2) * C::COUT + co);
-        } else {
-            bl = bmid = br = __ldg(bias_u + co);
-        }
-        float o[PW];
-#pragma unroll
-        for (int p = 0; p < PW; ++p) o[p] = acc[c][p] + bmid;
-        if (sx == 0) o[0] = acc[c][0] + bl;
-        if (sx == C::SPR - 1) o[PW - 1] = acc[c][PW - 1] + br;
-        const size_t off = (((size_t)b * C::COUT + co) * C::HO + oy) * C::WO + sx * PW;
-        if (skip_u && live) {
-#pragma unroll
-            for (int i = 0; i < PW / 4; ++i) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(skip_u + off) + i);
-                o[4 * i] += s4.x; o[4 * i + 1] += s4.y; o[4 * i + 2] += s4.z; o[4 * i + 3] += s4.w;
-            }
-        }
-        if (a.out_relu) {
-#pragma unroll
-            for (int p = 0; p < PW; ++p) o[p] = fmaxf(o[p], 0.f);
-        }
-        if (live) {
-#pragma unroll
-            for (int i = 0; i < PW / 4; ++i)
-                reinterpret_cast<float4*>(y_u + off)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-        }
-        float s = 0.f, q = 0.f;
-        if (a.stats) {
-#pragma unroll
-            for (int p = 0; p < PW; ++p) { s += o[p]; q = fmaf(o[p], o[p], q); }
-        }
-        ssum[c] = s; ssq[c] = q;
-    }
-
-    if (a.stats) {
-        // deterministic two-level reduction: thread partials -> smem -> one warp per (patch, channel).
-        // Slot order inside a (patch, channel) = (row, strip), i.e. independent of the lane mapping.
-        constexpr int SPP = C::TR * C::SPR;
-        float2* sp = reinterpret_cast<float2*>(smem);   // [NP][CC][SPP]  (all stages are idle after the last barrier)
-#pragma unroll
-        for (int c = 0; c < CO_T; ++c)
-            sp[((size_t)pl * CC + cgl * CO_T + c) * SPP + row * C::SPR + sx] = make_float2(ssum[c], ssq[c]);
-        __syncthreads();
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int pc = warp; pc < C::NP * CC; pc += NTHREADS / 32) {
-            const int lp = pc / CC, co = pc - lp * CC;
-            double s = 0.0, q = 0.0;
-            for (int i = lane; i < SPP; i += 32) {
-                const float2 v = sp[(size_t)pc * SPP + i];
-                s += (double)v.x; q += (double)v.y;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                q += __shfl_xor_sync(0xffffffffu, q, o);
-            }
-            if (lane == 0 && b0 + lp < a.B) {
-                double* dst = a.stats + (size_t)(cgz * CC) * 2 + ((((size_t)(b0 + lp)) * C::NBANDS + band) * C::COUT + co) * 2;
-                dst[0] = s; dst[1] = q;
-            }
-        }
-    }
-}
-
-// ---- host side ---------------------------------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled get_encoder() {
-    static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
-        if (q != cudaDriverEntryPointSuccess) return nullptr;
-        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-    }();
-    return fn;
-}
-
-// The constant pool is one region per device, rewritten ahead of every launch that uses it.  Launches on one stream
-// are ordered by the stream; a launch on a different stream first waits for the previous pool user's kernel.
-struct PoolState {
-    std::mutex mu;
-    cudaEvent_t ev = nullptr;
-    cudaStream_t last = nullptr;
-    bool used = false;
-};
-PoolState g_pool[64];
-
-template <class C>
-int launch_tma(const ConvFwdArgs& a, cudaStream_t st) {
-    PFN_cuTensorMapEncodeTiled enc = get_encoder();
-    DMB_CHECK(enc != nullptr, "conv_tma: cuTensorMapEncodeTiled is not available from this driver");
-    DMB_CHECK((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(a.y) & 15) == 0,
-              "conv_tma: x, y and w must be 16-byte aligned");
-    CUtensorMap map;
-    const cuuint64_t gdim[4] = {(cuuint64_t)C::W, (cuuint64_t)C::H, (cuuint64_t)a.B, (cuuint64_t)C::CIN};
-    const cuuint64_t gstr[3] = {(cuuint64_t)C::W * 4, (cuuint64_t)C::W * C::H * C::CIN * 4, (cuuint64_t)C::W * C::H * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)C::P, (cuuint32_t)C::RINP, (cuuint32_t)C::NP, (cuuint32_t)C::CIC};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.x), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DMB_CHECK(r == CUDA_SUCCESS, "conv_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
-
-    TmaConvArgs k{};
-    k.y = a.y; k.w = a.w; k.bias = a.bias; k.bias_classes = a.bias_classes;
-    k.in_scale = a.in_scale; k.in_shift = a.in_shift; k.in_per_sample = a.in_per_sample; k.in_relu = a.in_relu;
-    k.skip = a.skip; k.out_relu = a.out_relu; k.stats = a.stats; k.B = a.B;
-
-    auto kern = conv_tma_kernel<C>;
-    static bool configured[64] = {false};     // per instantiation, per device
-    int dev = 0;
-    DMB_CUDA(cudaGetDevice(&dev));
-    DMB_CHECK(dev >= 0 && dev < 64, "conv_tma: device index %d out of range", dev);
-    if (!configured[dev]) {
-        DMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        configured[dev] = true;
-    }
-    const int64_t groups = ((int64_t)a.B + C::NP - 1) / C::NP;
-    const int64_t gx = groups * C::NBANDS * C::CG_SPLIT;
-    DMB_CHECK(gx > 0 && gx < (1ll << 31), "conv_tma: grid %lld out of range", (long long)gx);
-    const dim3 grid((unsigned)gx);
-    if constexpr (C::WCONST) {
-        PoolState& ps = g_pool[dev];
-        std::lock_guard<std::mutex> lock(ps.mu);
-        if (!ps.ev) DMB_CUDA(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming));
-        if (ps.used && ps.last != st) DMB_CUDA(cudaStreamWaitEvent(st, ps.ev, 0));
-        DMB_CUDA(cudaMemcpyToSymbolAsync(c_pool, a.w, (size_t)C::W_FLOATS * 4, 0, cudaMemcpyDeviceToDevice, st));
-        kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(map, k);
-        DMB_CUDA(cudaGetLastError());
-        DMB_CUDA(cudaEventRecord(ps.ev, st));
-        ps.last = st; ps.used = true;
-    } else {
-        kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(map, k);
-        DMB_CUDA(cudaGetLastError());
-    }
-    DMB_LAUNCHED(1);
-    return 0;
-}
-
-// The shapes of the reference architectures (VQ_VAE / VQ_VAE_z16 / VQ_VAE_z32 at their default widths and at the
-// 64-hidden "quantizer-heavy" width of BASELINE.json configs[3]).  Anything else uses conv_fwd.cu.
-#define DMB_TMA_SHAPES(X)                                                                                          \
-    X(4, 2, 2, 8, 128) X(4, 2, 8, 16, 64) X(4, 2, 16, 16, 32) X(3, 1, 16, 16, 16) X(3, 1, 16, 32, 16)              \
-    X(1, 1, 32, 16, 16) X(3, 1, 16, 32, 32) X(1, 1, 32, 16, 32)                                                    \
-    X(4, 2, 2, 32, 128) X(4, 2, 32, 64, 64) X(4, 2, 64, 64, 32) X(3, 1, 64, 64, 16) X(3, 1, 64, 32, 16)            \
-    X(1, 1, 32, 64, 16) X(3, 1, 64, 64, 32) X(1, 1, 64, 64, 32)
-
-bool tma_plain(const ConvFwdArgs& a) {
-    return a.x2 == nullptr && a.mask_src == nullptr && a.stat_src == nullptr && a.in_b == nullptr;
-}
-
-// The constant-pool variant costs one extra device-to-device copy in the stream (a few microseconds): only for
-// launches with enough work to hide it, never while the stream is being captured into a graph (the copy would be
-// replayed, but the cross-stream event bookkeeping above would not).
-bool use_pool(const ConvFwdArgs& a, cudaStream_t st, int w_floats) {
-    if (w_floats > POOL_FLOATS) return false;
-    const char* e = getenv("DMB_CONV_WEIGHTS");      // "const" / "smem" force one form (tests, A/B timing)
-    const int mode = e ? (e[0] == 'c' ? 1 : (e[0] == 's' ? 2 : 0)) : 0;
-    if (mode == 2) return false;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
-    if (mode == 1) return true;
-    const double macs = (double)a.B * a.Ho * a.Wo * a.Cout * a.Cin * a.ks * a.ks;
-    return macs >= 2.0e9;     // ~50 us of FMA work on a B200
-}
-
-}  // namespace
 
 // Band count (BatchNorm partial rows per sample) of the TMA kernel for this geometry, or 0 if it has no instantiation.
 int conv_tma_bands(int ks, int stride, int Cin, int Cout, int H, int W) {
-    { const char* e = getenv("DMB_CONV_TMA"); if (e && e[0] == '0') return 0; }
-#define X(KS, S, CI, CO, WIN) \
-    if (ks == KS && stride == S && Cin == CI && Cout == CO && W == WIN && H == WIN) return TC<KS, S, CI, CO, WIN, false>::NBANDS;
-    DMB_TMA_SHAPES(X)
-#undef X
-    return 0;
+    if (tma_disabled()) return 0;
+    const int nb = conv_tma_bands_default(ks, stride, Cin, Cout, H, W);
+    return nb ? nb : conv_tma_bands_heavy(ks, stride, Cin, Cout, H, W);
 }
 
 // Returns 1 if the call was not taken (caller falls back to conv_fwd's generic kernel), 0 on success, <0 on error.
 int conv_tma(const ConvFwdArgs& a, cudaStream_t st) {
-    if (!tma_plain(a)) return 1;
-    { const char* e = getenv("DMB_CONV_TMA"); if (e && e[0] == '0') return 1; }      // A/B switch: generic kernel only
-#define X(KS, S, CI, CO, WIN)                                                                        \
-    if (a.ks == KS && a.stride == S && a.Cin == CI && a.Cout == CO && a.W == WIN && a.H == WIN) {   \
-        /* the 1x1 layers are HBM-bound: the shared-memory form (one tile read serves all channel groups) wins */ \
-        if constexpr (CI * KS * KS * CO <= POOL_FLOATS && KS > 1) {                                  \
-            if (use_pool(a, st, CI * KS * KS * CO)) {                                                \
-                if constexpr (KS == 3) {          /* residual-block 3x3: eval-mode ReLU on load in registers */ \
-                    if (a.in_relu && !a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, true, true>>(a, st); \
-                }                                                                                    \
-                return launch_tma<TC<KS, S, CI, CO, WIN, true>>(a, st);                              \
-            }                                                                                        \
-        }                                                                                            \
-        if constexpr (KS == 3) {                                                                     \
-            if (a.in_relu && !a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, false, true>>(a, st); \
-        }                                                                                            \
-        return launch_tma<TC<KS, S, CI, CO, WIN, false>>(a, st);                                     \
-    }
-    DMB_TMA_SHAPES(X)
-#undef X
-    return 1;
+    if (tma_disabled()) return 1;
+    const int r = conv_tma_default(a, st);
+    return r == 1 ? conv_tma_heavy(a, st) : r;
 }
 
 }  // namespace dmb

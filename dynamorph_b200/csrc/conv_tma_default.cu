@@ -1,0 +1,67 @@
+// Dispatch of the TMA-fed convolution (conv_tma.cuh) for one family of layer shapes.
+#include "conv_tma.cuh"
+
+namespace dmb {
+namespace {
+
+// VQ_VAE / VQ_VAE_z16 / VQ_VAE_z32 at the reference's default widths (num_hiddens 16, num_residual_hiddens 32)
+#define DMB_TMA_SHAPES(X)                                                                                          \
+    X(4, 2, 2, 8, 128) X(4, 2, 8, 16, 64) X(4, 2, 16, 16, 32) X(3, 1, 16, 16, 16) X(3, 1, 16, 32, 16)              \
+    X(1, 1, 32, 16, 16) X(3, 1, 16, 32, 32) X(1, 1, 32, 16, 32)
+
+bool tma_plain(const ConvFwdArgs& a) {
+    return a.x2 == nullptr && a.mask_src == nullptr && a.stat_src == nullptr && a.in_b == nullptr;
+}
+
+// The constant-pool variant costs one extra device-to-device copy in the stream (a few microseconds): only for
+// launches with enough work to hide it, never while the stream is being captured into a graph (the copy would be
+// replayed, but the cross-stream event bookkeeping of the pool would not).
+bool use_pool(const ConvFwdArgs& a, cudaStream_t st, int w_floats) {
+    if (w_floats > POOL_FLOATS) return false;
+    const char* e = getenv("DMB_CONV_WEIGHTS");      // "const" / "smem" force one form (tests, A/B timing)
+    const int mode = e ? (e[0] == 'c' ? 1 : (e[0] == 's' ? 2 : 0)) : 0;
+    if (mode == 2) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+    if (mode == 1) return true;
+    const double macs = (double)a.B * a.Ho * a.Wo * a.Cout * a.Cin * a.ks * a.ks;
+    return macs >= 2.0e9;     // ~50 us of FMA work on a B200
+}
+
+// transform form: BatchNorm affine pending -> 2; ReLU only on a 3x3 (eval-mode residual block) -> 1; else 0
+template <int KS, int S, int CI, int CO, int WIN, bool WC>
+int launch_xf(const ConvFwdArgs& a, cudaStream_t st) {
+    if (a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 2>>(a, st);
+    if constexpr (KS == 3) {
+        if (a.in_relu) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 1>>(a, st);
+    }
+    return launch_tma<TC<KS, S, CI, CO, WIN, WC, 0>>(a, st);
+}
+
+}  // namespace
+
+int conv_tma_bands_default(int ks, int stride, int Cin, int Cout, int H, int W) {
+#define X(KS, S, CI, CO, WIN) \
+    if (ks == KS && stride == S && Cin == CI && Cout == CO && W == WIN && H == WIN) return TC<KS, S, CI, CO, WIN, false>::NBANDS;
+    DMB_TMA_SHAPES(X)
+#undef X
+    return 0;
+}
+
+// Returns 1 if the call was not taken, 0 on success, <0 on error.
+int conv_tma_default(const ConvFwdArgs& a, cudaStream_t st) {
+    if (!tma_plain(a)) return 1;
+#define X(KS, S, CI, CO, WIN)                                                                        \
+    if (a.ks == KS && a.stride == S && a.Cin == CI && a.Cout == CO && a.W == WIN && a.H == WIN) {   \
+        /* the 1x1 layers are HBM-bound: the shared-memory form (one tile read serves all channel groups) wins */ \
+        if constexpr (CI * KS * KS * CO <= POOL_FLOATS && KS > 1) {                                  \
+            if (use_pool(a, st, CI * KS * KS * CO)) return launch_xf<KS, S, CI, CO, WIN, true>(a, st); \
+        }                                                                                            \
+        return launch_xf<KS, S, CI, CO, WIN, false>(a, st);                                          \
+    }
+    DMB_TMA_SHAPES(X)
+#undef X
+    return 1;
+}
+
+}  // namespace dmb

@@ -6,6 +6,49 @@
 namespace dmb {
 namespace {
 
+// Fixed-order block reduction of two doubles (256 threads): lane tree, then the eight warp sums in order.
+__device__ __forceinline__ void block_sum2(double& s, double& q, double (*red)[2]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) { red[warp][0] = s; red[warp][1] = q; }
+    __syncthreads();
+    s = 0.0; q = 0.0;
+    for (int w = 0; w < nw; ++w) { s += red[w][0]; q += red[w][1]; }
+}
+
+// BATCH mode: one CTA per channel, every thread sums B*nbands/256 partials with independent loads (the one-warp
+// version below spent ~10 us per launch walking up to 2048 partials as a latency chain).
+__global__ void __launch_bounds__(256) bn_finalize_batch_kernel(const BnFinalizeArgs a) {
+    __shared__ double red[8][2];
+    const int c = blockIdx.x;
+    const int n = a.B * a.nbands;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double2 v = *reinterpret_cast<const double2*>(a.partials + ((size_t)i * a.C + c) * 2);
+        s += v.x; q += v.y;
+    }
+    block_sum2(s, q, red);
+    if (threadIdx.x) return;
+    const double cnt = (double)a.count_per_sample * a.B;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float sc = a.gamma[c] * invstd;
+    a.scale[c] = sc;
+    a.shift[c] = a.beta[c] - (float)mean * sc;
+    if (a.save_mean) { a.save_mean[c] = (float)mean; a.save_invstd[c] = invstd; }
+    if (a.running_mean) {
+        const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+        a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)mean;
+        a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unbiased;
+    }
+}
+
 // one warp per output (channel, or sample*channel): fixed-order sum of the per-CTA partials
 __global__ void bn_finalize_kernel(const BnFinalizeArgs a) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -68,6 +111,12 @@ __global__ void affine_add_kernel(const AffineAddArgs a, int64_t total4) {
 }  // namespace
 
 int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
+    if (!a.per_sample && (int64_t)a.B * a.nbands >= 64) {
+        bn_finalize_batch_kernel<<<a.C, 256, 0, st>>>(a);
+        DMB_CUDA(cudaGetLastError());
+        DMB_LAUNCHED(1);
+        return 0;
+    }
     const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
     const int threads = 128;
     const int64_t blocks = (nout * 32 + threads - 1) / threads;
@@ -134,6 +183,37 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256) bn_bwd_finalize_batch_kernel(const BnBwdArgs a) {
+    __shared__ double red[8][2];
+    const int c = blockIdx.x;
+    const int n = a.B * a.nbands;
+    double sg = 0.0, sgy = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double2 v = *reinterpret_cast<const double2*>(a.partials + ((size_t)i * a.C + c) * 2);
+        sg += v.x; sgy += v.y;
+    }
+    block_sum2(sg, sgy, red);
+    if (threadIdx.x) return;
+    const double N = (double)a.count_per_sample * a.B;
+    const double mu = a.mean[c], is = a.invstd[c], g = a.gamma[c];
+    const double dbeta = sg;
+    const double dgamma = is * (sgy - mu * sg);
+    a.A[c] = (float)(g * is);
+    a.Bc[c] = (float)(-g * is * is * dgamma / N);
+    a.Cc[c] = (float)(-g * is * dbeta / N + g * is * is * mu * dgamma / N);
+    a.dgamma[c] = (float)dgamma;
+    a.dbeta[c] = (float)dbeta;
+}
+
+__global__ void __launch_bounds__(256) sum_partials_block_kernel(const double* partials, int n, int C, float* out) {
+    __shared__ double red[8][2];
+    const int c = blockIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partials[((size_t)i * C + c) * 2];
+    block_sum2(s, q, red);
+    if (threadIdx.x == 0) out[c] = (float)s;
+}
+
 __global__ void sum_partials_kernel(const double* partials, int n, int C, float* out) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -148,6 +228,12 @@ __global__ void sum_partials_kernel(const double* partials, int n, int C, float*
 }  // namespace
 
 int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st) {
+    if (!a.per_sample && (int64_t)a.B * a.nbands >= 64) {
+        bn_bwd_finalize_batch_kernel<<<a.C, 256, 0, st>>>(a);
+        DMB_CUDA(cudaGetLastError());
+        DMB_LAUNCHED(1);
+        return 0;
+    }
     const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
     const int threads = 128;
     bn_bwd_finalize_kernel<<<(unsigned)((nout * 32 + threads - 1) / threads), threads, 0, st>>>(a);
@@ -157,7 +243,8 @@ int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st) {
 }
 
 int sum_partials(const double* partials, int B, int nbands, int C, float* out, cudaStream_t st) {
-    sum_partials_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(partials, B * nbands, C, out);
+    if ((int64_t)B * nbands >= 64) sum_partials_block_kernel<<<C, 256, 0, st>>>(partials, B * nbands, C, out);
+    else sum_partials_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(partials, B * nbands, C, out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

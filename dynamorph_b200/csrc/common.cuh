@@ -72,7 +72,7 @@ struct ConvFwdArgs {
 int conv_fwd(const ConvFwdArgs& a, cudaStream_t st);
 // number of (sum, sumsq) partial rows per sample the kernel will write for this geometry; `plain` = a forward
 // call without the data-gradient extras (x2 / mask_src / stat_src), which the TMA kernel serves when it can
-int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool plain);
+int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool plain, int64_t B);
 // TMA-fed specialisation (conv_tma.cu): returns 1 when it does not take the call
 int conv_tma(const ConvFwdArgs& a, cudaStream_t st);
 int conv_tma_bands(int ks, int stride, int Cin, int Cout, int H, int W);

@@ -330,7 +330,22 @@ int plan(const ConvFwdArgs& a, int co_t, ConvK& k) {
     k.SPR = a.Wo / PW;
     const int strips_per_patch_full = a.Ho * k.SPR;
     const int tpp = strips_per_patch_full * ncg;
-    const int target = 128;
+    // 128 threads per CTA, unless that leaves most of the GPU idle (training batches: a few hundred patches of a
+    // 16x16 map are only ~128 such CTAs, one warp per scheduler and nothing to hide latency with): then smaller CTAs
+    int target = 128;
+    {
+        auto ctas = [&](int tgt) -> int64_t {
+            if (tpp >= tgt) {
+                int tr = 1;
+                for (int t = 1; t <= a.Ho; ++t)
+                    if (a.Ho % t == 0 && t * k.SPR * ncg <= tgt) tr = t;
+                return (int64_t)a.B * (a.Ho / tr);
+            }
+            const int np = tgt / tpp;
+            return ((int64_t)a.B + np - 1) / np;
+        };
+        while (target > 32 && ctas(target) < 4 * 148 && a.W / 4 <= target / 2) target >>= 1;
+    }
     if (tpp >= target) {
         k.NP = 1;
         k.TR = 1;
@@ -405,14 +420,14 @@ int pick_co_t(int Cout) { return (Cout % 8 == 0) ? 8 : ((Cout % 4 == 0) ? 4 : ((
 
 }  // namespace
 
-int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool plain) {
+int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool plain, int64_t B) {
     if (plain) {       // plain forward calls go to the TMA kernel when the geometry has an instantiation
         const int nb = conv_tma_bands(ks, stride, Cin, Cout, Ho * stride, Wo * stride);
         if (nb > 0) return nb;
     }
     ConvFwdArgs a{};
     a.ks = ks; a.stride = stride; a.Cin = Cin; a.Cout = Cout; a.Ho = Ho; a.Wo = Wo;
-    a.H = (stride == 2) ? Ho * 2 : Ho; a.W = (stride == 2) ? Wo * 2 : Wo; a.B = 1 << 20;
+    a.H = (stride == 2) ? Ho * 2 : Ho; a.W = (stride == 2) ? Wo * 2 : Wo; a.B = (int)B;
     ConvK k;
     const int co_t = pick_co_t(Cout);
     if (!co_t || Wo % PW || plan(a, co_t, k)) return -1;

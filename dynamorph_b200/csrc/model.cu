@@ -208,12 +208,12 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
                 Ho = 2 * L.lh; Wo = 2 * L.lw;
                 nb = convt_fwd_bands(c.cin, c.cout, L.lh, L.lw);
             } else if ((int)ci == L.e1) {
-                Ho = H / 2; Wo = W / 2; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo, true);
+                Ho = H / 2; Wo = W / 2; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo, true, B);
             } else if ((int)ci == L.e2) {
-                Ho = H / 4; Wo = W / 4; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo, true);
+                Ho = H / 4; Wo = W / 4; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo, true, B);
             } else {
                 (void)enc_side;
-                Ho = L.lh; Wo = L.lw; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo, true);
+                Ho = L.lh; Wo = L.lw; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo, true, B);
             }
             DMB_CHECK(nb > 0, "no launch plan for conv %zu", ci);
             BnWs& b = w.bn[c.bn];
@@ -603,7 +603,7 @@ struct Bwd {
         }
         if (nbands) {
             const bool plain = !a.x2 && !a.mask_src && !a.stat_src && !a.in_b;
-            *nbands = conv_fwd_bands(a.ks, a.stride, a.Cin, a.Cout, a.Ho, a.Wo, plain);
+            *nbands = conv_fwd_bands(a.ks, a.stride, a.Cin, a.Cout, a.Ho, a.Wo, plain, c.B);
         }
         return conv_fwd(a, st);
     }

@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
     float* acc = sm;                         // [k][d]
     float* zt = sm + (size_t)k * d;          // [d][ZT_PITCH]
     int* it = reinterpret_cast<int*>(zt + (((size_t)d * ZT_PITCH + 3) & ~(size_t)3));   // [256], 16-byte aligned
+    int* own = it + 256;                     // [256] owner class (code % pg) of each position, -1 = none
     const int tid = threadIdx.x;
     const float gl = (g_loss ? __ldg(g_loss) : 1.f) * g_loss_scale;
     const float coef = gl * 2.f / (float)((double)total * d);
@@ -350,19 +351,19 @@ __global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
             for (int cc = 0; cc < d; ++cc)
                 zt[cc * ZT_PITCH + tid] = coef * (__ldg(cb + (size_t)kk * d + cc) - __ldg(z + base + (size_t)cc * p));
             it[tid] = kk;
+            own[tid] = kk % pg;
         } else {
             it[tid] = -1;
+            own[tid] = -1;
         }
         __syncthreads();
         if (j < pg) {
             for (int pos4 = 0; pos4 < 256; pos4 += 4) {
-                const int4 k4 = *reinterpret_cast<const int4*>(it + pos4);
-                const int kks[4] = {k4.x, k4.y, k4.z, k4.w};
+                const int4 o4 = *reinterpret_cast<const int4*>(own + pos4);
+                const int os[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int kk = kks[u];
-                    if (kk >= 0 && (kk % pg) == j) acc[kk * d + c] += zt[c * ZT_PITCH + pos4 + u];
-                }
+                for (int u = 0; u < 4; ++u)
+                    if (os[u] == j) acc[it[pos4 + u] * d + c] += zt[c * ZT_PITCH + pos4 + u];
             }
         }
     }
@@ -376,11 +377,24 @@ __global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
     }
 }
 
-__global__ void vq_codebook_fold_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ grad_cb) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
+// grad_cb[e] = sum over the per-CTA partial rows, fixed order: block = 32 elements x 8 row groups
+__global__ void __launch_bounds__(256) vq_codebook_fold_kernel(const float* __restrict__ partial, int nparts, int n,
+                                                               float* __restrict__ grad_cb) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int i = 0; i < nparts; ++i) s += partial[(size_t)i * n + e];
+    if (e < n) {
+        const int per = (nparts + 7) / 8;
+        const int r0 = grp * per, r1 = min(nparts, r0 + per);
+        for (int i = r0; i < r1; ++i) s += partial[(size_t)i * n + e];
+    }
+    red[grp][lane] = s;
+    __syncthreads();
+    if (grp != 0 || e >= n) return;
+    s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += red[g][lane];
     grad_cb[e] = s;
 }
 
@@ -388,7 +402,7 @@ int vq_codebook_grad(const float* z, const float* cb, const int32_t* idx, const 
                      int64_t total, int d, int p, int k, float* grad_cb, float* scratch, int scratch_rows,
                      cudaStream_t st) {
     // scratch: scratch_rows x k x d floats, or nullptr -> global atomics straight into grad_cb
-    const size_t smem = ((size_t)k * d + (size_t)d * ZT_PITCH + 256 + 4) * sizeof(float);
+    const size_t smem = ((size_t)k * d + (size_t)d * ZT_PITCH + 512 + 4) * sizeof(float);
     DMB_CHECK(smem <= 220 * 1024, "vq codebook gradient: K=%d D=%d does not fit shared memory", k, d);
     if (smem > 48 * 1024)
         DMB_CUDA(cudaFuncSetAttribute(vq_codebook_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -399,7 +413,7 @@ int vq_codebook_grad(const float* z, const float* cb, const int32_t* idx, const 
         vq_codebook_scatter_kernel<<<grid, 256, smem, st>>>(z, cb, idx, g_loss, g_loss_scale, total, d, p, k, scratch, nullptr);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);
-        vq_codebook_fold_kernel<<<(k * d + 127) / 128, 128, 0, st>>>(scratch, grid, k * d, grad_cb);
+        vq_codebook_fold_kernel<<<(k * d + 31) / 32, 256, 0, st>>>(scratch, grid, k * d, grad_cb);
     } else {
         DMB_CUDA(cudaMemsetAsync(grad_cb, 0, sizeof(float) * (size_t)k * d, st));
         vq_codebook_scatter_kernel<<<grid, 256, smem, st>>>(z, cb, idx, g_loss, g_loss_scale, total, d, p, k, nullptr, grad_cb);

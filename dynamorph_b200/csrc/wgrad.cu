@@ -252,25 +252,26 @@ int launch(const WgK& k, int ncta, cudaStream_t st) {
     return 0;
 }
 
-// sum partials over CTAs and scatter to the torch layout.  Block = 32 consecutive elements x 8 CTA groups
-// (coalesced 128-byte rows, 8x the memory parallelism of a serial walk); groups are folded in fixed order.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, int out_floats,
-                                                           int cin_eff, int cout, int ks, float* __restrict__ dw,
-                                                           float* __restrict__ db, float* __restrict__ packed_out) {
-    __shared__ float red[8][32];
+// sum partials over CTAs and scatter to the torch layout.  Block = 32 consecutive elements x 32 CTA groups
+// (coalesced 128-byte rows, <= 10 independent loads per thread); groups are folded in fixed order.
+__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, int out_floats,
+                                                            int cin_eff, int cout, int ks, float* __restrict__ dw,
+                                                            float* __restrict__ db, float* __restrict__ packed_out) {
+    __shared__ float red[32][33];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
     float s = 0.f;
     if (e < out_floats) {
-        const int per = (ncta + 7) / 8;
+        const int per = (ncta + 31) / 32;
         const int c0 = grp * per, c1 = min(ncta, c0 + per);
         for (int c = c0; c < c1; ++c) s += partials[(size_t)c * out_floats + e];
     }
     red[grp][lane] = s;
     __syncthreads();
     if (grp != 0 || e >= out_floats) return;
-    s = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) +
-        ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+    s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) s += red[g][lane];
     if (packed_out) { packed_out[e] = s; return; }
     const int nt = ks * ks;
     const int nw = cin_eff * nt * cout;
@@ -352,7 +353,7 @@ int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStrea
         else DMB_TRY((launch<4, 2, 2>(k, ncta, st)));
     }
     const int blocks = (k.out_floats + 31) / 32;
-    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a.partials, ncta, k.out_floats, k.cin_eff, a.Cout, a.ks, dw, db, packed_out);
+    wgrad_reduce_kernel<<<blocks, 1024, 0, st>>>(a.partials, ncta, k.out_floats, k.cin_eff, a.Cout, a.ks, dw, db, packed_out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -21,6 +21,12 @@ class DmbModel(C.Structure):
     ]
 
 
+class DmbTimeMatching(C.Structure):
+    """struct dmb_time_matching -- the optional time-matching term of VQ_VAE.forward."""
+    _fields_ = [("mat", C.c_void_p), ("variant", C.c_int32), ("w_a", C.c_float), ("w_t", C.c_float),
+                ("w_n", C.c_float), ("margin", C.c_float), ("weight", C.c_float)]
+
+
 ARCH_Z16, ARCH_Z32 = 0, 1
 BN_EVAL, BN_BATCH, BN_PER_SAMPLE = 0, 1, 2
 BN_MODES = {"eval": BN_EVAL, "batch": BN_BATCH, "per_sample": BN_PER_SAMPLE}
@@ -56,6 +62,11 @@ SIGNATURES = {
     "dmb_recon_loss": [_P, _P, _P, _I32, _P, _I64, _I32, _I32, _P, _P],
     "dmb_train_forward": [_M, _P, _P, _P, _P, _I32, _P, _I64, _P, _P, _P, _P, C.c_size_t, _P],
     "dmb_train_backward": [_M, _P, _P, _P, _P, _I32, _P, _P, _I64, _F, _P, _P, C.c_size_t, _P],
+    "dmb_train_forward_tm": [_M, _P, _P, _P, _P, _I32, _P, _I64, C.POINTER(DmbTimeMatching), _P, _P, _P, _P, C.c_size_t, _P],
+    "dmb_train_backward_tm": [_M, _P, _P, _P, _P, _I32, _P, _P, _I64, C.POINTER(DmbTimeMatching), _F, _P, _P, C.c_size_t, _P],
+    "dmb_time_matching_scratch_floats": [_I64, _I64, C.POINTER(C.c_size_t)],
+    "dmb_time_matching_forward": [_P, _I64, _I64, C.POINTER(DmbTimeMatching), _P, _P, _P],
+    "dmb_time_matching_backward": [_P, _I64, _I64, _P, _F, _P, _I32, _P],
     "dmb_adam_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P],
     "dmb_adam_step_dev": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _F, _P],
     "dmb_zscore_patch": [_P, _I32, _I64, _I32, _P, _P],

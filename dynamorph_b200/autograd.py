@@ -51,7 +51,7 @@ class TrainStepFunction(torch.autograd.Function):
     trainable tensor computed by the fused backward schedule (dmb_train_forward / dmb_train_backward)."""
 
     @staticmethod
-    def forward(ctx, model, inputs, batch_mask, *params):
+    def forward(ctx, model, inputs, batch_mask, time_matching_mat, *params):
         import ctypes as C
         from ._lib import BN_BATCH
         eng = model._engine
@@ -69,29 +69,36 @@ class TrainStepFunction(torch.autograd.Function):
                 mc = Cin
         cv = model.channel_var.data.reshape(-1).contiguous()
         decoded = torch.empty_like(x)
-        losses = torch.empty(4, dtype=torch.float32, device=x.device)
-        call("dmb_train_forward", C.byref(s), ptr(packed), ptr(eng.flat_params), ptr(x), ptr(mask), mc, ptr(cv), B,
-             ptr(decoded), ptr(losses), ptr(eng.flat_bn), ptr(ws), n, _stream())
+        losses = torch.empty(8, dtype=torch.float32, device=x.device)
+        tm, tm_mat = None, None
+        if time_matching_mat is not None:
+            from .matching import descriptor
+            if tuple(time_matching_mat.shape) != (B, B):
+                raise AssertionError("sim_mat.shape == time_matching_mat.shape")      # vq_vae.py:329
+            tm, tm_mat = descriptor(model, time_matching_mat)
+        call("dmb_train_forward_tm", C.byref(s), ptr(packed), ptr(eng.flat_params), ptr(x), ptr(mask), mc, ptr(cv), B,
+             C.byref(tm) if tm is not None else None, ptr(decoded), ptr(losses), ptr(eng.flat_bn), ptr(ws), n, _stream())
+        ctx.tm, ctx.tm_mat = tm, tm_mat
         eng._bump_num_batches_tracked()
         ctx.model, ctx.spec, ctx.mc, ctx.nws = model, s, mc, n
         ctx.save_for_backward(x, mask if mask is not None else torch.empty(0, device=x.device), cv, decoded, packed)
         ctx.ws_token = eng.workspace_token()
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(decoded)
-        recon, commit, total, ppl = losses[0], losses[1], losses[2], losses[3]
+        recon, commit, total, ppl, tml = losses[0], losses[1], losses[2], losses[3], losses[4]
         ctx.mark_non_differentiable(ppl)
-        return decoded, recon, commit, total, ppl
+        return decoded, recon, commit, total, ppl, tml
 
     @staticmethod
-    def backward(ctx, g_dec, g_recon, g_commit, g_total, g_ppl):
+    def backward(ctx, g_dec, g_recon, g_commit, g_total, g_ppl, g_tm=None):
         import ctypes as C
         model = ctx.model
         eng = model._engine
-        if g_recon is not None or g_commit is not None:
+        if g_recon is not None or g_commit is not None or g_tm is not None:
             raise NotImplementedError("dynamorph_b200: back-propagate through `total_loss` (recon_loss / "
                                       "commitment_loss are reported values of the fused step)")
         if g_total is None:
-            return (None,) * (3 + len(eng.trainable()))
+            return (None,) * (4 + len(eng.trainable()))
         if eng.workspace_token() != ctx.ws_token:
             raise RuntimeError("dynamorph_b200: the activation workspace was reused by another call before "
                                "backward(); call backward() right after the forward of the same batch")
@@ -100,24 +107,24 @@ class TrainStepFunction(torch.autograd.Function):
         B = x.shape[0]
         flat_g = torch.empty_like(eng.flat_params)
         ws = eng._ws
-        call("dmb_train_backward", C.byref(ctx.spec), ptr(packed), ptr(eng.flat_params), ptr(x), ptr(mask_t), ctx.mc,
-             ptr(cv), ptr(decoded), B, 1.0, ptr(flat_g), ptr(ws), ctx.nws, _stream())
+        call("dmb_train_backward_tm", C.byref(ctx.spec), ptr(packed), ptr(eng.flat_params), ptr(x), ptr(mask_t), ctx.mc,
+             ptr(cv), ptr(decoded), B, C.byref(ctx.tm) if ctx.tm is not None else None, 1.0, ptr(flat_g), ptr(ws),
+             ctx.nws, _stream())
         flat_g.mul_(g_total)
         eng.last_flat_grad = flat_g
         grads = tuple(flat_g[off:off + n].view(p.shape) if p.requires_grad else None for p, off, n in eng._views)
-        return (None, None, None) + grads
+        return (None, None, None, None) + grads
 
 
 def train_forward(model, inputs, time_matching_mat=None, batch_mask=None):
     """VQ_VAE.forward in training mode with autograd attached (reference: vq_vae.py:300-338)."""
-    if time_matching_mat is not None:
-        raise NotImplementedError("time_matching_mat is not part of the fused training step yet "
-                                  "(SURVEY.md section 8f, row N3)")
     eng = model._engine
     eng.flatten()
     params = [p for p, _, _ in eng._views]
-    decoded, recon, commit, total, ppl = TrainStepFunction.apply(model, inputs, batch_mask, *params)
-    out = {'recon_loss': recon, 'commitment_loss': commit, 'time_matching_loss': 0.}
+    decoded, recon, commit, total, ppl, tml = TrainStepFunction.apply(model, inputs, batch_mask, time_matching_mat,
+                                                                      *params)
+    out = {'recon_loss': recon, 'commitment_loss': commit,
+           'time_matching_loss': tml if time_matching_mat is not None else 0.}
     if getattr(model, "_total_last", False):
         out['perplexity'] = ppl
         out['total_loss'] = total

@@ -191,7 +191,15 @@ struct VqArgs {
 };
 int vq_forward(const VqArgs& a, cudaStream_t st);
 // gradient of the quantiser; optional per-CTA BatchNorm-backward sums [B*p/128][d][2] against stat_src
-int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx, const float* g_zst,
+// time-matching loss (matching.cu)
+size_t tm_scratch_floats(int64_t B, int64_t L);
+int tm_forward(const float* z, int64_t B, int64_t L, const dmb_time_matching& tm, float* scratch, float* loss_out,
+               cudaStream_t st);
+int tm_backward(const float* z, int64_t B, int64_t L, const float* scratch, float scale, float* g, int accumulate,
+                cudaStream_t st);
+
+// g_extra (optional, same shape as z): added to the straight-through gradient (time-matching term)
+int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx, const float* g_zst, const float* g_extra,
                       float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
                       float* grad_codebook, double* stats, const float* stat_src, float* scratch, int scratch_rows,
                       cudaStream_t st);

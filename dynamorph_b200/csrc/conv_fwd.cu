@@ -344,7 +344,8 @@ int plan(const ConvFwdArgs& a, int co_t, ConvK& k) {
             const int np = tgt / tpp;
             return ((int64_t)a.B + np - 1) / np;
         };
-        while (target > 32 && ctas(target) < 4 * 148 && a.W / 4 <= target / 2) target >>= 1;
+        // (3x3 only: the 1x1 data-gradient convs got slower with smaller CTAs, their weights are re-read per CTA)
+        while (KS == 3 && target > 32 && ctas(target) < 4 * 148 && a.W / 4 <= target / 2) target >>= 1;
     }
     if (tpp >= target) {
         k.NP = 1;

@@ -278,6 +278,8 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
         w.vq_part_rows = (int)((B * lat + 255) / 256 < 296 ? (B * lat + 255) / 256 : 296);
         if (w.vq_part_rows < 2) w.vq_part_rows = 2;
         w.vq_part = bp.take<float>((size_t)w.vq_part_rows * m.num_embeddings * h);
+        w.tm_scratch = bp.take<float>(tm_scratch_floats(B, (int64_t)h * lat));
+        w.g_tm = bp.take<float>(B * h * lat);
     }
     w.vq_stats = bp.take<double>(2 + m.num_embeddings);
     w.recon_sum = bp.take<double>(4);
@@ -524,13 +526,16 @@ __global__ void recon_grad_kernel(const float* __restrict__ dec, const float* __
     }
 }
 
+// vq2: [0] vq loss, [1] perplexity, [4] time-matching loss (when w_tm != 0).  n_out = 4 (legacy) or 8.
 __global__ void train_losses_kernel(const float* vq2, const double* recon_sum, double n_recon, float w_r, float w_c,
-                                    float* out4) {
+                                    float w_tm, int has_tm, int n_out, float* out) {
     const float recon = (float)(recon_sum[0] / n_recon);
-    out4[0] = recon;
-    out4[1] = vq2[0];
-    out4[2] = w_r * recon + w_c * vq2[0];
-    out4[3] = vq2[1];
+    const float tm = has_tm ? vq2[4] : 0.f;
+    out[0] = recon;
+    out[1] = vq2[0];
+    out[2] = w_r * recon + w_c * vq2[0] + (has_tm ? w_tm * tm : 0.f);
+    out[3] = vq2[1];
+    if (n_out > 4) { out[4] = tm; out[5] = 0.f; out[6] = 0.f; out[7] = 0.f; }
 }
 
 struct GradT {            // dL/d(conv output) = A*g + Bc*y + Cc  (A == nullptr: just g)
@@ -697,7 +702,7 @@ int recon_grad(Ctx& c, const float* x, const float* mask, int mask_c, const floa
 }
 
 int run_backward_z16(Ctx& c, const float* params, const float* x, const float* mask, int mask_c,
-                     const float* cvar, const float* decoded, float grad_scale, float* grads) {
+                     const float* cvar, const float* decoded, float grad_scale, float* grads, const float* g_tm) {
     const Layout& L = c.L;
     const dmb_model& m = L.m;
     Workspace& w = c.w;
@@ -733,7 +738,7 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
     const int P = lh * lw;
     {
         const ConvL& lb = L.convs[L.enc_res[nres - 1].b];
-        DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, w.g_za, grad_scale * m.weight_commitment,
+        DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, w.g_za, g_tm, grad_scale * m.weight_commitment,
                                   m.commitment_cost, c.B, h, P, m.num_embeddings, w.g_zb, grads + L.codebook_off,
                                   w.bnb[lb.bn].part, w.erb[nres - 1], w.vq_part, w.vq_part_rows, st));
     }
@@ -781,7 +786,7 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
 // vae.py:401-414.  enc: conv4s2 -> BN -> ReLU -> conv4s2 -> BN -> ResidualBlock;  dec: ResidualBlock -> ConvT ->
 // BN -> ReLU -> ConvT.  total = recon + commitment (vae.py:440).
 int run_backward_z32(Ctx& c, const float* params, const float* x, const float* mask, int mask_c,
-                     const float* cvar, const float* decoded, float grad_scale, float* grads) {
+                     const float* cvar, const float* decoded, float grad_scale, float* grads, const float* g_tm) {
     const Layout& L = c.L;
     const dmb_model& m = L.m;
     Workspace& w = c.w;
@@ -823,7 +828,7 @@ int run_backward_z32(Ctx& c, const float* params, const float* x, const float* m
     // quantiser
     {
         const ConvL& lb = L.convs[L.enc_res[nres_e - 1].b];
-        DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, g_cur, grad_scale, m.commitment_cost, c.B, h, P,
+        DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, g_cur, g_tm, grad_scale, m.commitment_cost, c.B, h, P,
                                   m.num_embeddings, w.g_zb, grads + L.codebook_off, w.bnb[lb.bn].part,
                                   w.erb[nres_e - 1], w.vq_part, w.vq_part_rows, st));
     }
@@ -992,10 +997,10 @@ int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const fl
     return convt_fwd(a, (cudaStream_t)stream);
 }
 
-int dmb_train_forward(const dmb_model* m, const float* packed, const float* params, const float* x,
-                      const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
-                      float* decoded, float* losses_out, float* bnbuf_inout, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+static int train_forward_impl(const dmb_model* m, const float* packed, const float* params, const float* x,
+                              const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
+                              const dmb_time_matching* tm, int n_losses, float* decoded, float* losses_out,
+                              float* bnbuf_inout, void* workspace, size_t workspace_bytes, void* stream) {
     Layout L; Workspace w;
     DMB_CHECK(packed && params && x && channel_var && decoded && losses_out, "dmb_train_forward: null pointer");
     DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
@@ -1011,24 +1016,62 @@ int dmb_train_forward(const dmb_model* m, const float* packed, const float* para
     DMB_TRY(dmb_recon_loss(decoded, x, mask, mask_channels, channel_var, batch, m->num_inputs,
                            m->height * m->width, w.recon_sum, stream));
     const bool z32 = m->arch == DMB_ARCH_Z32;
+    if (tm) {
+        // pair similarities on z_before (vq_vae.py:325, vae.py:322) or, for VQ_VAE_z32, on z_after (vae.py:444)
+        DMB_CHECK(w.tm_scratch, "time matching needs a workspace carved with keep_activations=1");
+        DMB_TRY(tm_forward(z32 ? w.za : w.zb, batch, (int64_t)L.D * L.lh * L.lw, *tm, w.tm_scratch, w.scalars + 4, st));
+    }
     train_losses_kernel<<<1, 1, 0, st>>>(w.scalars, w.recon_sum, (double)batch * m->num_inputs * m->height * m->width,
-                                         z32 ? 1.f : m->weight_recon, z32 ? 1.f : m->weight_commitment, losses_out);
+                                         z32 ? 1.f : m->weight_recon, z32 ? 1.f : m->weight_commitment,
+                                         tm ? tm->weight : 0.f, tm ? 1 : 0, n_losses, losses_out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
+}
+
+int dmb_train_forward(const dmb_model* m, const float* packed, const float* params, const float* x,
+                      const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
+                      float* decoded, float* losses_out, float* bnbuf_inout, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    return train_forward_impl(m, packed, params, x, mask, mask_channels, channel_var, batch, nullptr, 4, decoded,
+                              losses_out, bnbuf_inout, workspace, workspace_bytes, stream);
+}
+
+int dmb_train_forward_tm(const dmb_model* m, const float* packed, const float* params, const float* x,
+                         const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
+                         const dmb_time_matching* tm, float* decoded, float* losses_out, float* bnbuf_inout,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    return train_forward_impl(m, packed, params, x, mask, mask_channels, channel_var, batch, tm, 8, decoded,
+                              losses_out, bnbuf_inout, workspace, workspace_bytes, stream);
+}
+
+int dmb_train_backward_tm(const dmb_model* m, const float* packed, const float* params, const float* x,
+                          const float* mask, int32_t mask_channels, const float* channel_var,
+                          const float* decoded, int64_t batch, const dmb_time_matching* tm, float grad_scale,
+                          float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+    Layout L; Workspace w;
+    DMB_CHECK(packed && params && x && channel_var && decoded && grads, "dmb_train_backward: null pointer");
+    DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
+    Ctx c{L, packed, w, batch, DMB_BN_BATCH, nullptr, (cudaStream_t)stream};
+    const float* g_tm = nullptr;
+    if (tm) {
+        // d(weight * tm_loss)/dz; z_after is a straight-through copy of z_before, so either source feeds dL/dz_before
+        const bool z32 = m->arch == DMB_ARCH_Z32;
+        DMB_TRY(tm_backward(z32 ? w.za : w.zb, batch, (int64_t)L.D * L.lh * L.lw, w.tm_scratch,
+                            grad_scale * tm->weight, w.g_tm, 0, c.st));
+        g_tm = w.g_tm;
+    }
+    if (m->arch == DMB_ARCH_Z32)
+        return run_backward_z32(c, params, x, mask, mask_channels, channel_var, decoded, grad_scale, grads, g_tm);
+    return run_backward_z16(c, params, x, mask, mask_channels, channel_var, decoded, grad_scale, grads, g_tm);
 }
 
 int dmb_train_backward(const dmb_model* m, const float* packed, const float* params, const float* x,
                        const float* mask, int32_t mask_channels, const float* channel_var,
                        const float* decoded, int64_t batch, float grad_scale, float* grads, void* workspace,
                        size_t workspace_bytes, void* stream) {
-    Layout L; Workspace w;
-    DMB_CHECK(packed && params && x && channel_var && decoded && grads, "dmb_train_backward: null pointer");
-    DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
-    Ctx c{L, packed, w, batch, DMB_BN_BATCH, nullptr, (cudaStream_t)stream};
-    if (m->arch == DMB_ARCH_Z32)
-        return run_backward_z32(c, params, x, mask, mask_channels, channel_var, decoded, grad_scale, grads);
-    return run_backward_z16(c, params, x, mask, mask_channels, channel_var, decoded, grad_scale, grads);
+    return dmb_train_backward_tm(m, packed, params, x, mask, mask_channels, channel_var, decoded, batch, nullptr,
+                                 grad_scale, grads, workspace, workspace_bytes, stream);
 }
 
 long long dmb_launch_count(int reset) {

@@ -76,7 +76,9 @@ struct Workspace {
     size_t wg_part_floats = 0;
     double* vq_stats = nullptr;            // [2+K]
     double* recon_sum = nullptr;           // [1]
-    float* scalars = nullptr;              // [8] vq loss, perplexity, ...
+    float* scalars = nullptr;              // [8] vq loss, perplexity, ..., [4] time-matching loss
+    float* tm_scratch = nullptr;           // time-matching pair sums + dloss/dsim (keep != 0)
+    float* g_tm = nullptr;                 // time-matching gradient at the latent (B, D, lh, lw)
     size_t bytes = 0;
 };
 int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* base, Workspace& w);

@@ -270,8 +270,8 @@ constexpr int VQB_MAXD = 128;
 // grad_z (+ optional BatchNorm-backward sums).  No atomics: the codebook gradient has its own kernel.
 __global__ void __launch_bounds__(128) vq_backward_kernel(
         const float* __restrict__ z, const float* __restrict__ cb, const int32_t* __restrict__ idx,
-        const float* __restrict__ g_zst, const float* __restrict__ g_loss, float g_loss_scale, float beta,
-        int64_t total, int d, int p, float* __restrict__ grad_z,
+        const float* __restrict__ g_zst, const float* __restrict__ g_extra, const float* __restrict__ g_loss,
+        float g_loss_scale, float beta, int64_t total, int d, int p, float* __restrict__ grad_z,
         double* __restrict__ stats, const float* __restrict__ stat_src) {
     // stats (optional): per-CTA (sum g, sum g*stat_src) per channel, layout [block][d][2] -- the BatchNorm
     // backward sums of the residual layer that produced z.  Needs p % 128 == 0 (a CTA stays in one patch).
@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
         if (live) {
             const float zv = __ldg(z + base + (size_t)c * p);
             const float q = __ldg(cb + (size_t)k * d + c);
-            const float g = g_zst ? __ldg(g_zst + base + (size_t)c * p) : 0.f;
+            float g = g_zst ? __ldg(g_zst + base + (size_t)c * p) : 0.f;
+            if (g_extra) g += __ldg(g_extra + base + (size_t)c * p);
             gz = g + coef * beta * (zv - q);
             if (grad_z) grad_z[base + (size_t)c * p] = gz;
             if (stats) sy = gz * __ldg(stat_src + base + (size_t)c * p);
@@ -428,14 +429,14 @@ int vq_codebook_grad(const float* z, const float* cb, const int32_t* idx, const 
 
 namespace dmb {
 int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx, const float* g_zst,
-                      float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
+                      const float* g_extra, float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
                       float* grad_codebook, double* stats, const float* stat_src, float* scratch, int scratch_rows,
                       cudaStream_t st) {
     const int64_t total = batch * p;
     DMB_CHECK(!stats || p % 128 == 0, "vq backward: positions per patch (%d) must be a multiple of 128", p);
     DMB_CHECK(d <= VQB_MAXD, "vq backward: embedding_dim %d > %d", d, VQB_MAXD);
     vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-        z, codebook, idx, g_zst, nullptr, g_loss_scale, beta, total, d, p, grad_z, stats, stat_src);
+        z, codebook, idx, g_zst, g_extra, nullptr, g_loss_scale, beta, total, d, p, grad_z, stats, stat_src);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     if (grad_codebook)
@@ -460,7 +461,7 @@ extern "C" int dmb_vq_backward(const float* z, const float* codebook, const int3
     }
     if (grad_z) {
         dmb::vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-            z, codebook, idx, g_zst, g_loss_dev, g_loss_scale, commitment_cost, total, d,
+            z, codebook, idx, g_zst, nullptr, g_loss_dev, g_loss_scale, commitment_cost, total, d,
             positions_per_patch, grad_z, nullptr, nullptr);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);

@@ -163,6 +163,23 @@ int dmb_bench_fma_conv(int32_t variant, int32_t blocks, int32_t iters, float* sc
 /* Number of kernels this library has launched in the process (reset != 0 zeroes it).        */
 long long dmb_launch_count(int reset);
 
+/* ---- time-matching loss (vq_vae.py:324-332; vae.py:321-336, :442-457) --------------------- */
+typedef struct dmb_time_matching {
+    const float* mat;     /* (B, B) device tensor: pair weights (variant 0) or pair classes 0 / 1 / 2 (variant 1) */
+    int32_t variant;      /* 0: VQ_VAE  loss = sum(sim * mat);  1: VQ_VAE_z16 / z32  weighted, hinged, mean        */
+    float w_a, w_t, w_n;  /* variant 1: weight of class 2 / 1 / 0 pairs                                            */
+    float margin;         /* variant 1: class-0 terms become max(sim * w_n + margin, 0)                             */
+    float weight;         /* weight_matching: total_loss += weight * time_matching_loss                            */
+} dmb_time_matching;
+/* sim[i][j] = mean_l (z[i][l] - z[j][l])^2 over z (B, L); loss_out[0] <- loss.  `scratch` needs
+ * dmb_time_matching_scratch_floats() floats (16-byte aligned) and keeps dloss/dsim for the backward.  */
+int dmb_time_matching_scratch_floats(int64_t batch, int64_t latent_len, size_t* floats);
+int dmb_time_matching_forward(const float* z, int64_t batch, int64_t latent_len, const dmb_time_matching* tm,
+                              float* scratch, float* loss_out, void* stream);
+/* grad_z (B, L) <- (accumulate != 0: +=) scale * dloss/dz, from the scratch of the forward call.      */
+int dmb_time_matching_backward(const float* z, int64_t batch, int64_t latent_len, const float* scratch,
+                               float scale, float* grad_z, int32_t accumulate, void* stream);
+
 /* ---- training step (run_training.py:404-408) ---------------------------------------- */
 /* Full forward in BATCH mode keeping activations, producing decoded and
  * losses_out float[4] = {recon_loss, commitment_loss, total_loss, perplexity}.           */
@@ -177,6 +194,19 @@ int dmb_train_backward(const dmb_model* m, const float* packed, const float* par
                        const float* x, const float* mask, int32_t mask_channels,
                        const float* channel_var, const float* decoded, int64_t batch, float grad_scale,
                        float* grads, void* workspace, size_t workspace_bytes, void* stream);
+/* The same two calls with the optional time-matching term (tm == NULL: identical to the above).  The pair
+ * similarities are taken on z_before (VQ_VAE, VQ_VAE_z16) or on the quantised z_after (VQ_VAE_z32), as in the
+ * reference; losses_out is float[8] = {recon, commitment, total, perplexity, time_matching, 0, 0, 0}.            */
+int dmb_train_forward_tm(const dmb_model* m, const float* packed, const float* params,
+                         const float* x, const float* mask, int32_t mask_channels,
+                         const float* channel_var, int64_t batch, const dmb_time_matching* tm, float* decoded,
+                         float* losses_out, float* bnbuf_inout, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int dmb_train_backward_tm(const dmb_model* m, const float* packed, const float* params,
+                          const float* x, const float* mask, int32_t mask_channels,
+                          const float* channel_var, const float* decoded, int64_t batch,
+                          const dmb_time_matching* tm, float grad_scale,
+                          float* grads, void* workspace, size_t workspace_bytes, void* stream);
 /* torch.optim.Adam (betas, eps, no weight decay), bias-corrected, step is 1-based.
  * grad_scale multiplies the gradient first (1/world_size after an allreduce-sum).        */
 int dmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,

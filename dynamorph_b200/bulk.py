@@ -10,7 +10,10 @@ import torch
 
 class BulkEncoder:
     def __init__(self, model, chunk: int = 8192, bn_mode: str = "eval", device=None,
-                 outputs=("z_before", "z_after", "idx")):
+                 outputs=("z_before", "z_after", "idx"), zscore: bool = False):
+        """zscore=True: `encode` takes RAW patches (float32 / float64 / uint16 on the host), ships them as they are
+        and applies pipeline/train_utils.py:252-274 `zscore_patch` on the device in front of the encoder (uint16
+        input halves the host->device bytes of the float32 path)."""
         if bn_mode not in ("eval", "per_sample"):
             raise ValueError("bulk encoding needs patch-independent statistics: bn_mode 'eval' or 'per_sample'")
         self.model = model
@@ -19,6 +22,8 @@ class BulkEncoder:
         self.bn_mode = bn_mode
         self.device = torch.device(device) if device is not None else self.engine.device
         self.outputs = tuple(outputs)
+        self.zscore = bool(zscore)
+        self._raw = None
         self._bufs = None
         self._streams = None
 
@@ -55,12 +60,21 @@ class BulkEncoder:
 
     @torch.no_grad()
     def encode(self, x_host: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
-        """x_host: (N, C, H, W) float32 on the host (pinned for full overlap).  Returns host tensors
-        'z_before' / 'z_after' (N, D*h*w) NCHW-flattened like patch_VAE.py:454-461, and 'idx'."""
+        """x_host: (N, C, H, W) float32 on the host (pinned for full overlap); with zscore=True raw float32 /
+        float64 / uint16.  Returns host tensors 'z_before' / 'z_after' (N, D*h*w) NCHW-flattened like
+        patch_VAE.py:454-461, and 'idx'."""
         if x_host.is_cuda:
             raise ValueError("BulkEncoder.encode takes host tensors; use model.encode_latents for device data")
         N, C, H, W = x_host.shape
         self._setup(C, H, W)
+        if not self.zscore and x_host.dtype != torch.float32:
+            raise ValueError("BulkEncoder.encode takes float32 patches (or construct it with zscore=True for raw data)")
+        if self.zscore:
+            from .pipeline.train_utils import _DTYPES
+            if x_host.dtype not in _DTYPES:
+                raise ValueError(f"raw patches must be float32, float64 or uint16, not {x_host.dtype}")
+            if self._raw is None or self._raw[0].dtype != x_host.dtype or self._raw[0].shape[1:] != (C, H, W):
+                self._raw = [torch.empty(self.chunk, C, H, W, dtype=x_host.dtype, device=self.device) for _ in range(2)]
         if out is None:
             out = self.allocate_outputs(N, C, H, W)
         b = self._bufs
@@ -82,12 +96,18 @@ class BulkEncoder:
             with torch.cuda.stream(s_in):
                 if used[j]:
                     s_in.wait_event(ev_cmp[j])          # x[j] consumed by the encode two chunks ago
-                b["x"][j][:n].copy_(x_host[a:e], non_blocking=True)
+                (self._raw if self.zscore else b["x"])[j][:n].copy_(x_host[a:e], non_blocking=True)
                 ev_in[j].record(s_in)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in[j])
                 if used[j]:
                     s_cmp.wait_event(ev_out[j])         # outputs[j] drained to the host
+                if self.zscore:
+                    import ctypes
+                    from ._lib import call, ptr
+                    from .pipeline.train_utils import _DTYPES
+                    call("dmb_zscore_patch", ptr(self._raw[j]), _DTYPES[x_host.dtype], n * C, H * W, ptr(b["x"][j]),
+                         ctypes.c_void_p(s_cmp.cuda_stream))
                 self.engine.encode(b["x"][j][:n], self.bn_mode, out=(b["zb"][j], b["za"][j], b["idx"][j]))
                 ev_cmp[j].record(s_cmp)
             with torch.cuda.stream(s_out):

@@ -26,24 +26,18 @@ def encode_patches(model, dataset: np.ndarray, device, bn_mode: str = "per_sampl
                    zscore: bool = True):
     """(N, C, H, W) raw patches on the host -> (z_before, z_after) float32 (N, D*h*w) on the host."""
     n = dataset.shape[0]
-    enc = BulkEncoder(model, chunk=chunk, bn_mode=bn_mode, device=device, outputs=("z_before", "z_after"))
+    enc = BulkEncoder(model, chunk=chunk, bn_mode=bn_mode, device=device, outputs=("z_before", "z_after"),
+                      zscore=zscore)
     out = enc.allocate_outputs(n, dataset.shape[1], dataset.shape[2], dataset.shape[3], pin=True)
     if not zscore:
-        x = torch.from_numpy(np.ascontiguousarray(dataset, dtype=np.float32))
-        enc.encode(x, out)
+        enc.encode(torch.from_numpy(np.ascontiguousarray(dataset, dtype=np.float32)), out)
     else:
-        # z-score needs the raw (float64 / uint16) values: stage chunk-wise, normalise on the device and
-        # feed the device tensor straight into the encoder (no float32 host copy)
-        eng = model._engine
-        zb_dev = za_dev = idx_dev = None
-        for a in range(0, n, chunk):
-            part = np.ascontiguousarray(dataset[a:a + chunk])
-            if part.dtype not in (np.float32, np.float64, np.uint16):
-                part = part.astype(np.float64)
-            xd = zscore_patch_device(torch.from_numpy(part).to(device, non_blocking=True))
-            zb, za, _ = eng.encode(xd, bn_mode)
-            out["z_before"][a:a + xd.shape[0]].copy_(zb.reshape(xd.shape[0], -1), non_blocking=True)
-            out["z_after"][a:a + xd.shape[0]].copy_(za.reshape(xd.shape[0], -1), non_blocking=True)
+        # z-score needs the raw (float64 / uint16) values: they are shipped as they are and normalised on the device
+        # in front of the encoder, chunk i+1 in flight while chunk i is encoded (no float32 host copy)
+        part = np.ascontiguousarray(dataset)
+        if part.dtype not in (np.float32, np.float64, np.uint16):
+            part = part.astype(np.float64)
+        enc.encode(torch.from_numpy(part), out)
     torch.cuda.synchronize(device)
     return out["z_before"].numpy(), out["z_after"].numpy()
 

@@ -14,9 +14,32 @@ from .optim import FusedAdam
 from .pipeline.train_utils import EarlyStopping
 
 
+def draw_augmentation(n):
+    """The reference's random draws, in its order (run_training.py:398,401): per sample a flip index in {0, 1, 2}
+    then a rot90 count in {0..3}.  Returns one byte per sample, flip | rot << 2."""
+    ops = np.empty(n, dtype=np.uint8)
+    for i in range(n):
+        flip_idx = int(np.random.choice([0, 1, 2]))
+        rot_idx = int(np.random.choice([0, 1, 2, 3]))
+        ops[i] = flip_idx | (rot_idx << 2)
+    return ops
+
+
 def augment_batch(batch):
     """run_training.py:396-403 -- per-sample flip over {none, H, W} then rot90 k in {0..3}; consumes
-    np.random in the reference's order (two draws per sample)."""
+    np.random in the reference's order (two draws per sample).  CUDA batches of square patches are transformed by
+    one kernel launch (dmb_augment_batch) instead of two tiny kernels per sample; the result is bit-identical."""
+    if batch.is_cuda and batch.dim() == 4 and batch.shape[2] == batch.shape[3] and batch.dtype == t.float32:
+        import ctypes as C
+        from ._lib import call, ptr
+        from .engine import _stream
+        ops = t.from_numpy(draw_augmentation(len(batch))).to(batch.device, non_blocking=True)
+        src = batch.contiguous()
+        out = t.empty_like(src)
+        B, Cc, H, W = src.shape
+        call("dmb_augment_batch", ptr(src), ptr(ops), B, Cc, H, W, ptr(out), _stream())
+        batch.copy_(out)            # the reference transforms `batch` in place
+        return batch
     for idx_in_batch in range(len(batch)):
         img = batch[idx_in_batch]
         flip_idx = np.random.choice([0, 1, 2])

@@ -163,6 +163,12 @@ int dmb_bench_fma_conv(int32_t variant, int32_t blocks, int32_t iters, float* sc
 /* Number of kernels this library has launched in the process (reset != 0 zeroes it).        */
 long long dmb_launch_count(int reset);
 
+/* ---- training augmentation (run_training.py:396-403) ------------------------------------ */
+/* out[b] = rot90(flip(x[b], dims=(flip,)), k=rot, dims=[1, 2]) for every sample in one launch; ops_dev holds one
+ * byte per sample: flip in {0 none, 1 H, 2 W} | rot in {0..3} << 2 (drawn on the host in the reference's order).  */
+int dmb_augment_batch(const float* x, const uint8_t* ops_dev, int64_t batch, int32_t channels,
+                      int32_t height, int32_t width, float* out, void* stream);
+
 /* ---- time-matching loss (vq_vae.py:324-332; vae.py:321-336, :442-457) --------------------- */
 typedef struct dmb_time_matching {
     const float* mat;     /* (B, B) device tensor: pair weights (variant 0) or pair classes 0 / 1 / 2 (variant 1) */

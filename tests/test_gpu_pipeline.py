@@ -69,6 +69,26 @@ def test_bulk_encoder_matches_device_path():
         assert torch.equal(out["idx"], idx.reshape(37, -1).cpu())
 
 
+@pytest.mark.parametrize("dtype", [np.uint16, np.float64, np.float32])
+def test_bulk_encoder_raw_input_zscore_on_device(dtype):
+    """zscore=True: raw host patches (uint16 camera counts / float64 as pickled) -> device z-score -> encode, equal
+    to the oracle's restatement of patch_VAE.py:413-449 (zscore_patch in float64 on the host, float32 cast)."""
+    import gpu_util as U
+    from dynamorph_b200.bulk import BulkEncoder
+    g = Golden("vqvae_default")
+    st = g.state()
+    m = U.model_from_state(st).eval()
+    n = 21
+    raw = _raw_patches(n, 9).reshape(n, 2, 128, 128)
+    raw = np.clip(raw, 0, 65535).astype(dtype)
+    out = BulkEncoder(m, chunk=8, bn_mode="per_sample", zscore=True).encode(torch.from_numpy(raw))
+    torch.cuda.synchronize()
+    rb, ra = O.process_vae_arrays(raw.astype(np.float64).reshape(n, 2, 1, 128, 128), st, O.PER_SAMPLE)
+    assert U.rel(out["z_before"], rb) < U.REL_TOL
+    with pytest.raises(ValueError):
+        BulkEncoder(m, chunk=8).encode(torch.from_numpy(raw.astype(np.float64)))       # float32 only without zscore
+
+
 def test_checkpoint_roundtrip_with_reference_keys(tmp_path):
     """model.pt written by the drop-in loads into a fresh drop-in and keeps the reference's keys."""
     import gpu_util as U

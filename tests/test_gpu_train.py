@@ -245,3 +245,21 @@ def test_fused_trainer_matches_run_one_batch(name, use_graph, U):
             assert float((sd1[k] - sd2[k]).abs().max()) <= 1e-6 + 1e-5 * float(sd1[k].abs().max()), k
         else:
             assert int(sd1[k]) == int(sd2[k]), k
+
+
+@pytest.mark.parametrize("shape", [(37, 2, 128, 128), (5, 3, 16, 16)])
+def test_device_augmentation_matches_reference_loop(shape):
+    """dmb_augment_batch (one launch) == the reference's per-sample flip / rot90 loop (run_training.py:396-403) with
+    the same np.random stream: bit-identical, and the RNG is left in the same state."""
+    from dynamorph_b200.run_training import augment_batch
+    x = torch.randn(*shape)
+    np.random.seed(1234)
+    ref = augment_batch(x.clone())                 # CPU tensors take the reference's own loop
+    after_ref = np.random.randint(1 << 30)
+    np.random.seed(1234)
+    xg = x.cuda()
+    got = augment_batch(xg)
+    after_got = np.random.randint(1 << 30)
+    assert got.data_ptr() == xg.data_ptr()          # transformed in place, like the reference
+    assert torch.equal(got.cpu(), ref)
+    assert after_ref == after_got

@@ -29,6 +29,18 @@ import torch  # noqa: E402
 # algorithmic figures per patch, defaults (SURVEY.md section 8d / BASELINE.md section 4)
 ENC_BYTES = 131072 + 16384 + 16384          # x in, z_before out, z_after out
 ENC_FLOPS_ALGO = 22151168                    # 2 * (enc MACs + VQ MACs), reference layer structure
+ENC_FLOPS_EXEC = 15335424                    # what the kernels execute: enc.0 (1x1) folded into enc.1 (4x4), DESIGN.md section 4
+# DRAM bytes per patch of each kernel (dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture of an
+# 8192-patch eval encode step, profiles/r1_launches_encode_step.csv), for roofline.traffic
+NCU_DRAM_BYTES_PER_PATCH = {
+    "enc.0+enc.1 composite conv4x4s2": (1074855424 + 1024772864) / 8192,
+    "enc.4 conv4x4s2": (1073797888 + 503004928) / 8192,
+    "enc.7 conv4x4s2": (536928256 + 110697472) / 8192,
+    "enc.10 conv3x3": (134327296 + 85530368) / 8192,
+    "res conv3x3": (134286592 + 208604672) / 8192,
+    "res conv1x1": (402726656 + 105679872) / 8192,
+    "vq fused": (134263808 + 95976448) / 8192,
+}
 CHUNK = 16384                                # patches per step per GPU (2.1 GB of input >> 126 MB L2)
 
 
@@ -60,16 +72,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count(self, t0, t1):
+        return sum(1 for ts, _ in self.rows if t0 <= ts <= t1)
+
+    def stop(self, windows):
+        """windows: list of (t0, t1) perf_counter intervals during which the measured step was running."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if any(t0 <= ts <= t1 + 0.05 for t0, t1 in windows)]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -203,12 +220,16 @@ def layer_table(model, x, hbm_peak, fp32_tf):
         w = torch.randn(cin * ks * ks * cout, device=dev) * 0.05
         b = torch.zeros(9 * cout, device=dev)
         y = torch.empty(B, cout, H // s, H // s, device=dev)
+        # the flags each layer runs with in the eval-mode schedule (csrc/model.cu:run_encoder / run_res)
+        in_relu = 1 if name == "res conv3x3" else 0
+        out_relu = 0 if name in ("enc.10 conv3x3", "res conv1x1") else 1
+        skip = torch.randn(B, cout, H // s, H // s, device=dev) if name == "res conv1x1" else None
         fn = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
-                          None, None, 0, 0, None, 1, st)
+                          None, None, 0, in_relu, ptr(skip), out_relu, st)
         fn(); torch.cuda.synchronize()
         ms = time_events(fn, 5)
         macs = (H // s) ** 2 * cout * cin * ks * ks
-        byts = (cin * H * H + cout * (H // s) ** 2) * 4
+        byts = (cin * H * H + cout * (H // s) ** 2 * (2 if skip is not None else 1)) * 4
         rows.append({"kernel": name, "launches_per_step": model.num_residual_layers if name.startswith("res") else 1,
                      "ms": ms, "gbs": byts * B / ms / 1e6, "tflops": 2 * macs * B / ms / 1e9,
                      "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "fp32_frac": 2 * macs * B / ms / 1e9 / fp32_tf})
@@ -264,23 +285,42 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     lib.dmb_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    w1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     launches = lib.dmb_launch_count(0)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    windows = [(w0, w1)]
+    # nvidia-smi samples every 100 ms: a short timed region can fall between two samples.  Then the SAME step keeps
+    # running (untimed) until a few samples exist, and the clock record says so.
+    extra = 0
+    if rank == 0:
+        p0 = time.perf_counter()
+        while sampler.proc is not None and sampler.count(w0, w1) + sampler.count(p0, time.perf_counter()) < 4 \
+                and time.perf_counter() - p0 < 3.0:
+            step()
+            torch.cuda.synchronize()
+            extra += 1
+        if extra:
+            windows.append((p0, time.perf_counter()))
+        clocks = sampler.stop(windows)
+        clocks["window"] = "timed region" + (f" + {extra} more identical untimed steps (timed region shorter than "
+                                             "the 100 ms sampling period x 4)" if extra else "")
+    barrier()
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -314,6 +354,25 @@ def run_ours(args):
     e2e_value = world * e2e_steps * chunk / (float(t[0]) * 1e-3)
     h2d = x_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out.values())
+    # ---- the same call fed RAW uint16 patches (camera counts), z-scored on the device in front of the encoder
+    # (pipeline/train_utils.py:252-274 on the GPU): half the host->device bytes of the float32 path
+    enc16 = BulkEncoder(model, chunk=min(chunk, 4096), bn_mode="eval", zscore=True)
+    x16 = torch.empty(chunk, 2, 128, 128, dtype=torch.uint16, pin_memory=True)
+    x16.copy_((x * 2000.0 + 30000.0).clamp_(0, 65535).to(torch.uint16))
+    enc16.encode(x16, out)
+    torch.cuda.synchronize()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        enc16.encode(x16, out)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e16_value = world * e2e_steps * chunk / (float(t[0]) * 1e-3)
+    enc.encode(x_host, out)          # leave the float32 result in `out` for the spot-check below
+    torch.cuda.synchronize()
     # parity spot-check of what came back to the host against the device-resident run
     step("eval")
     torch.cuda.synchronize()
@@ -355,7 +414,9 @@ def run_ours(args):
                    "l2_policy": f"inputs larger than L2 ({chunk * 131072 / 1e9:.2f} GB per step vs 126 MB)"},
         "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "dynamorph_b200.bulk.BulkEncoder.encode (pinned host -> HBM -> pinned host, 3-stream pipeline)",
-                "host_matches_device": same},
+                "host_matches_device": same,
+                "raw_uint16_input": {"value": e2e16_value, "unit": "patches/s", "h2d_bytes_per_step": x16.numel() * 2,
+                                     "note": "BulkEncoder(zscore=True): uint16 patches in, z-score on the device"}},
         "gpu_launches": int(launches),
         "train_step": {"ms": train_ms, "batch_per_gpu": tb, "global_batch": tb * world,
                        "patches_per_s": tb * world / (train_ms * 1e-3), "dtype": "f32",
@@ -371,8 +432,13 @@ def run_ours(args):
         rows = layer_table(model, x[:min(chunk, 8192)], hbm_peak, fp32_tf)
         total_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
         dom = max(rows, key=lambda r: r["ms"] * r["launches_per_step"])
+        nb = min(chunk, 8192)
+        traffic = NCU_DRAM_BYTES_PER_PATCH.get(dom["kernel"])
         line["roofline"] = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                            "frac": dom["hbm_frac"], "traffic": None, "kernel": dom["kernel"],
+                            "frac": dom["hbm_frac"], "traffic": traffic * nb if traffic else None,
+                            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per patch "
+                                              "(profiles/r1_launches_encode_step.csv) x patches per launch",
+                            "algorithmic_bytes": dom["gbs"] * 1e9 * dom["ms"] * 1e-3, "kernel": dom["kernel"],
                             "peak_source": peak_src,
                             "binding_roof": "fp32_fma (CUDA cores): the schema's bound is hbm|tensor, but this kernel "
                                             "is FP32-FMA bound -- see fp32 fields",
@@ -381,6 +447,8 @@ def run_ours(args):
                             "share_of_step": dom["ms"] * dom["launches_per_step"] / total_ms}
         line["whole_step"] = {"hbm_frac_algorithmic": value / world * ENC_BYTES / 1e9 / hbm_peak,
                               "fp32_frac_algorithmic_flops": value / world * ENC_FLOPS_ALGO / 1e12 / fp32_tf,
+                              "fp32_frac_executed_flops": value / world * ENC_FLOPS_EXEC / 1e12 / fp32_tf,
+                              "flops_per_patch_executed": ENC_FLOPS_EXEC,
                               "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
         line["layers"] = rows
         if world == 1 and not args.no_cpu:

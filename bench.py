@@ -31,16 +31,25 @@ ENC_BYTES = 131072 + 16384 + 16384          # x in, z_before out, z_after out
 ENC_FLOPS_ALGO = 22151168                    # 2 * (enc MACs + VQ MACs), reference layer structure
 ENC_FLOPS_EXEC = 15335424                    # what the kernels execute: enc.0 (1x1) folded into enc.1 (4x4), DESIGN.md section 4
 # DRAM bytes per patch of each kernel (dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture of an
-# 8192-patch eval encode step, profiles/r1_launches_encode_step.csv), for roofline.traffic
-NCU_DRAM_BYTES_PER_PATCH = {
-    "enc.0+enc.1 composite conv4x4s2": (1074855424 + 1024772864) / 8192,
-    "enc.4 conv4x4s2": (1073797888 + 503004928) / 8192,
-    "enc.7 conv4x4s2": (536928256 + 110697472) / 8192,
-    "enc.10 conv3x3": (134327296 + 85530368) / 8192,
-    "res conv3x3": (134286592 + 208604672) / 8192,
-    "res conv1x1": (402726656 + 105679872) / 8192,
-    "vq fused": (134263808 + 95976448) / 8192,
-}
+# 8192-patch eval encode step, profiles/r1_launches_encode_step.csv: launches in schedule order), for roofline.traffic
+def ncu_dram_bytes_per_patch():
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_launches_encode_step.csv")
+    order = ["enc.0+enc.1 composite conv4x4s2", "enc.4 conv4x4s2", "enc.7 conv4x4s2", "enc.10 conv3x3", "res conv3x3",
+             "res conv1x1", "res conv3x3", "res conv1x1", "vq fused"]
+    try:
+        rows = list(csv.reader(open(path)))
+        h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+        hdr = rows[h]
+        tot = {}
+        for r in rows[h + 1:]:
+            if len(r) == len(hdr) and r[hdr.index("Metric Name")].startswith("dram__bytes_"):
+                tot[int(r[0])] = tot.get(int(r[0]), 0.0) + float(r[hdr.index("Metric Value")])
+        return {order[i]: v / 8192 for i, v in sorted(tot.items()) if i < len(order)}
+    except Exception:
+        return {}
+
+
 CHUNK = 16384                                # patches per step per GPU (2.1 GB of input >> 126 MB L2)
 
 
@@ -433,7 +442,7 @@ def run_ours(args):
         total_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
         dom = max(rows, key=lambda r: r["ms"] * r["launches_per_step"])
         nb = min(chunk, 8192)
-        traffic = NCU_DRAM_BYTES_PER_PATCH.get(dom["kernel"])
+        traffic = ncu_dram_bytes_per_patch().get(dom["kernel"])
         line["roofline"] = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
                             "frac": dom["hbm_frac"], "traffic": traffic * nb if traffic else None,
                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per patch "

@@ -56,6 +56,34 @@ def test_vq_ties_first_index(U):
     assert U.rel(loss, g.t("loss")) < U.REL_TOL and U.rel(ppl, g.t("perplexity")) < U.REL_TOL
 
 
+@pytest.mark.parametrize("D,K", [(16, 64), (64, 512), (32, 7)])
+def test_vq_search_exact_on_adversarial_codebooks(D, K, U):
+    """The argmin must reproduce torch.argmax(-distances) of vq_vae.py:65-66 bit for bit on the hard cases: exactly
+    duplicated codebook rows (lowest index wins), rows that differ by 1e-7, latents sitting on a code, latents
+    equidistant from two codes.  (A two-phase search -- |e|^2 - 2 z.e scan + exact re-check of the candidates inside
+    an error margin -- passed this test too but was not faster under SIMT than the direct form, and was dropped.)"""
+    from dynamorph_b200.engine import vq_indices
+    g = torch.Generator().manual_seed(D * 1000 + K)
+    cb = torch.randn(K, D, generator=g)
+    if K >= 32:
+        cb[10:16] = cb[10]                                              # exact duplicates: lowest index must win
+        cb[20:28] = cb[20] + torch.randn(8, D, generator=g) * 1e-7      # near duplicates: > 4 candidates in the margin
+    B, H = 6, 16
+    z = torch.randn(B, D, H, H, generator=g) * 1.3
+    flat = z.permute(0, 2, 3, 1).reshape(-1, D)
+    n = flat.shape[0]
+    pick = torch.randint(0, K, (n,), generator=g)
+    near = cb[pick] + torch.randn(n, D, generator=g) * 1e-6
+    sel = torch.rand(n, generator=g)
+    flat = torch.where((sel < 0.4).unsqueeze(1), near, flat)             # 40 % of the positions hug a code
+    mid = 0.5 * (cb[pick] + cb[(pick + 1) % K])
+    flat = torch.where((sel > 0.9).unsqueeze(1), mid, flat)              # 10 % sit between two codes
+    z = flat.reshape(B, H, H, D).permute(0, 3, 1, 2).contiguous()
+    ref = O.vq_indices(z, cb)
+    got = vq_indices(z.cuda(), cb.cuda()).cpu().long()
+    assert torch.equal(got, ref), int((got != ref).sum())
+
+
 def test_eval_encode(golden_case, U):
     g = golden_case
     st = g.state()

@@ -213,6 +213,8 @@ class Engine:
         if Cin != s.num_inputs:
             raise RuntimeError(f"expected {s.num_inputs} input channels, got {Cin}")
         zb = torch.empty(B, d.value, lh.value, lw.value, dtype=torch.float32, device=x.device)
+        if B == 0:                       # empty batch: empty latents, like the reference's modules
+            return zb
         ws, n = self.workspace(s, B, mode, 0)
         upd = ptr(self._flat_bn) if mode == BN_BATCH else None
         call("dmb_encoder_forward", C.byref(s), ptr(packed), ptr(x), B, mode, ptr(zb), upd, ptr(ws), n, _stream())
@@ -240,6 +242,10 @@ class Engine:
             zb = torch.empty(B, d.value, lh.value, lw.value, dtype=torch.float32, device=x.device)
             za = torch.empty_like(zb)
             idx = torch.empty(B, lh.value, lw.value, dtype=torch.int32, device=x.device)
+        if B == 0 and not want_stats:
+            return zb[:0], za[:0], idx[:0]
+        if B == 0:
+            raise RuntimeError("encode(want_stats=True) needs at least one patch")
         ws, n = self.workspace(s, B, mode, 0)
         stats = None
         if want_stats:
@@ -261,6 +267,8 @@ class Engine:
         mode = self.bn_mode(B, bn_mode)
         packed = self.packed(mode, H, W)
         out = torch.empty(B, s.num_inputs, H, W, dtype=torch.float32, device=z.device)
+        if B == 0:
+            return out
         ws, n = self.workspace(s, B, mode, 1)
         upd = ptr(self._flat_bn) if mode == BN_BATCH else None
         call("dmb_decoder_forward", C.byref(s), ptr(packed), ptr(z), B, mode, ptr(out), upd, ptr(ws), n, _stream())

@@ -32,7 +32,7 @@ class FusedTrainer:
         self.grad = torch.zeros_like(flat)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=flat.device)
         self.bc_dev = torch.zeros(2, dtype=torch.float32, device=flat.device)
-        self.losses = torch.zeros(4, dtype=torch.float32, device=flat.device)
+        self.losses = torch.zeros(8, dtype=torch.float32, device=flat.device)
         self._key = None
         self._graphs = None
         self._static = None
@@ -43,11 +43,13 @@ class FusedTrainer:
         eng = self.eng
         s, B = st["spec"], st["x"].shape[0]
         call("dmb_pack_weights", C.byref(s), ptr(eng._flat), ptr(eng._flat_bn), BN_BATCH, ptr(st["packed"]), _stream())
-        call("dmb_train_forward", C.byref(s), ptr(st["packed"]), ptr(eng._flat), ptr(st["x"]), ptr(st["mask"]), st["mc"],
-             ptr(st["cv"]), B, ptr(st["decoded"]), ptr(self.losses), ptr(eng._flat_bn), ptr(st["ws"]), st["nws"], _stream())
+        tm = C.byref(st["tm"]) if st["tm"] is not None else None
+        call("dmb_train_forward_tm", C.byref(s), ptr(st["packed"]), ptr(eng._flat), ptr(st["x"]), ptr(st["mask"]), st["mc"],
+             ptr(st["cv"]), B, tm, ptr(st["decoded"]), ptr(self.losses), ptr(eng._flat_bn), ptr(st["ws"]), st["nws"],
+             _stream())
         eng._flat_nbt += 1
-        call("dmb_train_backward", C.byref(s), ptr(st["packed"]), ptr(eng._flat), ptr(st["x"]), ptr(st["mask"]), st["mc"],
-             ptr(st["cv"]), ptr(st["decoded"]), B, 1.0, ptr(self.grad), ptr(st["ws"]), st["nws"], _stream())
+        call("dmb_train_backward_tm", C.byref(s), ptr(st["packed"]), ptr(eng._flat), ptr(st["x"]), ptr(st["mask"]), st["mc"],
+             ptr(st["cv"]), ptr(st["decoded"]), B, tm, 1.0, ptr(self.grad), ptr(st["ws"]), st["nws"], _stream())
 
     def _adam(self):
         eng = self.eng
@@ -59,11 +61,11 @@ class FusedTrainer:
         if self.world > 1:
             torch.distributed.all_reduce(self.grad, group=self.pg)
 
-    def _prepare(self, x, mask):
+    def _prepare(self, x, mask, tm_mat=None):
         eng = self.eng
         B, Cin, H, W = x.shape
         mc = 0 if mask is None else mask.shape[1]
-        key = (B, Cin, H, W, mc, eng._flat.data_ptr())
+        key = (B, Cin, H, W, mc, eng._flat.data_ptr(), tm_mat is not None)
         if key == self._key:
             return
         eng.flatten()
@@ -79,7 +81,14 @@ class FusedTrainer:
             "cv": self.model.channel_var.data.reshape(-1).contiguous().clone(),
             "decoded": torch.empty_like(x), "packed": torch.empty(n.value, dtype=torch.float32, device=dev),
             "ws": torch.empty(nbytes.value, dtype=torch.uint8, device=dev),
+            "tm": None, "tm_mat": None,
         }
+        if tm_mat is not None:
+            from .matching import descriptor
+            if tuple(tm_mat.shape) != (B, B):
+                raise AssertionError("sim_mat.shape == time_matching_mat.shape")      # vq_vae.py:329
+            # static (B, B) buffer the captured graph reads; step() refreshes its contents
+            self._static["tm"], self._static["tm_mat"] = descriptor(self.model, torch.empty(B, B, device=dev))
         self._key = key
         self._graphs = None
 
@@ -110,17 +119,20 @@ class FusedTrainer:
         self._graphs = (g1, g2)
 
     # ------------------------------------------------------------------ public
-    def step(self, x: torch.Tensor, batch_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def step(self, x: torch.Tensor, batch_mask: Optional[torch.Tensor] = None,
+             time_matching_mat: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimisation step on batch x.  Returns a device tensor
-        [recon_loss, commitment_loss, total_loss, perplexity] (no host sync)."""
+        [recon_loss, commitment_loss, total_loss, perplexity, time_matching_loss, 0, 0, 0] (no host sync)."""
         x = _require_cuda(x, "batch")
         if batch_mask is not None:
             batch_mask = _require_cuda(batch_mask, "batch_mask")
-        self._prepare(x, batch_mask)
+        self._prepare(x, batch_mask, time_matching_mat)
         st = self._static
         st["x"].copy_(x)
         if batch_mask is not None:
             st["mask"].copy_(batch_mask)
+        if time_matching_mat is not None:
+            st["tm_mat"].copy_(_require_cuda(time_matching_mat, "time_matching_mat"))
         if self.use_graph:
             if self._graphs is None:
                 self._capture()

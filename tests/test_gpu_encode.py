@@ -189,3 +189,25 @@ def test_ragged_batches_match_oracle(B, U, golden_default):
         zb, za, idx = m.encode_latents(x.cuda(), "eval")
     assert U.rel(zb, ref) < U.REL_TOL
     U.check_indices(idx, ref, st["vq.w.weight"], O.vq_indices(ref, st["vq.w.weight"]), f"B={B}")
+
+
+def test_empty_and_single_patch_batches(U):
+    """Edge cases of the batch axis: B = 0 returns empty tensors (torch semantics of the reference modules; no kernel
+    launches), B = 1 and an odd B equal the corresponding rows of a larger batch bit for bit in the patch-independent
+    BatchNorm modes (ragged tails of a chunked bulk encode)."""
+    from dynamorph_b200.bulk import BulkEncoder
+    g = Golden("vqvae_default")
+    m = U.model_from_state(g.state()).eval()
+    x = O.synthetic_patches(9, 5).cuda()
+    for mode in ("eval", "per_sample"):
+        zb, za, idx = m.encode_latents(x, mode)
+        e = m.encode_latents(x[:0], mode)
+        assert e[0].shape == (0, 16, 16, 16) and e[1].shape == (0, 16, 16, 16) and e[2].shape[0] == 0
+        for n in (1, 7):
+            zb1, za1, idx1 = m.encode_latents(x[:n].contiguous(), mode)
+            assert torch.equal(zb1, zb[:n]) and torch.equal(za1, za[:n]) and torch.equal(idx1, idx[:n])
+    with torch.no_grad():
+        assert m.enc(x[:0]).shape == (0, 16, 16, 16)
+        assert m.dec(torch.empty(0, 16, 16, 16, device="cuda")).shape == (0, 2, 128, 128)
+    out = BulkEncoder(m, chunk=4).encode(torch.empty(0, 2, 128, 128))
+    assert out["z_before"].shape == (0, 4096) and out["idx"].shape == (0, 256)

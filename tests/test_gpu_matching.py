@@ -114,3 +114,31 @@ def test_train_step_with_time_matching(name, cls_name, variant, weight, U):
         assert e < bound, (k, e, ties)
     with pytest.raises(AssertionError):
         m(x.cuda(), time_matching_mat=mat[:-1].cuda())     # vq_vae.py:329 `assert sim_mat.shape == time_matching_mat.shape`
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_trainer_with_time_matching(use_graph, U):
+    """FusedTrainer.step(x, time_matching_mat=...) (C-ABI calls on flat buffers, optionally one CUDA graph) walks the
+    same loss curve as run_one_batch + FusedAdam on the autograd path."""
+    import numpy as np
+    from dynamorph_b200.optim import FusedAdam
+    from dynamorph_b200.run_training import run_one_batch
+    from dynamorph_b200.trainer import FusedTrainer
+    g = Golden("vqvae_default")
+    st = g.state()
+    x = g.t("x_train").cuda()
+    mat = _mat(x.shape[0], 1).cuda()
+    m1 = _model(U, st, "VQ_VAE_z16", 2.0).train()
+    opt = FusedAdam(m1, lr=1e-3)
+    tl = {}
+    for _ in range(3):
+        m1, tl = run_one_batch(m1, x.clone(), tl, model_kwargs={"time_matching_mat": mat}, optimizer=opt,
+                               transform=None, training=True)
+    m2 = _model(U, st, "VQ_VAE_z16", 2.0).train()
+    tr = FusedTrainer(m2, lr=1e-3, use_graph=use_graph)
+    curve, tms = [], []
+    for _ in range(3):
+        l = tr.step(x, time_matching_mat=mat).tolist()
+        curve.append(l[2]); tms.append(l[4])
+    assert np.allclose(curve, tl["total_loss"], rtol=1e-5)
+    assert np.allclose(tms, tl["time_matching_loss"], rtol=1e-5) and tms[0] != 0.0

@@ -86,3 +86,36 @@ def test_run_vae_cli_rejects_other_methods(tmp_path):
         run_VAE.main("assemble", str(tmp_path), None, cfg, "c.yml")
     with pytest.raises(AttributeError):
         run_VAE.main("process", None, None, cfg, "c.yml")
+
+
+def test_augmentation_draws_follow_the_reference_rng_order():
+    """draw_augmentation (the host half of the one-launch device augmentation) consumes np.random exactly like the
+    per-sample loop of run_training.py:396-403: applying its (flip, rot) bytes reproduces the oracle's augment_batch
+    on the same stream, and the CPU fallback of augment_batch is that loop itself."""
+    from dynamorph_b200.run_training import augment_batch, draw_augmentation
+    x = torch.randn(9, 2, 8, 8)
+    ref = O.augment_batch(x, np.random.RandomState(77))
+    np.random.seed(77)
+    ops = draw_augmentation(9)
+    nxt = np.random.randint(1 << 30)
+    out = x.clone()
+    for i, op in enumerate(ops):
+        img = x[i]
+        if op & 3:
+            img = torch.flip(img, dims=(int(op & 3),))
+        out[i] = torch.rot90(img, k=int(op >> 2), dims=[1, 2])
+    assert torch.equal(out, ref)
+    np.random.seed(77)
+    assert torch.equal(augment_batch(x.clone()), ref)
+    assert np.random.randint(1 << 30) == nxt
+
+
+def test_time_matching_descriptor_variants():
+    """VQ_VAE carries no w_a / margin (sum variant, vq_vae.py:324-332); VQ_VAE_z16 / z32 do (hinged mean,
+    vae.py:321-336).  The descriptor needs a CUDA matrix: CPU input fails loudly."""
+    from dynamorph_b200.HiddenStateExtractor.vq_vae import VQ_VAE
+    from dynamorph_b200.HiddenStateExtractor.vae import VQ_VAE_z16
+    from dynamorph_b200.matching import descriptor
+    assert not hasattr(VQ_VAE(), "w_a") and hasattr(VQ_VAE_z16(), "w_a")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        descriptor(VQ_VAE_z16(), torch.zeros(4, 4))

@@ -4,6 +4,7 @@
 //   z32: HiddenStateExtractor/vae.py:401-414
 #include <stdarg.h>
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 #include "model.h"
@@ -543,12 +544,58 @@ struct GradT {            // dL/d(conv output) = A*g + Bc*y + Cc  (A == nullptr:
     const float* A = nullptr; const float* Bc = nullptr; const float* Cc = nullptr;
 };
 
+// Weight gradients run on a library-owned side stream, concurrently with the data-gradient chain on the caller's
+// stream: at training batch sizes every backward kernel is a few hundred CTAs and latency-bound, and the weight
+// gradient of a layer is off the critical path (only the data gradient feeds the next layer).  Fork / join through
+// events, which a CUDA-graph capture of the caller's stream records as ordinary dependencies.  One side stream per
+// host thread and device; DMB_TRAIN_OVERLAP=0 keeps everything on the caller's stream.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+int side_stream(SideStream** out) {
+    static thread_local SideStream side[64];
+    *out = nullptr;
+    const char* e = getenv("DMB_TRAIN_OVERLAP");
+    if (e && e[0] == '0') return 0;
+    int dev = 0;
+    DMB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return 0;
+    SideStream& ss = side[dev];
+    if (!ss.s) {
+        DMB_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+        DMB_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        DMB_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    }
+    *out = &ss;
+    return 0;
+}
+
 struct Bwd {
     Ctx& c;
     const float* params;
     float* grads;
     cudaStream_t st;
+    SideStream* side = nullptr;
+    bool forked = false;
     bool ps() const { return c.per_sample(); }
+    // stream for the next weight-gradient launch: the side stream once it has seen everything issued so far
+    int wgrad_stream(cudaStream_t* out) {
+        if (!side) { *out = st; return 0; }
+        DMB_CUDA(cudaEventRecord(side->fork, st));
+        DMB_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+        forked = true;
+        *out = side->s;
+        return 0;
+    }
+    int join() {
+        if (side && forked) {
+            DMB_CUDA(cudaEventRecord(side->join, side->s));
+            DMB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+            forked = false;
+        }
+        return 0;
+    }
 
     // weight / bias gradient of conv layer li (input activation xin, H x W).  For ConvTranspose2d the roles
     // are swapped: `G` must be a plain tensor (no BN after the decoder's ConvT in z16) of shape (Cout,2H,2W).
@@ -572,7 +619,9 @@ struct Bwd {
         const int pf = wgrad_partial_floats(a, &ncta);
         DMB_CHECK(pf > 0 && (size_t)pf * ncta <= c.w.wg_part_floats, "wgrad scratch too small for layer %d", li);
         float* db = (with_bias && !l.transposed) ? grads + l.b_off : nullptr;
-        return wgrad(a, grads + l.w_off, db, nullptr, st);
+        cudaStream_t sw;
+        DMB_TRY(wgrad_stream(&sw));
+        return wgrad(a, grads + l.w_off, db, nullptr, sw);
     }
 
     // data gradient of conv layer li: G (at the layer's output, Ho x Wo) -> gout (at its input, H x W), gated by
@@ -708,6 +757,7 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
     Workspace& w = c.w;
     cudaStream_t st = c.st;
     Bwd B{c, params, grads, st};
+    DMB_TRY(side_stream(&B.side));
     const int H = m.height, W = m.width, lh = L.lh, lw = L.lw;
     const int h = m.num_hiddens, h2 = h / 2, h4 = h / 4;
     int nb = 0;
@@ -776,11 +826,13 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
         int ncta = 0;
         const int pf = wgrad_partial_floats(a, &ncta);
         DMB_CHECK(pf > 0 && (size_t)pf * ncta <= w.wg_part_floats, "wgrad scratch too small for the head");
-        DMB_TRY(wgrad(a, nullptr, nullptr, w.dweff, st));
+        cudaStream_t sw;
+        DMB_TRY(B.wgrad_stream(&sw));
+        DMB_TRY(wgrad(a, nullptr, nullptr, w.dweff, sw));
         DMB_TRY(composite_chain(w.dweff, params + l.w0_off, params + l.b0_off, params + l.w_off, l.cin, l.cmid,
-                                grads + l.w0_off, grads + l.b0_off, grads + l.w_off, grads + l.b_off, st));
+                                grads + l.w0_off, grads + l.b0_off, grads + l.w_off, grads + l.b_off, sw));
     }
-    return 0;
+    return B.join();
 }
 
 // vae.py:401-414.  enc: conv4s2 -> BN -> ReLU -> conv4s2 -> BN -> ResidualBlock;  dec: ResidualBlock -> ConvT ->
@@ -792,6 +844,7 @@ int run_backward_z32(Ctx& c, const float* params, const float* x, const float* m
     Workspace& w = c.w;
     cudaStream_t st = c.st;
     Bwd B{c, params, grads, st};
+    DMB_TRY(side_stream(&B.side));
     const int H = m.height, W = m.width, lh = L.lh, lw = L.lw;
     const int h = m.num_hiddens;
     const int P = lh * lw;
@@ -847,7 +900,7 @@ int run_backward_z32(Ctx& c, const float* params, const float* x, const float* m
     DMB_TRY(B.bn_bwd(L.e1, nb, (int64_t)(H / 2) * (W / 2), &G1, w.g_y1, w.y1));
     Act xin; xin.p = x;
     DMB_TRY(B.wgrad_layer(L.e1, G1, xin, false, H, W, true));
-    return 0;
+    return B.join();
 }
 
 }  // namespace

@@ -183,6 +183,12 @@ struct TmaConvArgs {
     int out_relu;
     double* stats;
     int B;
+    // data-gradient epilogue (training backward): ReLU gate of the layer below and BatchNorm-backward sums
+    const float* mask_src;   // (B, Cout, Ho, Wo): o = 0 where mask_src * mask_s[c] + mask_t[c] <= 0
+    const float* mask_s;     // nullptr = identity; [Cout] or [B][Cout]
+    const float* mask_t;
+    int mask_per_sample;
+    const float* stat_src;   // nullptr: stats = (sum o, sum o^2); else (sum o, sum o * stat_src)
 };
 
 template <class C>
@@ -376,6 +382,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
     const float* bias_u = a.bias + cgz * CC;
     float* y_u = a.y + (size_t)(cgz * CC) * (C::HO * C::WO);
     const float* skip_u = a.skip ? a.skip + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
+    const float* mask_u = a.mask_src ? a.mask_src + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
+    const float* stat_u = a.stat_src ? a.stat_src + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
+    const float* mask_s_u = a.mask_s ? a.mask_s + cgz * CC : nullptr;
+    const float* mask_t_u = a.mask_s ? a.mask_t + cgz * CC : nullptr;
     const int rc = (oy == 0) ? 0 : ((oy == C::HO - 1) ? 2 : 1);
     float ssum[CO_T], ssq[CO_T];
 #pragma unroll
@@ -395,6 +405,21 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
         if (sx == 0) o[0] = acc[c][0] + bl;
         if (sx == C::SPR - 1) o[PW - 1] = acc[c][PW - 1] + br;
         const size_t off = (((size_t)b * C::COUT + co) * C::HO + oy) * C::WO + sx * PW;
+        if (mask_u && live) {
+            float ms = 1.f, mt = 0.f;
+            if (mask_s_u) {
+                const size_t mi = (a.mask_per_sample ? (size_t)b * C::COUT : 0) + co;
+                ms = __ldg(mask_s_u + mi); mt = __ldg(mask_t_u + mi);
+            }
+#pragma unroll
+            for (int i = 0; i < PW / 4; ++i) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask_u + off) + i);
+                if (!(fmaf(m4.x, ms, mt) > 0.f)) o[4 * i] = 0.f;
+                if (!(fmaf(m4.y, ms, mt) > 0.f)) o[4 * i + 1] = 0.f;
+                if (!(fmaf(m4.z, ms, mt) > 0.f)) o[4 * i + 2] = 0.f;
+                if (!(fmaf(m4.w, ms, mt) > 0.f)) o[4 * i + 3] = 0.f;
+            }
+        }
         if (skip_u && live) {
 #pragma unroll
             for (int i = 0; i < PW / 4; ++i) {
@@ -413,8 +438,20 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
         }
         float s = 0.f, q = 0.f;
         if (a.stats) {
+            if (stat_u) {
+                if (live) {
 #pragma unroll
-            for (int p = 0; p < PW; ++p) { s += o[p]; q = fmaf(o[p], o[p], q); }
+                    for (int i = 0; i < PW / 4; ++i) {
+                        const float4 y4 = __ldg(reinterpret_cast<const float4*>(stat_u + off) + i);
+                        s += o[4 * i] + o[4 * i + 1] + o[4 * i + 2] + o[4 * i + 3];
+                        q = fmaf(o[4 * i], y4.x, q); q = fmaf(o[4 * i + 1], y4.y, q);
+                        q = fmaf(o[4 * i + 2], y4.z, q); q = fmaf(o[4 * i + 3], y4.w, q);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < PW; ++p) { s += o[p]; q = fmaf(o[p], o[p], q); }
+            }
         }
         ssum[c] = s; ssq[c] = q;
     }
@@ -475,9 +512,10 @@ template <class C>
 int launch_tma(const ConvFwdArgs& a, cudaStream_t st) {
     PFN_cuTensorMapEncodeTiled enc = get_encoder();
     DMB_CHECK(enc != nullptr, "conv_tma: cuTensorMapEncodeTiled is not available from this driver");
-    DMB_CHECK((reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(a.y) & 15) == 0,
-              "conv_tma: x, y and w must be 16-byte aligned");
+    // TMA / bulk copies need 16-byte aligned bases; anything else is left to the generic kernel
+    if ((reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15) ||
+        (reinterpret_cast<uintptr_t>(a.y) & 15))
+        return 1;
     CUtensorMap map;
     const cuuint64_t gdim[4] = {(cuuint64_t)C::W, (cuuint64_t)C::H, (cuuint64_t)a.B, (cuuint64_t)C::CIN};
     const cuuint64_t gstr[3] = {(cuuint64_t)C::W * 4, (cuuint64_t)C::W * C::H * C::CIN * 4, (cuuint64_t)C::W * C::H * 4};
@@ -492,6 +530,8 @@ int launch_tma(const ConvFwdArgs& a, cudaStream_t st) {
     k.y = a.y; k.w = a.w; k.bias = a.bias; k.bias_classes = a.bias_classes;
     k.in_scale = a.in_scale; k.in_shift = a.in_shift; k.in_per_sample = a.in_per_sample; k.in_relu = a.in_relu;
     k.skip = a.skip; k.out_relu = a.out_relu; k.stats = a.stats; k.B = a.B;
+    k.mask_src = a.mask_src; k.mask_s = a.mask_s; k.mask_t = a.mask_t; k.mask_per_sample = a.mask_per_sample;
+    k.stat_src = a.stat_src;
 
     auto kern = conv_tma_kernel<C>;
     static bool configured[64] = {false};     // per instantiation, per device

@@ -9,9 +9,9 @@ namespace {
     X(4, 2, 2, 32, 128) X(4, 2, 32, 64, 64) X(4, 2, 64, 64, 32) X(3, 1, 64, 64, 16) X(3, 1, 64, 32, 16)            \
     X(1, 1, 32, 64, 16) X(3, 1, 64, 64, 32) X(1, 1, 64, 64, 32)
 
-bool tma_plain(const ConvFwdArgs& a) {
-    return a.x2 == nullptr && a.mask_src == nullptr && a.stat_src == nullptr && a.in_b == nullptr;
-}
+// everything but the dual-tensor transform on load (x2 / in_b: BatchNorm backward folded into the load of a data
+// gradient) -- callers materialise that gradient first when they want this kernel (csrc/model.cu:dgrad_layer)
+bool tma_plain(const ConvFwdArgs& a) { return a.x2 == nullptr && a.in_b == nullptr; }
 
 // The constant-pool variant costs one extra device-to-device copy in the stream (a few microseconds): only for
 // launches with enough work to hide it, never while the stream is being captured into a graph (the copy would be

@@ -281,6 +281,7 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
         w.vq_part = bp.take<float>((size_t)w.vq_part_rows * m.num_embeddings * h);
         w.tm_scratch = bp.take<float>(tm_scratch_floats(B, (int64_t)h * lat));
         w.g_tm = bp.take<float>(B * h * lat);
+        w.g_tmp = bp.take<float>(B * (h > rh ? h : rh) * lat);
     }
     w.vq_stats = bp.take<double>(2 + m.num_embeddings);
     w.recon_sum = bp.take<double>(4);
@@ -579,6 +580,8 @@ struct Bwd {
     SideStream* side = nullptr;
     bool forked = false;
     bool ps() const { return c.per_sample(); }
+    int L_lat_h() const { return c.L.lh; }
+    int L_lat_w() const { return c.L.lw; }
     // stream for the next weight-gradient launch: the side stream once it has seen everything issued so far
     int wgrad_stream(cudaStream_t* out) {
         if (!side) { *out = st; return 0; }
@@ -655,8 +658,19 @@ struct Bwd {
         } else {
             a.ks = l.ks; a.stride = 1; a.H = H; a.W = W; a.Ho = H; a.Wo = W;
         }
+        // The TMA kernel has no dual-tensor transform on load.  Where it has an instantiation for this geometry the
+        // BatchNorm-backward gradient  A*g + Bc*y + Cc  is materialised first (one small elementwise launch; the
+        // latent-resolution tensors are a few MB at training batch sizes) and fed to it as a plain input.
+        if (G.A && !ps() && c.w.g_tmp && a.H == L_lat_h() && a.W == L_lat_w() &&
+            conv_tma_bands(a.ks, a.stride, a.Cin, a.Cout, a.H, a.W) > 0) {
+            AffineAddArgs aa{};
+            aa.a = G.g; aa.sa = G.A; aa.ta = G.Cc; aa.b = G.y; aa.sb = G.Bc; aa.tb = zero;
+            aa.per_sample = 0; aa.out = c.w.g_tmp; aa.B = c.B; aa.C = a.Cin; aa.HW = a.H * a.W;
+            DMB_TRY(affine_add(aa, st));
+            a.x = c.w.g_tmp; a.x2 = nullptr; a.in_scale = nullptr; a.in_b = nullptr; a.in_shift = nullptr;
+        }
         if (nbands) {
-            const bool plain = !a.x2 && !a.mask_src && !a.stat_src && !a.in_b;
+            const bool plain = !a.x2 && !a.in_b;
             *nbands = conv_fwd_bands(a.ks, a.stride, a.Cin, a.Cout, a.Ho, a.Wo, plain, c.B);
         }
         return conv_fwd(a, st);

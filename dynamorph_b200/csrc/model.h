@@ -79,6 +79,7 @@ struct Workspace {
     float* scalars = nullptr;              // [8] vq loss, perplexity, ..., [4] time-matching loss
     float* tm_scratch = nullptr;           // time-matching pair sums + dloss/dsim (keep != 0)
     float* g_tm = nullptr;                 // time-matching gradient at the latent (B, D, lh, lw)
+    float* g_tmp = nullptr;                // materialised BatchNorm-backward gradient feeding a TMA data-gradient conv
     size_t bytes = 0;
 };
 int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* base, Workspace& w);

@@ -9,6 +9,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) augment_kernel(const float* __restrict__ x, const uint8_t* __restrict__ ops,
                                                       int64_t B, int C, int H, float* __restrict__ out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     // square planes (H == W): rot90 keeps the shape.  One thread per output element, rows of the OUTPUT are contiguous.
     const int64_t total = B * C * H * H;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
@@ -43,7 +44,7 @@ extern "C" int dmb_augment_batch(const float* x, const uint8_t* ops_dev, int64_t
     const int64_t total = batch * channels * height * width;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    dmb::augment_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ops_dev, batch, channels, height, out);
+    DMB_LAUNCH((dmb::augment_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, ops_dev, batch, channels, height, out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -23,6 +23,7 @@ __device__ __forceinline__ void block_sum2(double& s, double& q, double (*red)[2
 // BATCH mode: one CTA per channel, every thread sums B*nbands/256 partials with independent loads (the one-warp
 // version below spent ~10 us per launch walking up to 2048 partials as a latency chain).
 __global__ void __launch_bounds__(256) bn_finalize_batch_kernel(const BnFinalizeArgs a) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[8][2];
     const int c = blockIdx.x;
     const int n = a.B * a.nbands;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) bn_finalize_batch_kernel(const BnFinalize
 
 // one warp per output (channel, or sample*channel): fixed-order sum of the per-CTA partials
 __global__ void bn_finalize_kernel(const BnFinalizeArgs a) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int nout = a.per_sample ? a.B * a.C : a.C;
@@ -88,6 +90,7 @@ __global__ void bn_finalize_kernel(const BnFinalizeArgs a) {
 }
 
 __global__ void affine_add_kernel(const AffineAddArgs a, int64_t total4) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const int hw4 = a.HW >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -112,7 +115,7 @@ __global__ void affine_add_kernel(const AffineAddArgs a, int64_t total4) {
 
 int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
     if (!a.per_sample && (int64_t)a.B * a.nbands >= 64) {
-        bn_finalize_batch_kernel<<<a.C, 256, 0, st>>>(a);
+        DMB_LAUNCH((bn_finalize_batch_kernel), a.C, 256, 0, st, a);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);
         return 0;
@@ -120,7 +123,7 @@ int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
     const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
     const int threads = 128;
     const int64_t blocks = (nout * 32 + threads - 1) / threads;
-    bn_finalize_kernel<<<(unsigned)blocks, threads, 0, st>>>(a);
+    DMB_LAUNCH((bn_finalize_kernel), (unsigned)blocks, threads, 0, st, a);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -131,7 +134,7 @@ int affine_add(const AffineAddArgs& a, cudaStream_t st) {
     const int64_t total4 = a.B * a.C * (a.HW >> 2);
     int64_t blocks = (total4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    affine_add_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, total4);
+    DMB_LAUNCH((affine_add_kernel), (unsigned)blocks, 256, 0, st, a, total4);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -146,6 +149,7 @@ namespace dmb {
 namespace {
 
 __global__ void bn_bwd_finalize_kernel(const BnBwdArgs a) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int nout = a.per_sample ? a.B * a.C : a.C;
@@ -184,6 +188,7 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs a) {
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_batch_kernel(const BnBwdArgs a) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[8][2];
     const int c = blockIdx.x;
     const int n = a.B * a.nbands;
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_batch_kernel(const BnBwdA
 }
 
 __global__ void __launch_bounds__(256) sum_partials_block_kernel(const double* partials, int n, int C, float* out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[8][2];
     const int c = blockIdx.x;
     double s = 0.0, q = 0.0;
@@ -215,6 +221,7 @@ __global__ void __launch_bounds__(256) sum_partials_block_kernel(const double* p
 }
 
 __global__ void sum_partials_kernel(const double* partials, int n, int C, float* out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= C) return;
@@ -229,22 +236,22 @@ __global__ void sum_partials_kernel(const double* partials, int n, int C, float*
 
 int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st) {
     if (!a.per_sample && (int64_t)a.B * a.nbands >= 64) {
-        bn_bwd_finalize_batch_kernel<<<a.C, 256, 0, st>>>(a);
+        DMB_LAUNCH((bn_bwd_finalize_batch_kernel), a.C, 256, 0, st, a);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);
         return 0;
     }
     const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
     const int threads = 128;
-    bn_bwd_finalize_kernel<<<(unsigned)((nout * 32 + threads - 1) / threads), threads, 0, st>>>(a);
+    DMB_LAUNCH((bn_bwd_finalize_kernel), (unsigned)((nout * 32 + threads - 1) / threads), threads, 0, st, a);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
 }
 
 int sum_partials(const double* partials, int B, int nbands, int C, float* out, cudaStream_t st) {
-    if ((int64_t)B * nbands >= 64) sum_partials_block_kernel<<<C, 256, 0, st>>>(partials, B * nbands, C, out);
-    else sum_partials_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(partials, B * nbands, C, out);
+    if ((int64_t)B * nbands >= 64) DMB_LAUNCH((sum_partials_block_kernel), C, 256, 0, st, partials, B * nbands, C, out);
+    else DMB_LAUNCH((sum_partials_kernel), (C * 32 + 127) / 128, 128, 0, st, partials, B * nbands, C, out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

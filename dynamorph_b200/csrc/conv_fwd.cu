@@ -48,6 +48,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int KS, int STRIDE, int CO_T>
 __global__ void __launch_bounds__(128, 4) conv_fwd_kernel(const ConvK k) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     extern __shared__ __align__(16) float smem[];
     const ConvFwdArgs& a = k.a;
     constexpr int PAD = (KS == 1) ? 0 : 1;
@@ -411,7 +412,7 @@ int launch(const ConvK& k, cudaStream_t st) {
     const int64_t groups = (a.B + k.NP - 1) / k.NP;
     const int64_t grid = groups * k.nbands;
     DMB_CHECK(grid > 0 && grid < (1ll << 31), "conv_fwd: grid %lld out of range", (long long)grid);
-    kern<<<(unsigned)grid, k.threads, smem, st>>>(k);
+    DMB_LAUNCH((kern), (unsigned)grid, k.threads, smem, st, k);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -194,6 +194,7 @@ struct TmaConvArgs {
 template <class C>
 __global__ void __launch_bounds__(NTHREADS, C::MIN_CTAS)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     constexpr int KS = C::KS, S = C::S, P = C::P;
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned carve-up: [stage 0 | stage 1 | barriers]
@@ -552,12 +553,12 @@ int launch_tma(const ConvFwdArgs& a, cudaStream_t st) {
         if (!ps.ev) DMB_CUDA(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming));
         if (ps.used && ps.last != st) DMB_CUDA(cudaStreamWaitEvent(st, ps.ev, 0));
         DMB_CUDA(cudaMemcpyToSymbolAsync(c_pool, a.w, (size_t)C::W_FLOATS * 4, 0, cudaMemcpyDeviceToDevice, st));
-        kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(map, k);
+        DMB_LAUNCH((kern), grid, NTHREADS, C::SMEM_BYTES, st, map, k);
         DMB_CUDA(cudaGetLastError());
         DMB_CUDA(cudaEventRecord(ps.ev, st));
         ps.last = st; ps.used = true;
     } else {
-        kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(map, k);
+        DMB_LAUNCH((kern), grid, NTHREADS, C::SMEM_BYTES, st, map, k);
         DMB_CUDA(cudaGetLastError());
     }
     DMB_LAUNCHED(1);

@@ -21,6 +21,7 @@ struct ConvTK {
 
 template <int CO_T>
 __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTK k) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     extern __shared__ __align__(16) float smem[];
     const ConvTFwdArgs& a = k.a;
     float* ws = smem;
@@ -278,7 +279,7 @@ int launch(const ConvTK& k, cudaStream_t st) {
     }
     const int64_t grid = ((a.B + k.NP - 1) / k.NP) * k.nbands;
     DMB_CHECK(grid > 0 && grid < (1ll << 31), "convt_fwd: grid out of range");
-    kern<<<(unsigned)grid, k.threads, smem, st>>>(k);
+    DMB_LAUNCH((kern), (unsigned)grid, k.threads, smem, st, k);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -19,6 +19,7 @@ constexpr int TL = 64;        // latent columns per stage
 
 __global__ void __launch_bounds__(256) tm_pair_kernel(const float* __restrict__ z, int B, int64_t L, int64_t lslice,
                                                       float* __restrict__ part) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ float zi[TP][TL + 1], zj[TP][TL + 1];
     const int nt = (B + TP - 1) / TP;
     const int ti = blockIdx.x / nt, tj = blockIdx.x % nt;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) tm_loss_kernel(const float* __restrict__ 
                                                       const float* __restrict__ mat, int variant, float w_a, float w_t,
                                                       float w_n, float margin, float* __restrict__ G,
                                                       double* __restrict__ loss_part) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[8];
     const int64_t n = (int64_t)B * B;
     const float inv_l = 1.f / (float)L;
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(256) tm_loss_kernel(const float* __restrict__ 
 
 __global__ void tm_fold_kernel(const double* __restrict__ loss_part, int n, int variant, double inv_pairs,
                                float* __restrict__ loss_out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     double t = 0.0;
     for (int i = 0; i < n; ++i) t += loss_part[i];
     loss_out[0] = (float)(variant == 0 ? t : t * inv_pairs);
@@ -109,6 +112,7 @@ __global__ void tm_fold_kernel(const double* __restrict__ loss_part, int n, int 
 // g[i][l] (+)= scale * (2/L) * sum_j (G[i][j] + G[j][i]) * (z[i][l] - z[j][l]);  CTA = 8 rows i x 256 columns l
 __global__ void __launch_bounds__(256) tm_grad_kernel(const float* __restrict__ z, const float* __restrict__ G, int B,
                                                       int64_t L, float scale, float* __restrict__ g, int accumulate) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     constexpr int TI = 8;
     extern __shared__ float S[];                 // [TI][B]
     const int i0 = blockIdx.y * TI;
@@ -169,13 +173,13 @@ int tm_forward(const float* z, int64_t B, int64_t L, const dmb_time_matching& tm
     lp_off += lp_off & 1;                       // 8-byte alignment of the double partials
     double* lp = reinterpret_cast<double*>(scratch + lp_off);
     const int nt = (int)((B + TP - 1) / TP);
-    tm_pair_kernel<<<dim3(nt * nt, ns), 256, 0, st>>>(z, (int)B, L, lslice, part);
+    DMB_LAUNCH((tm_pair_kernel), dim3(nt * nt, ns), 256, 0, st, z, (int)B, L, lslice, part);
     DMB_CUDA(cudaGetLastError());
     int nblk = (int)((B * B + 1023) / 1024);
     if (nblk > 296) nblk = 296;
-    tm_loss_kernel<<<nblk, 256, 0, st>>>(part, ns, (int)B, L, tm.mat, tm.variant, tm.w_a, tm.w_t, tm.w_n, tm.margin, G, lp);
+    DMB_LAUNCH((tm_loss_kernel), nblk, 256, 0, st, part, ns, (int)B, L, tm.mat, tm.variant, tm.w_a, tm.w_t, tm.w_n, tm.margin, G, lp);
     DMB_CUDA(cudaGetLastError());
-    tm_fold_kernel<<<1, 1, 0, st>>>(lp, nblk, tm.variant, 1.0 / ((double)B * (double)B), loss_out);
+    DMB_LAUNCH((tm_fold_kernel), 1, 1, 0, st, lp, nblk, tm.variant, 1.0 / ((double)B * (double)B), loss_out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(3);
     return 0;
@@ -191,8 +195,7 @@ int tm_backward(const float* z, int64_t B, int64_t L, const float* scratch, floa
     DMB_CHECK(smem <= 200 * 1024, "time matching backward: batch %lld too large", (long long)B);
     if (smem > 48 * 1024)
         DMB_CUDA(cudaFuncSetAttribute(tm_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tm_grad_kernel<<<dim3((unsigned)((L + 255) / 256), (unsigned)((B + 7) / 8)), 256, smem, st>>>(
-        z, tm_G(scratch, B, L), (int)B, L, scale, g, accumulate);
+    DMB_LAUNCH((tm_grad_kernel), dim3((unsigned)((L + 255) / 256), (unsigned)((B + 7) / 8)), 256, smem, st, z, tm_G(scratch, B, L), (int)B, L, scale, g, accumulate);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -13,6 +13,11 @@ namespace dmb {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("DMB_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -469,6 +474,7 @@ int run_decoder(Ctx& c, const float* za, float* decoded) {
 __global__ void recon_loss_kernel(const float* __restrict__ dec, const float* __restrict__ x,
                                   const float* __restrict__ mask, int mask_c, const float* __restrict__ cvar,
                                   int64_t total4, int C, int hw4, double* out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[8];
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
@@ -507,6 +513,7 @@ __global__ void recon_loss_kernel(const float* __restrict__ dec, const float* __
 __global__ void recon_grad_kernel(const float* __restrict__ dec, const float* __restrict__ x,
                                   const float* __restrict__ mask, int mask_c, const float* __restrict__ cvar,
                                   int64_t total4, int C, int hw4, float scale, float* __restrict__ gd) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     // d/d dec of  scale * sum ((dec*m - x*m)^2 / cv)  =  scale * 2 (dec*m - x*m) m / cv
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -531,6 +538,7 @@ __global__ void recon_grad_kernel(const float* __restrict__ dec, const float* __
 // vq2: [0] vq loss, [1] perplexity, [4] time-matching loss (when w_tm != 0).  n_out = 4 (legacy) or 8.
 __global__ void train_losses_kernel(const float* vq2, const double* recon_sum, double n_recon, float w_r, float w_c,
                                     float w_tm, int has_tm, int n_out, float* out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const float recon = (float)(recon_sum[0] / n_recon);
     const float tm = has_tm ? vq2[4] : 0.f;
     out[0] = recon;
@@ -693,6 +701,7 @@ struct Bwd {
 };
 
 __global__ void channel_sum_kernel(const float* __restrict__ g, int64_t B, int C, int hw, float* __restrict__ out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     // out[c] = sum over (b, pixel) of g[b][c][pixel]; one CTA per channel, fixed order
     __shared__ double red[8];
     const int c = blockIdx.x;
@@ -757,8 +766,7 @@ int recon_grad(Ctx& c, const float* x, const float* mask, int mask_c, const floa
     const int64_t total4 = nrec / 4;
     int64_t blocks = (total4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    recon_grad_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(decoded, x, mask, mask_c, cvar, total4, m.num_inputs,
-                                                          m.height * m.width / 4, scale / (float)nrec, c.w.gd);
+    DMB_LAUNCH((recon_grad_kernel), (unsigned)blocks, 256, 0, c.st, decoded, x, mask, mask_c, cvar, total4, m.num_inputs, m.height * m.width / 4, scale / (float)nrec, c.w.gd);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -868,7 +876,7 @@ int run_backward_z32(Ctx& c, const float* params, const float* x, const float* m
 
     DMB_TRY(recon_grad(c, x, mask, mask_c, cvar, decoded, grad_scale));
     // dec.4 ConvT (h/2 -> ni), input relu(bn(t1)); its bias gradient is the per-channel sum of the loss gradient
-    channel_sum_kernel<<<m.num_inputs, 256, 0, st>>>(w.gd, c.B, m.num_inputs, H * W, grads + L.convs[L.d1].b_off);
+    DMB_LAUNCH((channel_sum_kernel), m.num_inputs, 256, 0, st, w.gd, c.B, m.num_inputs, H * W, grads + L.convs[L.d1].b_off);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     const int bn_d = L.convs[L.d0].bn;
@@ -1088,9 +1096,7 @@ static int train_forward_impl(const dmb_model* m, const float* packed, const flo
         DMB_CHECK(w.tm_scratch, "time matching needs a workspace carved with keep_activations=1");
         DMB_TRY(tm_forward(z32 ? w.za : w.zb, batch, (int64_t)L.D * L.lh * L.lw, *tm, w.tm_scratch, w.scalars + 4, st));
     }
-    train_losses_kernel<<<1, 1, 0, st>>>(w.scalars, w.recon_sum, (double)batch * m->num_inputs * m->height * m->width,
-                                         z32 ? 1.f : m->weight_recon, z32 ? 1.f : m->weight_commitment,
-                                         tm ? tm->weight : 0.f, tm ? 1 : 0, n_losses, losses_out);
+    DMB_LAUNCH((train_losses_kernel), 1, 1, 0, st, w.scalars, w.recon_sum, (double)batch * m->num_inputs * m->height * m->width, z32 ? 1.f : m->weight_recon, z32 ? 1.f : m->weight_commitment, tm ? tm->weight : 0.f, tm ? 1 : 0, n_losses, losses_out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -1156,8 +1162,7 @@ int dmb_recon_loss(const float* decoded, const float* x, const float* mask, int3
     const int64_t total4 = batch * channels * (hw / 4);
     int64_t blocks = (total4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    recon_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        decoded, x, mask, mask_channels, channel_var, total4, channels, hw / 4, sum_out);
+    DMB_LAUNCH((recon_loss_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, decoded, x, mask, mask_channels, channel_var, total4, channels, hw / 4, sum_out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

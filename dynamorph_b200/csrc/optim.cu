@@ -11,6 +11,7 @@ namespace {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                             float bc1, float bc2_sqrt, float gscale) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     // torch (_single_tensor_adam): exp_avg.lerp_(grad, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2);
     // denom = sqrt(exp_avg_sq)/sqrt(bc2) + eps; param.addcdiv_(exp_avg, denom, value=-lr/bc1)
     const float step_size = lr / bc1;
@@ -26,6 +27,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 // device-resident step counter variant (CUDA-graph replay: nothing in the launch changes between steps)
 __global__ void adam_tick_kernel(int* step, float* bc, float b1, float b2) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const int t = ++step[0];
     bc[0] = (float)(1.0 - pow((double)b1, (double)t));
     bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
@@ -33,6 +35,7 @@ __global__ void adam_tick_kernel(int* step, float* bc, float b1, float b2) {
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                                 const float* __restrict__ bc, float gscale) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const float step_size = lr / bc[0];
     const float bc2_sqrt = bc[1];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -47,6 +50,7 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 // one CTA per (patch, channel) plane: mean / population std in double, output float32
 template <typename T>
 __global__ void zscore_kernel(const T* __restrict__ raw, int hw, float* __restrict__ out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[2][32];
     const T* src = raw + (size_t)blockIdx.x * hw;
     float* dst = out + (size_t)blockIdx.x * hw;
@@ -83,8 +87,7 @@ int dmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    dmb::adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+    DMB_LAUNCH((dmb::adam_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -96,13 +99,12 @@ int dmb_adam_step_dev(float* params, const float* grads, float* exp_avg, float* 
     DMB_CHECK(params && grads && exp_avg && exp_avg_sq && step_dev && bc_dev, "dmb_adam_step_dev: null pointer");
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    dmb::adam_tick_kernel<<<1, 1, 0, st>>>(step_dev, bc_dev, beta1, beta2);
+    DMB_LAUNCH((dmb::adam_tick_kernel), 1, 1, 0, st, step_dev, bc_dev, beta1, beta2);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    dmb::adam_dev_kernel<<<(unsigned)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                          eps, bc_dev, grad_scale);
+    DMB_LAUNCH((dmb::adam_dev_kernel), (unsigned)blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc_dev, grad_scale);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -114,9 +116,9 @@ int dmb_zscore_patch(const void* raw, int32_t in_dtype, int64_t planes, int32_t 
     if (planes == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (in_dtype) {
-        case 0: dmb::zscore_kernel<float><<<(unsigned)planes, 256, 0, st>>>((const float*)raw, hw, out); break;
-        case 1: dmb::zscore_kernel<double><<<(unsigned)planes, 256, 0, st>>>((const double*)raw, hw, out); break;
-        case 2: dmb::zscore_kernel<uint16_t><<<(unsigned)planes, 256, 0, st>>>((const uint16_t*)raw, hw, out); break;
+        case 0: DMB_LAUNCH((dmb::zscore_kernel<float>), (unsigned)planes, 256, 0, st, (const float*)raw, hw, out); break;
+        case 1: DMB_LAUNCH((dmb::zscore_kernel<double>), (unsigned)planes, 256, 0, st, (const double*)raw, hw, out); break;
+        case 2: DMB_LAUNCH((dmb::zscore_kernel<uint16_t>), (unsigned)planes, 256, 0, st, (const uint16_t*)raw, hw, out); break;
         default: DMB_CHECK(false, "dmb_zscore_patch: in_dtype %d not in {0:f32,1:f64,2:u16}", in_dtype);
     }
     DMB_CUDA(cudaGetLastError());

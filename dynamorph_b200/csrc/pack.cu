@@ -34,6 +34,7 @@ __device__ double bn_scale(const PackL& l, const float* params, const float* bnb
 
 __global__ void pack_kernel(const PackPlan p, const float* __restrict__ params,
                             const float* __restrict__ bnbuf, float* __restrict__ packed) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < p.total;
          id += (int64_t)gridDim.x * blockDim.x) {
         if (id >= p.bn_start) {      // gamma / beta copies, then the zero vector
@@ -156,7 +157,7 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
     const int threads = 256;
     int blocks = (int)((p.total + threads - 1) / threads);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    pack_kernel<<<blocks, threads, 0, st>>>(p, params, bnbuf, packed);
+    DMB_LAUNCH((pack_kernel), blocks, threads, 0, st, p, params, bnbuf, packed);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -53,6 +53,7 @@ __device__ __forceinline__ void dist_cascade(const float (&z)[D], const float* _
 
 template <int D>
 __global__ void __launch_bounds__(VQ_THREADS) vq_kernel(const VqArgs a, int kchunk) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     extern __shared__ __align__(16) float cb[];          // [kchunk][D]
     __shared__ int hist[1024];
     __shared__ double red[VQ_THREADS / 32];
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_kernel(const VqArgs a, int kchu
 }
 
 __global__ void vq_finalize_kernel(const double* stats, int d, int k, float beta, float* out2) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     // loss = mse(q, z.detach()) + beta * mse(q.detach(), z) (vq_vae.py:74-76); perplexity :79-82
     __shared__ double red[32];
     const double npos = stats[1];
@@ -170,6 +172,7 @@ __global__ void vq_finalize_kernel(const double* stats, int d, int k, float beta
 }
 
 __global__ void vq_gather_kernel(const int32_t* idx, const float* cb, int64_t total, int d, int p, int k, float* q) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= total) return;
     const int64_t b = n / p;
@@ -190,7 +193,7 @@ int launch_vq(const VqArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)kchunk * D * 4;
     auto kern = vq_kernel<D>;
     if (smem > 40 * 1024) DMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)blocks, VQ_THREADS, smem, st>>>(a, kchunk);
+    DMB_LAUNCH((kern), (unsigned)blocks, VQ_THREADS, smem, st, a, kchunk);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -237,7 +240,7 @@ int dmb_vq_forward(const float* z, const float* codebook, int64_t batch, int32_t
 int dmb_vq_finalize(const double* stats, int32_t d, int32_t k, float commitment_cost,
                     float* out2, void* stream) {
     DMB_CHECK(stats && out2, "dmb_vq_finalize: null pointer");
-    dmb::vq_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(stats, d, k, commitment_cost, out2);
+    DMB_LAUNCH((dmb::vq_finalize_kernel), 1, 256, 0, (cudaStream_t)stream, stats, d, k, commitment_cost, out2);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -248,8 +251,7 @@ int dmb_vq_gather(const int32_t* idx, const float* codebook, int64_t batch, int3
     DMB_CHECK(idx && codebook && q, "dmb_vq_gather: null pointer");
     const int64_t total = batch * positions_per_patch;
     if (total == 0) return 0;
-    dmb::vq_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        idx, codebook, total, d, positions_per_patch, k, q);
+    DMB_LAUNCH((dmb::vq_gather_kernel), (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, idx, codebook, total, d, positions_per_patch, k, q);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
         const float* __restrict__ g_zst, const float* __restrict__ g_extra, const float* __restrict__ g_loss,
         float g_loss_scale, float beta, int64_t total, int d, int p, float* __restrict__ grad_z,
         double* __restrict__ stats, const float* __restrict__ stat_src) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     // stats (optional): per-CTA (sum g, sum g*stat_src) per channel, layout [block][d][2] -- the BatchNorm
     // backward sums of the residual layer that produced z.  Needs p % 128 == 0 (a CTA stays in one patch).
     __shared__ float red[VQB_MAXD][4][2];
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
         const float* __restrict__ z, const float* __restrict__ cb, const int32_t* __restrict__ idx,
         const float* __restrict__ g_loss, float g_loss_scale, int64_t total, int d, int p, int k,
         float* __restrict__ partial, float* __restrict__ grad_cb) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     extern __shared__ float sm[];
     float* acc = sm;                         // [k][d]
     float* zt = sm + (size_t)k * d;          // [d][ZT_PITCH]
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(256) vq_codebook_scatter_kernel(
 // grad_cb[e] = sum over the per-CTA partial rows, fixed order: block = 32 elements x 8 row groups
 __global__ void __launch_bounds__(256) vq_codebook_fold_kernel(const float* __restrict__ partial, int nparts, int n,
                                                                float* __restrict__ grad_cb) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
@@ -411,13 +416,13 @@ int vq_codebook_grad(const float* z, const float* cb, const int32_t* idx, const 
     int grid = (int)(ntiles < 296 ? ntiles : 296);
     if (scratch && scratch_rows > 0) {
         if (grid > scratch_rows) grid = scratch_rows;
-        vq_codebook_scatter_kernel<<<grid, 256, smem, st>>>(z, cb, idx, g_loss, g_loss_scale, total, d, p, k, scratch, nullptr);
+        DMB_LAUNCH((vq_codebook_scatter_kernel), grid, 256, smem, st, z, cb, idx, g_loss, g_loss_scale, total, d, p, k, scratch, nullptr);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);
-        vq_codebook_fold_kernel<<<(k * d + 31) / 32, 256, 0, st>>>(scratch, grid, k * d, grad_cb);
+        DMB_LAUNCH((vq_codebook_fold_kernel), (k * d + 31) / 32, 256, 0, st, scratch, grid, k * d, grad_cb);
     } else {
         DMB_CUDA(cudaMemsetAsync(grad_cb, 0, sizeof(float) * (size_t)k * d, st));
-        vq_codebook_scatter_kernel<<<grid, 256, smem, st>>>(z, cb, idx, g_loss, g_loss_scale, total, d, p, k, nullptr, grad_cb);
+        DMB_LAUNCH((vq_codebook_scatter_kernel), grid, 256, smem, st, z, cb, idx, g_loss, g_loss_scale, total, d, p, k, nullptr, grad_cb);
     }
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
@@ -435,8 +440,7 @@ int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx,
     const int64_t total = batch * p;
     DMB_CHECK(!stats || p % 128 == 0, "vq backward: positions per patch (%d) must be a multiple of 128", p);
     DMB_CHECK(d <= VQB_MAXD, "vq backward: embedding_dim %d > %d", d, VQB_MAXD);
-    vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-        z, codebook, idx, g_zst, g_extra, nullptr, g_loss_scale, beta, total, d, p, grad_z, stats, stat_src);
+    DMB_LAUNCH((vq_backward_kernel), (unsigned)((total + 127) / 128), 128, 0, st, z, codebook, idx, g_zst, g_extra, nullptr, g_loss_scale, beta, total, d, p, grad_z, stats, stat_src);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     if (grad_codebook)
@@ -460,9 +464,7 @@ extern "C" int dmb_vq_backward(const float* z, const float* codebook, const int3
         return 0;
     }
     if (grad_z) {
-        dmb::vq_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-            z, codebook, idx, g_zst, nullptr, g_loss_dev, g_loss_scale, commitment_cost, total, d,
-            positions_per_patch, grad_z, nullptr, nullptr);
+        DMB_LAUNCH((dmb::vq_backward_kernel), (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, z, codebook, idx, g_zst, nullptr, g_loss_dev, g_loss_scale, commitment_cost, total, d, positions_per_patch, grad_z, nullptr, nullptr);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);
     }

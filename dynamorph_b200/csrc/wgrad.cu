@@ -28,6 +28,7 @@ struct WgK {
 
 template <int KS, int STRIDE, int TCO>
 __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgK k) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     extern __shared__ __align__(16) float smem[];
     const WgradArgs& a = k.a;
     constexpr int PAD = (KS == 1) ? 0 : 1;
@@ -246,7 +247,7 @@ int launch(const WgK& k, int ncta, cudaStream_t st) {
     if (red > smem) smem = red;
     auto kern = wgrad_kernel<KS, STRIDE, TCO>;
     if (smem > 48 * 1024) DMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(ncta, k.slices), k.threads, smem, st>>>(k);
+    DMB_LAUNCH((kern), dim3(ncta, k.slices), k.threads, smem, st, k);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -257,6 +258,7 @@ int launch(const WgK& k, int ncta, cudaStream_t st) {
 __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, int out_floats,
                                                             int cin_eff, int cout, int ks, float* __restrict__ dw,
                                                             float* __restrict__ db, float* __restrict__ packed_out) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ float red[32][33];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
@@ -288,6 +290,7 @@ __global__ void composite_chain_kernel(const float* __restrict__ dweff, const fl
                                        const float* __restrict__ b0, const float* __restrict__ w1, int ni, int cm,
                                        float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
                                        float* __restrict__ db1) {
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     // dweff: packed [ni+1][16][cm] then db[cm];  w0 (cm,ni)  b0 (cm)  w1 (cm,cm,4,4)
     const int n_w1 = cm * cm * 16, n_w0 = cm * ni;
     const int total = n_w1 + n_w0 + cm + cm;
@@ -353,7 +356,7 @@ int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStrea
         else DMB_TRY((launch<4, 2, 2>(k, ncta, st)));
     }
     const int blocks = (k.out_floats + 31) / 32;
-    wgrad_reduce_kernel<<<blocks, 1024, 0, st>>>(a.partials, ncta, k.out_floats, k.cin_eff, a.Cout, a.ks, dw, db, packed_out);
+    DMB_LAUNCH((wgrad_reduce_kernel), blocks, 1024, 0, st, a.partials, ncta, k.out_floats, k.cin_eff, a.Cout, a.ks, dw, db, packed_out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -362,7 +365,7 @@ int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStrea
 int composite_chain(const float* dweff, const float* w0, const float* b0, const float* w1, int ni, int cm,
                     float* dw0, float* db0, float* dw1, float* db1, cudaStream_t st) {
     const int total = cm * cm * 16 + cm * ni + 2 * cm;
-    composite_chain_kernel<<<(total + 127) / 128, 128, 0, st>>>(dweff, w0, b0, w1, ni, cm, dw0, db0, dw1, db1);
+    DMB_LAUNCH((composite_chain_kernel), (total + 127) / 128, 128, 0, st, dweff, w0, b0, w1, ni, cm, dw0, db0, dw1, db1);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -62,73 +62,108 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgK k) {
         const int oy0 = band * k.TRO;
         const int in_row0 = oy0 * STRIDE - PAD;
         __syncthreads();
-        // ---- activation band (with halo), transform applied
+        // ---- activation band (with halo), transform applied.  Both staging loops issue the global loads of LU
+        // elements before touching any of them (the loops were one dependent load -> transform -> store per trip and
+        // ncu showed the kernel stalled on long-scoreboard 4-6 warps per issue).
+        constexpr int LU = (TCO * NT >= 64) ? 2 : 4;      // 64 live accumulators leave room for two float4 pairs only
         {
             const int total = k.ci_per * k.RIN * W4;
-            for (int e = tid; e < total; e += blockDim.x) {
-                const int q = e % W4;
-                int t = e / W4;
-                const int r = t % k.RIN;
-                const int cl = t / k.RIN;
-                const int c = ci0 + cl;
-                const int iy = in_row0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (iy >= 0 && iy < a.H) {
-                    if (c < a.Cin) {
-                        v = __ldg(reinterpret_cast<const float4*>(a.x + (((size_t)b * a.Cin + c) * a.H + iy) * a.W) + q);
-                        if (a.xs) {
-                            const size_t ai = (a.x_per_sample ? (size_t)b * a.Cin : 0) + c;
-                            const float s = __ldg(a.xs + ai), sh = __ldg(a.xt + ai);
-                            if (a.x2) {
-                                const float bc = __ldg(a.xb + ai);
-                                const float4 u = __ldg(reinterpret_cast<const float4*>(a.x2 + (((size_t)b * a.Cin + c) * a.H + iy) * a.W) + q);
-                                v.x = fmaf(v.x, s, fmaf(u.x, bc, sh)); v.y = fmaf(v.y, s, fmaf(u.y, bc, sh));
-                                v.z = fmaf(v.z, s, fmaf(u.z, bc, sh)); v.w = fmaf(v.w, s, fmaf(u.w, bc, sh));
-                            } else {
-                                v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh); v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
-                            }
-                        }
-                        if (a.x_relu) {
-                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                        }
-                    } else {
-                        v = make_float4(1.f, 1.f, 1.f, 1.f);     // the constant-one channel of the composite head
+            for (int e0 = tid; e0 < total; e0 += LU * blockDim.x) {
+                float4 v[LU], u[LU];
+                int q_[LU], r_[LU], cl_[LU];
+                bool in_img[LU], real_c[LU];
+#pragma unroll
+                for (int j = 0; j < LU; ++j) {
+                    const int e = e0 + j * blockDim.x;
+                    const int ee = e < total ? e : 0;
+                    q_[j] = ee % W4;
+                    const int t = ee / W4;
+                    r_[j] = t % k.RIN;
+                    cl_[j] = t / k.RIN;
+                    const int c = ci0 + cl_[j];
+                    const int iy = in_row0 + r_[j];
+                    in_img[j] = e < total && iy >= 0 && iy < a.H;
+                    real_c[j] = c < a.Cin;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    u[j] = v[j];
+                    if (in_img[j] && real_c[j]) {
+                        const size_t gi = (((size_t)b * a.Cin + c) * a.H + iy) * a.W;
+                        v[j] = __ldg(reinterpret_cast<const float4*>(a.x + gi) + q_[j]);
+                        if (a.xs && a.x2) u[j] = __ldg(reinterpret_cast<const float4*>(a.x2 + gi) + q_[j]);
                     }
                 }
-                float* rowp = xs + cl * k.ci_stride + r * k.RSW;
-                *reinterpret_cast<float4*>(rowp + PADL + 4 * q) = v;
-                if (PAD) {
-                    if (q == 0) *reinterpret_cast<float4*>(rowp) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q == W4 - 1) *reinterpret_cast<float4*>(rowp + PADL + a.W) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < LU; ++j) {
+                    if (e0 + j * blockDim.x >= total) break;
+                    const int c = ci0 + cl_[j];
+                    float4 w = v[j];
+                    if (in_img[j]) {
+                        if (real_c[j]) {
+                            if (a.xs) {
+                                const size_t ai = (a.x_per_sample ? (size_t)b * a.Cin : 0) + c;
+                                const float sc = __ldg(a.xs + ai), sh = __ldg(a.xt + ai);
+                                if (a.x2) {
+                                    const float bc = __ldg(a.xb + ai);
+                                    w.x = fmaf(w.x, sc, fmaf(u[j].x, bc, sh)); w.y = fmaf(w.y, sc, fmaf(u[j].y, bc, sh));
+                                    w.z = fmaf(w.z, sc, fmaf(u[j].z, bc, sh)); w.w = fmaf(w.w, sc, fmaf(u[j].w, bc, sh));
+                                } else {
+                                    w.x = fmaf(w.x, sc, sh); w.y = fmaf(w.y, sc, sh); w.z = fmaf(w.z, sc, sh); w.w = fmaf(w.w, sc, sh);
+                                }
+                            }
+                            if (a.x_relu) {
+                                w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+                            }
+                        } else {
+                            w = make_float4(1.f, 1.f, 1.f, 1.f);     // the constant-one channel of the composite head
+                        }
+                    }
+                    float* rowp = xs + cl_[j] * k.ci_stride + r_[j] * k.RSW;
+                    *reinterpret_cast<float4*>(rowp + PADL + 4 * q_[j]) = w;
+                    if (PAD) {
+                        if (q_[j] == 0) *reinterpret_cast<float4*>(rowp) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (q_[j] == W4 - 1) *reinterpret_cast<float4*>(rowp + PADL + a.W) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
             }
         }
         // ---- output-gradient band, BatchNorm backward folded in
         {
             const int total = a.Cout * k.TRO * Wo4;
-            for (int e = tid; e < total; e += blockDim.x) {
-                const int q = e % Wo4;
-                int t = e / Wo4;
-                const int r = t % k.TRO;
-                const int c = t / k.TRO;
-                const size_t gi = (((size_t)b * a.Cout + c) * a.Ho + oy0 + r) * a.Wo;
-                float4 v = __ldg(reinterpret_cast<const float4*>(a.g + gi) + q);
-                if (a.ga) {
-                    const size_t ai = (a.g_per_sample ? (size_t)b * a.Cout : 0) + c;
-                    const float s = __ldg(a.ga + ai), sh = __ldg(a.gc + ai);
-                    if (a.y) {
-                        const float bc = __ldg(a.gb + ai);
-                        const float4 u = __ldg(reinterpret_cast<const float4*>(a.y + gi) + q);
-                        v.x = fmaf(v.x, s, fmaf(u.x, bc, sh)); v.y = fmaf(v.y, s, fmaf(u.y, bc, sh));
-                        v.z = fmaf(v.z, s, fmaf(u.z, bc, sh)); v.w = fmaf(v.w, s, fmaf(u.w, bc, sh));
-                    } else {
-                        v.x = fmaf(v.x, s, sh); v.y = fmaf(v.y, s, sh); v.z = fmaf(v.z, s, sh); v.w = fmaf(v.w, s, sh);
+            for (int e0 = tid; e0 < total; e0 += LU * blockDim.x) {
+                float4 v[LU], u[LU];
+                int q_[LU], r_[LU], c_[LU];
+#pragma unroll
+                for (int j = 0; j < LU; ++j) {
+                    const int e = e0 + j * blockDim.x;
+                    const int ee = e < total ? e : 0;
+                    q_[j] = ee % Wo4;
+                    const int t = ee / Wo4;
+                    r_[j] = t % k.TRO;
+                    c_[j] = t / k.TRO;
+                    const size_t gi = (((size_t)b * a.Cout + c_[j]) * a.Ho + oy0 + r_[j]) * a.Wo;
+                    v[j] = __ldg(reinterpret_cast<const float4*>(a.g + gi) + q_[j]);
+                    u[j] = (a.ga && a.y) ? __ldg(reinterpret_cast<const float4*>(a.y + gi) + q_[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < LU; ++j) {
+                    if (e0 + j * blockDim.x >= total) break;
+                    float4 w = v[j];
+                    if (a.ga) {
+                        const size_t ai = (a.g_per_sample ? (size_t)b * a.Cout : 0) + c_[j];
+                        const float sc = __ldg(a.ga + ai), sh = __ldg(a.gc + ai);
+                        if (a.y) {
+                            const float bc = __ldg(a.gb + ai);
+                            w.x = fmaf(w.x, sc, fmaf(u[j].x, bc, sh)); w.y = fmaf(w.y, sc, fmaf(u[j].y, bc, sh));
+                            w.z = fmaf(w.z, sc, fmaf(u[j].z, bc, sh)); w.w = fmaf(w.w, sc, fmaf(u[j].w, bc, sh));
+                        } else {
+                            w.x = fmaf(w.x, sc, sh); w.y = fmaf(w.y, sc, sh); w.z = fmaf(w.z, sc, sh); w.w = fmaf(w.w, sc, sh);
+                        }
                     }
+                    if (a.g_relu) {
+                        w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(gs + c_[j] * k.g_stride + r_[j] * a.Wo + 4 * q_[j]) = w;
                 }
-                if (a.g_relu) {
-                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                }
-                *reinterpret_cast<float4*>(gs + c * k.g_stride + r * a.Wo + 4 * q) = v;
             }
         }
         __syncthreads();

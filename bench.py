@@ -343,10 +343,13 @@ def run_ours(args):
     ms_ps = time_events(lambda: step("per_sample"), max(3, args.steps // 4))
 
     # ---- end to end through the public host-buffer API (pinned host in, pinned host out)
-    enc = BulkEncoder(model, chunk=min(chunk, 4096), bn_mode="eval")
-    x_host = torch.empty(chunk, 2, 128, 128, dtype=torch.float32, pin_memory=True)
-    x_host.copy_(x)
-    out = enc.allocate_outputs(chunk)
+    # host buffers are pinned: keep the per-rank footprint (x float32 + x uint16 + outputs ~ 232 KB / patch) within
+    # a fraction of the box's RAM when 4-8 ranks share it
+    ne = chunk if world <= 2 else max(4096, chunk // 2)
+    enc = BulkEncoder(model, chunk=min(ne, 4096), bn_mode="eval")
+    x_host = torch.empty(ne, 2, 128, 128, dtype=torch.float32, pin_memory=True)
+    x_host.copy_(x[:ne])
+    out = enc.allocate_outputs(ne)
     enc.encode(x_host, out)
     torch.cuda.synchronize()
     barrier()
@@ -360,14 +363,14 @@ def run_ours(args):
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * chunk / (float(t[0]) * 1e-3)
+    e2e_value = world * e2e_steps * ne / (float(t[0]) * 1e-3)
     h2d = x_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out.values())
     # ---- the same call fed RAW uint16 patches (camera counts), z-scored on the device in front of the encoder
     # (pipeline/train_utils.py:252-274 on the GPU): half the host->device bytes of the float32 path
-    enc16 = BulkEncoder(model, chunk=min(chunk, 4096), bn_mode="eval", zscore=True)
-    x16 = torch.empty(chunk, 2, 128, 128, dtype=torch.uint16, pin_memory=True)
-    x16.copy_((x * 2000.0 + 30000.0).clamp_(0, 65535).to(torch.uint16))
+    enc16 = BulkEncoder(model, chunk=min(ne, 4096), bn_mode="eval", zscore=True)
+    x16 = torch.empty(ne, 2, 128, 128, dtype=torch.uint16, pin_memory=True)
+    x16.copy_((x[:ne] * 2000.0 + 30000.0).clamp_(0, 65535).to(torch.uint16))
     enc16.encode(x16, out)
     torch.cuda.synchronize()
     barrier()
@@ -379,13 +382,13 @@ def run_ours(args):
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e16_value = world * e2e_steps * chunk / (float(t[0]) * 1e-3)
+    e2e16_value = world * e2e_steps * ne / (float(t[0]) * 1e-3)
     enc.encode(x_host, out)          # leave the float32 result in `out` for the spot-check below
     torch.cuda.synchronize()
     # parity spot-check of what came back to the host against the device-resident run
     step("eval")
     torch.cuda.synchronize()
-    same = bool(torch.equal(out["idx"].view(chunk, 16, 16), idx.cpu()))
+    same = bool(torch.equal(out["idx"].view(ne, 16, 16), idx[:ne].cpu()))
 
     # ---- train step (BASELINE.json configs[1] / [4]): forward + backward + (allreduce) + Adam, fp32, BATCH-mode BN
     from dynamorph_b200.trainer import FusedTrainer
@@ -423,7 +426,7 @@ def run_ours(args):
                    "l2_policy": f"inputs larger than L2 ({chunk * 131072 / 1e9:.2f} GB per step vs 126 MB)"},
         "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "dynamorph_b200.bulk.BulkEncoder.encode (pinned host -> HBM -> pinned host, 3-stream pipeline)",
-                "host_matches_device": same,
+                "patches_per_step_per_gpu": ne, "host_matches_device": same,
                 "raw_uint16_input": {"value": e2e16_value, "unit": "patches/s", "h2d_bytes_per_step": x16.numel() * 2,
                                      "note": "BulkEncoder(zscore=True): uint16 patches in, z-score on the device"}},
         "gpu_launches": int(launches),

@@ -15,6 +15,8 @@
 // ConvTranspose2d weight gradients use the same kernel with the roles of the two tensors swapped.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace dmb {
 namespace {
 
@@ -27,7 +29,7 @@ struct WgK {
 };
 
 template <int KS, int STRIDE, int TCO>
-__global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgK k) {
+__global__ void __launch_bounds__(256, (TCO * KS * KS >= 64) ? 2 : 3) wgrad_kernel(const WgK k) {
     pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     extern __shared__ __align__(16) float smem[];
     const WgradArgs& a = k.a;

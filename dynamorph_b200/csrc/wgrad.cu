@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256, (TCO * KS * KS >= 64) ? 2 : 3) wgrad_kern
         // ---- activation band (with halo), transform applied.  Both staging loops issue the global loads of LU
         // elements before touching any of them (the loops were one dependent load -> transform -> store per trip and
         // ncu showed the kernel stalled on long-scoreboard 4-6 warps per issue).
-        constexpr int LU = (TCO * NT >= 64) ? 2 : 4;      // 64 live accumulators leave room for two float4 pairs only
+        constexpr int LU = (TCO * NT >= 32) ? 2 : 4;      // live accumulators leave room for two float4 pairs only
         {
             const int total = k.ci_per * k.RIN * W4;
             for (int e0 = tid; e0 < total; e0 += LU * blockDim.x) {

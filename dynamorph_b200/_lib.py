@@ -67,6 +67,7 @@ SIGNATURES = {
     "dmb_time_matching_scratch_floats": [_I64, _I64, C.POINTER(C.c_size_t)],
     "dmb_time_matching_forward": [_P, _I64, _I64, C.POINTER(DmbTimeMatching), _P, _P, _P],
     "dmb_time_matching_backward": [_P, _I64, _I64, _P, _F, _P, _I32, _P],
+    "dmb_pca_transform": [_P, _I64, _I32, _P, _P, _I32, _P, _P, _P],
     "dmb_augment_batch": [_P, _P, _I64, _I32, _I32, _I32, _P, _P],
     "dmb_adam_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P],
     "dmb_adam_step_dev": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _F, _P],

@@ -163,6 +163,13 @@ int dmb_bench_fma_conv(int32_t variant, int32_t blocks, int32_t iters, float* sc
 /* Number of kernels this library has launched in the process (reset != 0 zeroes it).        */
 long long dmb_launch_count(int reset);
 
+/* ---- PCA projection of the latents (run_dim_reduction.py:53-92 process_PCA -> sklearn PCA.transform) ----------- */
+/* out (n, n_components) = (x (n, latent_len) - mean) @ components (n_components, latent_len)^T, times
+ * inv_scale[j] (= 1/sqrt(explained_variance_[j]) for a whitening PCA; NULL otherwise).  fp32.                      */
+int dmb_pca_transform(const float* x, int64_t n, int32_t latent_len, const float* mean,
+                      const float* components, int32_t n_components, const float* inv_scale, float* out,
+                      void* stream);
+
 /* ---- training augmentation (run_training.py:396-403) ------------------------------------ */
 /* out[b] = rot90(flip(x[b], dims=(flip,)), k=rot, dims=[1, 2]) for every sample in one launch; ops_dev holds one
  * byte per sample: flip in {0 none, 1 H, 2 W} | rot in {0..3} << 2 (drawn on the host in the reference's order).  */

@@ -50,6 +50,30 @@ __global__ void __launch_bounds__(256) bn_finalize_batch_kernel(const BnFinalize
     }
 }
 
+// PER_SAMPLE mode: one THREAD per (sample, channel) -- there are only nbands (1..8) partials to add, and B*C outputs
+// (131 k for an 8192-patch chunk); a warp per output left 31 lanes idle and cost 40-80 us per launch.
+__global__ void __launch_bounds__(256) bn_finalize_sample_kernel(const BnFinalizeArgs a) {
+    pdl_wait();
+    const int64_t o = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (o >= (int64_t)a.B * a.C) return;
+    const int c = (int)(o % a.C);
+    const int64_t bs = o / a.C;
+    double s = 0.0, q = 0.0;
+    for (int band = 0; band < a.nbands; ++band) {
+        const double2 v = *reinterpret_cast<const double2*>(a.partials + ((bs * a.nbands + band) * a.C + c) * 2);
+        s += v.x; q += v.y;
+    }
+    const double cnt = (double)a.count_per_sample;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float sc = a.gamma[c] * invstd;
+    a.scale[o] = sc;
+    a.shift[o] = a.beta[c] - (float)mean * sc;
+    if (a.save_mean) { a.save_mean[o] = (float)mean; a.save_invstd[o] = invstd; }
+}
+
 // one warp per output (channel, or sample*channel): fixed-order sum of the per-CTA partials
 __global__ void bn_finalize_kernel(const BnFinalizeArgs a) {
     pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
@@ -121,6 +145,12 @@ int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
         return 0;
     }
     const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
+    if (a.per_sample && a.nbands <= 16) {
+        DMB_LAUNCH((bn_finalize_sample_kernel), (unsigned)((nout + 255) / 256), 256, 0, st, a);
+        DMB_CUDA(cudaGetLastError());
+        DMB_LAUNCHED(1);
+        return 0;
+    }
     const int threads = 128;
     const int64_t blocks = (nout * 32 + threads - 1) / threads;
     DMB_LAUNCH((bn_finalize_kernel), (unsigned)blocks, threads, 0, st, a);

@@ -263,6 +263,10 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = None
+    if world > 1:
+        from dynamorph_b200.dist import bind_to_gpu_numa
+        numa_cores = bind_to_gpu_numa(local)      # pinned staging buffers land next to this rank's GPU
     if dist is not None:
         dist.init_process_group("nccl", device_id=dev)
     from dynamorph_b200 import _lib
@@ -427,6 +431,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "dynamorph_b200.bulk.BulkEncoder.encode (pinned host -> HBM -> pinned host, 3-stream pipeline)",
                 "patches_per_step_per_gpu": ne, "host_matches_device": same,
+                "rank0_cpu_affinity": (f"{len(numa_cores)} cores local to the GPU (NVML)" if numa_cores else "unchanged"),
                 "raw_uint16_input": {"value": e2e16_value, "unit": "patches/s", "h2d_bytes_per_step": x16.numel() * 2,
                                      "note": "BulkEncoder(zscore=True): uint16 patches in, z-score on the device"}},
         "gpu_launches": int(launches),

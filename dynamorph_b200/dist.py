@@ -100,3 +100,36 @@ class ShardedEncoder:
             idx = out["idx"].to(dev).view(b - a, side, lat // side)
             out["idx_all"] = gather_code_indices(idx, n, self.model.num_embeddings, self.group)
         return out
+
+
+def bind_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index`, BEFORE it allocates
+    pinned host buffers: first-touch then places the staging memory of the bulk encoder on the NUMA node next to that
+    GPU's PCIe root, so 4-8 ranks on one box do not pull their host->device traffic across the socket interconnect.
+    Returns the core list, or None when NVML / affinity control is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        h = None
+        if bus is not None:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                    h = hi
+                    break
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

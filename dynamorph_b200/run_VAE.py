@@ -26,6 +26,8 @@ def get_im_sites(input_dir):
 
 
 def _worker(gpu, jobs, config_path):
+    from .dist import bind_to_gpu_numa
+    bind_to_gpu_numa(gpu)          # staging buffers of this GPU's encoder on its own NUMA node
     config = YamlReader().read_config(config_path)
     for raw_dir, supp_dir, well_sites in jobs:
         process_VAE(raw_dir, supp_dir, well_sites, config, gpu=gpu)

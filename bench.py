@@ -263,10 +263,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa_cores = None
-    if world > 1:
-        from dynamorph_b200.dist import bind_to_gpu_numa
-        numa_cores = bind_to_gpu_numa(local)      # pinned staging buffers land next to this rank's GPU
+    from dynamorph_b200.dist import bind_to_gpu_numa
+    numa_cores = bind_to_gpu_numa(local)          # pinned staging buffers land next to this rank's GPU
     if dist is not None:
         dist.init_process_group("nccl", device_id=dev)
     from dynamorph_b200 import _lib

@@ -264,6 +264,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from dynamorph_b200.dist import bind_to_gpu_numa
+    all_cores = os.sched_getaffinity(0)
     numa_cores = bind_to_gpu_numa(local)          # pinned staging buffers land next to this rank's GPU
     if dist is not None:
         dist.init_process_group("nccl", device_id=dev)
@@ -467,6 +468,7 @@ def run_ours(args):
                               "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
         line["layers"] = rows
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cores)     # the CPU baseline gets every host core back
             v, cores, sec = cpu_reference_rate(1024, 256, 2)
             line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
                                     "sample": "1024 patches, batched eval enc+vq (B=256), best of 2 after 1 warm-up"}

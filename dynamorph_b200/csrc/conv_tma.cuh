@@ -52,7 +52,7 @@ __constant__ float c_pool[POOL_FLOATS];
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
-template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, int XF_ = 0>
+template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, int XF_ = 0, bool DGRAD_ = false>
 struct TC {
     static constexpr int KS = KS_, S = STRIDE_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
     static constexpr bool WCONST = WCONST_;
@@ -61,6 +61,9 @@ struct TC {
     // residual block; zero padding is a fixed point of ReLU), 2 BatchNorm affine + optional ReLU (train / per-sample
     // modes; padding is re-zeroed by a zero (scale, shift) pair for out-of-image rows and two border fix-ups).
     static constexpr int XF = XF_;
+    // data-gradient epilogue (ReLU-gate mask, BatchNorm-backward sums against stat_src) compiled in only on request:
+    // merely having that code in the kernel cost the forward instantiations 5 % (register allocation of the main loop)
+    static constexpr bool DGRAD = DGRAD_;
     static constexpr int PAD = (KS == 1) ? 0 : 1;
     static constexpr int WO = W / S, HO = H / S;
     static constexpr int NCG = COUT / CO_T;
@@ -383,10 +386,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
     const float* bias_u = a.bias + cgz * CC;
     float* y_u = a.y + (size_t)(cgz * CC) * (C::HO * C::WO);
     const float* skip_u = a.skip ? a.skip + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
-    const float* mask_u = a.mask_src ? a.mask_src + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
-    const float* stat_u = a.stat_src ? a.stat_src + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
-    const float* mask_s_u = a.mask_s ? a.mask_s + cgz * CC : nullptr;
-    const float* mask_t_u = a.mask_s ? a.mask_t + cgz * CC : nullptr;
+    [[maybe_unused]] const float* mask_u = nullptr;
+    [[maybe_unused]] const float* stat_u = nullptr;
+    [[maybe_unused]] const float* mask_s_u = nullptr;
+    [[maybe_unused]] const float* mask_t_u = nullptr;
+    if constexpr (C::DGRAD) {
+        mask_u = a.mask_src ? a.mask_src + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
+        stat_u = a.stat_src ? a.stat_src + (size_t)(cgz * CC) * (C::HO * C::WO) : nullptr;
+        mask_s_u = a.mask_s ? a.mask_s + cgz * CC : nullptr;
+        mask_t_u = a.mask_s ? a.mask_t + cgz * CC : nullptr;
+    }
     const int rc = (oy == 0) ? 0 : ((oy == C::HO - 1) ? 2 : 1);
     float ssum[CO_T], ssq[CO_T];
 #pragma unroll
@@ -406,7 +415,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
         if (sx == 0) o[0] = acc[c][0] + bl;
         if (sx == C::SPR - 1) o[PW - 1] = acc[c][PW - 1] + br;
         const size_t off = (((size_t)b * C::COUT + co) * C::HO + oy) * C::WO + sx * PW;
-        if (mask_u && live) {
+        if (C::DGRAD && mask_u && live) {
             float ms = 1.f, mt = 0.f;
             if (mask_s_u) {
                 const size_t mi = (a.mask_per_sample ? (size_t)b * C::COUT : 0) + co;
@@ -439,7 +448,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
         }
         float s = 0.f, q = 0.f;
         if (a.stats) {
-            if (stat_u) {
+            if (C::DGRAD && stat_u) {
                 if (live) {
 #pragma unroll
                     for (int i = 0; i < PW / 4; ++i) {

@@ -33,6 +33,13 @@ bool use_pool(const ConvFwdArgs& a, cudaStream_t st, int w_floats) {
 // transform form: BatchNorm affine pending -> 2; ReLU only on a 3x3 (eval-mode residual block) -> 1; else 0
 template <int KS, int S, int CI, int CO, int WIN, bool WC>
 int launch_xf(const ConvFwdArgs& a, cudaStream_t st) {
+    if (a.mask_src || a.stat_src) {
+        // training data gradient: plain input (the caller materialised it), shared-memory weights, gate + sums epilogue
+        if constexpr (!WC) {
+            if (!a.in_scale && !a.in_relu) return launch_tma<TC<KS, S, CI, CO, WIN, false, 0, true>>(a, st);
+        }
+        return 1;       // not taken: the generic kernel serves any other combination
+    }
     if (a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 2>>(a, st);
     if constexpr (KS == 3) {
         if (a.in_relu) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 1>>(a, st);
@@ -57,7 +64,8 @@ int conv_tma_default(const ConvFwdArgs& a, cudaStream_t st) {
     if (a.ks == KS && a.stride == S && a.Cin == CI && a.Cout == CO && a.W == WIN && a.H == WIN) {   \
         /* the 1x1 layers are HBM-bound: the shared-memory form (one tile read serves all channel groups) wins */ \
         if constexpr (CI * KS * KS * CO <= POOL_FLOATS && KS > 1) {                                  \
-            if (use_pool(a, st, CI * KS * KS * CO)) return launch_xf<KS, S, CI, CO, WIN, true>(a, st); \
+            if (!a.mask_src && !a.stat_src && use_pool(a, st, CI * KS * KS * CO))                   \
+                return launch_xf<KS, S, CI, CO, WIN, true>(a, st);                                   \
         }                                                                                            \
         return launch_xf<KS, S, CI, CO, WIN, false>(a, st);                                          \
     }

@@ -106,7 +106,7 @@ int conv_fwd(const ConvFwdArgs& a, cudaStream_t st);
 int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool plain, int64_t B);
 // TMA-fed specialisation (conv_tma.cu): returns 1 when it does not take the call
 int conv_tma(const ConvFwdArgs& a, cudaStream_t st);
-int conv_tma_bands(int ks, int stride, int Cin, int Cout, int H, int W);
+int conv_tma_bands(int ks, int stride, int Cin, int Cout, int H, int W, int64_t B);
 
 // transposed 4x4 stride-2 pad-1 convolution, forward (convt_fwd.cu)
 struct ConvTFwdArgs {

@@ -424,7 +424,7 @@ int pick_co_t(int Cout) { return (Cout % 8 == 0) ? 8 : ((Cout % 4 == 0) ? 4 : ((
 
 int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool plain, int64_t B) {
     if (plain) {       // plain forward calls go to the TMA kernel when the geometry has an instantiation
-        const int nb = conv_tma_bands(ks, stride, Cin, Cout, Ho * stride, Wo * stride);
+        const int nb = conv_tma_bands(ks, stride, Cin, Cout, Ho * stride, Wo * stride, B);
         if (nb > 0) return nb;
     }
     ConvFwdArgs a{};

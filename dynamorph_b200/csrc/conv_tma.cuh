@@ -43,7 +43,6 @@ namespace dmb {
 namespace {
 
 constexpr int PW = 8;      // output pixels per thread along x
-constexpr int CO_T = 8;    // output channels per thread
 constexpr int NTHREADS = 128;
 constexpr int NSTAGE = 2;
 constexpr int POOL_FLOATS = 15360;     // 60 KB of the 64 KB constant bank
@@ -52,8 +51,12 @@ __constant__ float c_pool[POOL_FLOATS];
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
-template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, int XF_ = 0, bool DGRAD_ = false>
+template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, int XF_ = 0, bool DGRAD_ = false, int COT_ = 8>
 struct TC {
+    // output channels per thread: 8 (64 accumulators); 4 for training-size batches, where the 8-channel tiling leaves
+    // most of the GPU without a CTA (a few hundred patches of a 16x16 map are ~128 CTAs) -- twice the CTAs, half the
+    // work each, at a slightly lower FFMA density
+    static constexpr int CO_T = COT_;
     static constexpr int KS = KS_, S = STRIDE_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
     static constexpr bool WCONST = WCONST_;
     // Producer transform applied to the activations in REGISTERS right after the tile loads (no pass over the tile,
@@ -70,13 +73,15 @@ struct TC {
     // Channel groups per CTA.  Shared-memory weights: up to four, one per warp-aligned slice of the CTA.  Constant-pool
     // weights: ONE, taken from blockIdx.x -- the weight address must be built from values ptxas can prove uniform
     // (blockIdx, loop counters), a warp index is not; the NCG CTAs of a tile re-read it through L2.
-    static constexpr int NCG_CTA = WCONST ? 1 : cmin(NCG, 4);
+    // (the 4-channel tiling keeps the group COUNT of the 8-channel one, i.e. twice the CTAs per tile: rows per CTA, the
+    // BatchNorm partial layout and the order of every statistics sum stay identical for both tilings)
+    static constexpr int NCG_CTA = WCONST ? 1 : cmin(COUT / 8 > 0 ? COUT / 8 : 1, 4);
     static constexpr int CG_SPLIT = NCG / NCG_CTA;            // CTAs per tile
     static constexpr int SPR = WO / PW;                       // strips per output row
     static constexpr bool ZS1 = (S == 1 && SPR >= 4);         // lane bit 2 = second strip bit (else patch bit)
     static constexpr int SR = ZS1 ? SPR / 4 : SPR / 2;
     static constexpr int REM = 16 / (SR * NCG_CTA);
-    static constexpr int RH = cmin(HO / 2, 16 / (SR * cmin(NCG, 4)));   // same rows per CTA in both weight forms
+    static constexpr int RH = cmin(HO / 2, 16 / (SR * cmin(COUT / 8 > 0 ? COUT / 8 : 1, 4)));   // same rows per CTA in every form
     static constexpr int PH = REM / RH;
     static constexpr int NP = (ZS1 ? 1 : 2) * PH;             // patches per CTA
     static constexpr int TR = 2 * RH;                         // output rows per CTA
@@ -123,7 +128,7 @@ struct TC {
     static constexpr int MIN_CTAS = (SMEM_BYTES + 1024) * 4 <= 227 * 1024 ? 4 : ((SMEM_BYTES + 1024) * 3 <= 227 * 1024 ? 3 : 2);
     static constexpr int W_FLOATS = CIN * KS * KS * COUT;
 
-    static_assert(COUT % CO_T == 0 && NCG % NCG_CTA == 0, "Cout must be a multiple of 8 (and of 32 beyond 32)");
+    static_assert((CO_T == 8 || CO_T == 4) && COUT % CO_T == 0 && NCG % NCG_CTA == 0, "Cout must be a multiple of the channel tile");
     static_assert(WO % PW == 0 && SPR >= 2 && (SPR & (SPR - 1)) == 0, "output width must be 16, 32, 64, ...");
     static_assert(SR >= 1 && 16 % (SR * NCG_CTA) == 0 && REM >= 1, "thread decomposition does not fit 128 threads");
     static_assert(SR * RH * PH * NCG_CTA == 16 && SR * RH * PH >= 4, "channel group must be warp-uniform");
@@ -198,7 +203,7 @@ template <class C>
 __global__ void __launch_bounds__(NTHREADS, C::MIN_CTAS)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
     pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
-    constexpr int KS = C::KS, S = C::S, P = C::P;
+    constexpr int KS = C::KS, S = C::S, P = C::P, CO_T = C::CO_T;
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned carve-up: [stage 0 | stage 1 | barriers]
     const uint32_t raw = smem_u32(smem_raw);

@@ -30,28 +30,42 @@ bool use_pool(const ConvFwdArgs& a, cudaStream_t st, int w_floats) {
     return macs >= 2.0e9;     // ~50 us of FMA work on a B200
 }
 
+// Training-size launches: would the 8-channel tiling fill less than one wave of CTA slots (4 per SM)?  Then the
+// 4-channel tiling (twice the CTAs) is used, with shared-memory weights.  Depends on the batch only, so that the
+// choice never depends on anything but the geometry; the BatchNorm partial layout is the same for both tilings.
+template <int KS, int S, int CI, int CO, int WIN>
+bool small_launch(int64_t B) {
+    using T8 = TC<KS, S, CI, CO, WIN, false>;
+    static_assert(T8::NBANDS == TC<KS, S, CI, CO, WIN, false, 0, false, 4>::NBANDS &&
+                      T8::NP == TC<KS, S, CI, CO, WIN, false, 0, false, 4>::NP, "tilings must agree on rows / patches per CTA");
+    if (B <= 0) return false;
+    const int64_t ctas = ((B + T8::NP - 1) / T8::NP) * T8::NBANDS * T8::CG_SPLIT;
+    return ctas < 4 * 148;
+}
+
 // transform form: BatchNorm affine pending -> 2; ReLU only on a 3x3 (eval-mode residual block) -> 1; else 0
-template <int KS, int S, int CI, int CO, int WIN, bool WC>
+template <int KS, int S, int CI, int CO, int WIN, bool WC, int COT>
 int launch_xf(const ConvFwdArgs& a, cudaStream_t st) {
     if (a.mask_src || a.stat_src) {
         // training data gradient: plain input (the caller materialised it), shared-memory weights, gate + sums epilogue
         if constexpr (!WC) {
-            if (!a.in_scale && !a.in_relu) return launch_tma<TC<KS, S, CI, CO, WIN, false, 0, true>>(a, st);
+            if (!a.in_scale && !a.in_relu) return launch_tma<TC<KS, S, CI, CO, WIN, false, 0, true, COT>>(a, st);
         }
         return 1;       // not taken: the generic kernel serves any other combination
     }
-    if (a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 2>>(a, st);
+    if (a.in_scale) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 2, false, COT>>(a, st);
     if constexpr (KS == 3) {
-        if (a.in_relu) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 1>>(a, st);
+        if (a.in_relu) return launch_tma<TC<KS, S, CI, CO, WIN, WC, 1, false, COT>>(a, st);
     }
-    return launch_tma<TC<KS, S, CI, CO, WIN, WC, 0>>(a, st);
+    return launch_tma<TC<KS, S, CI, CO, WIN, WC, 0, false, COT>>(a, st);
 }
 
 }  // namespace
 
-int conv_tma_bands_default(int ks, int stride, int Cin, int Cout, int H, int W) {
-#define X(KS, S, CI, CO, WIN) \
-    if (ks == KS && stride == S && Cin == CI && Cout == CO && W == WIN && H == WIN) return TC<KS, S, CI, CO, WIN, false>::NBANDS;
+int conv_tma_bands_default(int ks, int stride, int Cin, int Cout, int H, int W, int64_t /*B*/) {
+#define X(KS, S, CI, CO, WIN)                                                                        \
+    if (ks == KS && stride == S && Cin == CI && Cout == CO && W == WIN && H == WIN)                  \
+        return TC<KS, S, CI, CO, WIN, false>::NBANDS;     /* identical for the 4-channel tiling (static_assert below) */
     DMB_TMA_SHAPES(X)
 #undef X
     return 0;
@@ -62,12 +76,13 @@ int conv_tma_default(const ConvFwdArgs& a, cudaStream_t st) {
     if (!tma_plain(a)) return 1;
 #define X(KS, S, CI, CO, WIN)                                                                        \
     if (a.ks == KS && a.stride == S && a.Cin == CI && a.Cout == CO && a.W == WIN && a.H == WIN) {   \
+        if (small_launch<KS, S, CI, CO, WIN>(a.B)) return launch_xf<KS, S, CI, CO, WIN, false, 4>(a, st); \
         /* the 1x1 layers are HBM-bound: the shared-memory form (one tile read serves all channel groups) wins */ \
         if constexpr (CI * KS * KS * CO <= POOL_FLOATS && KS > 1) {                                  \
             if (!a.mask_src && !a.stat_src && use_pool(a, st, CI * KS * KS * CO))                   \
-                return launch_xf<KS, S, CI, CO, WIN, true>(a, st);                                   \
+                return launch_xf<KS, S, CI, CO, WIN, true, 8>(a, st);                                \
         }                                                                                            \
-        return launch_xf<KS, S, CI, CO, WIN, false>(a, st);                                          \
+        return launch_xf<KS, S, CI, CO, WIN, false, 8>(a, st);                                       \
     }
     DMB_TMA_SHAPES(X)
 #undef X

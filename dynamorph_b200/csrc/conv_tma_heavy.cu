@@ -47,7 +47,7 @@ int launch_xf(const ConvFwdArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-int conv_tma_bands_heavy(int ks, int stride, int Cin, int Cout, int H, int W) {
+int conv_tma_bands_heavy(int ks, int stride, int Cin, int Cout, int H, int W, int64_t /*B*/) {
 #define X(KS, S, CI, CO, WIN) \
     if (ks == KS && stride == S && Cin == CI && Cout == CO && W == WIN && H == WIN) return TC<KS, S, CI, CO, WIN, false>::NBANDS;
     DMB_TMA_SHAPES(X)

@@ -670,7 +670,7 @@ struct Bwd {
         // BatchNorm-backward gradient  A*g + Bc*y + Cc  is materialised first (one small elementwise launch; the
         // latent-resolution tensors are a few MB at training batch sizes) and fed to it as a plain input.
         if (G.A && !ps() && c.w.g_tmp && a.H == L_lat_h() && a.W == L_lat_w() &&
-            conv_tma_bands(a.ks, a.stride, a.Cin, a.Cout, a.H, a.W) > 0) {
+            conv_tma_bands(a.ks, a.stride, a.Cin, a.Cout, a.H, a.W, 0) > 0) {
             AffineAddArgs aa{};
             aa.a = G.g; aa.sa = G.A; aa.ta = G.Cc; aa.b = G.y; aa.sb = G.Bc; aa.tb = zero;
             aa.per_sample = 0; aa.out = c.w.g_tmp; aa.B = c.B; aa.C = a.Cin; aa.HW = a.H * a.W;

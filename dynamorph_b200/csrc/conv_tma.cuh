@@ -125,7 +125,8 @@ struct TC {
     static constexpr int XF_FLOATS = (XF == 2) ? 2 * NP * CIN : 0;            // per-patch (scale, shift) tables
     static constexpr size_t SMEM_BYTES = (size_t)(SMEM_FLOATS + XF_FLOATS) * 4 + 128 /*alignment slack*/ + 64 /*barriers*/;
     static constexpr uint32_t TX_BYTES = (uint32_t)((WCONST ? 0 : WCHUNK) + TILE) * 4u;
-    static constexpr int MIN_CTAS = (SMEM_BYTES + 1024) * 4 <= 227 * 1024 ? 4 : ((SMEM_BYTES + 1024) * 3 <= 227 * 1024 ? 3 : 2);
+    static constexpr int MIN_CTAS = (KS == 4 && CIN == 2 && COUT == 8 && WCONST && (SMEM_BYTES + 1024) * 5 <= 227 * 1024) ? 5 :
+        ((SMEM_BYTES + 1024) * 4 <= 227 * 1024 ? 4 : ((SMEM_BYTES + 1024) * 3 <= 227 * 1024 ? 3 : 2));
     static constexpr int W_FLOATS = CIN * KS * KS * COUT;
 
     static_assert((CO_T == 8 || CO_T == 4) && COUT % CO_T == 0 && NCG % NCG_CTA == 0, "Cout must be a multiple of the channel tile");

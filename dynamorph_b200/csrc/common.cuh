@@ -108,6 +108,23 @@ int conv_fwd_bands(int ks, int stride, int Cin, int Cout, int Ho, int Wo, bool p
 int conv_tma(const ConvFwdArgs& a, cudaStream_t st);
 int conv_tma_bands(int ks, int stride, int Cin, int Cout, int H, int W, int64_t B);
 
+// tensor-core (tcgen05, 3xTF32) convolution over NHWC activations (conv_tc.cu); EVAL-mode wide configurations
+struct ConvTcArgs {
+    const float* x;         // (B, H, W, Cin)  NHWC
+    const float* wtc;       // pack_tc_weights output: [tap][Cin/32][hi|lo][Cout][32], 128-byte swizzled rows
+    const float* bias;      // [Cout]
+    float* y;               // (B, Ho, Wo, Cout) when out_nhwc, else (B, Cout, Ho, Wo)
+    const float* skip;      // optional, added before the output ReLU; layout per skip_nhwc
+    int B, Cin, H, W, Cout, ks, stride;   // (1,1) (3,1) (4,2); pad = ks > 1
+    int in_relu, out_relu, out_nhwc, skip_nhwc;
+};
+bool conv_tc_supported(int cin, int cout, int ks, int stride, int H, int W);
+int64_t conv_tc_weight_floats(int cin, int cout, int ks);
+// w_packed = [Cin][ks][ks][Cout] (the layout every other conv kernel reads) -> tensor-core tiles
+int pack_tc_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);
+int nchw_to_nhwc(const float* x, float* y, int64_t B, int C, int HW, cudaStream_t st);
+int conv_tc(const ConvTcArgs& a, cudaStream_t st);
+
 // transposed 4x4 stride-2 pad-1 convolution, forward (convt_fwd.cu)
 struct ConvTFwdArgs {
     const float* x;         // (B, Cin, H, W)

@@ -47,6 +47,7 @@ struct Builder {
     int conv(const std::string& key, int cin, int cout, int ks, int stride, bool transposed) {
         ConvL c{};
         c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.transposed = transposed; c.bn = -1;
+        c.ptc_off = -1;
         c.w_off = take_param(key + ".weight", (int64_t)cin * cout * ks * ks);
         c.b_off = take_param(key + ".bias", cout);
         c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
@@ -62,6 +63,7 @@ struct Builder {
         ConvL c{};
         c.cin = cin; c.cout = cmid; c.cmid = cmid; c.ks = 4; c.stride = 2; c.composite = 1; c.bn = -1;
         c.bias_classes = 1;
+        c.ptc_off = -1;
         c.w0_off = take_param(key0 + ".weight", (int64_t)cmid * cin);
         c.b0_off = take_param(key0 + ".bias", cmid);
         c.w_off = take_param(key1 + ".weight", (int64_t)cmid * cmid * 16);
@@ -140,6 +142,30 @@ int build_layout(const dmb_model* m, Layout& L) {
         L.lh = m->height / 4; L.lw = m->width / 4;
     }
     L.D = h;
+    {   // tensor-core plan: all encoder layers behind the head must be tcgen05 shapes
+        std::vector<std::pair<int, int>> wide;      // (conv index, input height == width scale)
+        const int H = m->height, W = m->width;
+        bool ok = true;
+        auto want = [&](int ci, int hh, int ww) {
+            const ConvL& c = L.convs[ci];
+            ok = ok && conv_tc_supported(c.cin, c.cout, c.ks, c.stride, hh, ww);
+            wide.push_back({ci, 0});
+        };
+        if (m->arch == DMB_ARCH_Z16) {
+            want(L.e2, H / 2, W / 2); want(L.e3, H / 4, W / 4); want(L.e4, H / 8, W / 8);
+        } else {
+            want(L.e2, H / 2, W / 2);
+        }
+        for (const ResL& r : L.enc_res) { want(r.a, L.lh, L.lw); want(r.b, L.lh, L.lw); }
+        ok = ok && ((int64_t)(H / 2) * (W / 2)) % 32 == 0 && L.convs[L.e1].cout % 32 == 0;
+        if (ok) {
+            L.tc = true;
+            for (auto& wv : wide) {
+                ConvL& c = L.convs[wv.first];
+                c.ptc_off = B.take_packed(conv_tc_weight_floats(c.cin, c.cout, c.ks));
+            }
+        }
+    }
     L.pzero_off = B.take_packed(L.max_c);
     L.n_params = B.p; L.n_bnbuf = B.bb; L.n_packed = B.pk;
     return 0;
@@ -178,6 +204,7 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
         w.y1 = bp.take<float>(B * h2 * (H / 2) * (W / 2));
         w.y2 = bp.take<float>(B * h * lat);
     }
+    if (L.tc && bn_mode == DMB_BN_EVAL) w.y1t = bp.take<float>(B * h2 * (H / 2) * (W / 2));
     for (size_t i = 0; i < L.enc_res.size(); ++i) {
         w.era.push_back(bp.take<float>(B * rh * lat));
         w.erb.push_back(bp.take<float>(B * h * lat));
@@ -400,12 +427,63 @@ int run_res(Ctx& c, const std::vector<ResL>& res, std::vector<float*>& ra, std::
     return 0;
 }
 
+bool tc_enabled() {
+    const char* e = getenv("DMB_TC");      // read per call: tests flip it to compare with the CUDA-core kernels
+    return !(e && e[0] == '0');
+}
+
+// one tensor-core layer over NHWC activations (EVAL mode: BatchNorm folded into the packed weights / bias)
+int run_conv_tc(Ctx& c, int ci, const float* in, bool in_relu, int H, int W, float* out, const float* skip_nhwc,
+                bool out_relu, bool out_nhwc) {
+    const ConvL& l = c.L.convs[ci];
+    DMB_CHECK(l.ptc_off >= 0, "conv %d has no tensor-core weights", ci);
+    ConvTcArgs a{};
+    a.x = in; a.wtc = c.packed + l.ptc_off; a.bias = c.packed + l.pb_off; a.y = out; a.skip = skip_nhwc;
+    a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.ks = l.ks; a.stride = l.stride;
+    a.in_relu = in_relu; a.out_relu = out_relu; a.out_nhwc = out_nhwc; a.skip_nhwc = 1;
+    return conv_tc(a, c.st);
+}
+
+// EVAL-mode encoder of the wide configurations: CUDA-core head (thin input), NCHW -> NHWC once, then every layer on
+// tcgen05; the last layer writes NCHW (the layout of z_before and of the quantiser).
+int run_encoder_tc(Ctx& c, const float* x, float* zb_out) {
+    const Layout& L = c.L;
+    const dmb_model& m = L.m;
+    const int H = m.height, W = m.width;
+    Act in; in.p = x;
+    Act a1;
+    DMB_TRY(run_conv(c, L.e1, in, false, H, W, c.w.y1, nullptr, true, &a1));
+    DMB_TRY(nchw_to_nhwc(c.w.y1, c.w.y1t, c.B, L.convs[L.e1].cout, (H / 2) * (W / 2), c.st));
+    const bool no_res = L.enc_res.empty();
+    const float* h;
+    if (m.arch == DMB_ARCH_Z16) {
+        DMB_TRY(run_conv_tc(c, L.e2, c.w.y1t, false, H / 2, W / 2, c.w.y2, nullptr, true, true));
+        DMB_TRY(run_conv_tc(c, L.e3, c.w.y2, false, H / 4, W / 4, c.w.y3, nullptr, true, true));
+        float* y4 = no_res ? zb_out : c.w.y4;
+        DMB_TRY(run_conv_tc(c, L.e4, c.w.y3, false, H / 8, W / 8, y4, nullptr, false, !no_res));
+        h = y4;
+    } else {
+        float* y2 = no_res ? zb_out : c.w.y2;
+        DMB_TRY(run_conv_tc(c, L.e2, c.w.y1t, false, H / 2, W / 2, y2, nullptr, false, !no_res));
+        h = y2;
+    }
+    for (size_t i = 0; i < L.enc_res.size(); ++i) {
+        const bool last = (i + 1 == L.enc_res.size());
+        float* dst = last ? zb_out : c.w.ehs[i];
+        DMB_TRY(run_conv_tc(c, L.enc_res[i].a, h, true, L.lh, L.lw, c.w.era[i], nullptr, true, true));
+        DMB_TRY(run_conv_tc(c, L.enc_res[i].b, c.w.era[i], false, L.lh, L.lw, dst, h, false, !last));
+        h = dst;
+    }
+    return 0;
+}
+
 // encoder: x -> z_before (written to zb_out unless the final merge is handed to `fuse`)
 int run_encoder(Ctx& c, const float* x, float* zb_out, Pending* fuse) {
     const Layout& L = c.L;
     const dmb_model& m = L.m;
     const int H = m.height, W = m.width;
     const bool ev = c.mode == DMB_BN_EVAL;
+    if (ev && L.tc && c.w.y1t && zb_out && tc_enabled()) return run_encoder_tc(c, x, zb_out);
     Act in; in.p = x;
     Act a1, a2, a3, a4, out;
     if (m.arch == DMB_ARCH_Z16) {
@@ -1058,6 +1136,33 @@ int dmb_conv2d_forward(const float* x, const float* w_packed, const float* bias,
     a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
     a.Ho = h / stride; a.Wo = w / stride;
     return conv_fwd(a, (cudaStream_t)stream);
+}
+
+int dmb_conv2d_tc_scratch_floats(int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout, int32_t ksize,
+                                 int64_t* floats) {
+    DMB_CHECK(floats && batch > 0, "dmb_conv2d_tc_scratch_floats: bad arguments");
+    *floats = ((batch * cin * h * w + 63) & ~63ll) + conv_tc_weight_floats(cin, cout, ksize);
+    return 0;
+}
+
+int dmb_conv2d_tc(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                  int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, int32_t in_relu,
+                  const float* skip, int32_t out_relu, int32_t nhwc_io, float* scratch, void* stream) {
+    DMB_CHECK(x && w_packed && bias && y && scratch, "dmb_conv2d_tc: null pointer");
+    DMB_CHECK(conv_tc_supported(cin, cout, ksize, stride, h, w), "dmb_conv2d_tc: layer %dx%d s%d %d->%d @%dx%d is not "
+              "a tensor-core shape (Cin %% 32, Cout in {32,64}, output width in {8..128})", ksize, ksize, stride, cin,
+              cout, h, w);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* xt = scratch;
+    float* wtc = scratch + ((batch * cin * h * w + 63) & ~63ll);
+    DMB_TRY(pack_tc_weights(w_packed, wtc, cin, cout, ksize, st));
+    const float* xin = x;
+    if (!nhwc_io) { DMB_TRY(nchw_to_nhwc(x, xt, batch, cin, h * w, st)); xin = xt; }
+    ConvTcArgs a{};
+    a.x = xin; a.wtc = wtc; a.bias = bias; a.y = y; a.skip = skip;
+    a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
+    a.in_relu = in_relu; a.out_relu = out_relu; a.out_nhwc = nhwc_io; a.skip_nhwc = nhwc_io;
+    return conv_tc(a, st);
 }
 
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,

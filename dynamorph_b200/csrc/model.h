@@ -24,6 +24,7 @@ struct ConvL {
     int64_t pw_off, pb_off;      // packed weight [cin][ks][ks][cout], bias [cout] or [9][cout]
     int64_t pdw_off;             // packed weight of the data-gradient conv [cout][ks][ks][cin] (-1: none)
     int bias_classes;
+    int64_t ptc_off;             // tensor-core tiles of the EVAL-folded weights (conv_tc.cu) or -1
 };
 
 struct Entry { std::string key; int which; int64_t off, numel; };
@@ -45,6 +46,9 @@ struct Layout {
     // decoder
     int d0 = -1, d1 = -1, d2 = -1, d3 = -1;   // z16: three ConvT + conv1x1; z32: d0, d1 ConvT
     int D = 0, lh = 0, lw = 0;
+    // every encoder layer after the head is a tensor-core shape (conv_tc_supported): the EVAL-mode encoder runs
+    // them on tcgen05 over NHWC activations (64-wide configurations, BASELINE configs[3])
+    bool tc = false;
 };
 
 int build_layout(const dmb_model* m, Layout& L);
@@ -54,6 +58,7 @@ struct BnWs { double* part; float* scale; float* shift; float* mean; float* invs
 struct Workspace {
     // z16 encoder activations (raw conv outputs in BATCH/PER_SAMPLE mode, post-activation in EVAL)
     float *y1 = nullptr, *y2 = nullptr, *y3 = nullptr, *y4 = nullptr;
+    float* y1t = nullptr;                  // NHWC copy of y1 feeding the tensor-core layers (Layout::tc, EVAL)
     std::vector<float*> era, erb, ehs;     // encoder residual: 3x3 out, 1x1 out, running sum
     std::vector<float*> dra, drb, dhs;     // decoder residual (z32)
     float *zb = nullptr, *za = nullptr;

@@ -140,6 +140,16 @@ int dmb_conv2d_forward(const float* x, const float* w_packed, const float* bias,
                        int32_t stride, const float* in_scale, const float* in_shift,
                        int32_t in_per_sample, int32_t in_relu, const float* skip, int32_t out_relu,
                        void* stream);
+/* nn.Conv2d forward on the tensor cores (tcgen05, 3xTF32 operand split, fp32 accumulation in TMEM) for the wide
+ * layers of BASELINE configs[3]: Cin a multiple of 32, Cout 32 or 64, output width a power of two in [8, 128],
+ * same kernel/stride set as dmb_conv2d_forward (reference: vq_vae.py:279-289, :203-209).  nhwc_io = 0: x, skip, y
+ * are NCHW (x is transposed into `scratch` first); nhwc_io = 1: all three are NHWC.  `scratch` holds
+ * dmb_conv2d_tc_scratch_floats() floats (the transposed input and the split, swizzled weight tiles).            */
+int dmb_conv2d_tc_scratch_floats(int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout, int32_t ksize,
+                                 int64_t* floats);
+int dmb_conv2d_tc(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                  int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, int32_t in_relu,
+                  const float* skip, int32_t out_relu, int32_t nhwc_io, float* scratch, void* stream);
 /* nn.ConvTranspose2d(k=4, stride=2, padding=1) forward; w_packed is [Cin][4][4][Cout].        */
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,

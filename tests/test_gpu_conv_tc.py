@@ -1,0 +1,128 @@
+"""-m gpu: the tensor-core convolution (csrc/conv_tc.cu: tcgen05 implicit GEMM, 3xTF32 operand split, fp32 accumulation
+in TMEM) through the layer-level C ABI (dmb_conv2d_tc), against torch's CPU float64 conv2d on the same seeded inputs
+(the arithmetic of the reference's nn.Conv2d layers at the 64-wide widths, HiddenStateExtractor/vq_vae.py:279-289,
+:203-209; vae.py:401-407).  Tolerance 1e-5 of max|y|: the split keeps 21+ mantissa bits per operand, so the error is
+fp32-round-off sized (the path-level bar in BASELINE.json is 1e-4)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (ksize, stride, cin, cout, input width): every wide layer of VQ_VAE(64, 32, K) and VQ_VAE_z32(64, 64, K)
+SHAPES = [(4, 2, 32, 64, 64), (4, 2, 64, 64, 32), (3, 1, 64, 64, 16), (3, 1, 64, 32, 16), (1, 1, 32, 64, 16),
+          (3, 1, 64, 64, 32), (1, 1, 64, 64, 32)]
+
+
+def run_tc(x, w, bias, ks, stride, in_relu=False, skip=None, out_relu=False, nhwc=False):
+    from dynamorph_b200._lib import call, ptr
+    B, cin, H, W = x.shape
+    cout = w.shape[0]
+    wp = w.permute(1, 2, 3, 0).contiguous()          # [Cin][k][k][Cout]
+    n = C.c_int64(0)
+    call("dmb_conv2d_tc_scratch_floats", B, cin, H, W, cout, ks, C.byref(n))
+    scratch = torch.empty(n.value, device=x.device)
+    Ho, Wo = H // stride, W // stride
+    if nhwc:
+        xin = x.permute(0, 2, 3, 1).contiguous()
+        sk = skip.permute(0, 2, 3, 1).contiguous() if skip is not None else None
+        y = torch.empty(B, Ho, Wo, cout, device=x.device)
+    else:
+        xin, sk = x, skip
+        y = torch.empty(B, cout, Ho, Wo, device=x.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    call("dmb_conv2d_tc", ptr(xin), ptr(wp), ptr(bias), ptr(y), B, cin, H, W, cout, ks, stride, int(in_relu),
+         ptr(sk) if sk is not None else None, int(out_relu), int(nhwc), ptr(scratch), st)
+    torch.cuda.synchronize()
+    return y.permute(0, 3, 1, 2) if nhwc else y
+
+
+def reference(x, w, bias, ks, stride, in_relu=False, skip=None, out_relu=False):
+    x = x.double().cpu()
+    if in_relu:
+        x = x.relu()
+    y = F.conv2d(x, w.double().cpu(), bias.double().cpu(), stride=stride, padding=0 if ks == 1 else 1)
+    if skip is not None:
+        y = y + skip.double().cpu()
+    return y.relu() if out_relu else y
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "k%ds%d_%dto%d_w%d" % s)
+@pytest.mark.parametrize("B", [1, 5])
+@pytest.mark.parametrize("nhwc", [False, True], ids=["nchw", "nhwc"])
+def test_tc_conv_matches_torch(shape, B, nhwc):
+    ks, stride, cin, cout, W = shape
+    g = torch.Generator(device="cuda").manual_seed(ks * 1000 + cin * 10 + cout + B)
+    x = torch.randn(B, cin, W, W, device="cuda", generator=g)
+    w = torch.randn(cout, cin, ks, ks, device="cuda", generator=g) * (cin * ks * ks) ** -0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    y = run_tc(x, w, bias, ks, stride, nhwc=nhwc)
+    ref = reference(x, w, bias, ks, stride)
+    err = float((y.double().cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, f"plain: {err:.3e}"
+    skip = torch.randn(B, cout, W // stride, W // stride, device="cuda", generator=g)
+    kw = dict(in_relu=True, skip=skip, out_relu=True)
+    y = run_tc(x, w, bias, ks, stride, nhwc=nhwc, **kw)
+    ref = reference(x, w, bias, ks, stride, **kw)
+    err = float((y.double().cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, f"relu on load + skip + relu: {err:.3e}"
+
+
+def test_tc_conv_error_is_fp32_sized():
+    """The 3xTF32 split must not be a disguised single-pass TF32 (error ~1e-3): compare with an fp32 FFMA conv."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(8, 64, 32, 32, device="cuda", generator=g)
+    w = torch.randn(64, 64, 4, 4, device="cuda", generator=g) / 32.0
+    bias = torch.zeros(64, device="cuda")
+    y = run_tc(x, w, bias, 4, 2)
+    ref = reference(x, w, bias, 4, 2)
+    err = float((y.double().cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, f"{err:.3e}"
+
+
+def test_tc_conv_rejects_thin_layers():
+    from dynamorph_b200._lib import call, ptr
+    x = torch.zeros(1, 16, 16, 16, device="cuda")
+    with pytest.raises(RuntimeError):
+        call("dmb_conv2d_tc", ptr(x), ptr(x), ptr(x), ptr(x), 1, 16, 16, 16, 16, 3, 1, 0, None, 0, 0, ptr(x),
+             C.c_void_p(0))
+
+
+@pytest.mark.parametrize("arch,rh", [("z16", 32), ("z32", 64)], ids=["VQ_VAE_64_512", "VQ_VAE_z32_64_64_512"])
+def test_wide_encoder_on_tensor_cores_matches_oracle(arch, rh, monkeypatch):
+    """BASELINE configs[3] through the drop-in classes in eval mode (the tcgen05 encoder, csrc/model.cu:
+    run_encoder_tc) against the CPU oracle on seeded inputs; and against the CUDA-core schedule (DMB_TC=0)."""
+    import gpu_util as U
+    from oracle import vqvae_oracle as O
+    st = O.default_state(arch, num_hiddens=64, num_residual_hiddens=rh, num_embeddings=512, seed=3)
+    st = O.calibrate_state(st, O.synthetic_patches(8, 5), seed=1)
+    x = O.synthetic_patches(6, 11)
+    with torch.no_grad():
+        zb_ref = O.encoder(x, st, O.EVAL)
+    idx_ref = O.vq_indices(zb_ref, st["vq.w.weight"])
+    m = U.model_from_state(st).eval()
+    from dynamorph_b200._lib import load
+    lib = load()
+    m.encode_latents(x.cuda(), "eval")             # first call packs the weights
+    lib.dmb_launch_count(1)
+    zb, za, idx = m.encode_latents(x.cuda(), "eval")
+    n_tc = lib.dmb_launch_count(1)
+    assert U.rel(zb, zb_ref) < U.REL_TOL
+    flips = U.check_indices(idx, zb_ref, st["vq.w.weight"], idx_ref, arch)
+    if flips == 0:
+        assert U.rel(za, O.vq_gather(idx_ref, st["vq.w.weight"])) < U.REL_TOL
+    monkeypatch.setenv("DMB_TC", "0")
+    zb0, za0, idx0 = m.encode_latents(x.cuda(), "eval")
+    n_cc = lib.dmb_launch_count(1)
+    assert n_tc == n_cc + 1, (n_tc, n_cc)          # same layer count + the NCHW -> NHWC transpose
+    assert U.rel(zb, zb0) < 1e-5
+    # ragged batch: one patch, odd count
+    for nb in (1, 3):
+        zb1, _, idx1 = m.encode_latents(x[:nb].cuda(), "eval")
+        monkeypatch.delenv("DMB_TC")
+        zb2, _, idx2 = m.encode_latents(x[:nb].cuda(), "eval")
+        monkeypatch.setenv("DMB_TC", "0")
+        assert torch.equal(zb2, zb[:nb]) and torch.equal(idx2, idx[:nb])
+        assert U.rel(zb1, zb2) < 1e-5

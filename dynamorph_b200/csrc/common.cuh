@@ -238,6 +238,9 @@ struct VqArgs {
     double* stats;           // [2+K] or nullptr
 };
 int vq_forward(const VqArgs& a, cudaStream_t st);
+// tensor-core code search + exact refinement of the candidates (vq_tc.cu); returns 1 when it does not take the call
+// (K outside [16, 512], D not in {16, 32, 64}); vq_forward tries it first unless DMB_VQ_TC=0
+int vq_forward_tc(const VqArgs& a, cudaStream_t st);
 // gradient of the quantiser; optional per-CTA BatchNorm-backward sums [B*p/128][d][2] against stat_src
 // time-matching loss (matching.cu)
 size_t tm_scratch_floats(int64_t B, int64_t L);

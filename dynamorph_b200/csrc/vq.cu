@@ -204,6 +204,13 @@ int launch_vq(const VqArgs& a, cudaStream_t st) {
 int vq_forward(const VqArgs& a, cudaStream_t st) {
     DMB_CHECK(a.B > 0 && a.P > 0, "vq: empty input");
     DMB_CHECK(a.K >= 1 && a.K <= 1024, "vq: num_embeddings %d outside [1, 1024]", a.K);
+    {
+        const char* e = getenv("DMB_VQ_TC");           // read per call: tests compare both kernels
+        if (!(e && e[0] == '0')) {
+            const int r = vq_forward_tc(a, st);
+            if (r <= 0) return r;
+        }
+    }
     switch (a.D) {
         case 8: return launch_vq<8>(a, st);
         case 16: return launch_vq<16>(a, st);

@@ -378,13 +378,20 @@ int launch_vq_tc(const VqArgs& a, cudaStream_t st) {
         DMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = smem;
     }
-    int per_sm = 0;
-    DMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, VT, smem));
-    per_sm = std::min(per_sm, 512 / g.tmem_cols);        // every resident CTA holds its accumulator in tensor memory
+    // resident CTAs per SM by hand (the occupancy API answers 1 for a kernel that allocates tensor memory): shared
+    // memory (+1 KB the driver reserves per CTA), registers, and one accumulator of tmem_cols columns per CTA
+    cudaFuncAttributes fa;
+    DMB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int per_sm = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+    per_sm = std::min(per_sm, 65536 / std::max(1, fa.numRegs * VT));
+    per_sm = std::min(per_sm, 512 / g.tmem_cols);
+    per_sm = std::min(per_sm, 8);
     if (per_sm < 1) return 1;
     int sms = 148;
     DMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t grid = std::min<int64_t>(g.ntiles, (int64_t)sms * per_sm);
+    if (g.dbg == 3) fprintf(stderr, "vq_tc<%d>: K=%d smem=%zu per_sm=%d tmem_cols=%d grid=%lld tiles=%lld\n", D, a.K, smem,
+                            per_sm, g.tmem_cols, (long long)grid, (long long)g.ntiles);
     DMB_LAUNCH((kern), (unsigned)grid, VT, smem, st, a, g);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);

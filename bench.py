@@ -258,6 +258,49 @@ def layer_table(model, x, hbm_peak, fp32_tf):
     return rows
 
 
+def wide_config_table(dev, bf16_peak):
+    """BASELINE.json configs[3] (64-wide, 512 codes): eval-mode encode at batch 1024 on the tcgen05 path
+    (csrc/conv_tc.cu 3xTF32 convs + csrc/vq_tc.cu tensor-core code search) and, for comparison, with both switched
+    off (DMB_TC=0, DMB_VQ_TC=0: the CUDA-core kernels).  Timing only; parity is tests/test_gpu_conv_tc.py."""
+    from dynamorph_b200.HiddenStateExtractor.vq_vae import VQ_VAE
+    from dynamorph_b200.HiddenStateExtractor.vae import VQ_VAE_z32
+    from dynamorph_b200.synthetic import calibrate, synthetic_patches
+    B = 1024
+    x = torch.cat([synthetic_patches(256, 10 + i, dev) for i in range(B // 256)])
+    out = {}
+    for name, ctor, flops, tc_flops in (
+            ("VQ_VAE(num_hiddens=64,num_embeddings=512)", lambda: VQ_VAE(num_hiddens=64, num_embeddings=512),
+             293601280, 2 * (70254592 + 8388608)),
+            ("VQ_VAE_z32(64,64,512)", lambda: VQ_VAE_z32(num_hiddens=64, num_residual_hiddens=64, num_embeddings=512),
+             310378496, 2 * (117440512 + 33554432))):
+        torch.manual_seed(0)
+        m = ctor().to(dev)
+        calibrate(m, synthetic_patches(64, 1, dev))
+        m.eval()
+        row = {"batch": B, "flops_per_patch_reference": flops}
+        for tag, env in (("tensor_core", None), ("cuda_core", "0")):
+            for k in ("DMB_TC", "DMB_VQ_TC"):
+                if env is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = env
+            for _ in range(2):
+                m.encode_latents(x, "eval")
+            torch.cuda.synchronize()
+            ms = time_events(lambda: m.encode_latents(x, "eval"), 5)
+            row[tag] = {"ms": ms, "patches_per_s": B / (ms * 1e-3), "tflops_reference_count": flops * B / ms / 1e9}
+        for k in ("DMB_TC", "DMB_VQ_TC"):
+            os.environ.pop(k, None)
+        # MACs that run on the tensor cores (every conv behind the head + the code search), x3 passes for the convs
+        row["tensor_core"]["speedup_vs_cuda_core"] = row["cuda_core"]["ms"] / row["tensor_core"]["ms"]
+        out[name] = row
+        del m
+        torch.cuda.empty_cache()
+    out["note"] = ("tensor peak for TF32 is about half the measured bf16 peak (%.0f TFLOP/s); the 3xTF32 split executes "
+                   "three MMAs per fp32-accurate product" % (bf16_peak / 2))
+    return out
+
+
 def run_ours(args):
     world, rank, local, dist = dist_setup(args.gpus)
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists for the product path)"
@@ -467,6 +510,12 @@ def run_ours(args):
                               "flops_per_patch_executed": ENC_FLOPS_EXEC,
                               "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
         line["layers"] = rows
+        if world == 1:
+            try:
+                bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0)
+            except Exception:
+                bf16 = 1590.0
+            line["wide_config"] = wide_config_table(dev, bf16)
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cores)     # the CPU baseline gets every host core back
             v, cores, sec = cpu_reference_rate(1024, 256, 2)

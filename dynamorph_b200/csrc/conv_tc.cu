@@ -10,10 +10,11 @@
 //   the zero padding is the TMA out-of-bounds fill;
 // * weights are pre-split (hi = tf32(w), lo = tf32(w - hi)) and pre-swizzled by `pack_tc_weights`, one plain
 //   cp.async.bulk per k-block;
-// * warps 0-3 split the activation tile in shared memory (optional ReLU on load, hi in place, lo beside it) and
-//   later run the epilogue; warp 4 lane 0 is the TMA producer; warp 5 lane 0 issues the MMAs
-//   (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi into one TMEM accumulator) and commits stage release / accumulator-ready
-//   to mbarriers;
+// * warps 0-7 split the activation tile in shared memory (optional ReLU on load, hi in place, lo beside it) and
+//   later run the epilogue; warp 8 lane 0 is the TMA producer; warp 9 lane 0 issues the MMAs: per K=8 step ONE
+//   N = 2*Cout MMA  a_hi * [b_hi; b_lo]  (the hi and lo weight tiles are adjacent rows of one operand, so a_hi
+//   crosses the shared-memory port once) and one N = Cout MMA  a_lo * b_hi, into TMEM accumulators laid out as
+//   [main | small] column blocks, and commits stage release / accumulator-ready to mbarriers;
 // * epilogue: tcgen05.ld (lane = pixel, column = output channel) -> bias, skip, ReLU -> NCHW (coalesced over the
 //   128 consecutive pixels of the tile) or NHWC (16-byte stores) output.
 #include "common.cuh"
@@ -112,7 +113,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_THREADS = (TC_SPLIT_WARPS + 2) * 32;
 constexpr int TC_A_BYTES = 128 * 128;        // 128 pixels x 32 channels fp32
 
 template <int COUT, int NSTAGE, int NACC>
@@ -121,11 +123,11 @@ struct TcCfg {
     static constexpr int STAGE = 2 * TC_A_BYTES + B_BYTES;       // A, A_lo, B_hi, B_lo
     static constexpr int BAR_BYTES = 256;
     static constexpr size_t SMEM = (size_t)NSTAGE * STAGE + BAR_BYTES + 1024;
-    // accumulators in TMEM: NACC main ones (a_hi*b_hi, MMA k of every k-block goes to accumulator k % NACC) and one
-    // for the two small cross terms.  The tensor core truncates when it aligns and adds, so the error of a long
+    // accumulators in TMEM: NACC pairs (main = a_hi*b_hi, small = a_hi*b_lo + a_lo*b_hi); MMA k of every k-block goes
+    // to pair k % NACC.  The tensor core truncates when it aligns and adds, so the error of a long
     // accumulation chain is a bias that grows with its length and with the magnitude of the running sum; short
     // chains summed in fp32 round-to-nearest by the epilogue keep the result at FFMA-chain accuracy.
-    static constexpr int ACC_COLS = (NACC + 1) * COUT;
+    static constexpr int ACC_COLS = NACC * 2 * COUT;             // accumulator k: columns [2k*Cout, +Cout) main, next Cout small
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     static_assert(NACC == 1 || NACC == 2 || NACC == 4, "NACC must divide the four MMAs of a k-block");
     static_assert(ACC_COLS <= 512, "accumulators do not fit tensor memory");
@@ -139,11 +141,10 @@ struct TcKArgs {
     const float* skip;
     int Ho, Wo, TH, tiles_per_img, nkb, nhalf, ks, stride, pad;
     int in_relu, out_relu, out_nhwc, skip_nhwc;
-    int dbg;               // DMB_TC_DBG bit mask (profiling experiments only; results are wrong when set)
 };
 
 template <int COUT, int NSTAGE, int NACC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, NSTAGE == 2 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
     using C = TcCfg<COUT, NSTAGE, NACC>;
     extern __shared__ uint8_t smem_raw[];
@@ -156,17 +157,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
     static_assert(NSTAGE <= 8, "barrier map holds eight stages");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_TMA = TC_SPLIT_WARPS, W_MMA = TC_SPLIT_WARPS + 1;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(bar_full + 8u * s, 1u);
-            mbar_init(bar_split + 8u * s, 128u);
+            mbar_init(bar_split + 8u * s, (uint32_t)TC_SPLIT_WARPS);
             mbar_init(bar_empty + 8u * s, 1u);
         }
         mbar_init(bar_accum, 1u);
         fence_barrier_init();
     }
-    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
-    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)C::TMEM_COLS);
+    if (warp == W_TMA && lane == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
+    if (warp == W_MMA) tmem_alloc(tmem_slot, (uint32_t)C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -178,7 +180,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
     const int oy0 = (tile - b * a.tiles_per_img) * a.TH;
     const int nkb = a.nkb;
 
-    if (warp == 4) {
+    if (warp == W_TMA) {
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NSTAGE, it = kb / NSTAGE;
@@ -186,19 +188,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
                 const int tap = kb / a.nhalf, half = kb - tap * a.nhalf;
                 const int kh = tap / a.ks, kw = tap - kh * a.ks;
                 const uint32_t st = base + (uint32_t)s * C::STAGE;
-                if (a.dbg & 4) {
-                    mbar_expect_tx(bar_full + 8u * s, (uint32_t)(C::B_BYTES));
-                } else {
                 mbar_expect_tx(bar_full + 8u * s, (uint32_t)(TC_A_BYTES + C::B_BYTES));
                 tma_load_4d(st, &tmap, bar_full + 8u * s, half * 32, kw - a.pad, a.stride * oy0 + kh - a.pad, b);
-                }
                 bulk_load_1d(st + 2u * TC_A_BYTES, a.wtc + (size_t)kb * (C::B_BYTES / 4), (uint32_t)C::B_BYTES,
                              bar_full + 8u * s);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(128, COUT);
+            constexpr uint32_t idesc2 = make_idesc_tf32(128, 2 * COUT), idesc1 = make_idesc_tf32(128, COUT);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NSTAGE, it = kb / NSTAGE;
                 mbar_wait(bar_full + 8u * s, (uint32_t)(it & 1));
@@ -206,62 +204,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
                 tc_fence_after();
                 const uint32_t st = base + (uint32_t)s * C::STAGE;
                 const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_A_BYTES);
-                const uint64_t b_hi = make_desc_sw128(st + 2u * TC_A_BYTES);
-                const uint64_t b_lo = make_desc_sw128(st + 2u * TC_A_BYTES + COUT * 128u);
-                if (!(a.dbg & 2))
+                const uint64_t b_hl = make_desc_sw128(st + 2u * TC_A_BYTES);   // rows [0,Cout) hi, [Cout,2Cout) lo
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {                 // 4 x (K = 8 tf32 = 32 bytes) inside the swizzle atom
                     const uint64_t o = (uint64_t)(k * 2);
-                    const uint32_t d_small = tmem_base + (uint32_t)(NACC * COUT);
-                    const uint32_t d_main = tmem_base + (uint32_t)((k % NACC) * COUT);
-                    tc_mma_tf32(d_small, a_lo + o, b_hi + o, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_mma_tf32(d_small, a_hi + o, b_lo + o, idesc, 1u);
-                    tc_mma_tf32(d_main, a_hi + o, b_hi + o, idesc, (kb != 0 || k >= NACC) ? 1u : 0u);
+                    const uint32_t d = tmem_base + (uint32_t)((k % NACC) * 2 * COUT);
+                    tc_mma_tf32(d, a_hi + o, b_hl + o, idesc2, (kb != 0 || k >= NACC) ? 1u : 0u);   // [hi*hi | hi*lo]
+                    tc_mma_tf32(d + COUT, a_lo + o, b_hl + o, idesc1, 1u);                           // small += lo*hi
                 }
                 tc_commit(bar_empty + 8u * s);                // frees the stage once these MMAs have read it
             }
             tc_commit(bar_accum);
         }
     } else {
-        // ---- splitter: hi = tf32(relu?(a)) in place, lo = tf32(a - hi) beside it
+        // ---- splitter: hi = relu?(a) rounded to TF32 (round half away, on the bit pattern) in place, lo = a - hi
+        // (exact; at most 13 significant bits, of which the tensor core keeps 11: 2^-21 relative, sign-symmetric)
         const int tid = threadIdx.x;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % NSTAGE, it = kb / NSTAGE;
             mbar_wait(bar_full + 8u * s, (uint32_t)(it & 1));
             float* A = reinterpret_cast<float*>(base_ptr + (size_t)s * C::STAGE);
             float* Alo = A + TC_A_BYTES / 4;
-            if (!(a.dbg & 1))
+            constexpr int PER = TC_A_BYTES / 16 / (TC_SPLIT_WARPS * 32);
+            float4 v[PER];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int e = (i * 128 + tid) * 4;
-                float4 v = *reinterpret_cast<const float4*>(A + e);
-                if (a.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                float4 h, l;
-                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                *reinterpret_cast<float4*>(A + e) = h;
-                *reinterpret_cast<float4*>(Alo + e) = l;
+            for (int i = 0; i < PER; ++i) v[i] = *reinterpret_cast<const float4*>(A + (i * TC_SPLIT_WARPS * 32 + tid) * 4);
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                float h[4], l[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (a.in_relu) x[u] = fmaxf(x[u], 0.f);
+                    h[u] = __uint_as_float((__float_as_uint(x[u]) + 0x1000u) & 0xffffe000u);
+                    l[u] = x[u] - h[u];
+                }
+                const int e = (i * TC_SPLIT_WARPS * 32 + tid) * 4;
+                *reinterpret_cast<float4*>(A + e) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(Alo + e) = make_float4(l[0], l[1], l[2], l[3]);
             }
             fence_proxy_async();
-            mbar_arrive(bar_split + 8u * s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_split + 8u * s);
         }
-        // ---- epilogue
+        // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (its pixels) and columns 32 (w / 4) .. +31 (+64 ...)
         mbar_wait(bar_accum, 0u);
         tc_fence_after();
-        const int m = tid;                                      // pixel of the tile == TMEM lane
+        const int m = (warp & 3) * 32 + lane;                   // pixel of the tile == TMEM lane
         const int HoWo = a.Ho * a.Wo;
         const int64_t pix = (int64_t)oy0 * a.Wo + m;            // pixel inside the image (tiles are full-width rows)
 #pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
+        for (int c0 = (warp >> 2) * 32; c0 < COUT; c0 += 32 * (TC_SPLIT_WARPS / 4)) {
             uint32_t v[32];
             float o[32];
-            const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-            tmem_ld32(lane_base, v);
+            const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+            // small cross terms first (their own round-off is 2^-11 of a result ulp), then the main partial sums
+            tmem_ld32(lane_base + (uint32_t)COUT, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
 #pragma unroll
-            for (int q = 1; q <= NACC; ++q) {                  // remaining main accumulators, then the small terms
-                tmem_ld32(lane_base + (uint32_t)(q * COUT), v);
+            for (int q = 1; q < NACC; ++q) {
+                tmem_ld32(lane_base + (uint32_t)(q * 2 * COUT + COUT), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) {
+                tmem_ld32(lane_base + (uint32_t)(q * 2 * COUT), v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
             }
@@ -296,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == W_MMA) {
         __syncwarp();
         tmem_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);
     }
@@ -359,23 +368,15 @@ PFN_cuTensorMapEncodeTiled tc_encoder() {
     return fn;
 }
 
-int tc_stages() {
-    static int n = []() {
-        const char* e = getenv("DMB_TC_STAGES");
-        const int v = e ? atoi(e) : 4;
-        return (v == 2 || v == 3 || v == 4) ? v : 4;
-    }();
-    return n;
+// Variant choice (0 = automatic).  Two CTAs per SM hide the per-k-block handshake latency better than four stages in
+// one CTA, but need <= 256 TMEM columns and <= 113 KB each: that is Cout = 32 with four accumulator pairs, or Cout = 64
+// with two -- the latter only for the 1x1 layers, whose accumulation chains are too short to need four.
+int tc_env(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
 }
-
-int tc_nacc() {
-    static int n = []() {
-        const char* e = getenv("DMB_TC_NACC");
-        const int v = e ? atoi(e) : 4;
-        return (v == 1 || v == 2 || v == 4) ? v : 4;
-    }();
-    return n;
-}
+int tc_stages() { static const int n = tc_env("DMB_TC_STAGES"); return n; }
+int tc_nacc() { static const int n = tc_env("DMB_TC_NACC"); return n; }
 
 template <int COUT, int NSTAGE, int NACC>
 int launch_tc(const ConvTcArgs& a, const CUtensorMap& map, const TcKArgs& k, int64_t tiles, cudaStream_t st) {
@@ -398,14 +399,19 @@ int launch_tc(const ConvTcArgs& a, const CUtensorMap& map, const TcKArgs& k, int
 
 template <int COUT>
 int launch_tc_n(const ConvTcArgs& a, const CUtensorMap& map, const TcKArgs& k, int64_t tiles, cudaStream_t st) {
-    const int na = tc_nacc();
-    switch (tc_stages()) {
-        case 2: return na == 1 ? launch_tc<COUT, 2, 1>(a, map, k, tiles, st) : na == 2 ? launch_tc<COUT, 2, 2>(a, map, k, tiles, st)
-                                                                                      : launch_tc<COUT, 2, 4>(a, map, k, tiles, st);
-        case 3: return na == 1 ? launch_tc<COUT, 3, 1>(a, map, k, tiles, st) : na == 2 ? launch_tc<COUT, 3, 2>(a, map, k, tiles, st)
-                                                                                      : launch_tc<COUT, 3, 4>(a, map, k, tiles, st);
-        default: return na == 1 ? launch_tc<COUT, 4, 1>(a, map, k, tiles, st) : na == 2 ? launch_tc<COUT, 4, 2>(a, map, k, tiles, st)
-                                                                                       : launch_tc<COUT, 4, 4>(a, map, k, tiles, st);
+    int ns = tc_stages(), na = tc_nacc();
+    if (ns == 0) ns = (COUT == 32 || k.nkb <= 4) ? 2 : 4;
+    if (na == 0) na = (COUT == 64 && ns == 2) ? 2 : 4;
+    switch (ns * 10 + na) {
+        case 21: return launch_tc<COUT, 2, 1>(a, map, k, tiles, st);
+        case 22: return launch_tc<COUT, 2, 2>(a, map, k, tiles, st);
+        case 24: return launch_tc<COUT, 2, 4>(a, map, k, tiles, st);
+        case 31: return launch_tc<COUT, 3, 1>(a, map, k, tiles, st);
+        case 32: return launch_tc<COUT, 3, 2>(a, map, k, tiles, st);
+        case 34: return launch_tc<COUT, 3, 4>(a, map, k, tiles, st);
+        case 41: return launch_tc<COUT, 4, 1>(a, map, k, tiles, st);
+        case 42: return launch_tc<COUT, 4, 2>(a, map, k, tiles, st);
+        default: return launch_tc<COUT, 4, 4>(a, map, k, tiles, st);
     }
 }
 
@@ -468,8 +474,7 @@ int conv_tc(const ConvTcArgs& a, cudaStream_t st) {
     k.Ho = Ho; k.Wo = Wo; k.TH = TH; k.tiles_per_img = Ho / TH;
     k.nhalf = a.Cin / 32; k.nkb = a.ks * a.ks * k.nhalf; k.ks = a.ks; k.stride = S; k.pad = (a.ks == 1) ? 0 : 1;
     k.in_relu = a.in_relu; k.out_relu = a.out_relu; k.out_nhwc = a.out_nhwc; k.skip_nhwc = a.skip_nhwc;
-    static const int dbg = getenv("DMB_TC_DBG") ? atoi(getenv("DMB_TC_DBG")) : 0;
-    k.dbg = dbg;
+
     const int64_t tiles = (int64_t)a.B * k.tiles_per_img;
     DMB_CHECK(tiles > 0 && tiles < (1ll << 31), "conv_tc: grid %lld out of range", (long long)tiles);
     switch (a.Cout) {

@@ -126,7 +126,7 @@ struct VqTcGeom {
 };
 
 template <int D>
-__global__ void __launch_bounds__(VT) vq_tc_kernel(const VqArgs a, const VqTcGeom g) {
+__global__ void __launch_bounds__(VT, D == 16 ? 8 : (D == 32 ? 4 : 1)) vq_tc_kernel(const VqArgs a, const VqTcGeom g) {
     static_assert(D == 16 || D == 32 || D == 64, "embedding_dim must be 16, 32 or 64");
     constexpr int DP = D < 32 ? 32 : D;      // channels padded to whole 128-byte operand rows
     constexpr int NH = DP / 32;

@@ -43,9 +43,11 @@ def encode_patches(model, dataset: np.ndarray, device, bn_mode: str = "per_sampl
 
 
 def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: int = 0, bn_mode: str = "per_sample",
-                **kwargs):
+                shard_rows: int = 0, **kwargs):
     """Wrapper method for VAE encoding: loads the prepared dataset of one well and encodes its static
-    patches with the trained VQ-VAE; writes the two latent-space pickles (reference: patch_VAE.py:343-462)."""
+    patches with the trained VQ-VAE; writes the two latent-space pickles (reference: patch_VAE.py:343-462).
+    shard_rows > 0 additionally writes the same rows as `.npy` shards of that many rows plus a manifest
+    (latent_shards.py), the form multi-million-patch runs use instead of one pickle."""
     cfg = config_.latent_encoding
     channels = cfg.channels
     network = cfg.network
@@ -102,6 +104,12 @@ def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: in
     print(f"\tsaving {os.path.join(output_dir, '%s_latent_space_after.pkl' % well)}")
     with open(os.path.join(output_dir, '%s_latent_space_after.pkl' % well), 'wb') as f:
         pickle.dump(dats, f, protocol=4)
+    if shard_rows > 0:
+        from ..latent_shards import ShardedLatentWriter, merge_manifests
+        for kind, arr in (("latent_space", z_b), ("latent_space_after", z_a)):
+            with ShardedLatentWriter(output_dir, well, kind, int(np.prod(arr.shape[1:])), rows_per_shard=shard_rows) as w:
+                w.append(np.ascontiguousarray(arr[take]).reshape((len(fs), -1)))
+            merge_manifests(output_dir, well, kind)
     if save_output:
         # 20 reconstructions as .npy (the reference renders them to JPG with matplotlib, which is a
         # plotting concern outside this path)

@@ -99,6 +99,8 @@ struct ConvFwdArgs {
     const float* stat_src;  // nullptr: (sum o, sum o^2); else (sum o, sum o*stat_src)  (BatchNorm backward)
     int B, Cin, H, W, Cout, Ho, Wo;
     int ks, stride;         // (1,1) (3,1) (4,2)
+    int out_nhwc;           // y is (B, Ho, Wo, Cout): only the head shape of the 64-wide encoder (4x4 s2, 2 -> 32 @128),
+                            // plain call (no skip / statistics / transform); anything else is an error
 };
 int conv_fwd(const ConvFwdArgs& a, cudaStream_t st);
 // number of (sum, sumsq) partial rows per sample the kernel will write for this geometry; `plain` = a forward

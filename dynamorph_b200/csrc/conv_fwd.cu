@@ -445,6 +445,7 @@ int conv_fwd(const ConvFwdArgs& a, cudaStream_t st) {
         const int r = conv_tma(a, st);      // 1 = not taken (unsupported shape or a data-gradient call)
         if (r <= 0) return r;
     }
+    DMB_CHECK(!a.out_nhwc, "conv_fwd: channel-last output exists only for the plain 4x4 s2 2->32 @128 head (TMA kernel)");
     DMB_CHECK(a.Wo % PW == 0, "conv_fwd: output width %d must be a multiple of %d", a.Wo, PW);
     const int co_t = pick_co_t(a.Cout);
     DMB_CHECK(co_t != 0, "conv_fwd: Cout=%d must be even", a.Cout);

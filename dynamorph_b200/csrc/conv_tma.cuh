@@ -51,8 +51,12 @@ __constant__ float c_pool[POOL_FLOATS];
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
-template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, int XF_ = 0, bool DGRAD_ = false, int COT_ = 8>
+template <int KS_, int STRIDE_, int CIN_, int COUT_, int WIN_, bool WCONST_, int XF_ = 0, bool DGRAD_ = false, int COT_ = 8,
+          bool NHWC_ = false>
 struct TC {
+    // channel-last output (B, Ho, Wo, Cout): the head of the 64-wide encoder feeds the tensor-core layers (conv_tc.cu)
+    // directly; a separate instantiation so that the NCHW kernels keep their register allocation
+    static constexpr bool NHWC = NHWC_;
     // output channels per thread: 8 (64 accumulators); 4 for training-size batches, where the 8-channel tiling leaves
     // most of the GPU without a CTA (a few hundred patches of a 16x16 map are ~128 CTAs) -- twice the CTAs, half the
     // work each, at a slightly lower FFMA density
@@ -447,7 +451,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
 #pragma unroll
             for (int p = 0; p < PW; ++p) o[p] = fmaxf(o[p], 0.f);
         }
-        if (live) {
+        if constexpr (C::NHWC) {
+#pragma unroll
+            for (int p = 0; p < PW; ++p) acc[c][p] = o[p];       // stored pixel by pixel after the channel loop
+        } else if (live) {
 #pragma unroll
             for (int i = 0; i < PW / 4; ++i)
                 reinterpret_cast<float4*>(y_u + off)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -472,6 +479,17 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaConvArgs a) {
         ssum[c] = s; ssq[c] = q;
     }
 
+    if constexpr (C::NHWC) {
+        if (live) {
+            float* yp = a.y + ((((size_t)b * C::HO + oy) * C::WO + sx * PW) * C::COUT) + cgz * CC + cgl * CO_T;
+#pragma unroll
+            for (int p = 0; p < PW; ++p)
+#pragma unroll
+                for (int c = 0; c < CO_T; c += 4)
+                    *reinterpret_cast<float4*>(yp + (size_t)p * C::COUT + c) =
+                        make_float4(acc[c][p], acc[c + 1][p], acc[c + 2][p], acc[c + 3][p]);
+        }
+    }
     if (a.stats) {
         // deterministic two-level reduction: thread partials -> smem -> one warp per (patch, channel).
         // Slot order inside a (patch, channel) = (row, strip), i.e. independent of the lane mapping.

@@ -73,7 +73,7 @@ int conv_tma_bands_default(int ks, int stride, int Cin, int Cout, int H, int W, 
 
 // Returns 1 if the call was not taken, 0 on success, <0 on error.
 int conv_tma_default(const ConvFwdArgs& a, cudaStream_t st) {
-    if (!tma_plain(a)) return 1;
+    if (!tma_plain(a) || a.out_nhwc) return 1;
 #define X(KS, S, CI, CO, WIN)                                                                        \
     if (a.ks == KS && a.stride == S && a.Cin == CI && a.Cout == CO && a.W == WIN && a.H == WIN) {   \
         if (small_launch<KS, S, CI, CO, WIN>(a.B)) return launch_xf<KS, S, CI, CO, WIN, false, 4>(a, st); \

@@ -31,6 +31,13 @@ bool use_pool(const ConvFwdArgs& a, cudaStream_t st, int w_floats) {
 // transform form: BatchNorm affine pending -> 2; ReLU only on a 3x3 (eval-mode residual block) -> 1; else 0
 template <int KS, int S, int CI, int CO, int WIN, bool WC>
 int launch_xf(const ConvFwdArgs& a, cudaStream_t st) {
+    if (a.out_nhwc) {
+        if constexpr (KS == 4 && CI == 2 && CO == 32 && WIN == 128) {
+            if (!a.mask_src && !a.stat_src && !a.in_scale && !a.in_relu && !a.skip && !a.stats)
+                return launch_tma<TC<KS, S, CI, CO, WIN, WC, 0, false, 8, true>>(a, st);
+        }
+        return 1;
+    }
     if (a.mask_src || a.stat_src) {
         // training data gradient: plain input (the caller materialised it), shared-memory weights, gate + sums epilogue
         if constexpr (!WC) {

@@ -450,10 +450,24 @@ int run_encoder_tc(Ctx& c, const float* x, float* zb_out) {
     const Layout& L = c.L;
     const dmb_model& m = L.m;
     const int H = m.height, W = m.width;
-    Act in; in.p = x;
-    Act a1;
-    DMB_TRY(run_conv(c, L.e1, in, false, H, W, c.w.y1, nullptr, true, &a1));
-    DMB_TRY(nchw_to_nhwc(c.w.y1, c.w.y1t, c.B, L.convs[L.e1].cout, (H / 2) * (W / 2), c.st));
+    {   // head on the CUDA cores (2 input channels), written channel-last when the TMA kernel has that form
+        const ConvL& l = L.convs[L.e1];
+        ConvFwdArgs a{};
+        a.x = x; a.y = c.w.y1t; a.w = c.packed + l.pw_off; a.bias = c.packed + l.pb_off; a.bias_classes = l.bias_classes;
+        a.out_relu = 1; a.out_nhwc = 1;
+        a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.ks = l.ks; a.stride = l.stride;
+        a.Ho = H / l.stride; a.Wo = W / l.stride;
+        int r = 1;
+        const char* e = getenv("DMB_HEAD_NHWC");
+        if (!(e && e[0] == '0')) r = conv_tma(a, c.st);
+        if (r < 0) return r;
+        if (r == 1) {                        // no channel-last instantiation for this shape: NCHW + one transpose
+            Act in; in.p = x;
+            Act a1;
+            DMB_TRY(run_conv(c, L.e1, in, false, H, W, c.w.y1, nullptr, true, &a1));
+            DMB_TRY(nchw_to_nhwc(c.w.y1, c.w.y1t, c.B, l.cout, (H / 2) * (W / 2), c.st));
+        }
+    }
     const bool no_res = L.enc_res.empty();
     const float* h;
     if (m.arch == DMB_ARCH_Z16) {

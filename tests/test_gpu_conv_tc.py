@@ -116,7 +116,7 @@ def test_wide_encoder_on_tensor_cores_matches_oracle(arch, rh, monkeypatch):
     monkeypatch.setenv("DMB_TC", "0")
     zb0, za0, idx0 = m.encode_latents(x.cuda(), "eval")
     n_cc = lib.dmb_launch_count(1)
-    assert n_tc == n_cc + 1, (n_tc, n_cc)          # same layer count + the NCHW -> NHWC transpose
+    assert n_tc in (n_cc, n_cc + 1), (n_tc, n_cc)  # same layer count (+ a transpose when the head has no NHWC form)
     assert U.rel(zb, zb0) < 1e-5
     # ragged batch: one patch, odd count
     for nb in (1, 3):

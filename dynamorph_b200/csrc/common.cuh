@@ -127,6 +127,21 @@ int pack_tc_weights(const float* w_packed, float* out, int cin, int cout, int ks
 int nchw_to_nhwc(const float* x, float* y, int64_t B, int C, int HW, cudaStream_t st);
 int conv_tc(const ConvTcArgs& a, cudaStream_t st);
 
+// Winograd F(2x2,3x3) on the tensor cores for the 16-channel 3x3 layers at 16x16 (conv_wino_tc.cu); EVAL mode, no skip /
+// statistics / BatchNorm transform
+struct ConvWinoArgs {
+    const float* x;         // (B, 16, 16, 16) NCHW
+    const float* u;         // pack_wino_weights output: [hi|lo][xi pair][Cout][32], 128-byte swizzled rows
+    const float* bias;      // [Cout]
+    float* y;               // (B, Cout, 16, 16)
+    int B, Cout;
+    int in_relu, out_relu;
+};
+bool conv_wino_supported(int cin, int cout, int ks, int stride, int H, int W);
+int64_t conv_wino_weight_floats(int cin, int cout);
+int pack_wino_weights(const float* w_packed, float* out, int cin, int cout, cudaStream_t st);
+int conv_wino(const ConvWinoArgs& a, cudaStream_t st);
+
 // transposed 4x4 stride-2 pad-1 convolution, forward (convt_fwd.cu)
 struct ConvTFwdArgs {
     const float* x;         // (B, Cin, H, W)

@@ -83,6 +83,31 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// Converged-warp forms: the issuing warp stays converged and one elected lane executes the instruction.  Issued from a
+// divergent `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY loop.
+__device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        done = mbar_try(bar, parity) ? 1u : 0u;
+    } while (!__all_sync(0xffffffffu, done != 0));
+}
 // 32 lanes x 32 consecutive columns: thread t of the warp gets lane (base lane + t), v[j] = column (base col + j)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -195,12 +220,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
             }
         }
     } else if (warp == W_MMA) {
-        if (lane == 0) {
+        {   // whole warp, converged; one elected lane per tcgen05 instruction
             constexpr uint32_t idesc2 = make_idesc_tf32(128, 2 * COUT), idesc1 = make_idesc_tf32(128, COUT);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NSTAGE, it = kb / NSTAGE;
-                mbar_wait(bar_full + 8u * s, (uint32_t)(it & 1));
-                mbar_wait(bar_split + 8u * s, (uint32_t)(it & 1));
+                mbar_wait_warp(bar_full + 8u * s, (uint32_t)(it & 1));
+                mbar_wait_warp(bar_split + 8u * s, (uint32_t)(it & 1));
                 tc_fence_after();
                 const uint32_t st = base + (uint32_t)s * C::STAGE;
                 const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_A_BYTES);
@@ -209,12 +234,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
                 for (int k = 0; k < 4; ++k) {                 // 4 x (K = 8 tf32 = 32 bytes) inside the swizzle atom
                     const uint64_t o = (uint64_t)(k * 2);
                     const uint32_t d = tmem_base + (uint32_t)((k % NACC) * 2 * COUT);
-                    tc_mma_tf32(d, a_hi + o, b_hl + o, idesc2, (kb != 0 || k >= NACC) ? 1u : 0u);   // [hi*hi | hi*lo]
-                    tc_mma_tf32(d + COUT, a_lo + o, b_hl + o, idesc1, 1u);                           // small += lo*hi
+                    tc_mma_tf32_elect(d, a_hi + o, b_hl + o, idesc2, (kb != 0 || k >= NACC) ? 1u : 0u);   // [hi*hi | hi*lo]
+                    tc_mma_tf32_elect(d + COUT, a_lo + o, b_hl + o, idesc1, 1u);                           // small += lo*hi
                 }
-                tc_commit(bar_empty + 8u * s);                // frees the stage once these MMAs have read it
+                tc_commit_elect(bar_empty + 8u * s);          // frees the stage once these MMAs have read it
             }
-            tc_commit(bar_accum);
+            tc_commit_elect(bar_accum);
         }
     } else {
         // ---- splitter: hi = relu?(a) rounded to TF32 (round half away, on the bit pattern) in place, lo = a - hi

@@ -47,7 +47,7 @@ struct Builder {
     int conv(const std::string& key, int cin, int cout, int ks, int stride, bool transposed) {
         ConvL c{};
         c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.transposed = transposed; c.bn = -1;
-        c.ptc_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1;
         c.w_off = take_param(key + ".weight", (int64_t)cin * cout * ks * ks);
         c.b_off = take_param(key + ".bias", cout);
         c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
@@ -63,7 +63,7 @@ struct Builder {
         ConvL c{};
         c.cin = cin; c.cout = cmid; c.cmid = cmid; c.ks = 4; c.stride = 2; c.composite = 1; c.bn = -1;
         c.bias_classes = 1;
-        c.ptc_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1;
         c.w0_off = take_param(key0 + ".weight", (int64_t)cmid * cin);
         c.b0_off = take_param(key0 + ".bias", cmid);
         c.w_off = take_param(key1 + ".weight", (int64_t)cmid * cmid * 16);
@@ -164,6 +164,17 @@ int build_layout(const dmb_model* m, Layout& L) {
                 ConvL& c = L.convs[wv.first];
                 c.ptc_off = B.take_packed(conv_tc_weight_floats(c.cin, c.cout, c.ks));
             }
+        }
+    }
+    {   // Winograd tensor-core plan: the 16-channel 3x3 layers at a 16x16 latent (default configuration, EVAL mode)
+        std::vector<int> cand;
+        if (m->arch == DMB_ARCH_Z16) cand.push_back(L.e4);
+        for (const ResL& r : L.enc_res) cand.push_back(r.a);
+        for (int ci : cand) {
+            ConvL& c = L.convs[ci];
+            // (the kernel also takes 16 output channels, but there the direct CUDA-core kernel is still faster)
+            if (c.cout == 32 && conv_wino_supported(c.cin, c.cout, c.ks, c.stride, L.lh, L.lw))
+                c.pwn_off = B.take_packed(conv_wino_weight_floats(c.cin, c.cout));
         }
     }
     L.pzero_off = B.take_packed(L.max_c);
@@ -344,6 +355,15 @@ struct Ctx {
     bool per_sample() const { return mode == DMB_BN_PER_SAMPLE; }
 };
 
+// Smallest batch that takes the Winograd tensor-core kernel (persistent CTAs of two patches each: below a few hundred
+// patches most SMs would idle through its prologue).  DMB_WINO=0 switches it off, DMB_WINO_MIN_B overrides the threshold.
+int64_t wino_min_batch() {
+    const char* off = getenv("DMB_WINO");
+    if (off && off[0] == '0') return INT64_MAX;
+    const char* e = getenv("DMB_WINO_MIN_B");
+    return e ? atoll(e) : 512;
+}
+
 // conv (or convT) layer `ci`: in -> out, optional ReLU on load; in BN modes gathers statistics and
 // finalises them, returning the affine that the consumer must apply.
 int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* out,
@@ -361,6 +381,14 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout;
         DMB_TRY(convt_fwd(a, c.st));
         Ho = 2 * H; Wo = 2 * W;
+    } else if (c.mode == DMB_BN_EVAL && l.pwn_off >= 0 && !skip && !in.s && c.B >= wino_min_batch() &&
+               conv_wino_supported(l.cin, l.cout, l.ks, l.stride, H, W)) {
+        // default-width 3x3 at the latent resolution: Winograd F(2x2,3x3) on the tensor cores (conv_wino_tc.cu)
+        ConvWinoArgs a{};
+        a.x = in.p; a.u = c.packed + l.pwn_off; a.bias = c.packed + l.pb_off; a.y = out;
+        a.B = (int)c.B; a.Cout = l.cout; a.in_relu = in_relu; a.out_relu = out_relu;
+        DMB_TRY(conv_wino(a, c.st));
+        Ho = H; Wo = W;
     } else {
         ConvFwdArgs a{};
         a.x = in.p; a.y = out; a.w = c.packed + l.pw_off; a.bias = c.packed + l.pb_off;
@@ -1177,6 +1205,18 @@ int dmb_conv2d_tc(const float* x, const float* w_packed, const float* bias, floa
     a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
     a.in_relu = in_relu; a.out_relu = out_relu; a.out_nhwc = nhwc_io; a.skip_nhwc = nhwc_io;
     return conv_tc(a, st);
+}
+
+int dmb_conv2d_wino(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                    int32_t h, int32_t w, int32_t cout, int32_t in_relu, int32_t out_relu, float* scratch, void* stream) {
+    DMB_CHECK(x && w_packed && bias && y && scratch, "dmb_conv2d_wino: null pointer");
+    DMB_CHECK(conv_wino_supported(cin, cout, 3, 1, h, w), "dmb_conv2d_wino: only 3x3 stride-1 layers with 16 input and "
+              "16 or 32 output channels on 16x16 maps (got %d->%d @%dx%d)", cin, cout, h, w);
+    cudaStream_t st = (cudaStream_t)stream;
+    DMB_TRY(pack_wino_weights(w_packed, scratch, cin, cout, st));
+    ConvWinoArgs a{};
+    a.x = x; a.u = scratch; a.bias = bias; a.y = y; a.B = (int)batch; a.Cout = cout; a.in_relu = in_relu; a.out_relu = out_relu;
+    return conv_wino(a, st);
 }
 
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,

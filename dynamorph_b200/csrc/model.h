@@ -25,6 +25,7 @@ struct ConvL {
     int64_t pdw_off;             // packed weight of the data-gradient conv [cout][ks][ks][cin] (-1: none)
     int bias_classes;
     int64_t ptc_off;             // tensor-core tiles of the EVAL-folded weights (conv_tc.cu) or -1
+    int64_t pwn_off;             // Winograd-domain tensor-core tiles of the EVAL-folded weights (conv_wino_tc.cu) or -1
 };
 
 struct Entry { std::string key; int which; int64_t off, numel; };

@@ -160,6 +160,10 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
     DMB_LAUNCH((pack_kernel), blocks, threads, 0, st, p, params, bnbuf, packed);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
+    if (bn_mode == DMB_BN_EVAL) {                // Winograd-domain tensor-core tiles for conv_wino_tc.cu
+        for (const ConvL& c : L.convs)
+            if (c.pwn_off >= 0) DMB_TRY(pack_wino_weights(packed + c.pw_off, packed + c.pwn_off, c.cin, c.cout, st));
+    }
     if (L.tc && bn_mode == DMB_BN_EVAL) {        // split, swizzled tiles of the folded weights for conv_tc.cu
         for (const ConvL& c : L.convs)
             if (c.ptc_off >= 0) DMB_TRY(pack_tc_weights(packed + c.pw_off, packed + c.ptc_off, c.cin, c.cout, c.ks, st));

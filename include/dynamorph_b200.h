@@ -150,6 +150,12 @@ int dmb_conv2d_tc_scratch_floats(int64_t batch, int32_t cin, int32_t h, int32_t 
 int dmb_conv2d_tc(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
                   int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, int32_t in_relu,
                   const float* skip, int32_t out_relu, int32_t nhwc_io, float* scratch, void* stream);
+/* nn.Conv2d(16 -> 16|32, 3x3, padding 1) on 16x16 maps as Winograd F(2x2,3x3) on the tensor cores (16 batched TF32x3
+ * GEMMs, accumulators in tensor memory): the latent-resolution 3x3 layers of the default configuration in eval mode
+ * (reference: vq_vae.py:203-209, :288).  x, y NCHW; w_packed [Cin][3][3][Cout]; optional ReLU on load / on store.
+ * `scratch` holds 2*16*Cin*Cout floats (the transformed, split, swizzled weights).                                 */
+int dmb_conv2d_wino(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                    int32_t h, int32_t w, int32_t cout, int32_t in_relu, int32_t out_relu, float* scratch, void* stream);
 /* nn.ConvTranspose2d(k=4, stride=2, padding=1) forward; w_packed is [Cin][4][4][Cout].        */
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,

@@ -126,3 +126,59 @@ def test_wide_encoder_on_tensor_cores_matches_oracle(arch, rh, monkeypatch):
         monkeypatch.setenv("DMB_TC", "0")
         assert torch.equal(zb2, zb[:nb]) and torch.equal(idx2, idx[:nb])
         assert U.rel(zb1, zb2) < 1e-5
+
+
+def run_wino(x, w, bias, in_relu=False, out_relu=False):
+    from dynamorph_b200._lib import call, ptr
+    B, cin, H, W = x.shape
+    cout = w.shape[0]
+    wp = w.permute(1, 2, 3, 0).contiguous()          # [Cin][3][3][Cout]
+    scratch = torch.empty(2 * 16 * cin * cout, device=x.device)
+    y = torch.empty(B, cout, H, W, device=x.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    call("dmb_conv2d_wino", ptr(x), ptr(wp), ptr(bias), ptr(y), B, cin, H, W, cout, int(in_relu), int(out_relu),
+         ptr(scratch), st)
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("cout", [32, 16])
+@pytest.mark.parametrize("B", [1, 2, 5, 301])
+def test_winograd_tc_conv_matches_torch(cout, B):
+    """csrc/conv_wino_tc.cu: Winograd F(2x2,3x3) as 16 TF32x3 GEMMs in tensor memory, against an fp64 convolution
+    (the 16-channel 3x3 layers of the default configuration, vq_vae.py:203-209, :288)."""
+    g = torch.Generator(device="cuda").manual_seed(100 * cout + B)
+    x = torch.randn(B, 16, 16, 16, device="cuda", generator=g)
+    w = torch.randn(cout, 16, 3, 3, device="cuda", generator=g) / 12.0
+    bias = torch.randn(cout, device="cuda", generator=g)
+    for in_relu, out_relu in ((False, False), (True, True)):
+        y = run_wino(x, w, bias, in_relu, out_relu)
+        ref = reference(x, w, bias, 3, 1, in_relu=in_relu, out_relu=out_relu)
+        err = float((y.double().cpu() - ref).abs().max() / ref.abs().max())
+        assert err < 5e-6, f"relu {in_relu}/{out_relu}: {err:.3e}"
+
+
+def test_default_encoder_with_winograd_tc_matches_golden(monkeypatch):
+    """The eval-mode encoder of the DEFAULT configuration with its three latent-resolution 3x3 layers on the Winograd
+    tensor-core kernel (taken for batches >= 512 by default; forced here) against the fixture written by the
+    unmodified reference, and against the direct CUDA-core schedule."""
+    import gpu_util as U
+    from conftest import Golden
+    g = Golden("vqvae_default")
+    st = g.state()
+    m = U.model_from_state(st).eval()
+    x = g.t("x_eval").cuda()
+    monkeypatch.setenv("DMB_WINO_MIN_B", "1")
+    zb, za, idx = m.encode_latents(x, "eval")
+    assert U.rel(zb, g.t("eval/z_before")) < U.REL_TOL
+    flips = U.check_indices(idx, g.t("eval/z_before"), st["vq.w.weight"], g["eval/idx"], "winograd-tc")
+    if flips == 0:
+        assert U.rel(za, g.t("eval/z_after")) < U.REL_TOL
+    monkeypatch.setenv("DMB_WINO", "0")
+    zb0, _, idx0 = m.encode_latents(x, "eval")
+    assert not torch.equal(zb, zb0), "the Winograd kernel was not taken"
+    assert U.rel(zb, zb0) < 1e-5
+    # odd batch (the kernel works on pairs of patches)
+    monkeypatch.delenv("DMB_WINO")
+    zb3, _, idx3 = m.encode_latents(x[:3], "eval")
+    assert torch.equal(zb3, zb[:3]) and torch.equal(idx3, idx[:3])

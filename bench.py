@@ -29,7 +29,10 @@ import torch  # noqa: E402
 # algorithmic figures per patch, defaults (SURVEY.md section 8d / BASELINE.md section 4)
 ENC_BYTES = 131072 + 16384 + 16384          # x in, z_before out, z_after out
 ENC_FLOPS_ALGO = 22151168                    # 2 * (enc MACs + VQ MACs), reference layer structure
-ENC_FLOPS_EXEC = 15335424                    # what the kernels execute: enc.0 (1x1) folded into enc.1 (4x4), DESIGN.md section 4
+ENC_FLOPS_EXEC = 15335424                    # direct-form FLOPs after folding enc.0 (1x1) into enc.1 (4x4), DESIGN.md section 4
+# ... of which the CUDA cores still execute this much once the two residual 3x3 layers (2 x 1,179,648 MACs) run as
+# Winograd GEMMs on the tensor cores and the quantiser's search (262,144 MACs) as a TF32 GEMM
+ENC_FLOPS_CUDA_CORE = ENC_FLOPS_EXEC - 2 * (2 * 1179648 + 262144)
 # DRAM bytes per patch of each kernel (dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture of an
 # 8192-patch eval encode step, profiles/r1_launches_encode_step.csv: launches in schedule order), for roofline.traffic
 def ncu_dram_bytes_per_patch():
@@ -233,15 +236,34 @@ def layer_table(model, x, hbm_peak, fp32_tf):
         in_relu = 1 if name == "res conv3x3" else 0
         out_relu = 0 if name in ("enc.10 conv3x3", "res conv1x1") else 1
         skip = torch.randn(B, cout, H // s, H // s, device=dev) if name == "res conv1x1" else None
-        fn = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
-                          None, None, 0, in_relu, ptr(skip), out_relu, st)
+        wino = (name == "res conv3x3" and cin == 16 and cout == 32 and B >= 512 and os.environ.get("DMB_WINO", "1") != "0")
+        if wino:
+            # what the eval-mode step runs for this layer at bulk batch sizes: Winograd F(2x2,3x3) on the tensor cores
+            # (csrc/conv_wino_tc.cu); the direct CUDA-core kernel is timed beside it
+            scratch = torch.empty(2 * 16 * cin * cout, device=dev)
+            fn_direct = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
+                                     None, None, 0, in_relu, ptr(skip), out_relu, st)
+            fn_direct(); torch.cuda.synchronize()
+            ms_direct = time_events(fn_direct, 5)
+            fn = lambda: call("dmb_conv2d_wino", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, in_relu, out_relu,
+                              ptr(scratch), st)
+        else:
+            fn = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
+                              None, None, 0, in_relu, ptr(skip), out_relu, st)
         fn(); torch.cuda.synchronize()
         ms = time_events(fn, 5)
         macs = (H // s) ** 2 * cout * cin * ks * ks
         byts = (cin * H * H + cout * (H // s) ** 2 * (2 if skip is not None else 1)) * 4
-        rows.append({"kernel": name, "launches_per_step": model.num_residual_layers if name.startswith("res") else 1,
-                     "ms": ms, "gbs": byts * B / ms / 1e6, "tflops": 2 * macs * B / ms / 1e9,
-                     "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "fp32_frac": 2 * macs * B / ms / 1e9 / fp32_tf})
+        row = {"kernel": name, "launches_per_step": model.num_residual_layers if name.startswith("res") else 1,
+               "ms": ms, "gbs": byts * B / ms / 1e6, "tflops": 2 * macs * B / ms / 1e9,
+               "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "fp32_frac": 2 * macs * B / ms / 1e9 / fp32_tf}
+        if wino:
+            row.update({"kernel": name + " (Winograd on tensor cores)", "fp32_frac": None,
+                        "tflops": None, "direct_form_flops_equivalent_tflops": 2 * macs * B / ms / 1e9,
+                        "direct_cuda_core_kernel_ms": ms_direct,
+                        "note": "16 TF32x3 GEMMs per tile pair in tensor memory; executes 16/36 of the direct form's "
+                                "multiplies three times over in TF32"})
+        rows.append(row)
         del xin, y
     z = torch.randn(B, h, 16, 16, device=dev)
     cb = torch.randn(K, h, device=dev)
@@ -492,7 +514,7 @@ def run_ours(args):
         fp32_tf = fp32_peak(dev)
         rows = layer_table(model, x[:min(chunk, 8192)], hbm_peak, fp32_tf)
         total_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
-        dom = max(rows, key=lambda r: r["ms"] * r["launches_per_step"])
+        dom = max((r for r in rows if r.get("fp32_frac") is not None), key=lambda r: r["ms"] * r["launches_per_step"])
         nb = min(chunk, 8192)
         traffic = ncu_dram_bytes_per_patch().get(dom["kernel"])
         line["roofline"] = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
@@ -508,8 +530,11 @@ def run_ours(args):
                             "share_of_step": dom["ms"] * dom["launches_per_step"] / total_ms}
         line["whole_step"] = {"hbm_frac_algorithmic": value / world * ENC_BYTES / 1e9 / hbm_peak,
                               "fp32_frac_algorithmic_flops": value / world * ENC_FLOPS_ALGO / 1e12 / fp32_tf,
-                              "fp32_frac_executed_flops": value / world * ENC_FLOPS_EXEC / 1e12 / fp32_tf,
-                              "flops_per_patch_executed": ENC_FLOPS_EXEC,
+                              "fp32_frac_executed_flops": value / world * ENC_FLOPS_CUDA_CORE / 1e12 / fp32_tf,
+                              "flops_per_patch_executed": ENC_FLOPS_CUDA_CORE,
+                              "flops_per_patch_direct_form_folded_head": ENC_FLOPS_EXEC,
+                              "note": "executed = FP32 FLOPs left on the CUDA cores (head, enc.4, enc.7, enc.10, 1x1); the "
+                                      "residual 3x3 layers and the code search run on the tensor cores",
                               "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
         line["layers"] = rows
         if world == 1:

@@ -341,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
     pdl_wait();
     __shared__ float t[32][33];
-    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int b = blockIdx.x, c0 = blockIdx.y * 32, p0 = blockIdx.z * 32;     // batch on x: no 65535 limit
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float* xb = x + (int64_t)b * C * HW;
     float* yb = y + (int64_t)b * C * HW;
@@ -469,8 +469,8 @@ int pack_tc_weights(const float* w_packed, float* out, int cin, int cout, int ks
 
 int nchw_to_nhwc(const float* x, float* y, int64_t B, int C, int HW, cudaStream_t st) {
     DMB_CHECK(C % 32 == 0 && HW % 32 == 0, "nchw_to_nhwc: C=%d and HW=%d must be multiples of 32", C, HW);
-    DMB_CHECK(B > 0 && B < 65536, "nchw_to_nhwc: batch %lld out of range", (long long)B);
-    DMB_LAUNCH((nchw_to_nhwc_kernel), dim3(HW / 32, C / 32, (unsigned)B), 256, 0, st, x, y, C, HW);
+    DMB_CHECK(B > 0 && B < (1ll << 31) && HW / 32 < 65536, "nchw_to_nhwc: batch %lld / map size %d out of range", (long long)B, HW);
+    DMB_LAUNCH((nchw_to_nhwc_kernel), dim3((unsigned)B, C / 32, HW / 32), 256, 0, st, x, y, C, HW);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

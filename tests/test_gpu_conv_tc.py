@@ -182,3 +182,38 @@ def test_default_encoder_with_winograd_tc_matches_golden(monkeypatch):
     monkeypatch.delenv("DMB_WINO")
     zb3, _, idx3 = m.encode_latents(x[:3], "eval")
     assert torch.equal(zb3, zb[:3]) and torch.equal(idx3, idx[:3])
+
+
+@pytest.mark.parametrize("D,K,B,P", [(16, 16, 3, 100), (32, 100, 5, 77), (64, 250, 2, 129), (16, 512, 1, 256),
+                                      (64, 48, 7, 33)])
+def test_vq_tensor_core_search_is_bit_identical_to_exhaustive(D, K, B, P, monkeypatch):
+    """csrc/vq_tc.cu against csrc/vq.cu (the exhaustive direct-form search in torch's summation order, itself checked
+    against the reference in test_gpu_encode.py) on ragged sizes: codes not a multiple of 16, positions not a multiple
+    of the 128-position tile, near-duplicate codes, a collapsed codebook (overflow path) and NaN input (fallback)."""
+    from dynamorph_b200._lib import call, ptr
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(D * 1000 + K)
+    z = torch.randn(B, D, P, device="cuda", generator=g)
+    flat = z.permute(0, 2, 1).reshape(-1, D)
+    cb = flat[torch.randint(0, B * P, (K,), device="cuda", generator=g)].clone()
+    cb[1::3] += 1e-6 * torch.randn_like(cb[1::3])                    # near-duplicates of sampled positions
+    cb[2::5] = cb[0]                                                 # exact duplicates: first index must win
+    cases = {"sampled": cb.contiguous(), "collapsed": cb[:1].expand(K, D).contiguous()}
+    zn = z.clone()
+    zn[0, :, 0] = float("nan")
+    for name, codebook in cases.items():
+        for zin in (z, zn):
+            out = {}
+            for tc in ("1", "0"):
+                monkeypatch.setenv("DMB_VQ_TC", tc)
+                zst = torch.zeros_like(zin)
+                idx = torch.full((B, P), -7, dtype=torch.int32, device="cuda")
+                stats = torch.zeros(2 + K, dtype=torch.float64, device="cuda")
+                call("dmb_vq_forward", ptr(zin), ptr(codebook), B, D, P, K, ptr(zst), ptr(idx), ptr(stats), st)
+                torch.cuda.synchronize()
+                out[tc] = (zst, idx, stats)
+            assert torch.equal(out["1"][1], out["0"][1]), name
+            assert torch.equal(out["1"][0].nan_to_num(7.0), out["0"][0].nan_to_num(7.0)), name
+            assert torch.equal(out["1"][2][1:], out["0"][2][1:]), name           # position count + histogram
+            a, b = out["1"][2][0], out["0"][2][0]
+            assert (torch.isnan(a) and torch.isnan(b)) or abs(float(a - b)) <= 1e-9 * abs(float(b)), name

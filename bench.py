@@ -22,7 +22,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (NCCL prints its banner there)
+    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries the ONE JSON line and nothing else: NCCL writes its version banner (printed at WARN too) and any
+# warning to its debug file, stdout by default
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 

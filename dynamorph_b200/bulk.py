@@ -123,3 +123,34 @@ class BulkEncoder:
         for s in self._streams:
             cur.wait_stream(s)
         return out
+
+    @torch.no_grad()
+    def encode_stream(self, source, sink) -> int:
+        """Encode an arbitrarily long run without ever holding its outputs: `source` yields host tensors
+        (n_i, C, H, W) (slices of a memory-mapped array, successive pickles, ...), `sink(first_row, out)` receives the
+        host result of each block (`out` as returned by `encode`; valid only during the call) -- e.g.
+        `latent_shards.ShardedLatentWriter.append`.  Two pinned output sets alternate, so the sink of block i (disk)
+        runs while block i + 1 is copied in and encoded.  Returns the number of rows encoded."""
+        bufs = [None, None]
+        pending = None          # (first_row, n, out dict, completion event)
+        row = 0
+        for i, block in enumerate(source):
+            j = i & 1
+            n, C, H, W = block.shape
+            if bufs[j] is None or bufs[j]["_n"] < n:
+                bufs[j] = self.allocate_outputs(n, C, H, W)
+                bufs[j]["_n"] = n
+            out = {k: v[:n] for k, v in bufs[j].items() if k != "_n"}
+            self.encode(block, out)                                   # enqueues; returns before the GPU is done
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            if pending is not None:
+                pending[3].synchronize()
+                sink(pending[0], pending[2])
+            pending = (row, n, out, ev)
+            row += n
+        if pending is not None:
+            pending[3].synchronize()
+            sink(pending[0], pending[2])
+        return row
+

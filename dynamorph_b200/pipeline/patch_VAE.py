@@ -42,6 +42,35 @@ def encode_patches(model, dataset: np.ndarray, device, bn_mode: str = "per_sampl
     return out["z_before"].numpy(), out["z_after"].numpy()
 
 
+def encode_patches_to_shards(model, dataset: np.ndarray, device, out_dir: str, well: str, bn_mode: str = "per_sample",
+                             chunk: int = 4096, rows_per_shard: int = 65536, block_rows: int = 65536, rank: int = 0,
+                             world: int = 1, first_row: int = 0):
+    """Streaming form of `encode_patches` for runs whose (N, D*h*w) float32 outputs do not fit in host memory: the raw
+    patches are walked in blocks, each block's latents go straight from the pinned D2H buffers into the sharded store
+    (latent_shards.py: `<well>_latent_space.*.npy`, `<well>_latent_space_after.*.npy` + per-rank manifests; call
+    `merge_manifests` once every rank is done).  Rows keep the reference's layout (patch_VAE.py:454-461)."""
+    from ..latent_shards import ShardedLatentWriter
+    enc = BulkEncoder(model, chunk=chunk, bn_mode=bn_mode, device=device, outputs=("z_before", "z_after"), zscore=True)
+    part = dataset if dataset.dtype in (np.float32, np.float64, np.uint16) else dataset.astype(np.float64)
+    writers = {}
+
+    def source():
+        for a in range(0, part.shape[0], block_rows):
+            yield torch.from_numpy(np.ascontiguousarray(part[a:a + block_rows]))
+
+    def sink(_first, out):
+        for kind, key in (("latent_space", "z_before"), ("latent_space_after", "z_after")):
+            if kind not in writers:
+                writers[kind] = ShardedLatentWriter(out_dir, well, kind, out[key].shape[1], rank=rank, world=world,
+                                                    first_row=first_row, rows_per_shard=rows_per_shard)
+            writers[kind].append(out[key].numpy())
+
+    n = enc.encode_stream(source(), sink)
+    for w in writers.values():
+        w.close()
+    return n
+
+
 def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: int = 0, bn_mode: str = "per_sample",
                 shard_rows: int = 0, **kwargs):
     """Wrapper method for VAE encoding: loads the prepared dataset of one well and encodes its static
@@ -93,9 +122,18 @@ def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: in
 
     # the reference keys results by file name and re-stacks them in `fs` order (patch_VAE.py:450-455);
     # encoding in dataset order is the same thing as long as names are unique
-    z_b, z_a = encode_patches(model, dataset, device, bn_mode=bn_mode)
     order = {f: i for i, f in enumerate(fs)}
     take = np.asarray([order[f] for f in fs])
+    if shard_rows > 0 and kwargs.get("stream", False):
+        # multi-million-patch form: no (N, D*h*w) array is ever held; shards + manifest only (no single pickle)
+        assert np.array_equal(take, np.arange(len(fs))), "streaming needs unique file names (dataset order == fs order)"
+        from ..latent_shards import merge_manifests
+        encode_patches_to_shards(model, dataset, device, output_dir, well, bn_mode=bn_mode, rows_per_shard=shard_rows,
+                                 block_rows=kwargs.get("block_rows", 65536))
+        for kind in ("latent_space", "latent_space_after"):
+            merge_manifests(output_dir, well, kind)
+        return output_dir
+    z_b, z_a = encode_patches(model, dataset, device, bn_mode=bn_mode)
     dats = np.ascontiguousarray(z_b[take]).reshape((len(fs), -1))
     print(f"\tsaving {os.path.join(output_dir, '%s_latent_space.pkl' % well)}")
     with open(os.path.join(output_dir, '%s_latent_space.pkl' % well), 'wb') as f:

@@ -102,3 +102,32 @@ def test_checkpoint_roundtrip_with_reference_keys(tmp_path):
     assert list(sd) == list(st)
     for k in st:
         assert torch.equal(sd[k].cpu(), st[k]), k
+
+
+def test_process_vae_streams_into_shards(tmp_path):
+    """process_VAE(..., shard_rows=4, stream=True): blocks of patches go from the bulk encoder's D2H buffers straight into
+    the sharded store; the rows equal the single-pickle output of the default path bit for bit."""
+    from dynamorph_b200.latent_shards import open_latents
+    from dynamorph_b200.pipeline.patch_VAE import process_VAE
+    g = Golden("vqvae_default")
+    raw_dir = tmp_path / "raw"
+    wdir = tmp_path / "weights" / "my_model"
+    os.makedirs(raw_dir); os.makedirs(wdir)
+    torch.save(g.state(), wdir / "model.pt")
+    n = 13
+    raw = _raw_patches(n, 5)
+    fs = [f"/data/C5-Site_0/patch_{i}.h5" for i in range(n)]
+    pickle.dump(fs, open(raw_dir / "C5_file_paths.pkl", "wb"))
+    pickle.dump(raw, open(raw_dir / "C5_static_patches.pkl", "wb"), protocol=4)
+    cfg = types.SimpleNamespace(latent_encoding=types.SimpleNamespace(
+        weights=str(wdir), channels=[0, 1], num_hiddens=16, num_residual_hiddens=32, num_embeddings=64,
+        commitment_cost=0.25, network="VQ_VAE_z16", save_output=False, channel_mean=None, channel_std=None))
+    out_dir = process_VAE(str(raw_dir), None, ["C5-Site_0"], cfg, gpu=0)
+    zb = pickle.load(open(os.path.join(out_dir, "C5_latent_space.pkl"), "rb"))
+    za = pickle.load(open(os.path.join(out_dir, "C5_latent_space_after.pkl"), "rb"))
+    process_VAE(str(raw_dir), None, ["C5-Site_0"], cfg, gpu=0, shard_rows=4, stream=True, block_rows=5)
+    vb = open_latents(out_dir, "C5", "latent_space")
+    va = open_latents(out_dir, "C5", "latent_space_after")
+    assert vb.shape == zb.shape and len(vb.manifest["shards"]) == 4
+    assert np.array_equal(vb.to_array(), zb) and np.array_equal(va.to_array(), za)
+

@@ -249,7 +249,7 @@ def layer_table(model, x, hbm_peak, fp32_tf):
             fn_direct(); torch.cuda.synchronize()
             ms_direct = time_events(fn_direct, 5)
             fn = lambda: call("dmb_conv2d_wino", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, in_relu, out_relu,
-                              ptr(scratch), st)
+                              None, None, None, ptr(scratch), st)
         else:
             fn = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
                               None, None, 0, in_relu, ptr(skip), out_relu, st)

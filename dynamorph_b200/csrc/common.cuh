@@ -136,6 +136,10 @@ struct ConvWinoArgs {
     float* y;               // (B, Cout, 16, 16)
     int B, Cout;
     int in_relu, out_relu;
+    // optional fused ResidualBlock tail (Cout == 32): y2 = x + conv1x1(relu?(y)) + bias2, y itself is not written
+    const float* w2;        // [32][16] (the packed [Cin][1][1][Cout] layout of the 1x1) or nullptr
+    const float* bias2;     // [16]
+    float* y2;              // (B, 16, 16, 16)
 };
 bool conv_wino_supported(int cin, int cout, int ks, int stride, int H, int W);
 int64_t conv_wino_weight_floats(int cin, int cout);

@@ -22,6 +22,8 @@
 //     transform in registers, bias, ReLU, float2 stores to NCHW.
 #include "common.cuh"
 
+#include <mutex>
+
 namespace dmb {
 namespace {
 
@@ -56,17 +58,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 // The issuing warp stays CONVERGED and one elected lane executes the instruction: issued from a divergent
 // `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY loop (~100 clk per MMA, which
@@ -116,11 +107,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// weights [32 ci][16 co] and bias [16] of the 1x1 convolution fused behind the 3x3 (ResidualBlock tail, vq_vae.py:207-209)
+__constant__ float c_w2[32 * 16 + 16];
+
 struct WinoTcArgs {
     const float* x;     // (B, 16, 16, 16) NCHW
     const float* u;     // pack_wino_tc_weights output
     const float* bias;  // [COUT]
     float* y;           // (B, COUT, 16, 16)
+    float* y2;          // FUSE: (B, 16, 16, 16) = x + conv1x1(y) + bias2, the residual block's output (y itself is not written)
     int B;
     int in_relu, out_relu;
     int dbg;            // DMB_WINO_DBG bit mask (timing experiments only; results are wrong when set)
@@ -141,8 +136,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // barrier among the 16 transform / epilogue warps only (the MMA warp never joins it)
 __device__ __forceinline__ void work_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 
-template <int COUT>
+template <int COUT, bool FUSE>
 __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const WinoTcArgs a) {
+    static_assert(!FUSE || COUT == 32, "the fused 1x1 tail takes 32 channels in");
     using C = WtCfg<COUT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -328,7 +324,30 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
                         r1[jx][c] = (q1[c] - q2[c]) - q3[c];
                     }
                 }
-                if (p < a.B) {
+                if constexpr (FUSE) {
+                    // the 32 mid channels of a pixel are spread over four warps: park them in the (idle) operand buffers
+                    // as [pixel][32] rows, 16-byte chunk index XOR-ed with bits 1-3 of the pixel so that the eight tiles
+                    // of a quarter-warp (two pixels apart) store to eight different bank groups
+                    float yv[4][8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float b = __ldg(a.bias + cg * 8 + c);
+                        yv[0][c] = ((r0[0][c] + r0[1][c]) + r0[2][c]) + b; yv[1][c] = ((r0[1][c] - r0[2][c]) - r0[3][c]) + b;
+                        yv[2][c] = ((r1[0][c] + r1[1][c]) + r1[2][c]) + b; yv[3][c] = ((r1[1][c] - r1[2][c]) - r1[3][c]) + b;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int gpx = pl * 256 + (2 * ty + (i >> 1)) * 16 + 2 * tx + (i & 1);
+                        float* row = Vs + gpx * 32;
+                        const int sw = (gpx >> 1) & 7;
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq) {
+                            float4 v = make_float4(yv[i][4 * hq], yv[i][4 * hq + 1], yv[i][4 * hq + 2], yv[i][4 * hq + 3]);
+                            if (a.out_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4*>(row + (((2 * cg + hq) ^ sw) << 2)) = v;
+                        }
+                    }
+                } else if (p < a.B) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const int co = cg * 8 + c;
@@ -340,6 +359,33 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
                         *reinterpret_cast<float2*>(dst) = make_float2(y00, y01);
                         *reinterpret_cast<float2*>(dst + 16) = make_float2(y10, y11);
                     }
+                }
+            }
+            if constexpr (FUSE) {
+                // ---- fused tail: out = x + conv1x1(mid) + bias2; thread = one pixel, 16 output channels; weights
+                // from the constant bank (same for every thread: uniform operands), x from the staging planes
+                work_sync();
+                const int gpx = tid, pl = gpx >> 8, yy = (gpx >> 4) & 15, xx = gpx & 15;
+                const int64_t p = (int64_t)pair * 2 + pl;
+                const float* row = Vs + gpx * 32;
+                const int sw = (gpx >> 1) & 7;
+                float o[16];
+#pragma unroll
+                for (int co = 0; co < 16; ++co) o[co] = c_w2[512 + co];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + ((ch ^ sw) << 2));
+                    const float mv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int co = 0; co < 16; ++co) o[co] = fmaf(mv[u], c_w2[(ch * 4 + u) * 16 + co], o[co]);
+                }
+                if (p < a.B) {
+                    const float* xs = raw + buf * WT_RAW + (pl * WT_CIN) * WT_PLANE + (yy + 1) * WT_RP + xx + 1;
+                    float* dst = a.y2 + (size_t)p * 16 * 256 + yy * 16 + xx;
+#pragma unroll
+                    for (int co = 0; co < 16; ++co) dst[co * 256] = o[co] + xs[co * WT_PLANE];
                 }
             }
             if (nxt < npairs) scatter(buf ^ 1);   // (its previous contents were consumed one pair ago)
@@ -384,10 +430,18 @@ __global__ void __launch_bounds__(256) pack_wino_tc_kernel(const float* __restri
     }
 }
 
-template <int COUT>
+struct WinoPool {           // the constant bank of the fused tail is one region per device (see conv_tma.cuh: PoolState)
+    std::mutex mu;
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+};
+WinoPool g_wpool[64];
+
+template <int COUT, bool FUSE>
 int launch_wino_tc(const ConvWinoArgs& a, cudaStream_t st) {
     using C = WtCfg<COUT>;
-    auto kern = conv_wino_tc_kernel<COUT>;
+    auto kern = conv_wino_tc_kernel<COUT, FUSE>;
     int dev = 0;
     DMB_CUDA(cudaGetDevice(&dev));
     DMB_CHECK(dev >= 0 && dev < 64, "conv_wino_tc: device index %d out of range", dev);
@@ -401,10 +455,23 @@ int launch_wino_tc(const ConvWinoArgs& a, cudaStream_t st) {
     const int npairs = (a.B + 1) / 2;
     const int grid = std::min(npairs, sms);
     WinoTcArgs k{};
-    k.x = a.x; k.u = a.u; k.bias = a.bias; k.y = a.y; k.B = a.B; k.in_relu = a.in_relu; k.out_relu = a.out_relu;
+    k.x = a.x; k.u = a.u; k.bias = a.bias; k.y = a.y; k.y2 = a.y2; k.B = a.B; k.in_relu = a.in_relu; k.out_relu = a.out_relu;
     { const char* e = getenv("DMB_WINO_DBG"); k.dbg = e ? atoi(e) : 0; }
-    DMB_LAUNCH((kern), grid, WT_THREADS + 32, C::SMEM, st, k);
-    DMB_CUDA(cudaGetLastError());
+    if constexpr (FUSE) {
+        WinoPool& ps = g_wpool[dev];
+        std::lock_guard<std::mutex> lock(ps.mu);
+        if (!ps.ev) DMB_CUDA(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming));
+        if (ps.used && ps.last != st) DMB_CUDA(cudaStreamWaitEvent(st, ps.ev, 0));
+        DMB_CUDA(cudaMemcpyToSymbolAsync(c_w2, a.w2, 512 * 4, 0, cudaMemcpyDeviceToDevice, st));
+        DMB_CUDA(cudaMemcpyToSymbolAsync(c_w2, a.bias2, 16 * 4, 512 * 4, cudaMemcpyDeviceToDevice, st));
+        DMB_LAUNCH((kern), grid, WT_THREADS + 32, C::SMEM, st, k);
+        DMB_CUDA(cudaGetLastError());
+        DMB_CUDA(cudaEventRecord(ps.ev, st));
+        ps.last = st; ps.used = true;
+    } else {
+        DMB_LAUNCH((kern), grid, WT_THREADS + 32, C::SMEM, st, k);
+        DMB_CUDA(cudaGetLastError());
+    }
     DMB_LAUNCHED(1);
     return 0;
 }
@@ -430,8 +497,12 @@ int conv_wino(const ConvWinoArgs& a, cudaStream_t st) {
     DMB_CHECK(a.B > 0, "conv_wino: empty batch");
     DMB_CHECK(!(reinterpret_cast<uintptr_t>(a.u) & 15) && !(reinterpret_cast<uintptr_t>(a.y) & 7),
               "conv_wino: u must be 16-byte and y 8-byte aligned");
-    if (a.Cout == 32) return launch_wino_tc<32>(a, st);
-    if (a.Cout == 16) return launch_wino_tc<16>(a, st);
+    if (a.w2) {
+        DMB_CHECK(a.Cout == 32 && a.bias2 && a.y2, "conv_wino: the fused 1x1 tail needs 32 mid channels, bias2 and y2");
+        return launch_wino_tc<32, true>(a, st);
+    }
+    if (a.Cout == 32) return launch_wino_tc<32, false>(a, st);
+    if (a.Cout == 16) return launch_wino_tc<16, false>(a, st);
     DMB_CHECK(false, "conv_wino: Cout %d not in {16, 32}", a.Cout);
 }
 

@@ -425,6 +425,20 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
 // ResidualBlock (vq_vae.py:203-225).  `h` enters possibly with a pending affine; returns the block
 // output.  If `fuse_last` is given, the last layer's merge is left to the consumer (VQ kernel).
 struct Pending { Act a, b; bool valid = false; };
+
+// EVAL-mode residual layer whose 3x3 takes the Winograd tensor-core kernel and whose 1x1 is the 32 -> 16 tail that kernel
+// can fuse.  Opt-in (DMB_WINO_FUSE=1): measured on B200 the fused kernel takes as much longer as the separate HBM-bound
+// 1x1 launch costs (3.59 M vs 3.62 M patches/s) -- its phases run one after another, so the extra 512 FFMA per pixel
+// extend the critical path instead of filling idle issue slots.
+bool wino_fused_ok(const Ctx& c, const ResL& r, const Act& h, int H, int W) {
+    const ConvL& la = c.L.convs[r.a];
+    const ConvL& lb = c.L.convs[r.b];
+    const char* e = getenv("DMB_WINO_FUSE");
+    if (!(e && e[0] == '1')) return false;
+    return la.pwn_off >= 0 && !h.s && c.B >= wino_min_batch() && la.cout == 32 &&
+           conv_wino_supported(la.cin, la.cout, la.ks, la.stride, H, W) &&
+           lb.ks == 1 && lb.stride == 1 && lb.cin == 32 && lb.cout == 16 && !lb.transposed;
+}
 int run_res(Ctx& c, const std::vector<ResL>& res, std::vector<float*>& ra, std::vector<float*>& rb,
             std::vector<float*>& hs, Act h, int H, int W, float* final_out, Pending* fuse_last, Act* out) {
     const int64_t hw = (int64_t)H * W;
@@ -432,7 +446,17 @@ int run_res(Ctx& c, const std::vector<ResL>& res, std::vector<float*>& ra, std::
         const bool last = (i + 1 == res.size());
         float* dst = (last && final_out) ? final_out : hs[i];
         Act a1, b1;
-        if (c.mode == DMB_BN_EVAL) {
+        if (c.mode == DMB_BN_EVAL && wino_fused_ok(c, res[i], h, H, W)) {
+            // conv3x3 (Winograd, tensor cores) -> ReLU -> conv1x1 + skip in ONE kernel (conv_wino_tc.cu, FUSE)
+            const ConvL& la = c.L.convs[res[i].a];
+            const ConvL& lb = c.L.convs[res[i].b];
+            ConvWinoArgs a{};
+            a.x = h.p; a.u = c.packed + la.pwn_off; a.bias = c.packed + la.pb_off; a.y = nullptr;
+            a.B = (int)c.B; a.Cout = la.cout; a.in_relu = 1; a.out_relu = 1;
+            a.w2 = c.packed + lb.pw_off; a.bias2 = c.packed + lb.pb_off; a.y2 = dst;
+            DMB_TRY(conv_wino(a, c.st));
+            h = Act(); h.p = dst;
+        } else if (c.mode == DMB_BN_EVAL) {
             DMB_TRY(run_conv(c, res[i].a, h, true, H, W, ra[i], nullptr, true, &a1));
             DMB_TRY(run_conv(c, res[i].b, a1, false, H, W, dst, h.p, false, &b1));
             h = b1;
@@ -1208,14 +1232,18 @@ int dmb_conv2d_tc(const float* x, const float* w_packed, const float* bias, floa
 }
 
 int dmb_conv2d_wino(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
-                    int32_t h, int32_t w, int32_t cout, int32_t in_relu, int32_t out_relu, float* scratch, void* stream) {
-    DMB_CHECK(x && w_packed && bias && y && scratch, "dmb_conv2d_wino: null pointer");
+                    int32_t h, int32_t w, int32_t cout, int32_t in_relu, int32_t out_relu, const float* w2_packed,
+                    const float* bias2, float* y2, float* scratch, void* stream) {
+    DMB_CHECK(x && w_packed && bias && (y || y2) && scratch, "dmb_conv2d_wino: null pointer");
     DMB_CHECK(conv_wino_supported(cin, cout, 3, 1, h, w), "dmb_conv2d_wino: only 3x3 stride-1 layers with 16 input and "
               "16 or 32 output channels on 16x16 maps (got %d->%d @%dx%d)", cin, cout, h, w);
+    DMB_CHECK((w2_packed == nullptr) == (y2 == nullptr) && (w2_packed == nullptr) == (bias2 == nullptr),
+              "dmb_conv2d_wino: w2_packed, bias2 and y2 come together");
     cudaStream_t st = (cudaStream_t)stream;
     DMB_TRY(pack_wino_weights(w_packed, scratch, cin, cout, st));
     ConvWinoArgs a{};
     a.x = x; a.u = scratch; a.bias = bias; a.y = y; a.B = (int)batch; a.Cout = cout; a.in_relu = in_relu; a.out_relu = out_relu;
+    a.w2 = w2_packed; a.bias2 = bias2; a.y2 = y2;
     return conv_wino(a, st);
 }
 

@@ -153,9 +153,12 @@ int dmb_conv2d_tc(const float* x, const float* w_packed, const float* bias, floa
 /* nn.Conv2d(16 -> 16|32, 3x3, padding 1) on 16x16 maps as Winograd F(2x2,3x3) on the tensor cores (16 batched TF32x3
  * GEMMs, accumulators in tensor memory): the latent-resolution 3x3 layers of the default configuration in eval mode
  * (reference: vq_vae.py:203-209, :288).  x, y NCHW; w_packed [Cin][3][3][Cout]; optional ReLU on load / on store.
- * `scratch` holds 2*16*Cin*Cout floats (the transformed, split, swizzled weights).                                 */
+ * `scratch` holds 2*16*Cin*Cout floats (the transformed, split, swizzled weights).  With w2_packed / bias2 / y2 given
+ * (Cout = 32) the rest of a ResidualBlock layer is fused behind it: y2 = x + conv1x1(relu?(y)) + bias2 with w2_packed
+ * [32][16], and y itself is not written (vq_vae.py:203-209, eval mode with BatchNorm folded).                      */
 int dmb_conv2d_wino(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
-                    int32_t h, int32_t w, int32_t cout, int32_t in_relu, int32_t out_relu, float* scratch, void* stream);
+                    int32_t h, int32_t w, int32_t cout, int32_t in_relu, int32_t out_relu, const float* w2_packed,
+                    const float* bias2, float* y2, float* scratch, void* stream);
 /* nn.ConvTranspose2d(k=4, stride=2, padding=1) forward; w_packed is [Cin][4][4][Cout].        */
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,

@@ -22,7 +22,7 @@ for cout, in_relu, out_relu in ((32, 1, 1), (16, 0, 0)):
     wp = w.permute(1, 2, 3, 0).contiguous()
     scratch = torch.empty(2 * 16 * 16 * cout, device="cuda")
     y1 = torch.empty(B, cout, 16, 16, device="cuda"); y2 = torch.empty_like(y1)
-    f1 = lambda: call("dmb_conv2d_wino", ptr(x), ptr(wp), ptr(bias), ptr(y1), B, 16, 16, 16, cout, in_relu, out_relu, ptr(scratch), st)
+    f1 = lambda: call("dmb_conv2d_wino", ptr(x), ptr(wp), ptr(bias), ptr(y1), B, 16, 16, 16, cout, in_relu, out_relu, None, None, None, ptr(scratch), st)
     f2 = lambda: call("dmb_conv2d_forward", ptr(x), ptr(wp), ptr(bias), ptr(y2), B, 16, 16, 16, cout, 3, 1, None, None, 0, in_relu, None, out_relu, st)
     t1, t2 = timed(f1), timed(f2)
     nb = 16

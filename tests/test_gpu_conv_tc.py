@@ -137,7 +137,7 @@ def run_wino(x, w, bias, in_relu=False, out_relu=False):
     y = torch.empty(B, cout, H, W, device=x.device)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     call("dmb_conv2d_wino", ptr(x), ptr(wp), ptr(bias), ptr(y), B, cin, H, W, cout, int(in_relu), int(out_relu),
-         ptr(scratch), st)
+         None, None, None, ptr(scratch), st)
     torch.cuda.synchronize()
     return y
 
@@ -217,3 +217,46 @@ def test_vq_tensor_core_search_is_bit_identical_to_exhaustive(D, K, B, P, monkey
             assert torch.equal(out["1"][2][1:], out["0"][2][1:]), name           # position count + histogram
             a, b = out["1"][2][0], out["0"][2][0]
             assert (torch.isnan(a) and torch.isnan(b)) or abs(float(a - b)) <= 1e-9 * abs(float(b)), name
+
+
+@pytest.mark.parametrize("B", [1, 3, 300])
+def test_winograd_tc_fused_residual_tail_matches_torch(B):
+    """conv3x3(ReLU(x)) -> ReLU -> conv1x1 + x in one kernel (the eval-mode ResidualBlock layer, vq_vae.py:203-209 with
+    BatchNorm folded) against fp64 torch."""
+    from dynamorph_b200._lib import call, ptr
+    g = torch.Generator(device="cuda").manual_seed(B)
+    x = torch.randn(B, 16, 16, 16, device="cuda", generator=g)
+    w3 = torch.randn(32, 16, 3, 3, device="cuda", generator=g) / 12.0
+    b3 = torch.randn(32, device="cuda", generator=g)
+    w1 = torch.randn(16, 32, 1, 1, device="cuda", generator=g) / 6.0
+    b1 = torch.randn(16, device="cuda", generator=g)
+    w3p = w3.permute(1, 2, 3, 0).contiguous()
+    w1p = w1.permute(1, 2, 3, 0).contiguous()          # [32][1][1][16]
+    scratch = torch.empty(2 * 16 * 16 * 32, device="cuda")
+    y2 = torch.empty(B, 16, 16, 16, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    call("dmb_conv2d_wino", ptr(x), ptr(w3p), ptr(b3), None, B, 16, 16, 16, 32, 1, 1, ptr(w1p), ptr(b1), ptr(y2),
+         ptr(scratch), st)
+    torch.cuda.synchronize()
+    xd = x.double().cpu()
+    mid = F.conv2d(xd.relu(), w3.double().cpu(), b3.double().cpu(), padding=1).relu()
+    ref = xd + F.conv2d(mid, w1.double().cpu(), b1.double().cpu())
+    err = float((y2.double().cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 5e-6, f"{err:.3e}"
+
+
+def test_default_encoder_with_fused_winograd_tail(monkeypatch):
+    """DMB_WINO_FUSE=1: the whole eval-mode residual layer in one kernel, through the model path."""
+    import gpu_util as U
+    from conftest import Golden
+    g = Golden("vqvae_default")
+    st = g.state()
+    m = U.model_from_state(st).eval()
+    x = g.t("x_eval").cuda()
+    monkeypatch.setenv("DMB_WINO_MIN_B", "1")
+    zb0, _, idx0 = m.encode_latents(x, "eval")
+    monkeypatch.setenv("DMB_WINO_FUSE", "1")
+    zb, _, idx = m.encode_latents(x, "eval")
+    assert U.rel(zb, g.t("eval/z_before")) < U.REL_TOL
+    U.check_indices(idx, g.t("eval/z_before"), st["vq.w.weight"], g["eval/idx"], "winograd-tc fused")
+    assert not torch.equal(zb, zb0) and U.rel(zb, zb0) < 1e-5

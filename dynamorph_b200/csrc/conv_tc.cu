@@ -71,18 +71,7 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, FP32 accumulation
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, FP32 accumulation.
 // Converged-warp forms: the issuing warp stays converged and one elected lane executes the instruction.  Issued from a
 // divergent `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY loop.
 __device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -181,7 +170,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcKArgs a) {
     const uint32_t tmem_slot = bars + 200;
     static_assert(NSTAGE <= 8, "barrier map holds eight stages");
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the shuffle tells ptxas that the warp index is warp-uniform: role branches become uniform branches and the MMA
+    // warp's descriptor arithmetic stays in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     constexpr int W_TMA = TC_SPLIT_WARPS, W_MMA = TC_SPLIT_WARPS + 1;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {

@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
     // full[b]: the 16 transform warps have written operand buffer b; empty[b]: the MMAs that read it are complete
     const uint32_t bar_full = smem_u32(bar_mem), bar_empty = bar_full + 16u, slot = smem_u32(slot_mem);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (the shuffle tells ptxas that the warp index is warp-uniform: role branches become uniform branches and the MMA
+    // warp's descriptor arithmetic stays in uniform registers instead of vector registers + R2UR per instruction)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     constexpr int W_MMA = WT_THREADS / 32;
     if (tid == 0) {
         mbar_init(bar_full, 16u); mbar_init(bar_full + 8u, 16u);

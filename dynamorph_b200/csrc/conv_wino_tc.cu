@@ -121,12 +121,14 @@ struct WinoTcArgs {
     int dbg;            // DMB_WINO_DBG bit mask (timing experiments only; results are wrong when set)
 };
 
-template <int COUT>
+template <int COUT, int NVB = 2>
 struct WtCfg {
     static constexpr int U_FLOATS = 2 * 8 * COUT * 32;          // hi, lo: 8 xi-pairs x COUT rows x 32
-    static constexpr int V_FLOATS = 2 * 2 * 128 * 32;           // two buffers x (hi, lo) x one xi-pair x 128 tiles x 32
+    static constexpr int V_FLOATS = NVB * 2 * 128 * 32;         // NVB buffers x (hi, lo) x one xi-pair x 128 tiles x 32
     static constexpr int TMEM_COLS = 16 * COUT;                  // 512 / 256
-    static constexpr size_t SMEM = (size_t)(U_FLOATS + V_FLOATS + 2 * WT_RAW) * 4 + 64 + 1024;
+    static constexpr size_t SMEM = (size_t)(U_FLOATS + V_FLOATS + 2 * WT_RAW) * 4 + 128 + 1024;
+    static_assert(SMEM <= 227 * 1024, "does not fit shared memory");
+    static_assert(NVB == 2 || NVB == 3, "two or three operand buffers");
     static_assert(COUT == 32 || COUT == 16, "Cout must be 16 or 32");
 };
 
@@ -136,10 +138,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // barrier among the 16 transform / epilogue warps only (the MMA warp never joins it)
 __device__ __forceinline__ void work_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 
-template <int COUT, bool FUSE>
+template <int COUT, bool FUSE, int NVB>
 __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const WinoTcArgs a) {
     static_assert(!FUSE || COUT == 32, "the fused 1x1 tail takes 32 channels in");
-    using C = WtCfg<COUT>;
+    static_assert(!FUSE || NVB == 2, "the fused tail parks 64 KB of mid channels in exactly two operand buffers");
+    using C = WtCfg<COUT, NVB>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
@@ -148,19 +151,18 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
     float* raw = Vs + C::V_FLOATS;                                             // [2 buffers][2 patches][16 ci][325]
     uint64_t* bar_mem = reinterpret_cast<uint64_t*>(raw + 2 * WT_RAW + 1);
     bar_mem = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar_mem) + 7) & ~(uintptr_t)7);
-    uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bar_mem + 4);
+    uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bar_mem + 8);
     const uint32_t us_u = base, vs_u = base + C::U_FLOATS * 4u;
     const uint32_t raw_u = vs_u + C::V_FLOATS * 4u;
     // full[b]: the 16 transform warps have written operand buffer b; empty[b]: the MMAs that read it are complete
-    const uint32_t bar_full = smem_u32(bar_mem), bar_empty = bar_full + 16u, slot = smem_u32(slot_mem);
+    const uint32_t bar_full = smem_u32(bar_mem), bar_empty = bar_full + 32u, slot = smem_u32(slot_mem);
 
     // (the shuffle tells ptxas that the warp index is warp-uniform: role branches become uniform branches and the MMA
     // warp's descriptor arithmetic stays in uniform registers instead of vector registers + R2UR per instruction)
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     constexpr int W_MMA = WT_THREADS / 32;
     if (tid == 0) {
-        mbar_init(bar_full, 16u); mbar_init(bar_full + 8u, 16u);
-        mbar_init(bar_empty, 1u); mbar_init(bar_empty + 8u, 1u);
+        for (int b = 0; b < NVB; ++b) { mbar_init(bar_full + 8u * b, 16u); mbar_init(bar_empty + 8u * b, 1u); }
         fence_barrier_init();
     }
     if (warp == W_MMA) tmem_alloc(slot, (uint32_t)C::TMEM_COLS);
@@ -180,12 +182,12 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
         // (2 xi x 2 K-steps x 3 split products)
         {
             constexpr uint32_t idesc = make_idesc_tf32(128, COUT);
-            uint32_t pf0 = 0, pf1 = 0;
+            uint32_t pf[NVB] = {};
             for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
-                    const int vb = h & 1;
-                    if (vb == 0) { mbar_wait_warp(bar_full, pf0); pf0 ^= 1u; } else { mbar_wait_warp(bar_full + 8u, pf1); pf1 ^= 1u; }
+                    const int vb = h % NVB;
+                    mbar_wait_warp(bar_full + 8u * vb, pf[vb]); pf[vb] ^= 1u;
                     tc_fence_after();
                     const uint64_t a_hi = make_desc_sw128(vs_u + (uint32_t)vb * 2u * 128u * 128u);
                     const uint64_t a_lo = make_desc_sw128(vs_u + (uint32_t)(vb * 2 + 1) * 128u * 128u);
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
         // epilogue role: warp = (TMEM lane quarter, 8-channel group)
         constexpr int NCG = COUT / 8;
         const int quarter = warp & 3, cg = warp >> 2;
-        uint32_t pe0 = 0, pe1 = 0;
+        uint32_t pe[NVB] = {};
 
         // two patches: global NCHW -> the interior of zero-bordered planes (odd plane pitch: the transform reads them
         // with few bank conflicts).  The next pair is fetched with four 128-bit loads per thread that stay in flight
@@ -265,9 +267,9 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
             // of half-chunk h run while half-chunk h + 1 is transformed
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
-                const int chunk = h >> 1, pr = h & 1, vb = h & 1;
-                if (h >= 2) {                     // the MMAs that read this buffer two half-chunks ago are done
-                    if (vb == 0) { mbar_wait(bar_empty, pe0); pe0 ^= 1u; } else { mbar_wait(bar_empty + 8u, pe1); pe1 ^= 1u; }
+                const int chunk = h >> 1, pr = h & 1, vb = h % NVB;
+                if (h >= NVB) {                   // the MMAs that read this buffer NVB half-chunks ago are done
+                    mbar_wait(bar_empty + 8u * vb, pe[vb]); pe[vb] ^= 1u;
                 }
                 float* Vb = Vs + vb * (2 * 128 * 32);
                 float hi[2][4], lo[2][4];
@@ -301,8 +303,10 @@ __global__ void __launch_bounds__(WT_THREADS + 32, 1) conv_wino_tc_kernel(const 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full + 8u * vb);
             }
-            mbar_wait(bar_empty, pe0); pe0 ^= 1u;      // half-chunks 6 and 7: M is complete
-            mbar_wait(bar_empty + 8u, pe1); pe1 ^= 1u;
+#pragma unroll
+            for (int b = 0; b < NVB; ++b) {           // the last commit on every buffer: M is complete
+                mbar_wait(bar_empty + 8u * b, pe[b]); pe[b] ^= 1u;
+            }
             tc_fence_after();
 
             // ---- epilogue: Y = A^T M A for tile (quarter * 32 + lane), channels cg * 8 .. + 7
@@ -440,10 +444,10 @@ struct WinoPool {           // the constant bank of the fused tail is one region
 };
 WinoPool g_wpool[64];
 
-template <int COUT, bool FUSE>
+template <int COUT, bool FUSE, int NVB>
 int launch_wino_tc(const ConvWinoArgs& a, cudaStream_t st) {
-    using C = WtCfg<COUT>;
-    auto kern = conv_wino_tc_kernel<COUT, FUSE>;
+    using C = WtCfg<COUT, NVB>;
+    auto kern = conv_wino_tc_kernel<COUT, FUSE, NVB>;
     int dev = 0;
     DMB_CUDA(cudaGetDevice(&dev));
     DMB_CHECK(dev >= 0 && dev < 64, "conv_wino_tc: device index %d out of range", dev);
@@ -501,10 +505,15 @@ int conv_wino(const ConvWinoArgs& a, cudaStream_t st) {
               "conv_wino: u must be 16-byte and y 8-byte aligned");
     if (a.w2) {
         DMB_CHECK(a.Cout == 32 && a.bias2 && a.y2, "conv_wino: the fused 1x1 tail needs 32 mid channels, bias2 and y2");
-        return launch_wino_tc<32, true>(a, st);
+        return launch_wino_tc<32, true, 2>(a, st);
     }
-    if (a.Cout == 32) return launch_wino_tc<32, false>(a, st);
-    if (a.Cout == 16) return launch_wino_tc<16, false>(a, st);
+    if (a.Cout == 32) return launch_wino_tc<32, false, 2>(a, st);
+    if (a.Cout == 16) {
+        // a third operand buffer fits next to the smaller U tiles here, but measured slower (0.198 vs 0.181 ms per 8192
+        // patches): kept behind DMB_WINO_NVB=3 as an experiment
+        const char* e = getenv("DMB_WINO_NVB");
+        return (e && e[0] == '3') ? launch_wino_tc<16, false, 3>(a, st) : launch_wino_tc<16, false, 2>(a, st);
+    }
     DMB_CHECK(false, "conv_wino: Cout %d not in {16, 32}", a.Cout);
 }
 

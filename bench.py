@@ -285,6 +285,22 @@ def layer_table(model, x, hbm_peak, fp32_tf):
     return rows
 
 
+def pcie_h2d_peak(dev):
+    """Pinned host -> device copy bandwidth of this box (256 MB, best of 4; scripts/pcie_bw.py has the longer form):
+    the roof of the end-to-end number, whose step moves 128 KB per patch over PCIe."""
+    n = 64 << 20
+    h = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d = torch.empty(n, dtype=torch.float32, device=dev)
+    best = 0.0
+    for _ in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        best = max(best, n * 4 / (time.perf_counter() - t0) / 1e9)
+    return best
+
+
 def wide_config_table(dev, bf16_peak):
     """BASELINE.json configs[3] (64-wide, 512 codes): eval-mode encode at batch 1024 on the tcgen05 path
     (csrc/conv_tc.cu 3xTF32 convs + csrc/vq_tc.cu tensor-core code search) and, for comparison, with both switched
@@ -540,6 +556,12 @@ def run_ours(args):
                                       "residual 3x3 layers and the code search run on the tensor cores",
                               "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
         line["layers"] = rows
+        if world == 1:
+            h2d_peak = pcie_h2d_peak(dev)
+            h2d_ach = e2e_value * (h2d / ne) / 1e9
+            line["e2e"]["pcie"] = {"h2d_gbs_achieved": h2d_ach, "h2d_gbs_peak_measured": h2d_peak,
+                                   "frac": h2d_ach / h2d_peak,
+                                   "note": "the end-to-end step is bound by the host->device copy of the fp32 patches"}
         if world == 1:
             try:
                 bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0)

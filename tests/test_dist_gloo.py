@@ -121,3 +121,32 @@ def test_dp_gradient_allreduce_matches_rank_emulation():
     for rank, flat in res:
         assert np.allclose(flat, ref.numpy(), rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
     assert np.array_equal(res[0][1], res[1][1])     # replicas stay identical
+
+
+def _shard_writer(rank, world, out_dir, n, width):
+    """Each rank writes its patch range of a deterministic latent matrix into the sharded store; rank 0 merges."""
+    from dynamorph_b200.dist import shard_range
+    from dynamorph_b200.latent_shards import ShardedLatentWriter, merge_manifests
+    z = np.arange(n * width, dtype=np.float32).reshape(n, width)
+    a, b = shard_range(n, rank, world)
+    with ShardedLatentWriter(out_dir, "A1", "latent_space", width, rank=rank, world=world, first_row=a,
+                             rows_per_shard=5) as w:
+        for s in range(a, b, 3):                      # ragged appends crossing shard boundaries
+            w.append(z[s:min(b, s + 3)])
+    dist.barrier()                                    # every rank's manifest is on disk
+    if rank == 0:
+        merge_manifests(out_dir, "A1", "latent_space")
+    dist.barrier()
+    return b - a
+
+
+def test_sharded_latent_store_across_ranks(tmp_path):
+    """process_VAE at scale: ranks own contiguous patch ranges, write their own shards with no
+    data-path collective, and the merged manifest reads back as the reference's (N, D*h*w) matrix."""
+    from dynamorph_b200.latent_shards import open_latents
+    n, width = 23, 12
+    res = _run(_shard_writer, 2, str(tmp_path), n, width)
+    assert sum(r[1] for r in res) == n
+    v = open_latents(str(tmp_path), "A1", "latent_space")
+    assert v.shape == (n, width)
+    assert np.array_equal(v.to_array(), np.arange(n * width, dtype=np.float32).reshape(n, width))

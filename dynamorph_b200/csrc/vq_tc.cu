@@ -52,16 +52,23 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// converged-warp forms (one elected lane executes; see conv_tc.cu)
+__device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -151,7 +158,8 @@ __global__ void __launch_bounds__(VT, D == 16 ? 8 : (D == 32 ? 4 : 1)) vq_tc_ker
     uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bar_mem + 1);
     const uint32_t bar = smem_u32(bar_mem), slot = smem_u32(slot_mem);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    // (the shuffle makes the warp index provably warp-uniform for ptxas: `if (warp == 0)` is then a uniform branch)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) { mbar_init(bar, 1u); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(slot, (uint32_t)g.tmem_cols);
     pdl_wait();
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(VT, D == 16 ? 8 : (D == 32 ? 4 : 1)) vq_tc_ker
         fence_proxy_async();
         tc_fence_before();                   // last tile's tcgen05.ld are complete before the accumulator is overwritten
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {                     // converged warp; one elected lane per tcgen05 instruction
             tc_fence_after();
             for (int k0 = 0; k0 < Kp; k0 += 256) {
                 const int nn = min(256, Kp - k0);
@@ -244,11 +252,11 @@ __global__ void __launch_bounds__(VT, D == 16 ? 8 : (D == 32 ? 4 : 1)) vq_tc_ker
                     const uint64_t bd = make_desc_sw128(cbs_u + (uint32_t)(h * Kp + k0) * 128u);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tc_mma_tf32(tmem_base + (uint32_t)k0, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
-                                    (h | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32_elect(tmem_base + (uint32_t)k0, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                                          (h | k) != 0 ? 1u : 0u);
                 }
             }
-            tc_commit(bar);
+            tc_commit_elect(bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1u;

@@ -148,6 +148,39 @@ def cpu_reference_rate(n_patches: int, batch: int, repeats: int, warmup: int = 1
     return n_patches / min(times), torch.get_num_threads(), sum(times) / len(times)
 
 
+def library_gpu_rate(dev, n_patches: int = 2048, batch: int = 256):
+    """The reference's own layer structure executed by the library kernels on the SAME GPU (SURVEY.md section 8d:
+    "the kernel set to beat on the same box"): the oracle port's torch ops (cuDNN convolutions, ATen batch-norm / ReLU,
+    the (B,K,D,H,W) broadcast quantiser) on cuda, batched eval + no_grad, TF32 off (parity-comparable) and on (the
+    PyTorch default for convolutions).  A reported baseline beside cpu_baseline, nothing of ours runs in it."""
+    from oracle import vqvae_oracle as O
+    st = O.calibrate_state(O.default_state("z16"), O.synthetic_patches(32, 1), seed=0)
+    st = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in st.items()}
+    x = O.synthetic_patches(n_patches, 2).to(dev)
+    out = {}
+    keep = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, tf32 in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+            def step():
+                with torch.no_grad():
+                    for i in range(0, n_patches, batch):
+                        zb = O.encoder(x[i:i + batch], st, O.EVAL)
+                        O.vq_forward(zb, st["vq.w.weight"], 0.25)
+
+            step()
+            torch.cuda.synchronize()
+            ms = time_events(step, 3)
+            out[tag] = {"patches_per_s": n_patches / (ms * 1e-3), "ms_per_%d" % n_patches: ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = keep
+    out["kind"] = "oracle port of the reference modules on cuda (torch %s / cuDNN), batch %d, eval + no_grad" % (
+        torch.__version__, batch)
+    return out
+
+
 def run_reference(args):
     world, rank, local, dist = dist_setup(args.gpus)
     if rank != 0:
@@ -573,6 +606,10 @@ def run_ours(args):
             v, cores, sec = cpu_reference_rate(1024, 256, 2)
             line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
                                     "sample": "1024 patches, batched eval enc+vq (B=256), best of 2 after 1 warm-up"}
+            try:
+                line["library_gpu_baseline"] = library_gpu_rate(dev)
+            except Exception as ex:       # a baseline must never take the bench line down
+                line["library_gpu_baseline"] = {"unavailable": repr(ex)[:200]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

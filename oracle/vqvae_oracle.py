@@ -189,7 +189,7 @@ def vq_forward(z: Tensor, codebook: Tensor, commitment_cost: float
     e_latent = F.mse_loss(q.detach(), z)
     q_latent = F.mse_loss(q, z.detach())
     loss = q_latent + commitment_cost * e_latent
-    onehot = torch.zeros(idx.numel(), K)
+    onehot = torch.zeros(idx.numel(), K, device=idx.device)
     onehot.scatter_(1, idx.flatten().unsqueeze(1), 1)
     p = torch.mean(onehot, 0)
     perplexity = torch.exp(-torch.sum(p * torch.log(p + 1e-10)))

@@ -37,12 +37,14 @@ ENC_FLOPS_EXEC = 15335424                    # direct-form FLOPs after folding e
 # Winograd GEMMs on the tensor cores and the quantiser's search (262,144 MACs) as a TF32 GEMM
 ENC_FLOPS_CUDA_CORE = ENC_FLOPS_EXEC - 2 * (2 * 1179648 + 262144)
 # DRAM bytes per patch of each kernel (dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture of an
-# 8192-patch eval encode step, profiles/r1_launches_encode_step.csv: launches in schedule order), for roofline.traffic
+# 8192-patch eval encode step of the last build, profiles/r1_launches_encode_step_final.csv: launches in schedule order),
+# for roofline.traffic
 def ncu_dram_bytes_per_patch():
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_launches_encode_step.csv")
-    order = ["enc.0+enc.1 composite conv4x4s2", "enc.4 conv4x4s2", "enc.7 conv4x4s2", "enc.10 conv3x3", "res conv3x3",
-             "res conv1x1", "res conv3x3", "res conv1x1", "vq fused"]
+    path = os.path.join(ROOT, "profiles", "r1_launches_encode_step_final.csv")
+    order = ["enc.0+enc.1 composite conv4x4s2", "enc.4 conv4x4s2", "enc.7 conv4x4s2", "enc.10 conv3x3",
+             "res conv3x3 (Winograd on tensor cores)", "res conv1x1", "res conv3x3 (Winograd on tensor cores)", "res conv1x1",
+             "vq fused (tensor-core search)"]
     try:
         rows = list(csv.reader(open(path)))
         h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -572,7 +574,7 @@ def run_ours(args):
         line["roofline"] = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
                             "frac": dom["hbm_frac"], "traffic": traffic * nb if traffic else None,
                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per patch "
-                                              "(profiles/r1_launches_encode_step.csv) x patches per launch",
+                                              "(profiles/r1_launches_encode_step_final.csv) x patches per launch",
                             "algorithmic_bytes": dom["gbs"] * 1e9 * dom["ms"] * 1e-3, "kernel": dom["kernel"],
                             "peak_source": peak_src,
                             "binding_roof": "fp32_fma (CUDA cores): the schema's bound is hbm|tensor, but this kernel "

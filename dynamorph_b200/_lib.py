@@ -53,6 +53,9 @@ SIGNATURES = {
     "dmb_vq_backward": [_P, _P, _P, _P, _P, _F, _F, _I64, _I32, _I32, _I32, _P, _P, _P],
     "dmb_encode": [_M, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, C.c_size_t, _P],
     "dmb_decoder_forward": [_M, _P, _P, _I64, _I32, _P, _P, _P, C.c_size_t, _P],
+    "dmb_residual_block_sizes": [_I32, _I32, _I32, _I64, _I32, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64),
+                                 C.POINTER(C.c_size_t)],
+    "dmb_residual_block_forward": [_I32, _I32, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, C.c_size_t, _P],
     "dmb_conv2d_forward": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, _I32, _P],
     "dmb_conv2d_tc_scratch_floats": [_I64, _I32, _I32, _I32, _I32, _I32, C.POINTER(_I64)],
     "dmb_conv2d_tc": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P, _P],
@@ -78,10 +81,23 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 1             # include/dynamorph_b200.h: DMB_ABI_VERSION
 
 
 class DmbError(RuntimeError):
     pass
+
+
+class _DevPtr(C.c_void_p):
+    """A device pointer that remembers which GPU it lives on (`call` makes that GPU current)."""
+    dev = None
+
+
+class _CurrentStream:
+    """Placeholder for "the current stream of the device the pointers live on"; resolved inside `call`."""
+
+
+STREAM = _CurrentStream()
 
 
 def library_path() -> str:
@@ -89,7 +105,7 @@ def library_path() -> str:
 
 
 def load(build_if_missing: bool = True):
-    """Load (building first if needed) the shared library; raises if unavailable."""
+    """Load (building first if needed) the shared library; raises if it is unavailable, stale or of another ABI."""
     global _lib
     if _lib is not None:
         return _lib
@@ -98,9 +114,14 @@ def load(build_if_missing: bool = True):
         if os.path.isdir(_build.CSRC) and os.environ.get("DMB_NO_BUILD") != "1":
             try:
                 _build.build()
-            except Exception as e:  # stale lib may still be usable; a missing one is fatal
-                if not os.path.exists(path):
-                    raise DmbError(f"libdynamorph_b200.so is missing and could not be built: {e}") from e
+            except Exception as e:
+                # a library older than its sources may no longer match the signatures below: never run it silently
+                if not os.path.exists(path) or os.environ.get("DMB_ALLOW_STALE") != "1":
+                    raise DmbError("libdynamorph_b200.so is %s and could not be rebuilt (set DMB_ALLOW_STALE=1 to "
+                                   "load the stale binary anyway): %s"
+                                   % ("older than csrc/" if os.path.exists(path) else "missing", e)) from e
+                import warnings
+                warnings.warn(f"dynamorph_b200: loading a STALE libdynamorph_b200.so (rebuild failed: {e})")
     if not os.path.exists(path):
         raise DmbError("libdynamorph_b200.so not found (no CPU fallback exists); run "
                        "`python -c 'import __graft_entry__ as g; g.build()'`")
@@ -109,10 +130,16 @@ def load(build_if_missing: bool = True):
     lib.dmb_last_error.argtypes = []
     lib.dmb_abi_version.restype = C.c_int
     lib.dmb_abi_version.argtypes = []
+    if lib.dmb_abi_version() != ABI_VERSION:
+        raise DmbError(f"libdynamorph_b200.so has ABI version {lib.dmb_abi_version()}, this package binds "
+                       f"{ABI_VERSION}; rebuild it (python -m dynamorph_b200._build --force)")
     lib.dmb_launch_count.restype = C.c_longlong
     lib.dmb_launch_count.argtypes = [C.c_int]
     for name, args in SIGNATURES.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise DmbError(f"libdynamorph_b200.so does not export {name}: stale binary, rebuild it") from e
         fn.restype = C.c_int
         fn.argtypes = args
     _lib = lib
@@ -120,12 +147,34 @@ def load(build_if_missing: bool = True):
 
 
 def call(name: str, *args):
+    """Call one C-ABI entry point.  The GPU that owns the pointer arguments is made current for the call (the library
+    keeps per-device state keyed by cudaGetDevice), and a `STREAM` argument becomes that GPU's current stream."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    dev = None
+    for a in args:
+        dev = getattr(a, "dev", None)
+        if dev is not None:
+            break
+    if dev is None and not any(a is STREAM for a in args):
+        rc = getattr(lib, name)(*args)
+    else:
+        import torch
+        if dev is None or dev == torch.cuda.current_device():
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            rc = getattr(lib, name)(*[st if a is STREAM else a for a in args])
+        else:
+            with torch.cuda.device(dev):
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                rc = getattr(lib, name)(*[st if a is STREAM else a for a in args])
     if rc != 0:
         raise DmbError(f"{name} failed ({rc}): {lib.dmb_last_error().decode()}")
 
 
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    p = _DevPtr(t.data_ptr())
+    if t.is_cuda:
+        p.dev = t.device.index
+    return p

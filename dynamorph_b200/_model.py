@@ -67,9 +67,49 @@ class ResidualBlock(nn.Module):
                 nn.BatchNorm2d(self.num_hiddens)))
         self.layers = nn.ModuleList(self.layers)
 
-    def forward(self, x):
-        raise RuntimeError("dynamorph_b200.ResidualBlock is executed as part of the fused encoder/decoder "
-                           "schedule (model.enc / model.dec); it has no stand-alone kernel path")
+    def forward(self, x, bn_mode=None):
+        """output = x; output = output + layers[i](output) for every layer (vq_vae.py:212-225) as ONE C-ABI call
+        (dmb_residual_block_forward: the schedule `model.enc` / `model.dec` run for their block).  BatchNorm follows
+        `self.training` (batch statistics + running-stat update, or running statistics); forward only -- gradients
+        flow through the block as part of `model(...)`, the way the reference trains it."""
+        import ctypes as C
+        from ._lib import BN_BATCH, BN_EVAL, BN_MODES, call, ptr
+        x = _engine._require_cuda(x.detach(), "ResidualBlock input")
+        B, Cx, H, W = x.shape
+        if Cx != self.num_hiddens:
+            raise RuntimeError(f"expected {self.num_hiddens} channels, got {Cx}")
+        y = torch.empty_like(x)
+        if B == 0:
+            return y
+        mode = BN_MODES[bn_mode] if bn_mode is not None else (BN_BATCH if self.training else BN_EVAL)
+        dev = x.device
+        convs_bns = [(l[1], l[2], l[4], l[5]) for l in self.layers]
+        flat = [t.detach().reshape(-1).to(dev, torch.float32)
+                for ca, ba, cb, bb in convs_bns for m in (ca, ba, cb, bb) for t in (m.weight, m.bias)]
+        stats = [t.detach().reshape(-1).to(dev, torch.float32)
+                 for ca, ba, cb, bb in convs_bns for m in (ba, bb) for t in (m.running_mean, m.running_var)]
+        params = torch.cat(flat) if flat else torch.empty(0, device=dev)
+        bnbuf = torch.cat(stats) if stats else torch.empty(0, device=dev)
+        n_p, n_b, nbytes = C.c_int64(), C.c_int64(), C.c_size_t()
+        args = (self.num_hiddens, self.num_residual_hiddens, self.num_residual_layers)
+        call("dmb_residual_block_sizes", *args, B, H, W, mode, C.byref(n_p), C.byref(n_b), C.byref(nbytes))
+        if n_p.value != params.numel() or n_b.value != bnbuf.numel():
+            raise RuntimeError(f"ResidualBlock parameter layout mismatch: python {params.numel()}/{bnbuf.numel()} vs "
+                               f"library {n_p.value}/{n_b.value}")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        upd = ptr(bnbuf) if mode == BN_BATCH else None
+        call("dmb_residual_block_forward", *args, ptr(params), ptr(bnbuf), ptr(x), B, H, W, mode, ptr(y), upd, ptr(ws),
+             nbytes.value, _engine._stream())
+        if mode == BN_BATCH:                       # hand the updated running statistics back to the BatchNorm modules
+            off = 0
+            with torch.no_grad():
+                for ca, ba, cb, bb in convs_bns:
+                    for m in (ba, bb):
+                        c = m.num_features
+                        m.running_mean.copy_(bnbuf[off:off + c]); m.running_var.copy_(bnbuf[off + c:off + 2 * c])
+                        m.num_batches_tracked += 1
+                        off += 2 * c
+        return y
 
 
 class _Stage(nn.Sequential):

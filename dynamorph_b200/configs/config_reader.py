@@ -14,7 +14,7 @@ LATENT_ENCODING = {'raw_dirs', 'supp_dirs', 'val_dirs', 'weights', 'save_output'
                    'channel_mean', 'channel_std', 'num_classes', 'num_hiddens', 'num_residual_hiddens',
                    'num_embeddings', 'commitment_cost', 'network', 'patch_type', 'w_a', 'w_t', 'margin'}
 TRAINING = {'raw_dirs', 'supp_dirs', 'weights_dirs', 'network', 'num_inputs', 'num_hiddens', 'num_residual_hiddens',
-            'num_embeddings', 'weight_matching', 'margin', 'w_a', 'w_t', 'w_n', 'channel_mean', 'channel_std',
+            'num_residual_layers', 'num_embeddings', 'weight_matching', 'margin', 'w_a', 'w_t', 'w_n', 'channel_mean', 'channel_std',
             'commitment_cost', 'n_epochs', 'learn_rate', 'batch_size', 'val_split_ratio', 'shuffle_data',
             'transform', 'patience', 'n_pos_samples', 'num_workers', 'gpu_id', 'start_model_path', 'retrain',
             'start_epoch', 'earlystop_metric', 'model_name', 'use_mask', 'channels', 'temperature', 'augmentations'}

@@ -1259,6 +1259,85 @@ int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const fl
     return convt_fwd(a, (cudaStream_t)stream);
 }
 
+// ---- stand-alone ResidualBlock.forward (vq_vae.py:212-225): the same run_res schedule over a layout that holds
+// nothing but the block's layers
+namespace {
+struct ResPlan {
+    Layout L; std::vector<ResL> res; Workspace w; float* packed = nullptr; size_t bytes = 0;
+};
+int res_plan(int h, int rh, int nl, int64_t B, int H, int W, int bn_mode, void* base, ResPlan& p) {
+    DMB_CHECK(h >= 1 && rh >= 1 && nl >= 0 && nl <= 16, "residual block %d/%d x%d out of range", h, rh, nl);
+    DMB_CHECK(B > 0 && B < (1 << 24) && H > 0 && W > 0, "residual block: bad batch / map size");
+    DMB_CHECK(bn_mode >= 0 && bn_mode <= 2, "bad bn_mode %d", bn_mode);
+    p.L = Layout();
+    p.L.m = dmb_model{};
+    p.L.m.num_hiddens = h; p.L.m.num_residual_hiddens = rh; p.L.m.num_residual_layers = nl;
+    p.L.m.bn_eps = 1e-5f; p.L.m.bn_momentum = 0.1f;
+    Builder bd(p.L);
+    bd.res("", h, rh, nl, p.res);
+    p.L.pzero_off = bd.take_packed(p.L.max_c);
+    p.L.n_params = bd.p; p.L.n_bnbuf = bd.bb; p.L.n_packed = bd.pk;
+    p.L.D = h; p.L.lh = H; p.L.lw = W;
+    Bump bp(base);
+    const int64_t hw = (int64_t)H * W;
+    p.packed = bp.take<float>(p.L.n_packed);
+    p.w = Workspace();
+    for (int i = 0; i < nl; ++i) {
+        p.w.era.push_back(bp.take<float>(B * rh * hw));
+        p.w.erb.push_back(bp.take<float>(B * h * hw));
+        p.w.ehs.push_back(bp.take<float>(B * h * hw));
+    }
+    p.w.bn.resize(p.L.bns.size());
+    if (bn_mode != DMB_BN_EVAL) {
+        for (const ConvL& c : p.L.convs) {
+            const int nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, H, W, true, B);
+            DMB_CHECK(nb > 0, "no launch plan for a %dx%d %d->%d conv on %dx%d maps", c.ks, c.ks, c.cin, c.cout, H, W);
+            BnWs& b = p.w.bn[c.bn];
+            const int64_t rows = (bn_mode == DMB_BN_PER_SAMPLE) ? B : 1;
+            b.nbands = nb; b.count = hw;
+            b.part = bp.take<double>(B * nb * c.cout * 2);
+            b.scale = bp.take<float>(rows * c.cout); b.shift = bp.take<float>(rows * c.cout);
+            b.mean = bp.take<float>(rows * c.cout); b.invstd = bp.take<float>(rows * c.cout);
+        }
+    }
+    p.bytes = (bp.off + 255) & ~(size_t)255;
+    return 0;
+}
+}  // namespace
+
+int dmb_residual_block_sizes(int32_t num_hiddens, int32_t num_residual_hiddens, int32_t num_residual_layers,
+                             int64_t batch, int32_t h, int32_t w, int32_t bn_mode, int64_t* n_params,
+                             int64_t* n_bnbuf, size_t* workspace_bytes) {
+    ResPlan p;
+    DMB_TRY(res_plan(num_hiddens, num_residual_hiddens, num_residual_layers, batch, h, w, bn_mode, nullptr, p));
+    if (n_params) *n_params = p.L.n_params;
+    if (n_bnbuf) *n_bnbuf = p.L.n_bnbuf;
+    if (workspace_bytes) *workspace_bytes = p.bytes;
+    return 0;
+}
+
+int dmb_residual_block_forward(int32_t num_hiddens, int32_t num_residual_hiddens, int32_t num_residual_layers,
+                               const float* params, const float* bnbuf, const float* x, int64_t batch, int32_t h,
+                               int32_t w, int32_t bn_mode, float* y, float* bnbuf_inout, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    DMB_CHECK(x && y && workspace && (params || num_residual_layers == 0), "dmb_residual_block_forward: null pointer");
+    DMB_CHECK(bnbuf || bn_mode != DMB_BN_EVAL || num_residual_layers == 0,
+              "dmb_residual_block_forward: EVAL mode needs the running statistics");
+    ResPlan p;
+    DMB_TRY(res_plan(num_hiddens, num_residual_hiddens, num_residual_layers, batch, h, w, bn_mode, workspace, p));
+    DMB_CHECK(p.bytes <= workspace_bytes, "workspace too small: need %zu bytes, have %zu", p.bytes, workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (num_residual_layers == 0) {
+        DMB_CUDA(cudaMemcpyAsync(y, x, sizeof(float) * batch * num_hiddens * h * w, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    DMB_TRY(pack_weights(p.L, params, bnbuf, bn_mode, p.packed, st));
+    Ctx c{p.L, p.packed, p.w, batch, bn_mode, bnbuf_inout, st};
+    Act in; in.p = x;
+    Act out;
+    return run_res(c, p.res, p.w.era, p.w.erb, p.w.ehs, in, h, w, y, nullptr, &out);
+}
+
 static int train_forward_impl(const dmb_model* m, const float* packed, const float* params, const float* x,
                               const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
                               const dmb_time_matching* tm, int n_losses, float* decoded, float* losses_out,

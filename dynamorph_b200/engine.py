@@ -15,8 +15,10 @@ from . import _lib
 from ._lib import BN_BATCH, BN_EVAL, BN_PER_SAMPLE, BN_MODES, DmbModel, call, ptr
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream():
+    """The stream argument of a C-ABI call: the current stream of the GPU that owns the call's pointers
+    (resolved by `_lib.call`, which also makes that GPU current for the call)."""
+    return _lib.STREAM
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> torch.Tensor:

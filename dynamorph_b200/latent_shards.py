@@ -39,7 +39,7 @@ class ShardedLatentWriter:
     (dist.shard_range(N, rank, world)[0]); rows are buffered until a shard is full, so memory stays at one shard."""
 
     def __init__(self, out_dir: str, well: str, kind: str, width: int, rank: int = 0, world: int = 1,
-                 first_row: int = 0, rows_per_shard: int = 65536, dtype=np.float32):
+                 first_row: int = 0, rows_per_shard: int = 65536, dtype=np.float32, run_id: Optional[str] = None):
         if rows_per_shard <= 0 or width <= 0:
             raise ValueError("rows_per_shard and width must be positive")
         if not (0 <= rank < world):
@@ -48,7 +48,17 @@ class ShardedLatentWriter:
         self.width, self.rank, self.world = int(width), int(rank), int(world)
         self.first_row, self.rows_per_shard = int(first_row), int(rows_per_shard)
         self.dtype = np.dtype(dtype)
+        self.run_id = run_id
         os.makedirs(out_dir, exist_ok=True)
+        # a re-run into the same directory: this rank's manifest and shards of the earlier run go first (manifest
+        # before shards, so that a reader never sees a manifest whose shards are gone), and so does the merged manifest
+        stem = f"{well}_{kind}.r{self.rank:03d}."
+        old = [f for f in os.listdir(out_dir) if f.startswith(stem)]
+        for f in sorted(old, key=lambda f: not f.endswith(".manifest.json")) + [_manifest_name(well, kind)]:
+            try:
+                os.remove(os.path.join(out_dir, f))
+            except FileNotFoundError:
+                pass
         self._buf = np.empty((self.rows_per_shard, self.width), dtype=self.dtype)
         self._fill = 0
         self._rows = 0
@@ -88,7 +98,8 @@ class ShardedLatentWriter:
         if not self._closed:
             self._flush()
             man = {"format": FORMAT, "well": self.well, "kind": self.kind, "width": self.width,
-                   "dtype": self.dtype.str, "rank": self.rank, "world": self.world, "first_row": self.first_row,
+                   "dtype": self.dtype.str, "rank": self.rank, "world": self.world, "run_id": self.run_id,
+                   "first_row": self.first_row,
                    "rows": self._rows, "shards": self._shards}
             path = os.path.join(self.out_dir, _manifest_name(self.well, self.kind, self.rank))
             with open(path + ".tmp", "w") as f:
@@ -106,14 +117,18 @@ class ShardedLatentWriter:
 
 def merge_manifests(out_dir: str, well: str, kind: str) -> str:
     """Combine the per-rank manifests into `<well>_<kind>.manifest.json`; checks that the ranks are all there and
-    that their row ranges tile [0, N) without gap or overlap."""
+    that their row ranges tile [0, N) without gap or overlap.  Rank manifests left behind by an EARLIER run with
+    another world size or run id (ranks that no longer exist) are ignored: the newest manifest names the run."""
     parts = []
     for fn in sorted(os.listdir(out_dir)):
         if fn.startswith(f"{well}_{kind}.r") and fn.endswith(".manifest.json"):
-            with open(os.path.join(out_dir, fn)) as f:
-                parts.append(json.load(f))
+            path = os.path.join(out_dir, fn)
+            with open(path) as f:
+                parts.append((os.path.getmtime(path), json.load(f)))
     if not parts:
         raise FileNotFoundError(f"no rank manifests for {well}_{kind} in {out_dir}")
+    newest = max(parts, key=lambda p: p[0])[1]
+    parts = [p for _, p in parts if p["world"] == newest["world"] and p.get("run_id") == newest.get("run_id")]
     world = parts[0]["world"]
     ranks = sorted(p["rank"] for p in parts)
     if ranks != list(range(world)):

@@ -71,6 +71,40 @@ def encode_patches_to_shards(model, dataset: np.ndarray, device, out_dir: str, w
     return n
 
 
+def _contrast_u8(img, tol=1):
+    """SingleCellPatch/extract_patches.py:314-334 `im_adjust`: stretch the [tol, 100-tol] percentile range to 8 bit."""
+    lo, hi = np.percentile(img, [tol, 100 - tol])
+    return np.clip((img.astype(np.float32) - lo) / (hi - lo) * 255., 0, 255).astype(np.uint8)
+
+
+def save_reconstructions(model, dataset, output_dir, device, count=20):
+    """patch_VAE.py:464-489: `count` randomly chosen patches (np.random.seed(0)) and their reconstructions as
+    `recon_<i>.jpg`, a 2 x 2 panel phase | phase_recon / retardance | retardance_recon, contrast-adjusted like the
+    reference.  The panels are written with OpenCV (the reference renders them through matplotlib, absent here);
+    the model call is the reference's `model(sample)` in train mode."""
+    import cv2
+    np.random.seed(0)
+    picks = np.random.randint(0, len(dataset), (count,))
+    was_training = model.training
+    model.train()
+    with torch.no_grad():
+        for i in picks:
+            sample = zscore_patch_device(torch.from_numpy(np.ascontiguousarray(dataset[i:i + 1])).to(device))
+            output = model(sample)[0]
+            src, rec = sample[0].cpu().numpy(), output[0].cpu().numpy()
+            rows = []
+            for c, name in enumerate(('phase', 'retard')[:src.shape[0]]):
+                tiles = []
+                for img, label in ((src[c], name), (rec[c], name + '_recon')):
+                    tile = cv2.resize(_contrast_u8(img), None, fx=3, fy=3, interpolation=cv2.INTER_NEAREST)
+                    tile = cv2.copyMakeBorder(tile, 24, 4, 4, 4, cv2.BORDER_CONSTANT, value=255)
+                    cv2.putText(tile, label, (6, 17), cv2.FONT_HERSHEY_SIMPLEX, 0.5, 0, 1, cv2.LINE_AA)
+                    tiles.append(tile)
+                rows.append(np.hstack(tiles))
+            cv2.imwrite(os.path.join(output_dir, 'recon_%d.jpg' % i), np.vstack(rows))
+    model.train(was_training)
+
+
 def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: int = 0, bn_mode: str = "per_sample",
                 shard_rows: int = 0, **kwargs):
     """Wrapper method for VAE encoding: loads the prepared dataset of one well and encodes its static
@@ -102,6 +136,7 @@ def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: in
     assert dataset.ndim == 4, "dataset tensor dimension can only be 4, not {}".format(dataset.ndim)
     assert len(fs) == dataset.shape[0], "file paths and patches disagree"
     device = torch.device('cuda:%d' % gpu)
+    torch.cuda.set_device(device)       # streams, events and library state of this call belong to `gpu`
     print('Encoding images using gpu {}...'.format(gpu))
     if 'VAE' not in network:
         raise ValueError('Network {} is not available'.format(network))
@@ -149,15 +184,5 @@ def process_VAE(raw_folder: str, supp_folder: str, sites: list, config_, gpu: in
                 w.append(np.ascontiguousarray(arr[take]).reshape((len(fs), -1)))
             merge_manifests(output_dir, well, kind)
     if save_output:
-        # 20 reconstructions as .npy (the reference renders them to JPG with matplotlib, which is a
-        # plotting concern outside this path)
-        np.random.seed(0)
-        random_inds = np.random.randint(0, dataset.shape[0], (20,))
-        model.train()
-        with torch.no_grad():
-            for i in random_inds:
-                sample = zscore_patch_device(torch.from_numpy(np.ascontiguousarray(dataset[i:i + 1])).to(device))
-                output = model(sample)[0]
-                np.save(os.path.join(output_dir, 'recon_%d.npy' % i),
-                        np.stack([sample[0].cpu().numpy(), output[0].cpu().numpy()]))
+        save_reconstructions(model, dataset, output_dir, device)
     return output_dir

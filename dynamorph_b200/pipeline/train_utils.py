@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .._lib import call, ptr
+from .._lib import STREAM, call, ptr
 
 _DTYPES = {torch.float32: 0, torch.float64: 1, torch.uint16: 2}
 
@@ -20,9 +20,7 @@ def zscore_patch_device(imgs: torch.Tensor) -> torch.Tensor:
     x = imgs.contiguous()
     n, c, h, w = x.shape
     out = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
-    import ctypes as C
-    call("dmb_zscore_patch", ptr(x), _DTYPES[x.dtype], n * c, h * w, ptr(out),
-         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    call("dmb_zscore_patch", ptr(x), _DTYPES[x.dtype], n * c, h * w, ptr(out), STREAM)
     return out
 
 
@@ -43,38 +41,42 @@ def zscore_patch(imgs, device="cuda:0", chunk=4096):
 
 
 class EarlyStopping:
-    """Early stops the training if validation loss doesn't improve after a given patience; saves
-    `model.state_dict()` to `path` on every improvement (reference: train_utils.py:8-60)."""
+    """Stop training once the validation loss has failed to improve by `delta` for `patience` consecutive calls, and
+    checkpoint `model.state_dict()` to `path` at every improvement -- the contract of the reference's class
+    (train_utils.py:8-60: same constructor, `counter` / `best_score` / `early_stop` / `val_loss_min` attributes,
+    `__call__(val_loss, model)`, `save_checkpoint`).  `patience=None` never stops (run_training.train allows it)."""
 
     def __init__(self, patience=7, verbose=False, delta=0, path='checkpoint.pt', trace_func=print):
-        self.patience = patience
-        self.verbose = verbose
+        self.patience, self.verbose, self.delta = patience, verbose, delta
+        self.path, self.trace_func = path, trace_func
         self.counter = 0
-        self.best_score = None
         self.early_stop = False
-        self.val_loss_min = np.inf
-        self.delta = delta
-        self.path = path
-        self.trace_func = trace_func
+        self.val_loss_min = np.inf          # loss of the last checkpoint written
+        self._lowest = None                 # lowest validation loss accepted as an improvement
+
+    @property
+    def best_score(self):
+        """The reference tracks the negated loss."""
+        return None if self._lowest is None else -self._lowest
 
     def __call__(self, val_loss, model):
-        score = -val_loss
-        if self.best_score is None:
-            self.best_score = score
-            self.save_checkpoint(val_loss, model)
-        elif score < self.best_score + self.delta:
-            self.counter += 1
-            self.trace_func(f'EarlyStopping counter: {self.counter} out of {self.patience}')
-            if self.patience is not None and self.counter >= self.patience:
-                self.early_stop = True
-        else:
-            self.best_score = score
-            self.save_checkpoint(val_loss, model)
+        stalled = self._lowest is not None and val_loss > self._lowest - self.delta
+        if not stalled:                     # first call, an improvement of at least delta (or a NaN, as in the reference)
+            self._lowest = val_loss
             self.counter = 0
+            self.save_checkpoint(val_loss, model)
+            return
+        self.counter += 1
+        self.trace_func(f'EarlyStopping counter: {self.counter} out of {self.patience}')
+        self.early_stop = self.patience is not None and self.counter >= self.patience
 
     def save_checkpoint(self, val_loss, model):
         if self.verbose:
             self.trace_func(f'Validation loss decreased ({self.val_loss_min:.6f} --> {val_loss:.6f}).  Saving model ...')
-        # clone: the parameters are views of one flat buffer; save them as independent tensors
-        torch.save({k: v.detach().clone() for k, v in model.state_dict().items()}, self.path)
+        # the parameters are views of one flat device buffer: save independent tensors, written atomically
+        state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        tmp = f"{self.path}.tmp"
+        torch.save(state, tmp)
+        import os
+        os.replace(tmp, self.path)
         self.val_loss_min = val_loss

@@ -16,7 +16,9 @@ from ._lib import call, ptr
 
 
 def pca_transform(pca, dats: np.ndarray, device="cuda:0", chunk: int = 65536) -> np.ndarray:
-    """sklearn-compatible `pca.transform(dats)` -> float32 (N, n_components), computed on `device`."""
+    """sklearn-compatible `pca.transform(dats)` -> (N, n_components) in the dtype of `pca.components_` (what sklearn
+    returns), computed on `device` in float32: the 4096-long dot products are accumulated in fp32, so values agree
+    with sklearn's float64 result to ~1e-6 relative, not bit for bit (tests/test_gpu_pca.py states the tolerance)."""
     dats = np.asarray(dats)
     if dats.ndim != 2 or dats.shape[1] != pca.components_.shape[1]:
         raise ValueError(f"X has {dats.shape[1] if dats.ndim == 2 else '?'} features, but PCA is expecting "
@@ -56,7 +58,8 @@ def pca_transform(pca, dats: np.ndarray, device="cuda:0", chunk: int = 65536) ->
         pending.append((a, m, j))
     for pa, pm, pj in pending:
         out[pa:pa + pm] = outs[pj][:pm].cpu().numpy()
-    return out
+    want = np.asarray(pca.components_).dtype
+    return out if want == np.float32 else out.astype(want)
 
 
 def process_PCA(input_dir, output_dir, weights_dir, prefix, suffix='_after', device="cuda:0"):

@@ -131,6 +131,19 @@ int dmb_recon_loss(const float* decoded, const float* x, const float* mask, int3
                    const float* channel_var, int64_t batch, int32_t channels, int32_t hw,
                    double* sum_out, void* stream);
 
+/* ---- ResidualBlock.forward stand-alone (vq_vae.py:180-225) ------------------------------ */
+/* y = x; for every layer: y = y + BN(Conv1x1(ReLU(BN(Conv3x3(ReLU(y)))))) on x: (B, num_hiddens, h, w).
+ * `params` / `bnbuf` hold the block's own tensors in its state_dict order (layers.{i}.{1,2,4,5}: conv weight, bias,
+ * BatchNorm weight, bias / running_mean, running_var); dmb_residual_block_sizes() gives their lengths and the bytes
+ * of `workspace` (packed weights + intermediate maps).  BATCH mode updates the running statistics in bnbuf_inout.   */
+int dmb_residual_block_sizes(int32_t num_hiddens, int32_t num_residual_hiddens, int32_t num_residual_layers,
+                             int64_t batch, int32_t h, int32_t w, int32_t bn_mode, int64_t* n_params,
+                             int64_t* n_bnbuf, size_t* workspace_bytes);
+int dmb_residual_block_forward(int32_t num_hiddens, int32_t num_residual_hiddens, int32_t num_residual_layers,
+                               const float* params, const float* bnbuf, const float* x, int64_t batch, int32_t h,
+                               int32_t w, int32_t bn_mode, float* y, float* bnbuf_inout, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* ---- single layers (unit tests, micro-benchmarks) --------------------------------------- */
 /* nn.Conv2d forward, kernel/stride in {(1,1), (3,1) pad 1, (4,2) pad 1}; w_packed is
  * [Cin][k][k][Cout].  Optional on-load transform relu?(x*in_scale[c]+in_shift[c]) (tables [Cin] or

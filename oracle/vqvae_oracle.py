@@ -56,12 +56,17 @@ def num_residual_layers(state: State, prefix: str) -> int:
 # building blocks
 # --------------------------------------------------------------------------
 _RELU_TAPS = None   # when a list: every ReLU input of the forward pass is appended (near-tie analysis)
+_RELU_GRAPH = None  # when a list: (input, output) of every ReLU WITH their autograd graph (gate-flip envelopes)
 
 
 def _relu(t: Tensor) -> Tensor:
     if _RELU_TAPS is not None:
         _RELU_TAPS.append(t.detach())
-    return F.relu(t)
+    out = F.relu(t)
+    if _RELU_GRAPH is not None and out.requires_grad:
+        out.retain_grad()
+        _RELU_GRAPH.append((t, out))
+    return out
 
 
 def relu_near_ties(x: Tensor, state: State, mode: str, tol: float = 2e-6) -> int:
@@ -182,7 +187,8 @@ def vq_forward(z: Tensor, codebook: Tensor, commitment_cost: float
                ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """vq_vae.py:52-84.  Returns (straight-through output, loss, perplexity, indices)."""
     K = codebook.shape[0]
-    idx = vq_indices(z, codebook)
+    with torch.no_grad():      # argmax cuts the graph anyway; without this the (B,K,D,H,W) broadcast is kept for backward
+        idx = vq_indices(z.detach(), codebook.detach())
     q = vq_gather(idx, codebook)
     assert q.shape == z.shape
     z_st = z + (q - z).detach()
@@ -292,6 +298,44 @@ def loss_and_grads(x: Tensor, state: State, mode: str = BATCH, **fw
     g = {k: (gi if gi is not None else torch.zeros_like(leaf[k])) for k, gi in zip(keys, grads)}
     losses = {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in losses.items()}
     return decoded.detach(), losses, g, new_running
+
+
+def relu_gate_envelopes(x: Tensor, state: State, mode: str = BATCH, tol: float = 2e-6, max_positions: int = 64,
+                        **fw) -> Tuple[Dict[str, Tensor], int]:
+    """Per-ELEMENT bound on how far a gradient may move when ReLU gates flip under a different fp32 summation order.
+
+    A ReLU whose input p satisfies 0 < |pre_p| < tol can come out on the other side of zero in another implementation.
+    Flipping that one gate adds or removes exactly the paths through p:  delta_p = dL/d(relu_out_p) * d(pre_p)/d(theta).
+    Returns ({parameter key: sum_p |delta_p| elementwise}, number of near-tie positions): gradients must agree with the
+    reference to the normal tolerance PLUS this envelope, element by element -- zero wherever no near-tie can reach."""
+    global _RELU_GRAPH
+    keys = trainable_keys(state)
+    leaf = {k: (v.detach().clone().requires_grad_(True) if k in keys else v.detach().clone())
+            for k, v in state.items()}
+    _RELU_GRAPH = []
+    try:
+        _, losses = forward(x, leaf, mode, **fw)
+        taps = _RELU_GRAPH
+    finally:
+        _RELU_GRAPH = None
+    losses["total_loss"].backward(retain_graph=True)
+    env = {k: torch.zeros_like(leaf[k]) for k in keys}
+    n = 0
+    for pre, out in taps:
+        near = ((pre.detach().abs() < tol) & (pre.detach() != 0)).nonzero(as_tuple=False)
+        for pos in near:
+            n += 1
+            if n > max_positions:
+                raise RuntimeError(f"more than {max_positions} ReLU near-ties; use a larger tolerance budget")
+            pos = tuple(int(i) for i in pos)
+            g_out = float(out.grad[pos]) if out.grad is not None else 0.0
+            if g_out == 0.0:
+                continue
+            grads = torch.autograd.grad(pre[pos], [leaf[k] for k in keys], retain_graph=True, allow_unused=True)
+            for k, g in zip(keys, grads):
+                if g is not None:
+                    env[k] += (g * g_out).abs()
+    return env, n
 
 
 def adam_update(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float,

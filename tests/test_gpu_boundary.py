@@ -1,0 +1,291 @@
+"""-m gpu: the reference-facing entry points end to end -- stand-alone ResidualBlock.forward
+(vq_vae.py:212-225), run_training.train / main with the relation (time-matching) matrix, mask and augmentation
+(run_training.py:455-551, :771-948), run_VAE.main('process') over several wells and worker processes
+(run_VAE.py:28-93), and a model on a GPU that is not the current one."""
+import os
+import pickle
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden
+from oracle import vqvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------- ResidualBlock
+@pytest.mark.parametrize("h,rh,nl,hw,batch", [(16, 32, 2, 16, 5), (64, 32, 2, 16, 3), (8, 6, 3, 32, 2), (16, 32, 0, 16, 2)])
+def test_residual_block_forward_standalone(h, rh, nl, hw, batch):
+    """The class north_star names as API, called on its own: eval mode (running statistics), train mode (batch
+    statistics + running-stat update + num_batches_tracked) and the per-patch statistics of process_VAE."""
+    import gpu_util as U
+    from dynamorph_b200.HiddenStateExtractor.vq_vae import ResidualBlock
+    torch.manual_seed(h + nl)
+    blk = ResidualBlock(h, rh, nl)
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1)
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 2.0)
+    st = {"blk." + k: v.detach().clone() for k, v in blk.state_dict().items()}
+    x = torch.randn(batch, h, hw, hw)
+    blk = blk.cuda()
+    # eval
+    blk.eval()
+    y = blk(x.cuda())
+    ref = O.residual_block(x, st, "blk", O.EVAL)
+    assert U.rel(y, ref) < U.REL_TOL
+    # train: output, running statistics, counters
+    blk.train()
+    y = blk(x.cuda())
+    new_running = {}
+    ref = O.residual_block(x, st, "blk", O.BATCH, new_running)
+    assert U.rel(y, ref) < U.REL_TOL
+    sd = blk.state_dict()
+    for k, v in new_running.items():
+        k = k[len("blk."):]
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert U.rel(sd[k], v) < U.REL_TOL, k
+    # per-sample statistics == the block applied to each patch alone in train mode
+    y = blk(x.cuda(), bn_mode="per_sample")
+    ref = torch.cat([O.residual_block(x[i:i + 1], st, "blk", O.BATCH) for i in range(batch)])
+    assert U.rel(y, ref) < U.REL_TOL
+    assert blk(x[:0].cuda()).shape == (0, h, hw, hw)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        blk(x)
+
+
+def test_residual_block_inside_model_still_matches(golden_default):
+    """enc[12] called on its own on the activations that feed it == the tail of model.enc."""
+    import gpu_util as U
+    st = golden_default.state()
+    m = U.model_from_state(st).eval()
+    x = golden_default.t("x_eval")
+    with torch.no_grad():
+        z_ref = O.encoder(x, st, O.EVAL)
+        # the oracle's encoder over a state without the enc.12 keys has zero residual layers: it stops before the block
+        h4 = O.encoder(x, {k: v for k, v in st.items() if not k.startswith("enc.12")}, O.EVAL)
+    assert U.rel(m.enc(x.cuda()), z_ref) < U.REL_TOL
+    assert U.rel(m.enc[12](h4.cuda()), z_ref) < U.REL_TOL
+
+
+# ------------------------------------------------------------------------------------------- run_training.train
+def _relations(n, rng):
+    """Trajectories of 3 frames over the first 2n/3 samples: adjacent = 2, same trajectory = 1."""
+    from scipy.sparse import csr_matrix
+    rows, cols, vals = [], [], []
+    for a in range(0, (2 * n // 3) // 3 * 3, 3):
+        for i, j, v in ((a, a + 1, 2), (a + 1, a + 2, 2), (a, a + 2, 1)):
+            rows += [i, j]; cols += [j, i]; vals += [v, v]
+    return csr_matrix((np.asarray(vals), (np.asarray(rows), np.asarray(cols))), shape=(n, n))
+
+
+def _oracle_train(state, data, mask, relation, n_epochs, lr, batch_size, val_split_ratio, transform, model_kw, seed):
+    """The reference's `train` loop (run_training.py:485-541) driven on the oracle's functions: same RNG calls in the
+    same order, validation batches = train-mode forward without an update."""
+    np.random.seed(seed)
+    st = {k: v.clone() for k, v in state.items()}
+    opt = {"m": {}, "v": {}}
+    n = data.shape[0]
+    ids = list(range(n))
+    split = int(np.floor(val_split_ratio * n))
+    start = np.random.randint(0, n - split)
+    val_ids = ids[start:start + split]
+    train_ids = ids[:start] + ids[start + split:]
+    curves = []
+    step = 0
+    for _ in range(n_epochs):
+        ep = {"train": [], "val": []}
+        for phase, pool in (("train", train_ids), ("val", val_ids)):
+            for a in range(0, len(pool), batch_size):
+                b = pool[a:a + batch_size]
+                x = data[b].clone()
+                if transform:
+                    x = O.augment_batch(x, np.random)
+                rel = None
+                if relation is not None:
+                    rel = torch.from_numpy(np.asarray(relation[b, :][:, b].todense())).float()
+                bm = None if mask is None else (mask[b][:, 1:2] + 1.) / 2.
+                fw = dict(time_matching_mat=rel, batch_mask=bm, **model_kw)
+                if phase == "train":
+                    step += 1
+                    losses = O.train_step(x, st, opt, step, lr, O.BATCH, **fw)
+                else:
+                    new_running = {}
+                    with torch.no_grad():
+                        _, losses = O.forward(x, st, O.BATCH, new_running=new_running, **fw)
+                    st.update(new_running)
+                ep[phase].append({k: float(v) for k, v in losses.items()})
+        curves.append({p: {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]} for p, rows in ep.items()})
+    return st, curves
+
+
+@pytest.mark.parametrize("cls_name,use_mask", [("VQ_VAE_z16", True), ("VQ_VAE_z32", False)])
+def test_train_with_relations_mask_and_augmentation(tmp_path, cls_name, use_mask):
+    """`train(model, dataset, relation_mat=..., mask=..., transform=True)`: two epochs with ragged last batches against
+    the reference loop restated on the oracle -- epoch means of all five losses, the checkpoint EarlyStopping wrote,
+    and the BatchNorm counters (validation batches run in train mode too)."""
+    from torch.utils.data import TensorDataset
+    import gpu_util as U
+    from dynamorph_b200.HiddenStateExtractor import vae
+    from dynamorph_b200.run_training import train
+    g = Golden("z16_masked" if cls_name == "VQ_VAE_z16" else "z32_default")
+    st = g.state()
+    n, bs, lr, epochs = 22, 6, 1e-3, 2
+    data = O.synthetic_patches(n, 31)
+    rng = np.random.RandomState(5)
+    mask = torch.from_numpy(rng.choice([-1., 1.], size=(n, 2, 128, 128)).astype(np.float32)) if use_mask else None
+    relation = _relations(n, rng)
+    kw = dict(weight_matching=0.5, w_a=1.1, w_t=0.1, w_n=-0.5, margin=0.5)
+    m = U.model_from_state(st, cls=getattr(vae, cls_name), **kw)
+    np.random.seed(11)
+    out = train(m, TensorDataset(data), str(tmp_path), relation_mat=relation,
+                mask=None if mask is None else TensorDataset(mask), n_epochs=epochs, lr=lr, batch_size=bs,
+                device="cuda:0", transform=True, val_split_ratio=0.25, patience=5)
+    assert out is m
+    ref_state, curves = _oracle_train(st, data, mask, relation, epochs, lr, bs, 0.25, True,
+                                      dict(weight_matching=0.5, tm_variant="hinge", w_a=1.1, w_t=0.1, w_n=-0.5,
+                                           margin=0.5), seed=11)
+    # the scalar log holds the epoch means under the reference's tags
+    import json
+    rows = [json.loads(l) for l in open(tmp_path / "scalars.jsonl")]
+    got = {(r["tag"], r["step"]): r["value"] for r in rows}
+    for e, c in enumerate(curves):
+        for tag, phase in (("Loss/", "train"), ("Val loss/", "val")):
+            for k, v in c[phase].items():
+                assert abs(got[(tag + k, e)] - v) <= 2e-3 * max(abs(v), 1e-3), (e, tag, k, got[(tag + k, e)], v)
+    sd = torch.load(tmp_path / "model.pt")
+    assert list(sd) == list(st)
+    steps_total = epochs * int(np.ceil((n - int(np.floor(0.25 * n))) / bs))
+    for k, v in ref_state.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(m.state_dict()[k]) == int(v), k
+        elif "running" in k:
+            assert U.rel(m.state_dict()[k], v) < 2e-3, k
+        elif k != "channel_var":
+            assert float((m.state_dict()[k].cpu() - v).abs().max()) <= 2.01 * steps_total * lr, k
+
+
+def test_training_main_from_config(tmp_path):
+    """`python -m dynamorph_b200.run_training -c cfg.yml` on two tiny raw directories: pickles in, model.pt out under
+    <last weights dir>/<model_name>, loadable, with the reference's keys (run_training.py:771-948)."""
+    import yaml
+    from dynamorph_b200 import run_training
+    from dynamorph_b200.HiddenStateExtractor.vae import VQ_VAE_z16
+    raws, wdirs = [], []
+    rng = np.random.RandomState(0)
+    for d in range(2):
+        raw = tmp_path / f"raw{d}"; raw.mkdir()
+        n = 9 + d
+        patches = (O.synthetic_patches(n, 40 + d).numpy().astype(np.float64) * 50 + 300).reshape(n, 2, 1, 128, 128)
+        rel = {(0, 1): 2, (1, 0): 2, (1, 2): 2, (2, 1): 2, (0, 2): 1, (2, 0): 1}
+        pickle.dump([f"f{i}" for i in range(n)], open(raw / "im_file_paths.pkl", "wb"))
+        pickle.dump(patches, open(raw / "im_static_patches.pkl", "wb"), protocol=4)
+        pickle.dump(np.arange(n), open(raw / "im_static_patches_labels.pkl", "wb"))
+        pickle.dump(rel, open(raw / "im_static_patches_relations.pkl", "wb"))
+        raws.append(str(raw)); wdirs.append(str(tmp_path / f"w{d}"))
+    cfg = {"training": dict(raw_dirs=raws, supp_dirs=raws, weights_dirs=wdirs, network="VQ_VAE_z16", num_inputs=2,
+                            num_hiddens=16, num_residual_hiddens=32, num_residual_layers=2, num_embeddings=64,
+                            commitment_cost=0.25, weight_matching=0.005, w_a=1.1, w_t=0.1, w_n=-0.5, margin=0.5,
+                            channel_mean=None, channel_std=None, val_split_ratio=0.2, learn_rate=1e-3, patience=3,
+                            n_pos_samples=4, batch_size=8, num_workers=0, n_epochs=2, gpu_id=0, retrain=False,
+                            model_name="tiny", start_model_path=None, start_epoch=0, use_mask=False)}
+    path = tmp_path / "cfg.yml"
+    yaml.safe_dump(cfg, open(path, "w"))
+    np.random.seed(0); torch.manual_seed(0)
+    model = run_training.main(run_training.parse_args(["-c", str(path)]).config)
+    ckpt = os.path.join(wdirs[-1], "tiny", "model.pt")
+    assert os.path.exists(ckpt)
+    fresh = VQ_VAE_z16().cuda()
+    fresh.load_state_dict(torch.load(ckpt))
+    assert list(fresh.state_dict()) == list(model.state_dict())
+    assert int(model.state_dict()["enc.2.num_batches_tracked"]) == 2 * (2 + 1)      # 15 train -> 2 batches, 3 val -> 1
+    cfg["training"]["network"] = "ResNet50"
+    yaml.safe_dump(cfg, open(path, "w"))
+    with pytest.raises(ValueError, match="ResNet"):
+        run_training.main(str(path))
+
+
+# ------------------------------------------------------------------------------------------- run_VAE.main
+def _well(raw_dir, well, n, seed):
+    rng = np.random.RandomState(seed)
+    base = O.synthetic_patches(n, seed).numpy().astype(np.float64)
+    raw = (base * 700.0 + 20000.0).reshape(n, 2, 1, 128, 128) + rng.rand(n, 2, 1, 128, 128) * 1e-3
+    pickle.dump([f"/d/{well}-Site_{i % 2}/p{i}.h5" for i in range(n)], open(raw_dir / f"{well}_file_paths.pkl", "wb"))
+    pickle.dump(raw, open(raw_dir / f"{well}_static_patches.pkl", "wb"), protocol=4)
+    return raw
+
+
+def test_run_vae_process_two_wells_two_workers(tmp_path):
+    """`run_VAE.main('process', raw, supp, config)`: two wells, two spawned workers (both GPUs when the box has two,
+    else two workers on GPU 0), each writing its well's two latent pickles; rows equal the oracle's process_VAE loop.
+    Also writes the 20 `recon_<i>.jpg` panels (save_output)."""
+    import gpu_util as U
+    from dynamorph_b200 import run_VAE
+    g = Golden("vqvae_default")
+    st = g.state()
+    raw_dir = tmp_path / "raw"; raw_dir.mkdir()
+    wdir = tmp_path / "weights" / "m1"; os.makedirs(wdir)
+    torch.save(st, wdir / "model.pt")
+    raws = {"B2": _well(raw_dir, "B2", 7, 1), "C5": _well(raw_dir, "C5", 5, 2)}
+    gpus = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    cfg = types.SimpleNamespace(latent_encoding=types.SimpleNamespace(
+        weights=str(wdir), channels=[0, 1], num_hiddens=16, num_residual_hiddens=32, num_embeddings=64,
+        commitment_cost=0.25, network="VQ_VAE_z16", save_output=True, channel_mean=None, channel_std=None,
+        gpu_ids=gpus, fov=None, raw_dirs=[str(raw_dir)], supp_dirs=[None]))
+    run_VAE.main("process", str(raw_dir), None, cfg)
+    for well, raw in raws.items():
+        zb = pickle.load(open(raw_dir / "m1" / f"{well}_latent_space.pkl", "rb"))
+        za = pickle.load(open(raw_dir / "m1" / f"{well}_latent_space_after.pkl", "rb"))
+        rb, _ = O.process_vae_arrays(raw, st, O.PER_SAMPLE)
+        assert zb.dtype == np.float32 and zb.shape == rb.shape == za.shape
+        assert U.rel(zb, rb) < U.REL_TOL, well
+    jpgs = [f for f in os.listdir(raw_dir / "m1") if f.startswith("recon_") and f.endswith(".jpg")]
+    assert 1 <= len(jpgs) <= 20
+    import cv2
+    assert cv2.imread(str(raw_dir / "m1" / jpgs[0])) is not None
+
+
+# ------------------------------------------------------------------------------------------- non-current GPU
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_everything_runs_on_a_gpu_that_is_not_current(tmp_path):
+    """a model on cuda:1 while cuda:0 is the current device -- encode, bulk encode, z-score, train
+    step, FusedTrainer and the PCA projection must launch on cuda:1's stream with cuda:1 current inside the library."""
+    import gpu_util as U
+    from dynamorph_b200.bulk import BulkEncoder
+    from dynamorph_b200.pipeline.train_utils import zscore_patch_device
+    from dynamorph_b200.trainer import FusedTrainer
+    g = Golden("vqvae_default")
+    st = g.state()
+    torch.cuda.set_device(0)
+    m0 = U.model_from_state(st).eval()                       # cuda:0
+    m1 = U.model_from_state(st).to("cuda:1").eval()
+    x = g.t("x_eval")
+    zb0, za0, i0 = m0.encode_latents(x.cuda(0), "eval")
+    assert torch.cuda.current_device() == 0
+    zb1, za1, i1 = m1.encode_latents(x.to("cuda:1"), "eval")
+    torch.cuda.synchronize(1)
+    assert torch.equal(zb0.cpu(), zb1.cpu()) and torch.equal(i0.cpu(), i1.cpu())
+    out = BulkEncoder(m1, chunk=4, bn_mode="per_sample").encode(x.pin_memory())
+    torch.cuda.synchronize(1)
+    ref = m0.encode_latents(x.cuda(0), "per_sample")[0]
+    assert torch.equal(out["z_before"], ref.reshape(len(x), -1).cpu())
+    raw = (x * 100 + 1000).to(torch.float64)
+    assert torch.equal(zscore_patch_device(raw.to("cuda:1")).cpu(), zscore_patch_device(raw.cuda(0)).cpu())
+    xt = g.t("x_train")
+    losses = []
+    for dev in (0, 1):
+        mt = U.model_from_state(st).to(f"cuda:{dev}").train()
+        tr = FusedTrainer(mt, lr=1e-3)
+        for _ in range(2):
+            l = tr.step(xt.to(f"cuda:{dev}"))
+        losses.append(l.cpu())
+        _, d = mt(xt.to(f"cuda:{dev}"))
+        d["total_loss"].backward()
+    assert torch.equal(losses[0], losses[1])
+    assert torch.cuda.current_device() == 0

@@ -29,7 +29,7 @@ def test_pca_transform_matches_sklearn(n, l, whiten, n_components):
     ref = pca.transform(x)
     for chunk in (64, 65536):
         got = pca_transform(pca, x, chunk=chunk)
-        assert got.shape == ref.shape and got.dtype == np.float32
+        assert got.shape == ref.shape and got.dtype == pca.components_.dtype == ref.dtype
         err = float(np.abs(got - ref).max() / np.abs(ref).max())
         assert err < 1e-4, (chunk, err)
     with pytest.raises(ValueError):

@@ -39,10 +39,18 @@ def test_train_forward_matches_reference(name, U):
         assert U.rel(sd[k], v) < U.REL_TOL, k
 
 
-def _grad_errors(model, grads_ref, noise):
+STRICT = 2e-4          # of the tensor's max-abs (1e-4-level, fp32)
+
+
+def _check_grads(model, grads_ref, noise, envelope=None, what=""):
+    """Every gradient element within STRICT * max|reference tensor| of the reference, plus -- element by element --
+    the gate-flip envelope of the ReLU inputs that sit within 2e-6 of zero in the reference forward
+    (oracle.relu_gate_envelopes: exactly what flipping those gates adds or removes; zero where none can reach).
+    Conv biases that feed a train-mode BatchNorm have an exactly-zero gradient that autograd reports as rounding
+    noise: those are only required to be negligible.  Returns the worst error in units of the strict bound."""
     named = dict(model.named_parameters())
     scale = max(float(v.abs().max()) for k, v in grads_ref.items() if k not in noise)
-    errs = {}
+    worst = 0.0
     for k, ref in grads_ref.items():
         got = named[k].grad
         assert got is not None, k
@@ -50,44 +58,39 @@ def _grad_errors(model, grads_ref, noise):
         if k in noise:
             assert float(got.abs().max()) <= 1e-5 * scale, (k, float(got.abs().max()))
             continue
-        errs[k] = float((got - ref).abs().max() / ref.abs().max().clamp(min=1e-30))
+        allowed = STRICT * float(ref.abs().max().clamp(min=1e-30))
+        slack = (got - ref).abs() - (1.05 * envelope[k] if envelope is not None else 0.0)
+        e = float(slack.max()) / allowed
+        worst = max(worst, e)
+        assert e < 1.0, (what, k, e, "x the strict bound after the per-element gate-flip envelope")
     assert named["channel_var"].grad is None
-    return errs
-
-
-STRICT, RELAXED = 2e-4, 2e-2
+    return worst
 
 
 @pytest.mark.parametrize("name", Z16_CASES)
 def test_gradients_match_reference(name, U):
-    """All 43 parameter gradients; tolerance 1e-4-level of the tensor's max-abs.
-    * Conv biases that feed a train-mode BatchNorm have an exactly-zero gradient that autograd reports as
-      rounding noise: those are only required to be negligible.
-    * If the reference forward has ReLU inputs within 2e-6 of zero, a gate may flip under a different fp32
-      summation order (the ReLU analogue of a VQ near-tie); then the bound is relaxed and the count printed."""
+    """All 43 parameter gradients against the reference module's autograd (fixtures)."""
     g = Golden(name)
     st = g.state()
     m = U.model_from_state(st).train()
     x = g.t("x_train").cuda()
     m.zero_grad()
+    mask = g.t("mask_train") if g.has("mask_train") else None
     _, d = m(x, batch_mask=_mask(g))
     d["total_loss"].backward()
-    errs = _grad_errors(m, g.group("train/grad"), set(O.bias_feeds_train_bn(st)))
-    ties = O.relu_near_ties(g.t("x_train"), st, O.BATCH)
-    bound = STRICT if ties == 0 else RELAXED
-    print(f"{name}: relu near-ties {ties}, worst grad err {max(errs.values()):.2e}")
-    for k, e in errs.items():
-        assert e < bound, (k, e, ties)
+    env, ties = O.relu_gate_envelopes(g.t("x_train"), st, O.BATCH, batch_mask=mask,
+                                      commitment_cost=float(g["hp/commitment_cost"]))
+    worst = _check_grads(m, g.group("train/grad"), set(O.bias_feeds_train_bn(st)), env, name)
+    print(f"{name}: relu near-ties {ties}, worst grad err {worst:.2f} x strict")
 
 
 def test_gradients_heavy_over_seeds(U):
-    """Gate flips are rare events: over several seeded batches most must meet the strict bound outright,
-    and none may exceed the relaxed one."""
+    """Several seeded batches of the 64-wide configuration: each within the strict bound plus its own per-element
+    gate-flip envelope (most batches have no near-tie at all and the envelope is identically zero)."""
     g = Golden("vqvae_heavy")
     st = g.state()
     m = U.model_from_state(st).train()
     noise = set(O.bias_feeds_train_bn(st))
-    strict = 0
     for seed in range(5):
         x = O.synthetic_patches(2, 5000 + seed)
         m.load_state_dict(st)
@@ -95,10 +98,9 @@ def test_gradients_heavy_over_seeds(U):
         _, d = m(x.cuda())
         d["total_loss"].backward()
         _, _, grads, _ = O.loss_and_grads(x, st, O.BATCH)
-        worst = max(_grad_errors(m, grads, noise).values())
-        assert worst < RELAXED, (seed, worst)
-        strict += worst < STRICT
-    assert strict >= 3, strict
+        env, ties = O.relu_gate_envelopes(x, st, O.BATCH)
+        worst = _check_grads(m, grads, noise, env, f"seed {seed}")
+        print(f"seed {seed}: near-ties {ties}, worst {worst:.2f} x strict")
 
 
 def _check_after_steps(g, st, model, steps, lr):
@@ -254,7 +256,7 @@ def test_device_augmentation_matches_reference_loop(shape):
     from dynamorph_b200.run_training import augment_batch
     x = torch.randn(*shape)
     np.random.seed(1234)
-    ref = augment_batch(x.clone())                 # CPU tensors take the reference's own loop
+    ref = O.augment_batch(x.clone(), np.random)    # the reference's per-sample loop on the module-level stream
     after_ref = np.random.randint(1 << 30)
     np.random.seed(1234)
     xg = x.cuda()

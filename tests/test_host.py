@@ -76,6 +76,48 @@ def test_early_stopping_counts_and_saves(tmp_path):
     assert es.counter == 1 and not es.early_stop
     es(0.96, net)
     assert es.early_stop
+    assert es.best_score == -0.9 and es.val_loss_min == 0.9        # the reference tracks the negated loss
+    never = EarlyStopping(patience=None, path=str(tmp_path / "n.pt"))
+    for v in (1.0, 2.0, 3.0, 4.0):
+        never(v, net)
+    assert never.counter == 3 and not never.early_stop
+    es2 = EarlyStopping(patience=1, delta=0.1, path=str(tmp_path / "d.pt"))
+    es2(1.0, net); es2(0.95, net)                                  # better, but by less than delta
+    assert es2.early_stop and es2.val_loss_min == 1.0
+
+
+def test_training_data_assembly_helpers():
+    """run_training.py:97-159 / :299-321 / :335-355 restated: trajectories stay contiguous, the relation matrix follows
+    the permutation, offsets shift ids, and the batch relation block is the dense slice."""
+    from scipy.sparse import csr_matrix
+    from torch.utils.data import TensorDataset
+    from dynamorph_b200.run_training import concat_relations, get_relation_tensor, reorder_with_trajectories, zscore
+    rel_a = {(0, 1): 2, (1, 0): 2, (1, 2): 2, (2, 1): 2, (0, 2): 1, (2, 0): 1}
+    rel_b = {(0, 1): 2, (1, 0): 2}
+    merged, labels = concat_relations([rel_a, rel_b], [np.arange(4), np.arange(3)], [0, 4])
+    assert merged[(4, 5)] == 2 and merged[(0, 2)] == 1 and len(merged) == 8
+    assert labels.tolist() == [0, 1, 2, 3, 4, 5, 6]
+    ds = TensorDataset(torch.arange(7.).reshape(7, 1, 1, 1))
+    out, mat, order = reorder_with_trajectories(ds, merged, seed=5)
+    assert sorted(order) == list(range(7))
+    pos = {v: i for i, v in enumerate(order)}
+    assert max(pos[0], pos[1], pos[2]) - min(pos[0], pos[1], pos[2]) == 2       # trajectory {0,1,2} is contiguous
+    assert abs(pos[4] - pos[5]) == 1
+    assert out.tensors[0].reshape(-1).tolist() == [float(v) for v in order]
+    dense = np.asarray(mat.todense())
+    for (a, b), v in merged.items():
+        assert dense[pos[a], pos[b]] == v
+    assert dense.sum() == sum(merged.values())
+    again = reorder_with_trajectories(ds, merged, seed=5)[2]
+    assert again == order
+    blk = get_relation_tensor(mat, [pos[0], pos[1], pos[6]], device=None)
+    assert blk.dtype == torch.float32 and blk.tolist() == [[0., 2., 0.], [2., 0., 0.], [0., 0., 0.]]
+    assert get_relation_tensor(None, [0, 1]) is None
+    x = np.random.RandomState(0).rand(5, 2, 4, 4) * 3 + 1
+    z = zscore(x)
+    assert np.allclose(z.mean(axis=(0, 2, 3)), 0, atol=1e-12) and np.allclose(z.std(axis=(0, 2, 3)), 1, atol=1e-9)
+    z2 = zscore(x, channel_mean=[1., 2.], channel_std=[2., 4.])
+    assert np.allclose(z2[:, 1], (x[:, 1] - 2.) / (4. + np.finfo(float).eps))
 
 
 def test_run_vae_cli_rejects_other_methods(tmp_path):
@@ -83,15 +125,31 @@ def test_run_vae_cli_rejects_other_methods(tmp_path):
     import types
     cfg = types.SimpleNamespace(latent_encoding=types.SimpleNamespace(weights="w", gpu_ids=[0], fov=None))
     with pytest.raises(ValueError):
-        run_VAE.main("assemble", str(tmp_path), None, cfg, "c.yml")
+        run_VAE.main("assemble", str(tmp_path), None, cfg)
     with pytest.raises(AttributeError):
-        run_VAE.main("process", None, None, cfg, "c.yml")
+        run_VAE.main("process", None, None, cfg)
+    cfg.latent_encoding.weights = None
+    with pytest.raises(AttributeError):
+        run_VAE.main("process", str(tmp_path), None, cfg)
+
+
+def test_get_im_sites_follows_the_reference(tmp_path):
+    """SingleCellPatch/extract_patches.py:337-350: stems of the .npy files, `_NN` maps excluded; assembled-only
+    directories fall back to one pseudo-site per well."""
+    from dynamorph_b200.run_VAE import get_im_sites
+    for f in ("B2-Site_0.npy", "B2-Site_0_NN.npy", "B2-Site_3.npy", "C5-Site_1.npy", "notes.txt"):
+        (tmp_path / f).write_bytes(b"")
+    assert get_im_sites(str(tmp_path)) == ["B2-Site_0", "B2-Site_3", "C5-Site_1"]
+    only = tmp_path / "assembled"
+    only.mkdir()
+    (only / "D4_static_patches.pkl").write_bytes(b"")
+    assert get_im_sites(str(only)) == ["D4-Site_0"]
 
 
 def test_augmentation_draws_follow_the_reference_rng_order():
     """draw_augmentation (the host half of the one-launch device augmentation) consumes np.random exactly like the
     per-sample loop of run_training.py:396-403: applying its (flip, rot) bytes reproduces the oracle's augment_batch
-    on the same stream, and the CPU fallback of augment_batch is that loop itself."""
+    on the same stream.  augment_batch itself is GPU-only (no CPU fallback): CPU input fails loudly."""
     from dynamorph_b200.run_training import augment_batch, draw_augmentation
     x = torch.randn(9, 2, 8, 8)
     ref = O.augment_batch(x, np.random.RandomState(77))
@@ -106,8 +164,10 @@ def test_augmentation_draws_follow_the_reference_rng_order():
         out[i] = torch.rot90(img, k=int(op >> 2), dims=[1, 2])
     assert torch.equal(out, ref)
     np.random.seed(77)
-    assert torch.equal(augment_batch(x.clone()), ref)
+    assert torch.equal(O.augment_batch(x, np.random), ref)      # the module-level stream is the same generator
     assert np.random.randint(1 << 30) == nxt
+    with pytest.raises(RuntimeError, match="GPU"):
+        augment_batch(x.clone())
 
 
 def test_time_matching_descriptor_variants():

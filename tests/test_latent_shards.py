@@ -75,3 +75,19 @@ def test_empty_rank_is_fine(tmp_path):
                 w.append(z[a:b])
     merge_manifests(str(tmp_path), "D4", "latent_space")
     assert np.array_equal(open_latents(str(tmp_path), "D4", "latent_space").to_array(), z)
+
+
+def test_rerun_into_same_directory_ignores_earlier_world(tmp_path):
+    """process_VAE re-runs into the same output directory: rank files of an earlier run with MORE ranks must not be
+    merged in, and this run's ranks replace their own earlier shards."""
+    rng = np.random.default_rng(1)
+    old = rng.standard_normal((40, 8)).astype(np.float32)
+    new = rng.standard_normal((23, 8)).astype(np.float32)
+    _write(tmp_path, old, 4, 5, pieces=[3, 9])
+    _write(tmp_path, new, 2, 50, pieces=[7])
+    v = open_latents(str(tmp_path), "B2", "latent_space")
+    assert np.array_equal(v.to_array(), new)
+    # ranks 0 and 1 dropped every shard of the earlier run (s00001.. would otherwise linger beside the manifest)
+    left = sorted(f for f in os.listdir(tmp_path) if ".r000." in f or ".r001." in f)
+    assert left == ["B2_latent_space.r000.manifest.json", "B2_latent_space.r000.s00000.npy",
+                    "B2_latent_space.r001.manifest.json", "B2_latent_space.r001.s00000.npy"]

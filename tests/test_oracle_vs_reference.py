@@ -159,3 +159,46 @@ def test_zscore_patch_and_process_loop(ref):
     za = np.stack(za, 0).reshape((3, -1))
     ob, oa = O.process_vae_arrays(raw, st, O.PER_SAMPLE)
     assert np.array_equal(zb, ob) and np.array_equal(za, oa)
+
+
+def test_training_glue_matches_reference(ref, tmp_path):
+    """The host glue of the drop-in trainer (dynamorph_b200/run_training.py, pipeline/train_utils.py) against the
+    reference's own functions on the same inputs and seeds: trajectory reordering (run_training.py:97-159), relation
+    merging (:299-321), the batch relation block (:335-355), dataset z-score (train_utils.py:228-250) and
+    EarlyStopping's decisions (train_utils.py:8-60)."""
+    from torch.utils.data import TensorDataset
+    from dynamorph_b200 import run_training as mine
+    from dynamorph_b200.pipeline.train_utils import EarlyStopping
+    rng = np.random.RandomState(3)
+    n = 40
+    rel = {}
+    for a in range(0, 30, 5):                      # six trajectories of five frames, rest singletons
+        for i in range(a, a + 4):
+            rel[(i, i + 1)] = 2; rel[(i + 1, i)] = 2
+        for i in range(a, a + 5):
+            for j in range(a, a + 5):
+                if abs(i - j) > 1:
+                    rel[(i, j)] = 1
+    ds = TensorDataset(torch.from_numpy(rng.rand(n, 2, 4, 4).astype(np.float32)))
+    r_ds, r_mat, r_order = ref.rt.reorder_with_trajectories(ds, rel, seed=123)
+    m_ds, m_mat, m_order = mine.reorder_with_trajectories(ds, rel, seed=123)
+    assert [int(v) for v in r_order] == [int(v) for v in m_order]
+    assert torch.equal(r_ds.tensors[0], m_ds.tensors[0])
+    assert (r_mat != m_mat).nnz == 0
+    ids = [3, 17, 4, 29, 30, 5]
+    assert torch.equal(ref.rt.get_relation_tensor(r_mat, ids, device=None),
+                       mine.get_relation_tensor(m_mat, ids, device=None))
+    r_rel, r_lab = ref.rt.concat_relations([rel, {(0, 1): 2}], [np.arange(n), np.arange(2)], [0, n])
+    m_rel, m_lab = mine.concat_relations([rel, {(0, 1): 2}], [np.arange(n), np.arange(2)], [0, n])
+    assert r_rel == m_rel and np.array_equal(r_lab, m_lab)
+    x = rng.rand(6, 2, 8, 8) * 5
+    assert np.array_equal(ref.tu.zscore(x), mine.zscore(x))
+    assert np.array_equal(ref.tu.zscore(x, [1., 2.], [3., 4.]), mine.zscore(x, [1., 2.], [3., 4.]))
+    net = torch.nn.Linear(2, 2)
+    losses = [1.0, 0.8, 0.85, 0.79, 0.795, 0.9, 0.91, 0.5]
+    a = ref.tu.EarlyStopping(patience=3, delta=0.005, path=str(tmp_path / "a.pt"), trace_func=lambda *_: None)
+    b = EarlyStopping(patience=3, delta=0.005, path=str(tmp_path / "b.pt"), trace_func=lambda *_: None)
+    for v in losses:
+        a(v, net); b(v, net)
+        assert (a.counter, a.early_stop, a.best_score, a.val_loss_min) == (b.counter, b.early_stop, b.best_score,
+                                                                           b.val_loss_min)

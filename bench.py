@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import argparse
 import json
+
+import numpy as np
 import os
 import statistics
 import subprocess
@@ -183,7 +185,16 @@ def library_gpu_rate(dev, n_patches: int = 2048, batch: int = 256):
     return out
 
 
+def raw_u16_like(x):
+    """Synthetic RAW patches in camera-count range from z-scored ones (what `zscore_patch` receives in the pipeline):
+    per-channel offset + gain, rounded to uint16.  Works on CPU and CUDA tensors."""
+    return (x * 2000.0 + 30000.0).clamp_(0, 65535).to(torch.uint16)
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the SAME work as our `e2e` headline: raw uint16 patches ->
+    `zscore_patch` (pipeline/train_utils.py:252-274, float64 on the host) -> float32 -> enc + vq (batched, eval-mode BN,
+    no_grad: the fastest configuration of the reference's own code).  Oracle port on all host threads; bounded sample."""
     world, rank, local, dist = dist_setup(args.gpus)
     if rank != 0:
         return
@@ -191,10 +202,11 @@ def run_reference(args):
     from oracle import vqvae_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     st = O.calibrate_state(O.default_state("z16"), O.synthetic_patches(32, 1), seed=0)
-    x = O.synthetic_patches(sample, 2)
+    raw = raw_u16_like(O.synthetic_patches(sample, 2)).numpy()
 
     def step():
         with torch.no_grad():
+            x = torch.from_numpy(O.zscore_patch(raw.astype(np.float64)).astype(np.float32))
             zb = O.encoder(x, st, O.EVAL)
             O.vq_forward(zb, st["vq.w.weight"], 0.25)
 
@@ -209,15 +221,53 @@ def run_reference(args):
         "impl": "reference", "metric": "encoded patches/sec", "value": value, "unit": "patches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "process_VAE bulk encode (enc+vq), VQ_VAE_z16 defaults, 2x128x128 patches, eval-BN batched "
-                               f"B={batch}; reference CPU path = oracle port on host cores (Python reference cannot travel)",
+        "config": {"workload": "process_VAE bulk encode (zscore_patch + enc + vq), VQ_VAE_z16 defaults, raw uint16 2x128x128 "
+                               f"patches, eval-BN batched B={batch}; reference CPU path = oracle port on host cores "
+                               "(the Python reference cannot travel to the GPU box)",
                    "sample_patches_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample} patches per step x {args.steps} steps, batched eval enc+vq"},
+                         "sample": f"{sample} raw patches per step x {args.steps} steps: zscore_patch + batched eval enc+vq"},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_legs(no_loop=False):
+    """BASELINE.md section 5 CPU baselines beside the batched-eval one: (3a) the as-written process_VAE loop (batch 1,
+    train-mode BN, autograd on, pipeline/patch_VAE.py:443-452) and (3c) one `run_one_batch` training step at batch 256
+    (run_training.py:404-408 + Adam) -- oracle port, all host threads, bounded samples."""
+    from oracle import vqvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = O.calibrate_state(O.default_state("z16"), O.synthetic_patches(32, 1), seed=0)
+    out = {}
+    if not no_loop:
+        x = O.synthetic_patches(96, 3)
+        leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k in O.trainable_keys(st) else v)
+                for k, v in st.items()}
+        t0 = None
+        for i in range(x.shape[0]):
+            if i == 32:
+                t0 = time.perf_counter()          # first 32 patches = warm-up
+            zb = O.encoder(x[i:i + 1], leaf, O.BATCH)
+            za = O.vq_forward(zb, leaf["vq.w.weight"], 0.25)[0]
+            zb.detach().numpy(); za.detach().numpy()            # the loop's two per-patch read-backs
+        dt = time.perf_counter() - t0
+        out["as_written_loop"] = {"value": 64 / dt, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                                  "sample": "64 patches one at a time after 32 warm-up: train-mode BN, autograd on, two "
+                                            "read-backs per patch (patch_VAE.py:443-452)"}
+    xb = O.synthetic_patches(256, 4321)
+    state = {k: v.clone() for k, v in st.items()}
+    opt = {"m": {}, "v": {}}
+    times = []
+    for step in range(1, 4):
+        t0 = time.perf_counter()
+        O.train_step(xb, state, opt, step, 1e-4)
+        times.append(time.perf_counter() - t0)
+    out["train_step_b256"] = {"value": min(times[1:]) * 1e3, "unit": "ms/step", "cores": torch.get_num_threads(),
+                              "kind": "port", "sample": "best of 2 steps after 1 warm-up: forward + backward + Adam, "
+                                                        "batch 256 (run_training.py:404-408, :485)"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -320,20 +370,53 @@ def layer_table(model, x, hbm_peak, fp32_tf):
     return rows
 
 
-def pcie_h2d_peak(dev):
-    """Pinned host -> device copy bandwidth of this box (256 MB, best of 4; scripts/pcie_bw.py has the longer form):
-    the roof of the end-to-end number, whose step moves 128 KB per patch over PCIe."""
+def pcie_h2d_peak(dev, barrier=None):
+    """Pinned host -> device copy bandwidth of this rank (256 MB, best of 5) WHILE every other rank does the same
+    (`barrier` lines them up): summed over ranks it is the roof of the end-to-end number."""
     n = 64 << 20
     h = torch.empty(n, dtype=torch.float32, pin_memory=True)
     d = torch.empty(n, dtype=torch.float32, device=dev)
     best = 0.0
     for _ in range(5):
+        if barrier is not None:
+            barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         d.copy_(h, non_blocking=True)
         torch.cuda.synchronize()
         best = max(best, n * 4 / (time.perf_counter() - t0) / 1e9)
     return best
+
+
+def parity_sample(model, x_dev, zb_rows, idx_rows, k, raw=None, seed=0):
+    """Oracle parity of `k` patches spread over a timed batch (first / last 16 + random rows): z_before within 1e-4
+    relative, code indices equal except where the oracle's best / second-best gap is below 1e-6 relative (the bar of
+    BASELINE.json north_star).  `raw` (host uint16): the oracle also restates zscore_patch (patch_VAE.py:413-419)."""
+    from oracle import vqvae_oracle as O
+    n = zb_rows.shape[0]
+    rng = np.random.RandomState(seed)
+    edge = list(range(16)) + list(range(n - 16, n))
+    rows = sorted(edge + rng.choice(np.arange(16, n - 16), size=k - len(edge), replace=False).tolist())
+    rt = torch.tensor(rows)
+    state = {kk: v.detach().cpu().clone() for kk, v in model.state_dict().items()}
+    if raw is not None:
+        xs = torch.from_numpy(O.zscore_patch(raw[rt].numpy().astype(np.float64)).astype(np.float32))
+    else:
+        xs = x_dev[rt.to(x_dev.device)].cpu()
+    got_z = zb_rows[rt.to(zb_rows.device)].cpu().reshape(len(rows), -1)
+    got_i = idx_rows[rt.to(idx_rows.device)].cpu().long()
+    with torch.no_grad():
+        ref = O.encoder(xs, state, O.EVAL)
+        ref_idx = O.vq_indices(ref, state["vq.w.weight"])
+        gap = O.best_second_gap(ref, state["vq.w.weight"])
+    max_rel = float((got_z - ref.reshape(len(rows), -1)).abs().max() / ref.abs().max())
+    bad = got_i != ref_idx
+    unexplained = int((bad & (gap >= 1e-6)).sum())
+    res = {"patches": len(rows), "of": n, "max_rel": max_rel, "mismatches": int(bad.sum()),
+           "mismatches_not_near_tie": unexplained, "positions": int(bad.numel()),
+           "ok": bool(max_rel < 1e-4 and unexplained == 0), "checker": "oracle/vqvae_oracle.py (CPU)"}
+    assert res["ok"], f"bench output fails oracle parity: {res}"
+    return res
 
 
 def wide_config_table(dev, bf16_peak):
@@ -466,77 +549,104 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_ps = time_events(lambda: step("per_sample"), max(3, args.steps // 4))
 
-    # ---- end to end through the public host-buffer API (pinned host in, pinned host out)
-    # host buffers are pinned: keep the per-rank footprint (x float32 + x uint16 + outputs ~ 232 KB / patch) within
-    # a fraction of the box's RAM when 4-8 ranks share it
-    ne = chunk if world <= 2 else max(4096, chunk // 2)
-    enc = BulkEncoder(model, chunk=min(ne, 4096), bn_mode="eval")
+    # ---- end to end through the public host-buffer API: pinned host in -> HBM -> pinned host out, every step.
+    # The SAME number of patches per rank at every N (the per-rank pinned footprint is ~232 KB / patch).
+    # Headline: the call process_VAE makes -- RAW patches (uint16, camera-count range) shipped as they are, z-scored on
+    # the device in front of the encoder (pipeline/train_utils.py:252-274), latents back to the host; the reference
+    # arm does the same work on the host cores.  Beside it: pre-z-scored float32 patches (twice the H2D bytes).
+    ne = min(chunk, 8192)
     x_host = torch.empty(ne, 2, 128, 128, dtype=torch.float32, pin_memory=True)
     x_host.copy_(x[:ne])
-    out = enc.allocate_outputs(ne)
-    enc.encode(x_host, out)
-    torch.cuda.synchronize()
-    barrier()
-    e2e_steps = max(3, min(args.steps, 8))
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(e2e_steps):
-        enc.encode(x_host, out)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * ne / (float(t[0]) * 1e-3)
-    h2d = x_host.numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in out.values())
-    # ---- the same call fed RAW uint16 patches (camera counts), z-scored on the device in front of the encoder
-    # (pipeline/train_utils.py:252-274 on the GPU): half the host->device bytes of the float32 path
-    enc16 = BulkEncoder(model, chunk=min(ne, 4096), bn_mode="eval", zscore=True)
     x16 = torch.empty(ne, 2, 128, 128, dtype=torch.uint16, pin_memory=True)
-    x16.copy_((x[:ne] * 2000.0 + 30000.0).clamp_(0, 65535).to(torch.uint16))
-    enc16.encode(x16, out)
-    torch.cuda.synchronize()
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        enc16.encode(x16, out)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    x16.copy_(raw_u16_like(x[:ne].clone()))
+    e2e_steps = max(3, min(args.steps, 8))
+
+    def time_e2e(encoder, src, out):
+        encoder.encode(src, out)
+        torch.cuda.synchronize()
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            encoder.encode(src, out)
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * e2e_steps * ne / (float(tt[0]) * 1e-3)
+
+    enc16 = BulkEncoder(model, chunk=min(ne, 4096), bn_mode="eval", zscore=True)
+    out = enc16.allocate_outputs(ne)
+    e2e16_value = time_e2e(enc16, x16, out)
+    d2h = sum(v.numel() * v.element_size() for v in out.values())
+    # parity of what came back to the host: 256 patches of the raw-input run against the oracle's process_VAE restatement
+    parity_e2e = None
+    if rank == 0:
+        parity_e2e = parity_sample(model, None, out["z_before"].view(ne, -1), out["idx"].view(ne, 16, 16), 64,
+                                   raw=x16, seed=7)
+    enc = BulkEncoder(model, chunk=min(ne, 4096), bn_mode="eval")
+    e2e_value = time_e2e(enc, x_host, out)
+    del enc16
+    # aggregate pinned host -> device bandwidth with every rank copying at once: the roof of the end-to-end number
+    h2d_peak = pcie_h2d_peak(dev, barrier)
+    tt = torch.tensor([h2d_peak], device=dev, dtype=torch.float64)
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e16_value = world * e2e_steps * ne / (float(t[0]) * 1e-3)
-    enc.encode(x_host, out)          # leave the float32 result in `out` for the spot-check below
-    torch.cuda.synchronize()
-    # parity spot-check of what came back to the host against the device-resident run
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+    h2d_peak_total = float(tt[0])
+
+    # ---- parity of the TIMED device path: 256 patches spread over the timed batch against the oracle
     step("eval")
     torch.cuda.synchronize()
-    same = bool(torch.equal(out["idx"].view(ne, 16, 16), idx[:ne].cpu()))
+    parity = parity_sample(model, x, zb.view(chunk, -1), idx, 256, seed=rank) if rank == 0 else None
 
-    # ---- train step (BASELINE.json configs[1] / [4]): forward + backward + (allreduce) + Adam, fp32, BATCH-mode BN
+    # ---- train step (BASELINE.json configs[1] / [4]): forward + backward + (allreduce) + Adam, fp32, BATCH-mode BN.
+    # Batch 256 per GPU (configs[1]) AND 512 per GPU (configs[4]: 8 x 512) at every N, so efficiency is computable.
     from dynamorph_b200.trainer import FusedTrainer
-    tb = 256 if world == 1 else 512
-    torch.manual_seed(0)
-    tmodel = VQ_VAE_z16().to(dev)
-    calibrate(tmodel, synthetic_patches(64, 1, dev))
-    tmodel.train()
-    trainer = FusedTrainer(tmodel, lr=1e-4, use_graph=True)
-    xt = synthetic_patches(tb, 4321 + rank, dev)
-    for _ in range(5):
-        trainer.step(xt)
-    barrier()
-    tsteps = max(10, args.steps)
-    e0.record()
-    for _ in range(tsteps):
-        tl = trainer.step(xt)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / tsteps], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    train_ms = float(t[0])
-    train_losses = [float(v) for v in tl.tolist()]
+    train = {}
+    for tb in (256, 512):
+        torch.manual_seed(0)
+        tmodel = VQ_VAE_z16().to(dev)
+        calibrate(tmodel, synthetic_patches(64, 1, dev))
+        tmodel.train()
+        trainer = FusedTrainer(tmodel, lr=1e-4, use_graph=True)
+        xt = synthetic_patches(tb, 4321 + rank, dev)
+        for _ in range(5):
+            trainer.step(xt)
+        barrier()
+        tsteps = max(10, args.steps)
+        e0.record()
+        for _ in range(tsteps):
+            tl = trainer.step(xt)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / tsteps], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        train[tb] = {"ms": float(t[0]), "batch_per_gpu": tb, "global_batch": tb * world,
+                     "patches_per_s": tb * world / (float(t[0]) * 1e-3), "total_loss_after": float(tl.tolist()[2])}
+        del trainer, tmodel
+    # the reference's own API for the same step (run_one_batch: autograd + optimiser.step + 1 host sync), N = 1 only
+    eager_ms = None
+    if world == 1:
+        from dynamorph_b200.optim import FusedAdam
+        from dynamorph_b200.run_training import run_one_batch
+        torch.manual_seed(0)
+        tmodel = VQ_VAE_z16().to(dev)
+        calibrate(tmodel, synthetic_patches(64, 1, dev))
+        tmodel.train()
+        opt = FusedAdam(tmodel, lr=1e-4)
+        xt = synthetic_patches(256, 4321, dev)
+        tl_ = {}
+        for _ in range(3):
+            run_one_batch(tmodel, xt, tl_, model_kwargs={}, optimizer=opt, transform=None, training=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            run_one_batch(tmodel, xt, tl_, model_kwargs={}, optimizer=opt, transform=None, training=True)
+        torch.cuda.synchronize()
+        eager_ms = (time.perf_counter() - t0) / 10 * 1e3
+        del tmodel, opt
+    train_ms = train[256]["ms"]
 
     line = {
         "metric": "encoded patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
@@ -548,40 +658,66 @@ def run_ours(args):
                                "patch ranges sharded across ranks, no data-path collective",
                    "chunk_patches": chunk, "bn_mode": "eval",
                    "l2_policy": f"inputs larger than L2 ({chunk * 131072 / 1e9:.2f} GB per step vs 126 MB)"},
-        "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "dynamorph_b200.bulk.BulkEncoder.encode (pinned host -> HBM -> pinned host, 3-stream pipeline)",
-                "patches_per_step_per_gpu": ne, "host_matches_device": same,
+        "e2e": {"value": e2e16_value, "unit": "patches/s", "h2d_bytes_per_step": x16.numel() * 2, "d2h_bytes_per_step": d2h,
+                "api": "dynamorph_b200.bulk.BulkEncoder(zscore=True).encode -- the body of process_VAE: RAW uint16 patches in "
+                       "pinned host memory -> HBM -> zscore_patch on the device -> enc + vq -> z_before, z_after, idx "
+                       "back in pinned host memory (3-stream pipeline)",
+                "patches_per_step_per_gpu": ne,
                 "rank0_cpu_affinity": (f"{len(numa_cores)} cores local to the GPU (NVML)" if numa_cores else "unchanged"),
-                "raw_uint16_input": {"value": e2e16_value, "unit": "patches/s", "h2d_bytes_per_step": x16.numel() * 2,
-                                     "note": "BulkEncoder(zscore=True): uint16 patches in, z-score on the device"}},
+                "float32_zscored_input": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                                          "note": "BulkEncoder.encode on pre-z-scored float32 patches (round 1's e2e "
+                                                  "configuration): twice the host->device bytes"},
+                "pcie": {"h2d_gbs_achieved_all_ranks": e2e16_value * (x16.numel() * 2 / ne) / 1e9,
+                         "h2d_gbs_achieved_all_ranks_float32": e2e_value * (x_host.numel() * 4 / ne) / 1e9,
+                         "h2d_gbs_peak_all_ranks_measured": h2d_peak_total,
+                         "frac": e2e16_value * (x16.numel() * 2 / ne) / 1e9 / h2d_peak_total,
+                         "frac_float32": e2e_value * (x_host.numel() * 4 / ne) / 1e9 / h2d_peak_total,
+                         "note": "peak = pinned host->device copies issued by all ranks at the same time (256 MB each, "
+                                 "best of 5), summed; the end-to-end step is bound by it"}},
         "gpu_launches": int(launches),
-        "train_step": {"ms": train_ms, "batch_per_gpu": tb, "global_batch": tb * world,
-                       "patches_per_s": tb * world / (train_ms * 1e-3), "dtype": "f32",
-                       "what": "forward + backward + one flat-gradient NCCL allreduce (N>1) + fused Adam, CUDA-graph replay; "
-                               "per-rank BatchNorm statistics", "total_loss_after": train_losses[2]},
+        "train_step": {"ms": train_ms, "batch_per_gpu": 256, "global_batch": 256 * world,
+                       "patches_per_s": 256 * world / (train_ms * 1e-3), "dtype": "f32",
+                       "what": "forward + backward + one flat-gradient NCCL allreduce (N>1) + fused Adam, CUDA-graph replay "
+                               "(trainer.FusedTrainer); per-rank BatchNorm statistics",
+                       "total_loss_after": train[256]["total_loss_after"],
+                       "batch_512_per_gpu": train[512],
+                       "run_one_batch_ms": eager_ms,
+                       "run_one_batch_note": "the reference's own step API (run_training.run_one_batch: autograd + "
+                                             "optimizer.step + zero_grad + one host read-back), batch 256, wall clock"},
         "per_sample_bn": {"value": world * chunk / (ms_ps * 1e-3), "unit": "patches/s", "ms_per_step": ms_ps,
                           "note": "as-written process_VAE semantics (train-mode BN, batch 1) at batch speed"},
     }
     if rank == 0:
+        line["parity_sample"] = parity
+        line["e2e"]["parity_sample"] = parity_e2e
         line["clocks"] = clocks
         hbm_peak, peak_src = measured_peaks()
         fp32_tf = fp32_peak(dev)
         rows = layer_table(model, x[:min(chunk, 8192)], hbm_peak, fp32_tf)
         total_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
-        dom = max((r for r in rows if r.get("fp32_frac") is not None), key=lambda r: r["ms"] * r["launches_per_step"])
+        dom = max(rows, key=lambda r: r["ms"] * r["launches_per_step"])
         nb = min(chunk, 8192)
         traffic = ncu_dram_bytes_per_patch().get(dom["kernel"])
-        line["roofline"] = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                            "frac": dom["hbm_frac"], "traffic": traffic * nb if traffic else None,
-                            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per patch "
-                                              "(profiles/r1_launches_encode_step_final.csv) x patches per launch",
-                            "algorithmic_bytes": dom["gbs"] * 1e9 * dom["ms"] * 1e-3, "kernel": dom["kernel"],
-                            "peak_source": peak_src,
-                            "binding_roof": "fp32_fma (CUDA cores): the schema's bound is hbm|tensor, but this kernel "
-                                            "is FP32-FMA bound -- see fp32 fields",
-                            "fp32_achieved_tflops": dom["tflops"], "fp32_peak_tflops": fp32_tf,
-                            "fp32_frac": dom["fp32_frac"],
-                            "share_of_step": dom["ms"] * dom["launches_per_step"] / total_ms}
+        fp32_bound = dom.get("fp32_frac") is not None and dom["fp32_frac"] > dom["hbm_frac"]
+        line["roofline"] = {
+            "kernel": dom["kernel"], "share_of_step": dom["ms"] * dom["launches_per_step"] / total_ms,
+            # the binding roof of this kernel, named for what it is: FP32 FMA on the CUDA cores when its arithmetic
+            # intensity sits above the FP32 ridge (11 FLOP/B), else HBM
+            "bound": "fp32_fma" if fp32_bound else "hbm",
+            "achieved": dom["tflops"] if fp32_bound else dom["gbs"],
+            "peak": fp32_tf if fp32_bound else hbm_peak,
+            "unit": "TFLOP/s" if fp32_bound else "GB/s",
+            "frac": dom["fp32_frac"] if fp32_bound else dom["hbm_frac"],
+            "peak_source": ("measured live (dmb_bench_fp32_fma register-resident FMA chains; nominal 74.4)" if fp32_bound
+                            else peak_src),
+            "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"],
+                    "peak_source": peak_src, "algorithmic_bytes": dom["gbs"] * 1e9 * dom["ms"] * 1e-3},
+            "traffic": traffic * nb if traffic else None,
+            "traffic_source": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per patch of the "
+                              "committed ncu capture of the same kernel (profiles/, see ncu_dram_bytes_per_patch) x "
+                              "patches per launch",
+            "timing": "CUDA events around 5 launches of the kernel alone on the model's layer shape (random tensors "
+                      "through the layer-level C ABI), after one warm-up launch"}
         line["whole_step"] = {"hbm_frac_algorithmic": value / world * ENC_BYTES / 1e9 / hbm_peak,
                               "fp32_frac_algorithmic_flops": value / world * ENC_FLOPS_ALGO / 1e12 / fp32_tf,
                               "fp32_frac_executed_flops": value / world * ENC_FLOPS_CUDA_CORE / 1e12 / fp32_tf,
@@ -591,12 +727,6 @@ def run_ours(args):
                                       "residual 3x3 layers and the code search run on the tensor cores",
                               "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
         line["layers"] = rows
-        if world == 1:
-            h2d_peak = pcie_h2d_peak(dev)
-            h2d_ach = e2e_value * (h2d / ne) / 1e9
-            line["e2e"]["pcie"] = {"h2d_gbs_achieved": h2d_ach, "h2d_gbs_peak_measured": h2d_peak,
-                                   "frac": h2d_ach / h2d_peak,
-                                   "note": "the end-to-end step is bound by the host->device copy of the fp32 patches"}
         if world == 1:
             try:
                 bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0)
@@ -608,6 +738,11 @@ def run_ours(args):
             v, cores, sec = cpu_reference_rate(1024, 256, 2)
             line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
                                     "sample": "1024 patches, batched eval enc+vq (B=256), best of 2 after 1 warm-up"}
+            try:
+                line["cpu_baseline"]["other_legs"] = cpu_legs()
+                line["train_step"]["cpu_baseline"] = line["cpu_baseline"]["other_legs"]["train_step_b256"]
+            except Exception as ex:
+                line["cpu_baseline"]["other_legs"] = {"unavailable": repr(ex)[:200]}
             try:
                 line["library_gpu_baseline"] = library_gpu_rate(dev)
             except Exception as ex:       # a baseline must never take the bench line down

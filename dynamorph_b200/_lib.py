@@ -27,6 +27,14 @@ class DmbTimeMatching(C.Structure):
                 ("w_n", C.c_float), ("margin", C.c_float), ("weight", C.c_float)]
 
 
+SYNC_ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+class DmbSyncBN(C.Structure):
+    """struct dmb_sync_bn -- the cross-rank sum the library calls for every BatchNorm under synchronised statistics."""
+    _fields_ = [("allreduce", SYNC_ALLREDUCE_FN), ("user", C.c_void_p), ("world", C.c_int32)]
+
+
 ARCH_Z16, ARCH_Z32 = 0, 1
 BN_EVAL, BN_BATCH, BN_PER_SAMPLE = 0, 1, 2
 BN_MODES = {"eval": BN_EVAL, "batch": BN_BATCH, "per_sample": BN_PER_SAMPLE}
@@ -60,6 +68,8 @@ SIGNATURES = {
     "dmb_conv2d_tc_scratch_floats": [_I64, _I32, _I32, _I32, _I32, _I32, C.POINTER(_I64)],
     "dmb_conv2d_tc": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P, _P],
     "dmb_conv2d_wino": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "dmb_conv2d_tm_scratch_floats": [_I32, _I32, _I32, C.POINTER(_I64)],
+    "dmb_conv2d_tm": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P],
     "dmb_conv_transpose2d_forward": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _P],
     "dmb_bench_fp32_fma": [_I32, _I32, _I32, _P, C.POINTER(C.c_double), _P],
     "dmb_bench_fma_tile": [_I32, _I32, _I32, _P, C.POINTER(C.c_double), _P],
@@ -70,10 +80,16 @@ SIGNATURES = {
     "dmb_train_backward": [_M, _P, _P, _P, _P, _I32, _P, _P, _I64, _F, _P, _P, C.c_size_t, _P],
     "dmb_train_forward_tm": [_M, _P, _P, _P, _P, _I32, _P, _I64, C.POINTER(DmbTimeMatching), _P, _P, _P, _P, C.c_size_t, _P],
     "dmb_train_backward_tm": [_M, _P, _P, _P, _P, _I32, _P, _P, _I64, C.POINTER(DmbTimeMatching), _F, _P, _P, C.c_size_t, _P],
+    "dmb_train_forward_sync": [_M, _P, _P, _P, _P, _I32, _P, _I64, C.POINTER(DmbTimeMatching), C.POINTER(DmbSyncBN), _P, _P,
+                               _P, _P, C.c_size_t, _P],
+    "dmb_train_backward_sync": [_M, _P, _P, _P, _P, _I32, _P, _P, _I64, C.POINTER(DmbTimeMatching), C.POINTER(DmbSyncBN),
+                                _F, _P, _P, C.c_size_t, _P],
     "dmb_time_matching_scratch_floats": [_I64, _I64, C.POINTER(C.c_size_t)],
     "dmb_time_matching_forward": [_P, _I64, _I64, C.POINTER(DmbTimeMatching), _P, _P, _P],
     "dmb_time_matching_backward": [_P, _I64, _I64, _P, _F, _P, _I32, _P],
     "dmb_pca_transform": [_P, _I64, _I32, _P, _P, _I32, _P, _P, _P],
+    "dmb_pca_transform_scratch_floats": [_I64, _I32, C.POINTER(_I64)],
+    "dmb_pca_transform_tc": [_P, _I64, _I32, _P, _P, _I32, _P, _P, _P, _P],
     "dmb_augment_batch": [_P, _P, _I64, _I32, _I32, _I32, _P, _P],
     "dmb_adam_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P],
     "dmb_adam_step_dev": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _F, _P],

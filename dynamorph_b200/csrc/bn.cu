@@ -208,12 +208,13 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs a) {
     a.A[warp] = (float)(g * is);
     a.Bc[warp] = (float)(-g * is * is * dgamma / N);
     a.Cc[warp] = (float)(-g * is * dbeta / N + g * is * is * mu * dgamma / N);
+    const double div = a.grad_div > 1 ? (double)a.grad_div : 1.0;
     if (a.per_sample) {
         atomicAdd(a.dgamma + c, (float)dgamma);
         atomicAdd(a.dbeta + c, (float)dbeta);
     } else {
-        a.dgamma[c] = (float)dgamma;
-        a.dbeta[c] = (float)dbeta;
+        a.dgamma[c] = (float)(dgamma / div);
+        a.dbeta[c] = (float)(dbeta / div);
     }
 }
 
@@ -236,8 +237,22 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_batch_kernel(const BnBwdA
     a.A[c] = (float)(g * is);
     a.Bc[c] = (float)(-g * is * is * dgamma / N);
     a.Cc[c] = (float)(-g * is * dbeta / N + g * is * is * mu * dgamma / N);
-    a.dgamma[c] = (float)dgamma;
-    a.dbeta[c] = (float)dbeta;
+    const double div = a.grad_div > 1 ? (double)a.grad_div : 1.0;
+    a.dgamma[c] = (float)(dgamma / div);
+    a.dbeta[c] = (float)(dbeta / div);
+}
+
+__global__ void __launch_bounds__(256) fold_partials_kernel(const double* partials, int64_t n, int C, double* out) {
+    pdl_wait();
+    __shared__ double red[8][2];
+    const int c = blockIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
+        const double2 v = *reinterpret_cast<const double2*>(partials + ((size_t)i * C + c) * 2);
+        s += v.x; q += v.y;
+    }
+    block_sum2(s, q, red);
+    if (threadIdx.x == 0) { out[2 * c] = s; out[2 * c + 1] = q; }
 }
 
 __global__ void __launch_bounds__(256) sum_partials_block_kernel(const double* partials, int n, int C, float* out) {
@@ -274,6 +289,13 @@ int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st) {
     const int64_t nout = a.per_sample ? (int64_t)a.B * a.C : a.C;
     const int threads = 128;
     DMB_LAUNCH((bn_bwd_finalize_kernel), (unsigned)((nout * 32 + threads - 1) / threads), threads, 0, st, a);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int fold_partials(const double* partials, int64_t n, int C, double* out, cudaStream_t st) {
+    DMB_LAUNCH((fold_partials_kernel), C, 256, 0, st, partials, n, C, out);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

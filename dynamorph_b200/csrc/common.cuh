@@ -146,6 +146,21 @@ int64_t conv_wino_weight_floats(int cin, int cout);
 int pack_wino_weights(const float* w_packed, float* out, int cin, int cout, cudaStream_t st);
 int conv_wino(const ConvWinoArgs& a, cudaStream_t st);
 
+// thin-channel convolutions on tcgen05 with the activation operand in tensor memory (conv_tm.cu); EVAL mode, NCHW in/out
+struct ConvTmArgs {
+    const float* x;         // (B, Cin, H, W) NCHW
+    const float* wtm;       // pack_tm_weights output
+    const float* bias;      // [Cout]
+    float* y;               // (B, Cout, Ho, Wo)
+    const float* skip;      // optional (B, Cout, Ho, Wo), added before the output ReLU
+    int B, Cin, H, W, Cout, ks, stride;
+    int in_relu, out_relu;
+};
+bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
+int64_t conv_tm_weight_floats(int cin, int cout, int ks);
+int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);
+int conv_tm(const ConvTmArgs& a, cudaStream_t st);
+
 // transposed 4x4 stride-2 pad-1 convolution, forward (convt_fwd.cu)
 struct ConvTFwdArgs {
     const float* x;         // (B, Cin, H, W)
@@ -228,10 +243,14 @@ struct BnBwdArgs {
     const float* invstd;
     float* A; float* Bc; float* Cc;     // [C] or [B][C]
     float* dgamma; float* dbeta;        // [C]; written (BATCH) or accumulated over samples (PER_SAMPLE)
+    int grad_div;                       // > 1: dgamma / dbeta are divided by it (synchronised BatchNorm: the sums are global)
 };
 int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st);
 // out[c] = sum over (b, band) of partials[b][band][c][0]   (bias gradient of a layer without BatchNorm)
 int sum_partials(const double* partials, int B, int nbands, int C, float* out, cudaStream_t st);
+// out[c][0..1] = sum over n rows of partials[row][c][0..1], in double, fixed order (synchronised BatchNorm: the 2*C
+// doubles that cross the ranks)
+int fold_partials(const double* partials, int64_t n, int C, double* out, cudaStream_t st);
 
 // out = (a*sa+ta) + (b*sb+tb), all (B, C, HW); the affine tables follow the per_sample flag.
 struct AffineAddArgs {

@@ -1,0 +1,463 @@
+// Thin-channel convolutions on the tensor cores with the ACTIVATION operand in tensor memory (tcgen05.mma with A in
+// TMEM), 3xTF32 operand split: the default configuration's encoder layers behind the head (EVAL mode; reference layers
+// HiddenStateExtractor/vq_vae.py:278-289 and the ResidualBlock convs at :203-209).
+//
+// Why this form.  These layers are implicit GEMMs  D[128 pixels x Cout] += A[128 x K] * B[Cout x K]^T  with K = C*kh*kw
+// = 32..256 but only N = Cout = 16..32 output channels.  With both operands in shared memory (conv_tc.cu) every
+// activation element crosses the shared-memory port five times (TMA write, split read, split writes of hi and lo, MMA
+// reads of hi and lo) for 16 multiply-adds: no faster than the CUDA-core kernel.  Here the im2col row of a pixel is
+// built in REGISTERS by the thread that owns the pixel (one 8-byte shared-memory load per input row and channel, the
+// horizontal neighbours by warp shuffle), split hi/lo in registers, and written straight into tensor memory
+// (tcgen05.st, lane = pixel, column = k).  The tensor core then reads A from TMEM; only the small weight operand
+// ([b_hi; b_lo] rows of one K-major 128-byte-swizzled tile set, resident for the whole persistent CTA) is read from
+// shared memory.  Shared-memory traffic per activation element: one TMA write + one read.
+//
+//   warps 0-3  one thread = one output pixel = one TMEM lane: gather + split + tcgen05.st of K-chunk `ky` into one of
+//              two A buffers; later the epilogue (tcgen05.ld of [main | small] -> bias, skip, ReLU -> NCHW store)
+//   warp 4     issues, per K=8 step, a_hi * [b_hi; b_lo] (N = 2*Cout) and a_lo * b_hi (N = Cout, into the `small`
+//              columns); tcgen05.commit releases the A buffer / publishes the accumulator
+//   warp 5     TMA producer: the input rows of the next tiles (zero padding above/below = out-of-bounds fill)
+#include "common.cuh"
+
+#include <algorithm>
+#include <stdlib.h>
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace dmb {
+namespace {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try(bar, parity)) {}
+}
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {      // keeps the warp converged
+    uint32_t done;
+    do {
+        done = mbar_try(bar, parity) ? 1u : 0u;
+    } while (!__all_sync(0xffffffffu, done != 0));
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, TF32 inputs, fp32 accumulation; converged warp, one elected lane issues
+__device__ __forceinline__ void tc_mma_tf32_ts_elect(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive columns, registers -> tensor memory: thread t of the warp writes lane (base lane + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+    return r;
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (see conv_tc.cu)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int TM_THREADS = 192;      // 4 gather/epilogue warps + MMA warp + TMA warp
+constexpr int cpow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+template <int KS_, int S_, int CIN_, int COUT_, int WIN_>
+struct TM {
+    static constexpr int KS = KS_, S = S_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
+    static constexpr int PAD = (KS == 1) ? 0 : 1;
+    static constexpr int WO = W / S, HO = H / S;
+    static constexpr int TH = 128 / WO;                      // output rows per tile (one tile = 128 pixels)
+    static constexpr int TILES = HO / TH;                    // tiles per patch
+    static constexpr int RIN = (TH - 1) * S + KS;            // input rows per tile
+    static constexpr int KC = KS * CIN;                      // K of one chunk (one kernel row): k = ky*KC + ci*KS + kx
+    static constexpr int K = KS * KC;
+    static constexpr int NT = (K + 31) / 32;                 // 128-byte operand tiles along K
+    static constexpr int NROWS = 2 * COUT;                   // [b_hi; b_lo]
+    static constexpr int B_FLOATS = NT * NROWS * 32;
+    static constexpr int IN_FLOATS = CIN * RIN * W;          // one input stage
+    static constexpr int IN_BYTES = IN_FLOATS * 4;
+    static constexpr int A_COLS = 2 * KC;                    // hi | lo of one chunk
+    static constexpr int D_COL = 2 * A_COLS;                 // two A buffers, then the accumulator [main | small]
+    static constexpr int TMEM_COLS = cpow2(D_COL + 2 * COUT);
+    static constexpr int CTAS = (TMEM_COLS <= 256) ? 2 : 1;  // per SM
+    static constexpr int SMEM_BUDGET = (CTAS == 2 ? 110 : 200) * 1024;
+    static constexpr int NSTAGE_RAW = (SMEM_BUDGET - B_FLOATS * 4 - 2048) / ((IN_BYTES + 127) & ~127);
+    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
+    static constexpr int STAGE_BYTES = (IN_BYTES + 127) & ~127;
+    static constexpr size_t SMEM = 1024 + (size_t)B_FLOATS * 4 + (size_t)NSTAGE * STAGE_BYTES + 256;
+    static_assert(128 % WO == 0 && HO % TH == 0, "a tile is 128 consecutive output pixels of one patch");
+    static_assert(WO <= 32 && 32 % WO == 0, "a warp covers whole output rows (shuffle neighbours)");
+    static_assert(KC % 16 == 0 && KC <= 64, "chunk = one kernel row of 16..64 k values");
+    static_assert(COUT == 16 || COUT == 32, "N = Cout and 2*Cout must be legal MMA widths");
+    static_assert((NROWS * 128) % 1024 == 0, "operand tiles stay 1024-byte aligned");
+    static_assert(TMEM_COLS <= 512 && NSTAGE >= 2, "resources");
+    static_assert((KS == 1 && S == 1) || (KS == 3 && S == 1) || (KS == 4 && S == 2), "unsupported kernel");
+    static_assert((W * 4) % 16 == 0 && W <= 256 && RIN <= 256 && CIN <= 256, "TMA box");
+};
+
+struct TmKArgs {
+    const float* wtm;       // pack_tm_weights image: [NT][NROWS][32] swizzled
+    const float* bias;      // [Cout]
+    float* y;               // (B, Cout, Ho, Wo)
+    const float* skip;      // (B, Cout, Ho, Wo) or nullptr
+    int64_t ntiles;
+    int in_relu, out_relu;
+    int dbg;                // DMB_TM_DBG=1: skip the a_lo * b_hi pass (error analysis)
+};
+
+template <class C>
+__global__ void __launch_bounds__(TM_THREADS, C::CTAS)
+conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
+    constexpr int KS = C::KS, S = C::S, CIN = C::CIN, COUT = C::COUT, W = C::W, KC = C::KC;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+    float* bs = reinterpret_cast<float*>(bp);                                  // weight operand tiles
+    const uint32_t bs_u = base;
+    uint8_t* stage0 = bp + (size_t)C::B_FLOATS * 4;
+    const uint32_t stage0_u = base + (uint32_t)C::B_FLOATS * 4u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)C::NSTAGE * C::STAGE_BYTES);
+    const uint32_t bars_u = stage0_u + (uint32_t)(C::NSTAGE * C::STAGE_BYTES);
+    // barrier slots: in_full[NSTAGE] | in_empty[NSTAGE] | a_full[2] | a_empty[2] | d_full | tmem slot
+    const uint32_t in_full = bars_u, in_empty = bars_u + 8u * C::NSTAGE, a_full = bars_u + 16u * C::NSTAGE;
+    const uint32_t a_empty = a_full + 16u, d_full = a_empty + 16u;
+    uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 5);
+    const uint32_t slot = smem_u32(slot_mem);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(in_full + 8u * s, 1u); mbar_init(in_empty + 8u * s, 4u); }
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full + 8u * s, 4u); mbar_init(a_empty + 8u * s, 1u); }
+        mbar_init(d_full, 1u);
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
+    }
+    if (warp == 4) tmem_alloc(slot, (uint32_t)C::TMEM_COLS);
+    pdl_wait();      // programmatic dependent launch: everything below may read the previous kernels' output
+    for (int i = tid; i < C::B_FLOATS / 4; i += TM_THREADS)
+        reinterpret_cast<float4*>(bs)[i] = __ldg(reinterpret_cast<const float4*>(a.wtm) + i);
+    fence_proxy_async();                     // weight tiles were written through the generic proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(slot_mem);
+
+    if (warp == 5) {
+        // ---- TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+                const int stage = it % C::NSTAGE, n = it / C::NSTAGE;
+                if (n > 0) mbar_wait(in_empty + 8u * stage, (uint32_t)((n - 1) & 1));
+                const int b = (int)(tile / C::TILES), t = (int)(tile % C::TILES);
+                const uint32_t bar = in_full + 8u * stage;
+                mbar_expect_tx(bar, (uint32_t)C::IN_BYTES);
+                tma_load_4d(stage0_u + (uint32_t)(stage * C::STAGE_BYTES), &tmap, bar, 0, t * C::TH * S - C::PAD, b, 0);
+            }
+        }
+    } else if (warp == 4) {
+        // ---- MMA issuer (whole warp converged, one elected lane per instruction)
+        const uint32_t idesc_main = make_idesc_tf32(128, 2 * COUT), idesc_lo = make_idesc_tf32(128, COUT);
+        const uint32_t d_tmem = tmem_base + (uint32_t)C::D_COL;
+        uint32_t cc = 0;
+        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+#pragma unroll 1
+            for (int ky = 0; ky < KS; ++ky, ++cc) {
+                const uint32_t buf = cc & 1u, n = cc >> 1;
+                mbar_wait_warp(a_full + 8u * buf, n & 1u);
+                tc_fence_after();
+                const uint32_t a_hi = tmem_base + buf * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
+#pragma unroll
+                for (int s = 0; s < KC / 8; ++s) {
+                    const int kg = ky * KC + 8 * s;
+                    const uint64_t bd = make_desc_sw128(bs_u + (uint32_t)((kg >> 5) * C::NROWS * 128)) +
+                                        (uint64_t)(2 * ((kg & 31) >> 3));
+                    tc_mma_tf32_ts_elect(d_tmem, a_hi + 8u * s, bd, idesc_main, (ky | s) != 0 ? 1u : 0u);
+                    if (a.dbg != 1) tc_mma_tf32_ts_elect(d_tmem + (uint32_t)COUT, a_lo + 8u * s, bd, idesc_lo, 1u);
+                }
+                tc_commit_elect(a_empty + 8u * buf);
+            }
+            tc_commit_elect(d_full);
+        }
+    } else {
+        // ---- gather / split / store into tensor memory, then the epilogue.  thread = pixel = TMEM lane
+        const int p = tid;                                   // pixel inside the tile, row-major (row, ox)
+        const int prow = p / C::WO, ox = p % C::WO;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const bool left = (ox == 0), right = (ox == C::WO - 1);
+        uint32_t cc = 0;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+            const int stage = it % C::NSTAGE;
+            mbar_wait(in_full + 8u * stage, (uint32_t)((it / C::NSTAGE) & 1));
+            const float* tin = reinterpret_cast<const float*>(stage0 + (size_t)stage * C::STAGE_BYTES);
+#pragma unroll 1
+            for (int ky = 0; ky < KS; ++ky, ++cc) {
+                const uint32_t buf = cc & 1u, n = cc >> 1;
+                // gather first (shared memory only), then wait for the buffer: the MMAs of chunk cc-2 overlap the loads
+                float v[KC];
+                const float* rp = tin + (prow * S + ky) * W + S * ox;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    if constexpr (KS == 4) {
+                        float2 f = *reinterpret_cast<const float2*>(rp + ci * C::RIN * W);
+                        if (a.in_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                        const float up = __shfl_up_sync(0xffffffffu, f.y, 1), dn = __shfl_down_sync(0xffffffffu, f.x, 1);
+                        v[ci * 4 + 0] = left ? 0.f : up;
+                        v[ci * 4 + 1] = f.x;
+                        v[ci * 4 + 2] = f.y;
+                        v[ci * 4 + 3] = right ? 0.f : dn;
+                    } else if constexpr (KS == 3) {
+                        float f = rp[ci * C::RIN * W];
+                        if (a.in_relu) f = fmaxf(f, 0.f);
+                        const float up = __shfl_up_sync(0xffffffffu, f, 1), dn = __shfl_down_sync(0xffffffffu, f, 1);
+                        v[ci * 3 + 0] = left ? 0.f : up;
+                        v[ci * 3 + 1] = f;
+                        v[ci * 3 + 2] = right ? 0.f : dn;
+                    } else {
+                        float f = rp[ci * C::RIN * W];
+                        if (a.in_relu) f = fmaxf(f, 0.f);
+                        v[ci] = f;
+                    }
+                }
+                if (n > 0) mbar_wait(a_empty + 8u * buf, (n - 1) & 1u);
+                tc_fence_after();
+                const uint32_t a_hi = lane_base + buf * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
+#pragma unroll
+                for (int j0 = 0; j0 < KC; j0 += 16) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        hi[j] = tf32_rna_bits(v[j0 + j]);
+                        lo[j] = __float_as_uint(v[j0 + j] - __uint_as_float(hi[j]));
+                    }
+                    tmem_st16(a_hi + (uint32_t)j0, hi);
+                    tmem_st16(a_lo + (uint32_t)j0, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8u * buf);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(in_empty + 8u * stage);      // this warp is done with the input stage
+
+            // ---- epilogue
+            mbar_wait(d_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            const int b = (int)(tile / C::TILES), t = (int)(tile % C::TILES);
+            const size_t pix = (size_t)(t * C::TH + prow) * C::WO + ox;
+            float* yp = a.y + (size_t)b * COUT * (C::HO * C::WO) + pix;
+            const float* sp = a.skip ? a.skip + (size_t)b * COUT * (C::HO * C::WO) + pix : nullptr;
+            const uint32_t d_tmem = lane_base + (uint32_t)C::D_COL;
+            float o[COUT];
+            if constexpr (COUT == 16) {
+                uint32_t r[32];
+                tmem_ld32(d_tmem, r);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) o[c] = __uint_as_float(r[c]) + __uint_as_float(r[16 + c]);
+            } else {
+                uint32_t r[32], q[32];
+                tmem_ld32(d_tmem, r);
+                tmem_ld32(d_tmem + 32u, q);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(r[c]) + __uint_as_float(q[c]);
+            }
+            tc_fence_before();               // the accumulator may be overwritten once every warp has arrived again
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                float val = o[c] + __ldg(a.bias + c);
+                if (sp) val += __ldg(sp + (size_t)c * (C::HO * C::WO));
+                if (a.out_relu) val = fmaxf(val, 0.f);
+                yp[(size_t)c * (C::HO * C::WO)] = val;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);
+    }
+}
+
+// ---- weight image ---------------------------------------------------------------------------------------------
+// w_packed [Cin][ks][ks][Cout] -> [NT][2*Cout][32] K-major rows, 16-byte chunks XOR-swizzled by (row & 7); row n < Cout:
+// tf32(w) of channel n, row Cout + n: w - tf32(w); k = ky*(ks*Cin) + ci*ks + kx, zero beyond K.
+__global__ void pack_tm_kernel(const float* __restrict__ w, float* __restrict__ out, int cin, int cout, int ks) {
+    pdl_wait();
+    const int KC = ks * cin, K = ks * KC, NT = (K + 31) / 32, NR = 2 * cout;
+    const int total = NT * 32 * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / cout, co = i - k * cout;
+        float hi = 0.f, lo = 0.f;
+        if (k < K) {
+            const int ky = k / KC, r = k - ky * KC, ci = r / ks, kx = r - ci * ks;
+            const float wv = __ldg(w + ((size_t)(ci * ks + ky) * ks + kx) * cout + co);
+            hi = __uint_as_float(tf32_rna_bits(wv));
+            lo = wv - hi;
+        }
+        const int tile = k >> 5, q = (k & 31) >> 2, e = k & 3;
+        const size_t tb = (size_t)tile * NR * 32;
+        out[tb + (size_t)co * 32 + (((q ^ (co & 7)) << 2) | e)] = hi;
+        const int n2 = cout + co;
+        out[tb + (size_t)n2 * 32 + (((q ^ (n2 & 7)) << 2) | e)] = lo;
+    }
+}
+
+PFN_cuTensorMapEncodeTiled tm_encoder() {
+    static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        if (q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }();
+    return fn;
+}
+
+template <class C>
+int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
+    PFN_cuTensorMapEncodeTiled enc = tm_encoder();
+    DMB_CHECK(enc != nullptr, "conv_tm: cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap map;
+    const cuuint64_t gdim[4] = {(cuuint64_t)C::W, (cuuint64_t)C::H, (cuuint64_t)a.B, (cuuint64_t)C::CIN};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C::W * 4, (cuuint64_t)C::W * C::H * C::CIN * 4, (cuuint64_t)C::W * C::H * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)C::W, (cuuint32_t)C::RIN, 1u, (cuuint32_t)C::CIN};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.x), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DMB_CHECK(r == CUDA_SUCCESS, "conv_tm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    TmKArgs k{};
+    k.wtm = a.wtm; k.bias = a.bias; k.y = a.y; k.skip = a.skip;
+    k.ntiles = (int64_t)a.B * C::TILES;
+    k.in_relu = a.in_relu; k.out_relu = a.out_relu;
+    { const char* e = getenv("DMB_TM_DBG"); k.dbg = e ? atoi(e) : 0; }
+    auto kern = conv_tm_kernel<C>;
+    int dev = 0;
+    DMB_CUDA(cudaGetDevice(&dev));
+    DMB_CHECK(dev >= 0 && dev < 64, "conv_tm: device index %d out of range", dev);
+    static bool configured[64] = {false};
+    if (!configured[dev]) {
+        DMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured[dev] = true;
+    }
+    int sms = 148;
+    DMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t grid = std::min<int64_t>(k.ntiles, (int64_t)sms * C::CTAS);
+    DMB_CHECK(grid > 0, "conv_tm: empty launch");
+    DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+}  // namespace
+
+bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W) {
+    if (H != W) return false;
+    return (ks == 4 && stride == 2 && cin == 8 && cout == 16 && W == 64) ||
+           (ks == 4 && stride == 2 && cin == 16 && cout == 16 && W == 32) ||
+           (ks == 3 && stride == 1 && cin == 16 && cout == 16 && W == 16) ||
+           (ks == 3 && stride == 1 && cin == 16 && cout == 32 && W == 16) ||
+           (ks == 1 && stride == 1 && cin == 32 && cout == 16 && W == 16);
+}
+
+int64_t conv_tm_weight_floats(int cin, int cout, int ks) {
+    const int K = ks * ks * cin;
+    return (int64_t)((K + 31) / 32) * 2 * cout * 32;
+}
+
+int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st) {
+    const int total = ((ks * ks * cin + 31) / 32) * 32 * cout;
+    DMB_LAUNCH((pack_tm_kernel), (total + 255) / 256, 256, 0, st, w_packed, out, cin, cout, ks);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
+    DMB_CHECK(conv_tm_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W), "conv_tm: unsupported layer %dx%d s%d %d->%d @%dx%d",
+              a.ks, a.ks, a.stride, a.Cin, a.Cout, a.H, a.W);
+    DMB_CHECK(!(reinterpret_cast<uintptr_t>(a.x) & 15) && !(reinterpret_cast<uintptr_t>(a.wtm) & 15),
+              "conv_tm: x and the weight image must be 16-byte aligned");
+    DMB_CHECK(a.B > 0, "conv_tm: empty batch");
+    if (a.ks == 4 && a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 64>>(a, st);
+    if (a.ks == 4) return launch_tm<TM<4, 2, 16, 16, 32>>(a, st);
+    if (a.ks == 3 && a.Cout == 16) return launch_tm<TM<3, 1, 16, 16, 16>>(a, st);
+    if (a.ks == 3) return launch_tm<TM<3, 1, 16, 32, 16>>(a, st);
+    return launch_tm<TM<1, 1, 32, 16, 16>>(a, st);
+}
+
+}  // namespace dmb

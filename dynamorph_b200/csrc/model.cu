@@ -47,7 +47,7 @@ struct Builder {
     int conv(const std::string& key, int cin, int cout, int ks, int stride, bool transposed) {
         ConvL c{};
         c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.transposed = transposed; c.bn = -1;
-        c.ptc_off = -1; c.pwn_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1;
         c.w_off = take_param(key + ".weight", (int64_t)cin * cout * ks * ks);
         c.b_off = take_param(key + ".bias", cout);
         c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
@@ -63,7 +63,7 @@ struct Builder {
         ConvL c{};
         c.cin = cin; c.cout = cmid; c.cmid = cmid; c.ks = 4; c.stride = 2; c.composite = 1; c.bn = -1;
         c.bias_classes = 1;
-        c.ptc_off = -1; c.pwn_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1;
         c.w0_off = take_param(key0 + ".weight", (int64_t)cmid * cin);
         c.b0_off = take_param(key0 + ".bias", cmid);
         c.w_off = take_param(key1 + ".weight", (int64_t)cmid * cmid * 16);
@@ -177,6 +177,17 @@ int build_layout(const dmb_model* m, Layout& L) {
                 c.pwn_off = B.take_packed(conv_wino_weight_floats(c.cin, c.cout));
         }
     }
+    {   // tensor-memory-operand plan (conv_tm.cu): the thin encoder layers behind the head, EVAL mode
+        const int H = m->height, W = m->width;
+        auto want = [&](int ci, int hh, int ww) {
+            ConvL& c = L.convs[ci];
+            if (!c.transposed && !c.composite && conv_tm_supported(c.cin, c.cout, c.ks, c.stride, hh, ww))
+                c.ptm_off = B.take_packed(conv_tm_weight_floats(c.cin, c.cout, c.ks));
+        };
+        if (m->arch == DMB_ARCH_Z16) { want(L.e2, H / 2, W / 2); want(L.e3, H / 4, W / 4); want(L.e4, H / 8, W / 8); }
+        else want(L.e2, H / 2, W / 2);
+        for (const ResL& r : L.enc_res) { want(r.a, L.lh, L.lw); want(r.b, L.lh, L.lw); }
+    }
     L.pzero_off = B.take_packed(L.max_c);
     L.n_params = B.p; L.n_bnbuf = B.bb; L.n_packed = B.pk;
     return 0;
@@ -269,6 +280,7 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             b.shift = bp.take<float>(rows * c.cout);
             b.mean = bp.take<float>(rows * c.cout);
             b.invstd = bp.take<float>(rows * c.cout);
+            b.gsum = bp.take<double>(2 * c.cout);
         }
     }
     if (keep && bn_mode != DMB_BN_EVAL) {
@@ -287,6 +299,7 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             b.A = bp.take<float>(rows * c.cout);
             b.Bc = bp.take<float>(rows * c.cout);
             b.Cc = bp.take<float>(rows * c.cout);
+            b.gsum = bp.take<double>(2 * c.cout);
         }
         w.gd = bp.take<float>(B * m.num_inputs * H * W);
         if (m.arch == DMB_ARCH_Z16) {
@@ -352,7 +365,17 @@ struct Ctx {
     int mode;
     float* bnbuf;      // running stats to update in BATCH mode (may be null)
     cudaStream_t st;
+    const dmb_sync_bn* sync = nullptr;     // synchronised BatchNorm across data-parallel ranks (BATCH mode only)
     bool per_sample() const { return mode == DMB_BN_PER_SAMPLE; }
+    bool synced() const { return sync && sync->world > 1 && sync->allreduce && mode == DMB_BN_BATCH; }
+    // fold the per-CTA partials of one BatchNorm into [C][2] doubles and sum those across the ranks
+    int exchange(const double* partials, int64_t rows, int C, double* gsum) const {
+        DMB_CHECK(gsum != nullptr, "synchronised BatchNorm needs a BATCH-mode workspace");
+        DMB_TRY(fold_partials(partials, rows, C, gsum, st));
+        const int r = sync->allreduce(sync->user, gsum, 2 * (int64_t)C, (void*)st);
+        DMB_CHECK(r == 0, "the BatchNorm allreduce callback failed (%d)", r);
+        return 0;
+    }
 };
 
 // Smallest batch that takes the Winograd tensor-core kernel (persistent CTAs of two patches each: below a few hundred
@@ -362,6 +385,17 @@ int64_t wino_min_batch() {
     if (off && off[0] == '0') return INT64_MAX;
     const char* e = getenv("DMB_WINO_MIN_B");
     return e ? atoll(e) : 512;
+}
+
+// Smallest batch that takes the tensor-memory-operand kernels (persistent CTAs; tiles = batch x 2..8).  DMB_TM=0 switches
+// them off, DMB_TM_MIN_B overrides the threshold.
+constexpr bool TM_DEFAULT_ON = false;      // flipped once the kernels are validated on the GPU
+int64_t tm_min_batch() {
+    const char* sw = getenv("DMB_TM");
+    const bool on = sw ? (sw[0] != '0') : TM_DEFAULT_ON;
+    if (!on) return INT64_MAX;
+    const char* e = getenv("DMB_TM_MIN_B");
+    return e ? atoll(e) : 256;
 }
 
 // conv (or convT) layer `ci`: in -> out, optional ReLU on load; in BN modes gathers statistics and
@@ -381,6 +415,15 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout;
         DMB_TRY(convt_fwd(a, c.st));
         Ho = 2 * H; Wo = 2 * W;
+    } else if (c.mode == DMB_BN_EVAL && l.ptm_off >= 0 && !in.s && c.B >= tm_min_batch() &&
+               conv_tm_supported(l.cin, l.cout, l.ks, l.stride, H, W)) {
+        // thin layers of the default configuration: tcgen05 with the activation operand in tensor memory (conv_tm.cu)
+        ConvTmArgs a{};
+        a.x = in.p; a.wtm = c.packed + l.ptm_off; a.bias = c.packed + l.pb_off; a.y = out; a.skip = skip;
+        a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.ks = l.ks; a.stride = l.stride;
+        a.in_relu = in_relu; a.out_relu = out_relu;
+        DMB_TRY(conv_tm(a, c.st));
+        Ho = H / l.stride; Wo = W / l.stride;
     } else if (c.mode == DMB_BN_EVAL && l.pwn_off >= 0 && !skip && !in.s && c.B >= wino_min_batch() &&
                conv_wino_supported(l.cin, l.cout, l.ks, l.stride, H, W)) {
         // default-width 3x3 at the latent resolution: Winograd F(2x2,3x3) on the tensor cores (conv_wino_tc.cu)
@@ -409,6 +452,11 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         BnFinalizeArgs f{};
         f.partials = bw->part; f.B = (int)c.B; f.nbands = bw->nbands; f.C = l.cout;
         f.count_per_sample = (int64_t)Ho * Wo;
+        if (c.synced()) {          // statistics of the GLOBAL batch: one row of summed partials, global element count
+            DMB_TRY(c.exchange(bw->part, c.B * bw->nbands, l.cout, bw->gsum));
+            f.partials = bw->gsum; f.B = 1; f.nbands = 1;
+            f.count_per_sample = (int64_t)Ho * Wo * c.B * c.sync->world;
+        }
         f.per_sample = c.per_sample();
         f.gamma = c.packed + b.pg_off; f.beta = c.packed + b.pb_off;
         f.eps = c.L.m.bn_eps; f.momentum = c.L.m.bn_momentum;
@@ -836,6 +884,11 @@ struct Bwd {
         BnWs& bw = c.w.bn[l.bn];
         BnBwdArgs a{};
         a.partials = bb.part; a.B = (int)c.B; a.nbands = nbands; a.C = l.cout; a.count_per_sample = count;
+        if (c.synced()) {
+            DMB_TRY(c.exchange(bb.part, c.B * nbands, l.cout, bb.gsum));
+            a.partials = bb.gsum; a.B = 1; a.nbands = 1; a.count_per_sample = count * c.B * c.sync->world;
+            a.grad_div = c.sync->world;
+        }
         a.per_sample = ps(); a.gamma = c.packed + b.pg_off; a.mean = bw.mean; a.invstd = bw.invstd;
         a.A = bb.A; a.Bc = bb.Bc; a.Cc = bb.Cc; a.dgamma = grads + b.g_off; a.dbeta = grads + b.b_off;
         DMB_TRY(bn_backward_finalize(a, st));
@@ -1247,6 +1300,27 @@ int dmb_conv2d_wino(const float* x, const float* w_packed, const float* bias, fl
     return conv_wino(a, st);
 }
 
+int dmb_conv2d_tm_scratch_floats(int32_t cin, int32_t cout, int32_t ksize, int64_t* floats) {
+    DMB_CHECK(floats != nullptr, "dmb_conv2d_tm_scratch_floats: null output");
+    *floats = conv_tm_weight_floats(cin, cout, ksize);
+    return 0;
+}
+
+int dmb_conv2d_tm(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                  int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, int32_t in_relu, const float* skip,
+                  int32_t out_relu, float* scratch, void* stream) {
+    DMB_CHECK(x && w_packed && bias && y && scratch, "dmb_conv2d_tm: null pointer");
+    DMB_CHECK(conv_tm_supported(cin, cout, ksize, stride, h, w), "dmb_conv2d_tm: layer %dx%d s%d %d->%d @%dx%d is not one "
+              "of the thin encoder shapes this kernel is built for", ksize, ksize, stride, cin, cout, h, w);
+    cudaStream_t st = (cudaStream_t)stream;
+    DMB_TRY(pack_tm_weights(w_packed, scratch, cin, cout, ksize, st));
+    ConvTmArgs a{};
+    a.x = x; a.wtm = scratch; a.bias = bias; a.y = y; a.skip = skip;
+    a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
+    a.in_relu = in_relu; a.out_relu = out_relu;
+    return conv_tm(a, st);
+}
+
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,
                                  const float* in_scale, const float* in_shift, int32_t in_per_sample,
@@ -1298,6 +1372,7 @@ int res_plan(int h, int rh, int nl, int64_t B, int H, int W, int bn_mode, void* 
             b.part = bp.take<double>(B * nb * c.cout * 2);
             b.scale = bp.take<float>(rows * c.cout); b.shift = bp.take<float>(rows * c.cout);
             b.mean = bp.take<float>(rows * c.cout); b.invstd = bp.take<float>(rows * c.cout);
+            b.gsum = nullptr;
         }
     }
     p.bytes = (bp.off + 255) & ~(size_t)255;
@@ -1341,12 +1416,13 @@ int dmb_residual_block_forward(int32_t num_hiddens, int32_t num_residual_hiddens
 static int train_forward_impl(const dmb_model* m, const float* packed, const float* params, const float* x,
                               const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
                               const dmb_time_matching* tm, int n_losses, float* decoded, float* losses_out,
-                              float* bnbuf_inout, void* workspace, size_t workspace_bytes, void* stream) {
+                              float* bnbuf_inout, void* workspace, size_t workspace_bytes, void* stream,
+                              const dmb_sync_bn* sync = nullptr) {
     Layout L; Workspace w;
     DMB_CHECK(packed && params && x && channel_var && decoded && losses_out, "dmb_train_forward: null pointer");
     DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
     cudaStream_t st = (cudaStream_t)stream;
-    Ctx c{L, packed, w, batch, DMB_BN_BATCH, bnbuf_inout, st};
+    Ctx c{L, packed, w, batch, DMB_BN_BATCH, bnbuf_inout, st, sync};
     Pending pend;
     DMB_TRY(run_encoder(c, x, w.zb, &pend));
     DMB_CUDA(cudaMemsetAsync(w.vq_stats, 0, sizeof(double) * (2 + m->num_embeddings), st));
@@ -1384,14 +1460,30 @@ int dmb_train_forward_tm(const dmb_model* m, const float* packed, const float* p
                               losses_out, bnbuf_inout, workspace, workspace_bytes, stream);
 }
 
+int dmb_train_forward_sync(const dmb_model* m, const float* packed, const float* params, const float* x,
+                           const float* mask, int32_t mask_channels, const float* channel_var, int64_t batch,
+                           const dmb_time_matching* tm, const dmb_sync_bn* sync, float* decoded, float* losses_out,
+                           float* bnbuf_inout, void* workspace, size_t workspace_bytes, void* stream) {
+    return train_forward_impl(m, packed, params, x, mask, mask_channels, channel_var, batch, tm, 8, decoded,
+                              losses_out, bnbuf_inout, workspace, workspace_bytes, stream, sync);
+}
+
 int dmb_train_backward_tm(const dmb_model* m, const float* packed, const float* params, const float* x,
                           const float* mask, int32_t mask_channels, const float* channel_var,
                           const float* decoded, int64_t batch, const dmb_time_matching* tm, float grad_scale,
                           float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+    return dmb_train_backward_sync(m, packed, params, x, mask, mask_channels, channel_var, decoded, batch, tm, nullptr,
+                                   grad_scale, grads, workspace, workspace_bytes, stream);
+}
+
+int dmb_train_backward_sync(const dmb_model* m, const float* packed, const float* params, const float* x,
+                            const float* mask, int32_t mask_channels, const float* channel_var,
+                            const float* decoded, int64_t batch, const dmb_time_matching* tm, const dmb_sync_bn* sync,
+                            float grad_scale, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
     Layout L; Workspace w;
     DMB_CHECK(packed && params && x && channel_var && decoded && grads, "dmb_train_backward: null pointer");
     DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
-    Ctx c{L, packed, w, batch, DMB_BN_BATCH, nullptr, (cudaStream_t)stream};
+    Ctx c{L, packed, w, batch, DMB_BN_BATCH, nullptr, (cudaStream_t)stream, sync};
     const float* g_tm = nullptr;
     if (tm) {
         // d(weight * tm_loss)/dz; z_after is a straight-through copy of z_before, so either source feeds dL/dz_before

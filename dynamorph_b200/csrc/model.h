@@ -26,6 +26,7 @@ struct ConvL {
     int bias_classes;
     int64_t ptc_off;             // tensor-core tiles of the EVAL-folded weights (conv_tc.cu) or -1
     int64_t pwn_off;             // Winograd-domain tensor-core tiles of the EVAL-folded weights (conv_wino_tc.cu) or -1
+    int64_t ptm_off;             // [b_hi; b_lo] operand image of the EVAL-folded weights for conv_tm.cu or -1
 };
 
 struct Entry { std::string key; int which; int64_t off, numel; };
@@ -55,7 +56,8 @@ struct Layout {
 int build_layout(const dmb_model* m, Layout& L);
 
 // Every scratch buffer a forward (and the backward that follows) touches.
-struct BnWs { double* part; float* scale; float* shift; float* mean; float* invstd; int nbands; int64_t count; };
+struct BnWs { double* part; float* scale; float* shift; float* mean; float* invstd; int nbands; int64_t count;
+              double* gsum; };   // gsum: [C][2] folded sums that cross the ranks under synchronised BatchNorm
 struct Workspace {
     // z16 encoder activations (raw conv outputs in BATCH/PER_SAMPLE mode, post-activation in EVAL)
     float *y1 = nullptr, *y2 = nullptr, *y3 = nullptr, *y4 = nullptr;
@@ -68,7 +70,7 @@ struct Workspace {
     float* dec = nullptr;
     std::vector<BnWs> bn;                  // one per BatchNorm, same order as Layout::bns
     // ---- backward (keep != 0)
-    struct BnB { double* part; float *A, *Bc, *Cc; };
+    struct BnB { double* part; float *A, *Bc, *Cc; double* gsum; };
     std::vector<BnB> bnb;
     float *gd = nullptr, *g_t3 = nullptr, *g_t2 = nullptr, *g_t1 = nullptr, *g_za = nullptr, *g_zb = nullptr;
     std::vector<float*> g_era, g_eh;       // encoder residual: grad at BN_a output (masked), grad at layer input

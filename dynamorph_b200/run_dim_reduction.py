@@ -36,6 +36,9 @@ def pca_transform(pca, dats: np.ndarray, device="cuda:0", chunk: int = 65536) ->
     copy, comp_s = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
     bufs = [torch.empty(min(chunk, max(n, 1)), l, dtype=torch.float32, device=dev) for _ in range(2)]
     outs = [torch.empty(min(chunk, max(n, 1)), k, dtype=torch.float32, device=dev) for _ in range(2)]
+    nf = C.c_int64()
+    call("dmb_pca_transform_scratch_floats", min(chunk, max(n, 1)), l, C.byref(nf))
+    scratch = torch.empty(nf.value, dtype=torch.float32, device=dev)      # tensor-core form: packed weights + (rows, 64) tile
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
     pending = []
@@ -52,7 +55,7 @@ def pca_transform(pca, dats: np.ndarray, device="cuda:0", chunk: int = 65536) ->
         if i >= 2:                                   # outs[j] of chunk i-2 must be on the host before it is reused
             pa, pm, pj = pending.pop(0)
             out[pa:pa + pm] = outs[pj][:pm].cpu().numpy()
-        call("dmb_pca_transform", ptr(bufs[j]), m, l, ptr(mean), ptr(comp), k, ptr(inv), ptr(outs[j]),
+        call("dmb_pca_transform_tc", ptr(bufs[j]), m, l, ptr(mean), ptr(comp), k, ptr(inv), ptr(outs[j]), ptr(scratch),
              C.c_void_p(comp_s.cuda_stream))
         ev_done[j].record(comp_s)
         pending.append((a, m, j))

@@ -212,6 +212,8 @@ class FusedTrainer:
                     with torch.cuda.graph(st.fwd_graph):
                         self._forward(st)
                 st.fwd_graph.replay()
+            elif self.sync_bn:
+                self._sync.forward(st)
             else:
                 self._forward(st)
             self.eng._bn_dirty += 1

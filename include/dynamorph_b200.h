@@ -172,6 +172,15 @@ int dmb_conv2d_tc(const float* x, const float* w_packed, const float* bias, floa
 int dmb_conv2d_wino(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
                     int32_t h, int32_t w, int32_t cout, int32_t in_relu, int32_t out_relu, const float* w2_packed,
                     const float* bias2, float* y2, float* scratch, void* stream);
+/* nn.Conv2d forward for the THIN layers of the default configuration (8 -> 16 4x4 s2 @64, 16 -> 16 4x4 s2 @32,
+ * 16 -> 16|32 3x3 @16, 32 -> 16 1x1 @16; vq_vae.py:280-289, :203-209) on the tensor cores with the activation operand
+ * in tensor memory: each thread builds the im2col row of its output pixel in registers, splits it hi/lo (3xTF32) and
+ * writes it with tcgen05.st; tcgen05.mma reads A from TMEM and [b_hi; b_lo] from shared memory.  x, skip, y NCHW;
+ * w_packed [Cin][k][k][Cout]; `scratch` holds dmb_conv2d_tm_scratch_floats() floats (the split, swizzled weight image). */
+int dmb_conv2d_tm_scratch_floats(int32_t cin, int32_t cout, int32_t ksize, int64_t* floats);
+int dmb_conv2d_tm(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                  int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, int32_t in_relu,
+                  const float* skip, int32_t out_relu, float* scratch, void* stream);
 /* nn.ConvTranspose2d(k=4, stride=2, padding=1) forward; w_packed is [Cin][4][4][Cout].        */
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,
@@ -201,6 +210,15 @@ long long dmb_launch_count(int reset);
 int dmb_pca_transform(const float* x, int64_t n, int32_t latent_len, const float* mean,
                       const float* components, int32_t n_components, const float* inv_scale, float* out,
                       void* stream);
+
+/* The same projection on the tensor cores (tcgen05, 3xTF32 operand split, fp32 accumulation): x is read as the NHWC
+ * input of a 1x1 convolution with latent_len input and 64 output channels per pass, mean folded into the bias.
+ * `scratch`: dmb_pca_transform_scratch_floats(n, latent_len) floats, 16-byte aligned.  Rows past the last multiple of
+ * 128 and shapes the tensor-core kernel does not take (latent_len % 32 != 0) run on the kernel above.               */
+int dmb_pca_transform_scratch_floats(int64_t n, int32_t latent_len, int64_t* floats);
+int dmb_pca_transform_tc(const float* x, int64_t n, int32_t latent_len, const float* mean,
+                         const float* components, int32_t n_components, const float* inv_scale, float* out,
+                         float* scratch, void* stream);
 
 /* ---- training augmentation (run_training.py:396-403) ------------------------------------ */
 /* out[b] = rot90(flip(x[b], dims=(flip,)), k=rot, dims=[1, 2]) for every sample in one launch; ops_dev holds one
@@ -252,6 +270,30 @@ int dmb_train_backward_tm(const dmb_model* m, const float* packed, const float* 
                           const float* channel_var, const float* decoded, int64_t batch,
                           const dmb_time_matching* tm, float grad_scale,
                           float* grads, void* workspace, size_t workspace_bytes, void* stream);
+/* The same two calls for data-parallel training with SYNCHRONISED BatchNorm: every BatchNorm's per-channel sums
+ * (forward: sum y, sum y^2; backward: sum g, sum g*y) are folded on the device into `2 * channels` doubles and handed
+ * to `allreduce` (which must sum them in place across the ranks, ordered on `stream` -- e.g. ncclAllReduce /
+ * torch.distributed.all_reduce), then finalised with the GLOBAL element count, so that `world` ranks with `batch`
+ * patches each compute exactly the step a single process computes on the concatenated batch (the reference's
+ * single-GPU semantics, run_training.py:404).  BatchNorm weight / bias gradients come out pre-divided by `world`
+ * so that the usual allreduce-sum of `grads` followed by Adam's 1/world yields the global-batch gradient.
+ * sync == NULL or sync->world <= 1: identical to the _tm calls.                                                     */
+typedef int (*dmb_allreduce_fn)(void* user, double* sums_dev, int64_t n, void* stream);
+typedef struct dmb_sync_bn {
+    dmb_allreduce_fn allreduce;
+    void* user;
+    int32_t world;
+} dmb_sync_bn;
+int dmb_train_forward_sync(const dmb_model* m, const float* packed, const float* params,
+                           const float* x, const float* mask, int32_t mask_channels,
+                           const float* channel_var, int64_t batch, const dmb_time_matching* tm,
+                           const dmb_sync_bn* sync, float* decoded, float* losses_out, float* bnbuf_inout,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int dmb_train_backward_sync(const dmb_model* m, const float* packed, const float* params,
+                            const float* x, const float* mask, int32_t mask_channels,
+                            const float* channel_var, const float* decoded, int64_t batch,
+                            const dmb_time_matching* tm, const dmb_sync_bn* sync, float grad_scale,
+                            float* grads, void* workspace, size_t workspace_bytes, void* stream);
 /* torch.optim.Adam (betas, eps, no weight decay), bias-corrected, step is 1-based.
  * grad_scale multiplies the gradient first (1/world_size after an allreduce-sum).        */
 int dmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,

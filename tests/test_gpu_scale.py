@@ -1,0 +1,219 @@
+"""-m gpu: parity AT THE BATCH SIZES THE BENCH TIMES (BASELINE.json configs[1..3]), with the
+library's default dispatch -- no DMB_* overrides, so the Winograd / tensor-core / constant-weight / persistent-CTA
+variants that only switch on at bulk batch sizes are the ones compared with the oracle:
+
+  C3  encode of 16,384 patches (eval and per-patch statistics): 256 patches spread over the batch vs the oracle
+  --  the quantiser alone over 2,048 patches (its persistent CTAs wrap many times): every position vs the oracle
+  C2  one training step at batch 256: decoded, 5 losses, all 43 gradients, weights after 1 and 10 Adam steps
+  C4  VQ_VAE(num_hiddens=64, num_embeddings=512) and VQ_VAE_z32(64, 64, 512) encode at batch 1024 (64-patch sample),
+      and one batch-1024 training step of the former (losses + gradients)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DISPATCH_ENV = ("DMB_TC", "DMB_VQ_TC", "DMB_WINO", "DMB_WINO_MIN_B", "DMB_WINO_FUSE", "DMB_CONV_WEIGHTS", "DMB_HEAD_NHWC",
+                "DMB_PDL", "DMB_FUSE")
+
+
+@pytest.fixture(autouse=True)
+def default_dispatch(monkeypatch):
+    for k in DISPATCH_ENV:
+        monkeypatch.delenv(k, raising=False)
+
+
+def _state(arch="z16", seed=0, **kw):
+    return O.calibrate_state(O.default_state(arch, **kw), O.synthetic_patches(32, 1), seed=seed)
+
+
+def _bulk_input(n, seed):
+    from dynamorph_b200.synthetic import synthetic_patches
+    return torch.cat([synthetic_patches(min(2048, n - a), seed + a, "cuda") for a in range(0, n, 2048)])
+
+
+def _sample_rows(n, k, seed=0):
+    """k rows spread over [0, n): the first and last 16 (first / last CTAs and the ragged tail) plus random ones."""
+    rng = np.random.RandomState(seed)
+    edge = list(range(16)) + list(range(n - 16, n))
+    rest = rng.choice(np.arange(16, n - 16), size=k - len(edge), replace=False).tolist()
+    return torch.tensor(sorted(edge + rest))
+
+
+@pytest.mark.parametrize("bn_mode,n", [("eval", 16384), ("per_sample", 16384), ("eval", 16384 - 37)])
+def test_c3_bulk_encode_sample_matches_oracle(bn_mode, n):
+    import gpu_util as U
+    st = _state()
+    m = U.model_from_state(st).eval()
+    x = _bulk_input(n, 1234)
+    zb, za, idx = m.encode_latents(x, bn_mode)
+    torch.cuda.synchronize()
+    rows = _sample_rows(n, 256)
+    xs = x[rows.cuda()].cpu()
+    with torch.no_grad():
+        ref = O.encoder(xs, st, O.EVAL if bn_mode == "eval" else O.PER_SAMPLE)
+        ref_idx = O.vq_indices(ref, st["vq.w.weight"])
+    err = U.rel(zb[rows.cuda()], ref)
+    assert err < U.REL_TOL, err
+    flips = U.check_indices(idx[rows.cuda()], ref, st["vq.w.weight"], ref_idx, f"C3 {bn_mode}")
+    # z_after is the gathered codebook row: exact wherever the index agrees
+    same = (idx[rows.cuda()].cpu().long() == ref_idx)
+    q = O.vq_gather(ref_idx, st["vq.w.weight"])
+    sel = same.unsqueeze(1).expand_as(q)
+    assert torch.equal(za[rows.cuda()].cpu()[sel], (ref + (q - ref))[sel]) or \
+        U.rel(za[rows.cuda()].cpu()[sel], q[sel]) < 1e-6
+    print(f"C3 {bn_mode} n={n}: z_before rel err {err:.2e}, index flips at near-ties {flips}/{same.numel()}")
+
+
+@pytest.mark.parametrize("K,D,B", [(64, 16, 2048), (512, 64, 1024)])
+def test_quantiser_wrap_regime_bit_exact(K, D, B):
+    """dmb_vq_forward on a batch large enough that every persistent CTA of the tensor-core search loops over many
+    tiles: indices AND straight-through values bit-exact against the oracle at every position; loss and perplexity
+    to 1e-6 (the kernel accumulates them in double)."""
+    from dynamorph_b200 import engine
+    g = torch.Generator().manual_seed(K)
+    cb = torch.randn(K, D, generator=g)
+    z = torch.randn(B, D, 16, 16, generator=g) * 0.8
+    pick = torch.randint(0, K, (B, 16, 16), generator=g)
+    z = z * 0.3 + O.vq_gather(pick, cb) * 0.7                         # clustered around codes, like trained latents
+    z_st, loss, ppl, idx = engine.vq_forward(z.cuda(), cb.cuda(), 0.25, want_indices=True)
+    ref_st, ref_loss, ref_ppl, ref_idx = O.vq_forward(z, cb, 0.25)
+    assert torch.equal(idx.cpu().long(), ref_idx)
+    assert torch.equal(z_st.cpu(), ref_st)
+    assert abs(float(loss) - float(ref_loss)) <= 2e-6 * float(ref_loss)
+    assert abs(float(ppl) - float(ref_ppl)) <= 1e-5 * float(ref_ppl)
+
+
+def test_c2_train_step_batch_256():
+    """BASELINE configs[1]: reference-default training step, batch 256, fp32.  FusedTrainer (the graph-replayed step
+    bench.py times) and run_one_batch (the reference's API) against the oracle's step."""
+    import gpu_util as U
+    from dynamorph_b200.optim import FusedAdam
+    from dynamorph_b200.run_training import run_one_batch
+    from dynamorph_b200.trainer import FusedTrainer
+    B, lr = 256, 1e-4
+    st = _state()
+    x = O.synthetic_patches(B, 4321)
+    dec_ref, loss_ref, grad_ref, _ = O.loss_and_grads(x, st, O.BATCH)
+    noise = set(O.bias_feeds_train_bn(st))
+
+    # ---- eager API: forward values, gradients
+    m = U.model_from_state(st).train()
+    dec, d = m(x.cuda())
+    assert U.rel(dec, dec_ref) < U.REL_TOL
+    for k in ("recon_loss", "commitment_loss", "total_loss", "perplexity"):
+        assert abs(float(d[k]) - float(loss_ref[k])) <= U.REL_TOL * abs(float(loss_ref[k])), k
+    d["total_loss"].backward()
+    named = dict(m.named_parameters())
+    scale = max(float(v.abs().max()) for k, v in grad_ref.items() if k not in noise)
+    worst = 0.0
+    for k, ref in grad_ref.items():
+        got = named[k].grad.detach().cpu()
+        if k in noise:
+            assert float(got.abs().max()) <= 1e-5 * scale, k
+            continue
+        e = float((got - ref).abs().max() / ref.abs().max().clamp(min=1e-30))
+        worst = max(worst, e)
+        # a flipped ReLU gate moves a batch-256 gradient by ~1/256 of one position's contribution: no envelope needed
+        assert e < 2e-4, (k, e)
+    print(f"C2: worst gradient error {worst:.2e} of max|g| over {len(grad_ref)} tensors")
+
+    # ---- weights after 1 and 10 Adam steps (same batch every step), both step implementations
+    ref_state = {k: v.clone() for k, v in st.items()}
+    opt = {"m": {}, "v": {}}
+    ref_curve, ref_after = [], {}
+    for step in range(1, 11):
+        ref_curve.append(float(O.train_step(x, ref_state, opt, step, lr)["total_loss"]))
+        if step in (1, 10):
+            ref_after[step] = {k: v.clone() for k, v in ref_state.items()}
+    sig = {k: grad_ref[k].abs() > 1e-3 * grad_ref[k].abs().max() for k in grad_ref}
+    for kind in ("fused_trainer", "run_one_batch"):
+        m = U.model_from_state(st).train()
+        curve = []
+        if kind == "fused_trainer":
+            tr = FusedTrainer(m, lr=lr, use_graph=True)
+            step_fn = lambda: curve.append(float(tr.step(x.cuda())[2]))
+        else:
+            o = FusedAdam(m, lr=lr)
+            tl = {}
+            step_fn = lambda: (run_one_batch(m, x.cuda(), tl, model_kwargs={}, optimizer=o, transform=None,
+                                             training=True), curve.append(tl["total_loss"][-1]))
+        for step in range(1, 11):
+            step_fn()
+            if step not in (1, 10):
+                continue
+            sd = m.state_dict()
+            for k, ref in ref_after[step].items():
+                got = sd[k].detach().cpu()
+                if k.endswith("num_batches_tracked"):
+                    assert int(got) == int(ref), k
+                elif "running" in k:
+                    assert U.rel(got, ref) < U.REL_TOL, (kind, step, k)
+                elif k == "channel_var":
+                    assert torch.equal(got, ref)
+                else:
+                    diff = (got - ref).abs()
+                    assert float(diff.max()) <= 2.01 * step * lr, (kind, step, k)       # Adam's reach
+                    if k not in noise and step == 1:      # where the gradient is significant the update is tight
+                        assert float(diff[sig[k]].max()) <= 2e-3 * lr + 1e-7, (kind, k, float(diff[sig[k]].max()))
+        assert np.allclose(curve, ref_curve, rtol=2e-4), (kind, curve, ref_curve)
+
+
+HEAVY = [("z16", dict(num_hiddens=64, num_embeddings=512), 64),
+         ("z32", dict(num_hiddens=64, num_residual_hiddens=64, num_embeddings=512), 32)]
+
+
+@pytest.mark.parametrize("arch,kw,sample", HEAVY)
+@pytest.mark.parametrize("bn_mode", ["eval", "per_sample"])
+def test_c4_heavy_encode_batch_1024(arch, kw, sample, bn_mode):
+    """BASELINE configs[3]: the quantiser-heavy 64 / 512 models at batch 1024 -- tcgen05 convolutions and code search in
+    eval mode, the CUDA-core kernels with per-patch statistics."""
+    import gpu_util as U
+    st = _state(arch, seed=3, **kw)
+    m = U.model_from_state(st).eval()
+    x = _bulk_input(1024, 99)
+    zb, za, idx = m.encode_latents(x, bn_mode)
+    torch.cuda.synchronize()
+    rows = _sample_rows(1024, sample, seed=1)
+    with torch.no_grad():
+        ref = O.encoder(x[rows.cuda()].cpu(), st, O.EVAL if bn_mode == "eval" else O.PER_SAMPLE)
+        ref_idx = O.vq_indices(ref, st["vq.w.weight"], chunk=2)
+    err = U.rel(zb[rows.cuda()], ref)
+    assert err < U.REL_TOL, err
+    flips = U.check_indices(idx[rows.cuda()], ref, st["vq.w.weight"], ref_idx, f"C4 {arch} {bn_mode}")
+    print(f"C4 {arch} {bn_mode}: z_before rel err {err:.2e}, near-tie flips {flips}/{ref_idx.numel()}")
+
+
+def test_c4_heavy_train_step_batch_1024():
+    """BASELINE configs[3] "encode+train at batch 1024": one training step of VQ_VAE(64, ., 512) against the oracle
+    (its quantiser chunked over the batch -- the reference's broadcast would need 32 GiB)."""
+    import gpu_util as U
+    B = 1024
+    st = _state("z16", seed=3, num_hiddens=64, num_embeddings=512)
+    x = torch.cat([O.synthetic_patches(256, 700 + i) for i in range(B // 256)])
+    dec_ref, loss_ref, grad_ref, new_running = O.loss_and_grads(x, st, O.BATCH)
+    m = U.model_from_state(st).train()
+    dec, d = m(x.cuda())
+    assert U.rel(dec, dec_ref) < U.REL_TOL
+    for k in ("recon_loss", "commitment_loss", "total_loss", "perplexity"):
+        assert abs(float(d[k]) - float(loss_ref[k])) <= U.REL_TOL * abs(float(loss_ref[k])), k
+    d["total_loss"].backward()
+    sd = m.state_dict()
+    for k, v in new_running.items():
+        if not k.endswith("num_batches_tracked"):
+            assert U.rel(sd[k], v) < U.REL_TOL, k
+    noise = set(O.bias_feeds_train_bn(st))
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, ref in grad_ref.items():
+        if k in noise:
+            continue
+        e = float((named[k].grad.detach().cpu() - ref).abs().max() / ref.abs().max().clamp(min=1e-30))
+        worst = max(worst, e)
+        assert e < 2e-4, (k, e)
+    print(f"C4 train B=1024: worst gradient error {worst:.2e}")

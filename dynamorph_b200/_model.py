@@ -96,7 +96,7 @@ class ResidualBlock(nn.Module):
         if n_p.value != params.numel() or n_b.value != bnbuf.numel():
             raise RuntimeError(f"ResidualBlock parameter layout mismatch: python {params.numel()}/{bnbuf.numel()} vs "
                                f"library {n_p.value}/{n_b.value}")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
         upd = ptr(bnbuf) if mode == BN_BATCH else None
         call("dmb_residual_block_forward", *args, ptr(params), ptr(bnbuf), ptr(x), B, H, W, mode, ptr(y), upd, ptr(ws),
              nbytes.value, _engine._stream())

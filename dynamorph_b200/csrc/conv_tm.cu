@@ -127,8 +127,41 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int TM_THREADS = 192;      // 4 gather/epilogue warps + MMA warp + TMA warp
+constexpr int TM_THREADS = 320;      // 8 gather/epilogue warps (two per TMEM lane quadrant) + MMA warp + TMA warp
 constexpr int cpow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+// waits of the two helper warps back off: a bare try_wait loop returns every ~10 cycles and the spinning producer
+// thread alone took 20 % of the SM's issue slots (ncu, profiles/r2_ncu_conv_tm_enc4_v1.txt)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    while (!mbar_try(bar, parity)) __nanosleep(128);
+}
+__device__ __forceinline__ void mbar_wait_warp_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        done = mbar_try(bar, parity) ? 1u : 0u;
+        if (!done) __nanosleep(64);
+    } while (!__all_sync(0xffffffffu, done != 0));
+}
+// tensor memory -> registers, 32 lanes x N consecutive columns
+template <int N> struct TmemLd;
+template <> struct TmemLd<8> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t* v) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr) : "memory");
+    }
+};
+template <> struct TmemLd<16> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t* v) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr) : "memory");
+    }
+};
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 template <int KS_, int S_, int CIN_, int COUT_, int WIN_>
 struct TM {
@@ -146,14 +179,21 @@ struct TM {
     static constexpr int IN_FLOATS = CIN * RIN * W;          // one input stage
     static constexpr int IN_BYTES = IN_FLOATS * 4;
     static constexpr int A_COLS = 2 * KC;                    // hi | lo of one chunk
-    static constexpr int D_COL = 2 * A_COLS;                 // two A buffers, then the accumulator [main | small]
-    static constexpr int TMEM_COLS = cpow2(D_COL + 2 * COUT);
+    static constexpr int D_COL = 2 * A_COLS;                 // two A buffers, then the accumulators [main | small]
+    // The tensor core TRUNCATES when it aligns and adds into the fp32 accumulator, a bias that grows with the number of
+    // MMAs chained on one accumulator (measured: 2.8e-6 on z_before after five layers with one accumulator, against
+    // 1.2e-6 for the FFMA kernels).  Chunk ky therefore accumulates into accumulator ky % NACC and the epilogue adds the
+    // partial sums in round-to-nearest fp32.  Two accumulators where tensor memory allows it without losing the second
+    // resident CTA: reading them back (LDTM, 64 B/clk per SM) is what a third and fourth would cost.
+    static constexpr int NACC = (KS >= 2 && cpow2(D_COL + 2 * 2 * COUT) <= cpow2(D_COL + 2 * COUT)) ? 2 : 1;
+    static constexpr int TMEM_COLS = cpow2(D_COL + NACC * 2 * COUT);
     static constexpr int CTAS = (TMEM_COLS <= 256) ? 2 : 1;  // per SM
     static constexpr int SMEM_BUDGET = (CTAS == 2 ? 110 : 200) * 1024;
     static constexpr int NSTAGE_RAW = (SMEM_BUDGET - B_FLOATS * 4 - 2048) / ((IN_BYTES + 127) & ~127);
     static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
     static constexpr int STAGE_BYTES = (IN_BYTES + 127) & ~127;
     static constexpr size_t SMEM = 1024 + (size_t)B_FLOATS * 4 + (size_t)NSTAGE * STAGE_BYTES + 256;
+    static constexpr int HALF = COUT / 2;                    // output channels per epilogue warp group
     static_assert(128 % WO == 0 && HO % TH == 0, "a tile is 128 consecutive output pixels of one patch");
     static_assert(WO <= 32 && 32 % WO == 0, "a warp covers whole output rows (shuffle neighbours)");
     static_assert(KC % 16 == 0 && KC <= 64, "chunk = one kernel row of 16..64 k values");
@@ -171,13 +211,14 @@ struct TmKArgs {
     const float* skip;      // (B, Cout, Ho, Wo) or nullptr
     int64_t ntiles;
     int in_relu, out_relu;
-    int dbg;                // DMB_TM_DBG=1: skip the a_lo * b_hi pass (error analysis)
+    int dbg;                // DMB_TM_DBG skip experiments (results are wrong): 1 no a_lo*b_hi MMAs, 2 no a_hi MMAs,
+                            // 4 no gather (zeros), 8 no split / tensor-memory stores
 };
 
 template <class C>
 __global__ void __launch_bounds__(TM_THREADS, C::CTAS)
 conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
-    constexpr int KS = C::KS, S = C::S, CIN = C::CIN, COUT = C::COUT, W = C::W, KC = C::KC;
+    constexpr int KS = C::KS, S = C::S, CIN = C::CIN, COUT = C::COUT, W = C::W, KC = C::KC, HALF = C::HALF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
@@ -187,22 +228,23 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
     const uint32_t stage0_u = base + (uint32_t)C::B_FLOATS * 4u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)C::NSTAGE * C::STAGE_BYTES);
     const uint32_t bars_u = stage0_u + (uint32_t)(C::NSTAGE * C::STAGE_BYTES);
-    // barrier slots: in_full[NSTAGE] | in_empty[NSTAGE] | a_full[2] | a_empty[2] | d_full | tmem slot
+    // barrier slots: in_full[NSTAGE] | in_empty[NSTAGE] | a_full[2] | a_empty[2] | d_full | d_empty | tmem slot
     const uint32_t in_full = bars_u, in_empty = bars_u + 8u * C::NSTAGE, a_full = bars_u + 16u * C::NSTAGE;
-    const uint32_t a_empty = a_full + 16u, d_full = a_empty + 16u;
-    uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 5);
+    const uint32_t a_empty = a_full + 16u, d_full = a_empty + 16u, d_empty = d_full + 8u;
+    uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 6);
     const uint32_t slot = smem_u32(slot_mem);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(in_full + 8u * s, 1u); mbar_init(in_empty + 8u * s, 4u); }
+        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(in_full + 8u * s, 1u); mbar_init(in_empty + 8u * s, 8u); }
         for (int s = 0; s < 2; ++s) { mbar_init(a_full + 8u * s, 4u); mbar_init(a_empty + 8u * s, 1u); }
         mbar_init(d_full, 1u);
+        mbar_init(d_empty, 8u);
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
     }
-    if (warp == 4) tmem_alloc(slot, (uint32_t)C::TMEM_COLS);
+    if (warp == 8) tmem_alloc(slot, (uint32_t)C::TMEM_COLS);
     pdl_wait();      // programmatic dependent launch: everything below may read the previous kernels' output
     for (int i = tid; i < C::B_FLOATS / 4; i += TM_THREADS)
         reinterpret_cast<float4*>(bs)[i] = __ldg(reinterpret_cast<const float4*>(a.wtm) + i);
@@ -212,63 +254,80 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(slot_mem);
 
-    if (warp == 5) {
+    if (warp == 9) {
         // ---- TMA producer
         if (lane == 0) {
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
                 const int stage = it % C::NSTAGE, n = it / C::NSTAGE;
-                if (n > 0) mbar_wait(in_empty + 8u * stage, (uint32_t)((n - 1) & 1));
+                if (n > 0) mbar_wait_sleep(in_empty + 8u * stage, (uint32_t)((n - 1) & 1));
                 const int b = (int)(tile / C::TILES), t = (int)(tile % C::TILES);
                 const uint32_t bar = in_full + 8u * stage;
                 mbar_expect_tx(bar, (uint32_t)C::IN_BYTES);
                 tma_load_4d(stage0_u + (uint32_t)(stage * C::STAGE_BYTES), &tmap, bar, 0, t * C::TH * S - C::PAD, b, 0);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ---- MMA issuer (whole warp converged, one elected lane per instruction)
         const uint32_t idesc_main = make_idesc_tf32(128, 2 * COUT), idesc_lo = make_idesc_tf32(128, COUT);
         const uint32_t d_tmem = tmem_base + (uint32_t)C::D_COL;
-        uint32_t cc = 0;
-        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-#pragma unroll 1
-            for (int ky = 0; ky < KS; ++ky, ++cc) {
-                const uint32_t buf = cc & 1u, n = cc >> 1;
-                mbar_wait_warp(a_full + 8u * buf, n & 1u);
+        uint32_t nuse0 = 0, nuse1 = 0;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+            // the epilogue of the previous tile (both warp groups) has read the accumulators
+            if (it > 0) mbar_wait_warp_sleep(d_empty, (uint32_t)((it - 1) & 1));
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+                const uint32_t buf = (uint32_t)(ky & 1);
+                const uint32_t n = buf ? nuse1 : nuse0;
+                mbar_wait_warp_sleep(a_full + 8u * buf, n & 1u);
+                if (buf) ++nuse1; else ++nuse0;
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + buf * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
+                const uint32_t dacc = d_tmem + (uint32_t)((ky % C::NACC) * 2 * COUT);
 #pragma unroll
                 for (int s = 0; s < KC / 8; ++s) {
                     const int kg = ky * KC + 8 * s;
                     const uint64_t bd = make_desc_sw128(bs_u + (uint32_t)((kg >> 5) * C::NROWS * 128)) +
                                         (uint64_t)(2 * ((kg & 31) >> 3));
-                    tc_mma_tf32_ts_elect(d_tmem, a_hi + 8u * s, bd, idesc_main, (ky | s) != 0 ? 1u : 0u);
-                    if (a.dbg != 1) tc_mma_tf32_ts_elect(d_tmem + (uint32_t)COUT, a_lo + 8u * s, bd, idesc_lo, 1u);
+                    if (!(a.dbg & 2)) tc_mma_tf32_ts_elect(dacc, a_hi + 8u * s, bd, idesc_main, (ky >= C::NACC || s != 0) ? 1u : 0u);
+                    if (!(a.dbg & 1)) tc_mma_tf32_ts_elect(dacc + (uint32_t)COUT, a_lo + 8u * s, bd, idesc_lo, 1u);
                 }
                 tc_commit_elect(a_empty + 8u * buf);
             }
             tc_commit_elect(d_full);
         }
     } else {
-        // ---- gather / split / store into tensor memory, then the epilogue.  thread = pixel = TMEM lane
-        const int p = tid;                                   // pixel inside the tile, row-major (row, ox)
+        // ---- gather / split / store into tensor memory, then the epilogue.  thread = pixel = TMEM lane; the two warp
+        // groups (warps 0-3, 4-7) share the pixels: group g builds the chunks ky = g, g+2 (it owns A buffer g) and
+        // writes output channels [g*Cout/2, (g+1)*Cout/2)
+        const int wg = warp >> 2, q = warp & 3;
+        const int p = q * 32 + lane;                         // pixel inside the tile, row-major (row, ox)
         const int prow = p / C::WO, ox = p % C::WO;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool left = (ox == 0), right = (ox == C::WO - 1);
-        uint32_t cc = 0;
+        float bias_r[HALF];
+#pragma unroll
+        for (int c = 0; c < HALF; ++c) bias_r[c] = __ldg(a.bias + wg * HALF + c);
+        uint32_t my_n = 0;                                   // chunks this group has produced (uses of its A buffer)
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
             const int stage = it % C::NSTAGE;
             mbar_wait(in_full + 8u * stage, (uint32_t)((it / C::NSTAGE) & 1));
             const float* tin = reinterpret_cast<const float*>(stage0 + (size_t)stage * C::STAGE_BYTES);
 #pragma unroll 1
-            for (int ky = 0; ky < KS; ++ky, ++cc) {
-                const uint32_t buf = cc & 1u, n = cc >> 1;
-                // gather first (shared memory only), then wait for the buffer: the MMAs of chunk cc-2 overlap the loads
+            for (int ky = wg; ky < KS; ky += 2, ++my_n) {
+                // gather first (shared memory only), then wait for the buffer: the MMAs of this group's previous chunk
+                // overlap the loads
                 float v[KC];
                 const float* rp = tin + (prow * S + ky) * W + S * ox;
+                if (a.dbg & 4) {
+#pragma unroll
+                    for (int j = 0; j < KC; ++j) v[j] = 0.f;
+                }
 #pragma unroll
                 for (int ci = 0; ci < CIN; ++ci) {
+                    if (a.dbg & 4) break;
                     if constexpr (KS == 4) {
                         float2 f = *reinterpret_cast<const float2*>(rp + ci * C::RIN * W);
                         if (a.in_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
@@ -290,15 +349,18 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                         v[ci] = f;
                     }
                 }
-                if (n > 0) mbar_wait(a_empty + 8u * buf, (n - 1) & 1u);
+                if (my_n > 0) mbar_wait(a_empty + 8u * wg, (my_n - 1) & 1u);
                 tc_fence_after();
-                const uint32_t a_hi = lane_base + buf * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
+                const uint32_t a_hi = lane_base + (uint32_t)wg * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
 #pragma unroll
                 for (int j0 = 0; j0 < KC; j0 += 16) {
+                    if (a.dbg & 8) break;
+                    // hi = x rounded to TF32 on the bit pattern (cvt.rna.tf32 compiles to a five-instruction sequence),
+                    // lo = x - hi exactly; the tensor core drops the 13 low bits of lo
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        hi[j] = tf32_rna_bits(v[j0 + j]);
+                        hi[j] = (__float_as_uint(v[j0 + j]) + 0x1000u) & 0xFFFFE000u;
                         lo[j] = __float_as_uint(v[j0 + j] - __uint_as_float(hi[j]));
                     }
                     tmem_st16(a_hi + (uint32_t)j0, hi);
@@ -307,36 +369,36 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + 8u * buf);
+                if (lane == 0) mbar_arrive(a_full + 8u * wg);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(in_empty + 8u * stage);      // this warp is done with the input stage
 
-            // ---- epilogue
+            // ---- epilogue: this group's half of the output channels
             mbar_wait(d_full, (uint32_t)(it & 1));
             tc_fence_after();
+            const uint32_t d_tmem = lane_base + (uint32_t)C::D_COL + (uint32_t)(wg * HALF);
+            uint32_t r[C::NACC][2][HALF];
+#pragma unroll
+            for (int j = 0; j < C::NACC; ++j) {
+                TmemLd<HALF>::ld(d_tmem + (uint32_t)(j * 2 * COUT), r[j][0]);
+                TmemLd<HALF>::ld(d_tmem + (uint32_t)(j * 2 * COUT + COUT), r[j][1]);
+            }
+            tmem_ld_wait();
+            tc_fence_before();               // the accumulators may be overwritten once every warp has arrived
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_empty);
             const int b = (int)(tile / C::TILES), t = (int)(tile % C::TILES);
             const size_t pix = (size_t)(t * C::TH + prow) * C::WO + ox;
-            float* yp = a.y + (size_t)b * COUT * (C::HO * C::WO) + pix;
-            const float* sp = a.skip ? a.skip + (size_t)b * COUT * (C::HO * C::WO) + pix : nullptr;
-            const uint32_t d_tmem = lane_base + (uint32_t)C::D_COL;
-            float o[COUT];
-            if constexpr (COUT == 16) {
-                uint32_t r[32];
-                tmem_ld32(d_tmem, r);
+            const size_t chan0 = ((size_t)b * COUT + wg * HALF) * (C::HO * C::WO) + pix;
+            float* yp = a.y + chan0;
+            const float* sp = a.skip ? a.skip + chan0 : nullptr;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) o[c] = __uint_as_float(r[c]) + __uint_as_float(r[16 + c]);
-            } else {
-                uint32_t r[32], q[32];
-                tmem_ld32(d_tmem, r);
-                tmem_ld32(d_tmem + 32u, q);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(r[c]) + __uint_as_float(q[c]);
-            }
-            tc_fence_before();               // the accumulator may be overwritten once every warp has arrived again
-#pragma unroll
-            for (int c = 0; c < COUT; ++c) {
-                float val = o[c] + __ldg(a.bias + c);
+            for (int c = 0; c < HALF; ++c) {
+                float val = __uint_as_float(r[0][0][c]) + __uint_as_float(r[0][1][c]);
+                if constexpr (C::NACC == 2)
+                    val += __uint_as_float(r[1][0][c]) + __uint_as_float(r[1][1][c]);
+                val += bias_r[c];
                 if (sp) val += __ldg(sp + (size_t)c * (C::HO * C::WO));
                 if (a.out_relu) val = fmaxf(val, 0.f);
                 yp[(size_t)c * (C::HO * C::WO)] = val;
@@ -345,7 +407,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         __syncwarp();
         tmem_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);
     }

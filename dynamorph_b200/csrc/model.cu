@@ -106,8 +106,8 @@ int build_layout(const dmb_model* m, Layout& L) {
     DMB_CHECK(m->arch == DMB_ARCH_Z16 || m->arch == DMB_ARCH_Z32, "unknown arch %d", m->arch);
     DMB_CHECK(m->num_inputs >= 1 && m->num_hiddens >= 8 && m->num_hiddens % 8 == 0,
               "num_hiddens=%d must be a positive multiple of 8", m->num_hiddens);
-    DMB_CHECK(m->num_residual_hiddens >= 2 && m->num_residual_hiddens % 2 == 0,
-              "num_residual_hiddens=%d must be even", m->num_residual_hiddens);
+    DMB_CHECK(m->num_residual_hiddens >= 8 && m->num_residual_hiddens % 8 == 0,
+              "num_residual_hiddens=%d must be a positive multiple of 8", m->num_residual_hiddens);
     DMB_CHECK(m->num_residual_layers >= 0 && m->num_residual_layers <= 6, "num_residual_layers out of range");
     DMB_CHECK(m->num_embeddings >= 1 && m->num_embeddings <= 1024, "num_embeddings=%d outside [1,1024]", m->num_embeddings);
     const int down = (m->arch == DMB_ARCH_Z16) ? 8 : 4;
@@ -1340,7 +1340,10 @@ struct ResPlan {
     Layout L; std::vector<ResL> res; Workspace w; float* packed = nullptr; size_t bytes = 0;
 };
 int res_plan(int h, int rh, int nl, int64_t B, int H, int W, int bn_mode, void* base, ResPlan& p) {
-    DMB_CHECK(h >= 1 && rh >= 1 && nl >= 0 && nl <= 16, "residual block %d/%d x%d out of range", h, rh, nl);
+    DMB_CHECK(nl >= 0 && nl <= 16, "residual block: %d layers out of range", nl);
+    DMB_CHECK(h >= 8 && h % 8 == 0 && rh >= 8 && rh % 8 == 0,
+              "residual block: num_hiddens=%d and num_residual_hiddens=%d must be positive multiples of 8", h, rh);
+    DMB_CHECK(W % 8 == 0, "residual block: map width %d must be a multiple of 8", W);
     DMB_CHECK(B > 0 && B < (1 << 24) && H > 0 && W > 0, "residual block: bad batch / map size");
     DMB_CHECK(bn_mode >= 0 && bn_mode <= 2, "bad bn_mode %d", bn_mode);
     p.L = Layout();

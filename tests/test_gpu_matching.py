@@ -88,7 +88,7 @@ def test_eval_forward_with_time_matching(name, cls_name, variant, weight, U):
 
 @pytest.mark.parametrize("name,cls_name,variant,weight", CASES)
 def test_train_step_with_time_matching(name, cls_name, variant, weight, U):
-    from test_gpu_train import _grad_errors, STRICT, RELAXED
+    from test_gpu_train import _check_grads
     g = Golden(name)
     st = g.state()
     m = _model(U, st, cls_name, weight).train()
@@ -106,12 +106,9 @@ def test_train_step_with_time_matching(name, cls_name, variant, weight, U):
     # the term must matter in this test: it changes the encoder gradients visibly
     key = "enc.0.weight"
     assert float((grads_ref[key] - grads_base[key]).abs().max()) > 1e-3 * float(grads_base[key].abs().max())
-    errs = _grad_errors(m, grads_ref, set(O.bias_feeds_train_bn(st)))
-    ties = O.relu_near_ties(x, st, O.BATCH)
-    bound = STRICT if ties == 0 else RELAXED
-    print(f"{name}/{cls_name}: relu near-ties {ties}, worst grad err {max(errs.values()):.2e}")
-    for k, e in errs.items():
-        assert e < bound, (k, e, ties)
+    env, ties = O.relu_gate_envelopes(x, st, O.BATCH, time_matching_mat=mat, **kw)
+    worst = _check_grads(m, grads_ref, set(O.bias_feeds_train_bn(st)), env, f"{name}/{cls_name}")
+    print(f"{name}/{cls_name}: relu near-ties {ties}, worst grad err {worst:.2f} x strict")
     with pytest.raises(AssertionError):
         m(x.cuda(), time_matching_mat=mat[:-1].cuda())     # vq_vae.py:329 `assert sim_mat.shape == time_matching_mat.shape`
 

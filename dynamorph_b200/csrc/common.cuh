@@ -155,6 +155,10 @@ struct ConvTmArgs {
     const float* skip;      // optional (B, Cout, Ho, Wo), added before the output ReLU
     int B, Cin, H, W, Cout, ks, stride;
     int in_relu, out_relu;
+    // fused ResidualBlock layer (3x3 16 -> 32 only): bias2 != nullptr -> y (B, 16, Ho, Wo) = x + conv1x1(relu(conv3x3(
+    // relu?(x)) + bias)) + bias2; the weight image then holds the 1x1's image (pack_tm_weights(w2, ., 32, 16, 1)) right
+    // behind the 3x3's; out_relu here names the ReLU BETWEEN the two convolutions and must be set, skip must be null
+    const float* bias2;
 };
 bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);

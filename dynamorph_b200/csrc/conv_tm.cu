@@ -163,19 +163,32 @@ template <> struct TmemLd<16> {
 };
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-template <int KS_, int S_, int CIN_, int COUT_, int WIN_>
+// FUSE_ (3x3, 16 -> 32 only): the rest of a ResidualBlock layer rides on the same tile -- ReLU, the 1x1 convolution back
+// to COUT2 = 16 channels as a second small GEMM (its A operand is the first GEMM's activated output, split and stored
+// to tensor memory by the epilogue warps), bias and the skip connection (vq_vae.py:203-209, :222-225).
+template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false>
 struct TM {
     static constexpr int KS = KS_, S = S_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
+    static constexpr bool FUSE = FUSE_;
+    static constexpr int COUT2 = 16;                         // FUSE: output channels of the 1x1
+    static constexpr int K2 = COUT;                          // FUSE: its reduction length
+    static constexpr int NROWS2 = 2 * COUT2;
     static constexpr int PAD = (KS == 1) ? 0 : 1;
     static constexpr int WO = W / S, HO = H / S;
     static constexpr int TH = 128 / WO;                      // output rows per tile (one tile = 128 pixels)
     static constexpr int TILES = HO / TH;                    // tiles per patch
     static constexpr int RIN = (TH - 1) * S + KS;            // input rows per tile
-    static constexpr int KC = KS * CIN;                      // K of one chunk (one kernel row): k = ky*KC + ci*KS + kx
-    static constexpr int K = KS * KC;
+    // K order: k = (ky*CIN + ci)*KS + kx.  A chunk is CPC input channels of one kernel row (16..48 k values): what one
+    // warp group gathers, splits and stores to tensor memory at a time
+    static constexpr int CPC = (KS * CIN > 48) ? CIN / 2 : CIN;
+    static constexpr int CPR = CIN / CPC;                    // chunks per kernel row
+    static constexpr int KC = KS * CPC;                      // K of one chunk
+    static constexpr int NCH = KS * CPR;                     // chunks per tile
+    static constexpr int K = KS * KS * CIN;
     static constexpr int NT = (K + 31) / 32;                 // 128-byte operand tiles along K
     static constexpr int NROWS = 2 * COUT;                   // [b_hi; b_lo]
-    static constexpr int B_FLOATS = NT * NROWS * 32;
+    static constexpr int B1_FLOATS = NT * NROWS * 32;
+    static constexpr int B_FLOATS = B1_FLOATS + (FUSE ? (K2 / 32) * NROWS2 * 32 : 0);
     static constexpr int IN_FLOATS = CIN * RIN * W;          // one input stage
     static constexpr int IN_BYTES = IN_FLOATS * 4;
     static constexpr int A_COLS = 2 * KC;                    // hi | lo of one chunk
@@ -185,7 +198,7 @@ struct TM {
     // 1.2e-6 for the FFMA kernels).  Chunk ky therefore accumulates into accumulator ky % NACC and the epilogue adds the
     // partial sums in round-to-nearest fp32.  Two accumulators where tensor memory allows it without losing the second
     // resident CTA: reading them back (LDTM, 64 B/clk per SM) is what a third and fourth would cost.
-    static constexpr int NACC = (KS >= 2 && cpow2(D_COL + 2 * 2 * COUT) <= cpow2(D_COL + 2 * COUT)) ? 2 : 1;
+    static constexpr int NACC = (NCH >= 2 && cpow2(D_COL + 2 * 2 * COUT) <= cpow2(D_COL + 2 * COUT)) ? 2 : 1;
     static constexpr int TMEM_COLS = cpow2(D_COL + NACC * 2 * COUT);
     static constexpr int CTAS = (TMEM_COLS <= 256) ? 2 : 1;  // per SM
     static constexpr int SMEM_BUDGET = (CTAS == 2 ? 110 : 200) * 1024;
@@ -196,12 +209,14 @@ struct TM {
     static constexpr int HALF = COUT / 2;                    // output channels per epilogue warp group
     static_assert(128 % WO == 0 && HO % TH == 0, "a tile is 128 consecutive output pixels of one patch");
     static_assert(WO <= 32 && 32 % WO == 0, "a warp covers whole output rows (shuffle neighbours)");
-    static_assert(KC % 16 == 0 && KC <= 64, "chunk = one kernel row of 16..64 k values");
+    static_assert(KC % 16 == 0 && KC <= 48 && CIN % CPC == 0, "chunk = 16..48 k values");
     static_assert(COUT == 16 || COUT == 32, "N = Cout and 2*Cout must be legal MMA widths");
     static_assert((NROWS * 128) % 1024 == 0, "operand tiles stay 1024-byte aligned");
     static_assert(TMEM_COLS <= 512 && NSTAGE >= 2, "resources");
     static_assert((KS == 1 && S == 1) || (KS == 3 && S == 1) || (KS == 4 && S == 2), "unsupported kernel");
     static_assert((W * 4) % 16 == 0 && W <= 256 && RIN <= 256 && CIN <= 256, "TMA box");
+    static_assert(!FUSE || (KS == 3 && COUT == 32 && CIN == COUT2 && NACC == 1 && A_COLS >= 2 * K2),
+                  "the fused tail is the 3x3 16 -> 32 -> 1x1 -> 16 residual layer");
 };
 
 struct TmKArgs {
@@ -209,6 +224,7 @@ struct TmKArgs {
     const float* bias;      // [Cout]
     float* y;               // (B, Cout, Ho, Wo)
     const float* skip;      // (B, Cout, Ho, Wo) or nullptr
+    const float* bias2;     // FUSE: bias of the 1x1 [16]
     int64_t ntiles;
     int in_relu, out_relu;
     int dbg;                // DMB_TM_DBG skip experiments (results are wrong): 1 no a_lo*b_hi MMAs, 2 no a_hi MMAs,
@@ -228,10 +244,11 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
     const uint32_t stage0_u = base + (uint32_t)C::B_FLOATS * 4u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)C::NSTAGE * C::STAGE_BYTES);
     const uint32_t bars_u = stage0_u + (uint32_t)(C::NSTAGE * C::STAGE_BYTES);
-    // barrier slots: in_full[NSTAGE] | in_empty[NSTAGE] | a_full[2] | a_empty[2] | d_full | d_empty | tmem slot
+    // barrier slots: in_full[NSTAGE] | in_empty[NSTAGE] | a_full[2] | a_empty[2] | d_full | d_empty | a2_full | d2_full | slot
     const uint32_t in_full = bars_u, in_empty = bars_u + 8u * C::NSTAGE, a_full = bars_u + 16u * C::NSTAGE;
     const uint32_t a_empty = a_full + 16u, d_full = a_empty + 16u, d_empty = d_full + 8u;
-    uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 6);
+    const uint32_t a2_full = d_empty + 8u, d2_full = a2_full + 8u;
+    uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 8);
     const uint32_t slot = smem_u32(slot_mem);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -241,6 +258,8 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
         for (int s = 0; s < 2; ++s) { mbar_init(a_full + 8u * s, 4u); mbar_init(a_empty + 8u * s, 1u); }
         mbar_init(d_full, 1u);
         mbar_init(d_empty, 8u);
+        mbar_init(a2_full, 8u);
+        mbar_init(d2_full, 1u);
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
     }
@@ -277,29 +296,43 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
             // the epilogue of the previous tile (both warp groups) has read the accumulators
             if (it > 0) mbar_wait_warp_sleep(d_empty, (uint32_t)((it - 1) & 1));
 #pragma unroll
-            for (int ky = 0; ky < KS; ++ky) {
-                const uint32_t buf = (uint32_t)(ky & 1);
+            for (int ch = 0; ch < C::NCH; ++ch) {
+                const uint32_t buf = (uint32_t)(ch & 1);
                 const uint32_t n = buf ? nuse1 : nuse0;
                 mbar_wait_warp_sleep(a_full + 8u * buf, n & 1u);
                 if (buf) ++nuse1; else ++nuse0;
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + buf * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
-                const uint32_t dacc = d_tmem + (uint32_t)((ky % C::NACC) * 2 * COUT);
+                const uint32_t dacc = d_tmem + (uint32_t)((ch % C::NACC) * 2 * COUT);
 #pragma unroll
                 for (int s = 0; s < KC / 8; ++s) {
-                    const int kg = ky * KC + 8 * s;
+                    const int kg = ch * KC + 8 * s;
                     const uint64_t bd = make_desc_sw128(bs_u + (uint32_t)((kg >> 5) * C::NROWS * 128)) +
                                         (uint64_t)(2 * ((kg & 31) >> 3));
-                    if (!(a.dbg & 2)) tc_mma_tf32_ts_elect(dacc, a_hi + 8u * s, bd, idesc_main, (ky >= C::NACC || s != 0) ? 1u : 0u);
+                    if (!(a.dbg & 2)) tc_mma_tf32_ts_elect(dacc, a_hi + 8u * s, bd, idesc_main, (ch >= C::NACC || s != 0) ? 1u : 0u);
                     if (!(a.dbg & 1)) tc_mma_tf32_ts_elect(dacc + (uint32_t)COUT, a_lo + 8u * s, bd, idesc_lo, 1u);
                 }
                 tc_commit_elect(a_empty + 8u * buf);
             }
             tc_commit_elect(d_full);
+            if constexpr (C::FUSE) {
+                // second GEMM: relu(3x3 output) [128 x 32] (A buffer 0, written by the epilogue warps) x W2 [16 x 32]^T
+                mbar_wait_warp_sleep(a2_full, (uint32_t)(it & 1));
+                tc_fence_after();
+                const uint32_t idesc2_main = make_idesc_tf32(128, 2 * C::COUT2), idesc2_lo = make_idesc_tf32(128, C::COUT2);
+                const uint32_t a2_hi = tmem_base, a2_lo = tmem_base + (uint32_t)C::K2;
+                const uint64_t bd2 = make_desc_sw128(bs_u + (uint32_t)(C::B1_FLOATS * 4));
+#pragma unroll
+                for (int s = 0; s < C::K2 / 8; ++s) {
+                    tc_mma_tf32_ts_elect(d_tmem, a2_hi + 8u * s, bd2 + (uint64_t)(2 * s), idesc2_main, s != 0 ? 1u : 0u);
+                    tc_mma_tf32_ts_elect(d_tmem + (uint32_t)C::COUT2, a2_lo + 8u * s, bd2 + (uint64_t)(2 * s), idesc2_lo, 1u);
+                }
+                tc_commit_elect(d2_full);
+            }
         }
     } else {
         // ---- gather / split / store into tensor memory, then the epilogue.  thread = pixel = TMEM lane; the two warp
-        // groups (warps 0-3, 4-7) share the pixels: group g builds the chunks ky = g, g+2 (it owns A buffer g) and
+        // groups (warps 0-3, 4-7) share the pixels: group g builds the chunks g, g+2, ... (it owns A buffer g) and
         // writes output channels [g*Cout/2, (g+1)*Cout/2)
         const int wg = warp >> 2, q = warp & 3;
         const int p = q * 32 + lane;                         // pixel inside the tile, row-major (row, ox)
@@ -316,17 +349,18 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
             mbar_wait(in_full + 8u * stage, (uint32_t)((it / C::NSTAGE) & 1));
             const float* tin = reinterpret_cast<const float*>(stage0 + (size_t)stage * C::STAGE_BYTES);
 #pragma unroll 1
-            for (int ky = wg; ky < KS; ky += 2, ++my_n) {
+            for (int ch = wg; ch < C::NCH; ch += 2, ++my_n) {
                 // gather first (shared memory only), then wait for the buffer: the MMAs of this group's previous chunk
                 // overlap the loads
                 float v[KC];
-                const float* rp = tin + (prow * S + ky) * W + S * ox;
+                const int ky = ch / C::CPR, ci0 = (ch % C::CPR) * C::CPC;
+                const float* rp = tin + ((size_t)ci0 * C::RIN + prow * S + ky) * W + S * ox;
                 if (a.dbg & 4) {
 #pragma unroll
                     for (int j = 0; j < KC; ++j) v[j] = 0.f;
                 }
 #pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
+                for (int ci = 0; ci < C::CPC; ++ci) {
                     if (a.dbg & 4) break;
                     if constexpr (KS == 4) {
                         float2 f = *reinterpret_cast<const float2*>(rp + ci * C::RIN * W);
@@ -371,8 +405,10 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full + 8u * wg);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(in_empty + 8u * stage);      // this warp is done with the input stage
+            if constexpr (!C::FUSE) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(in_empty + 8u * stage);  // this warp is done with the input stage
+            }
 
             // ---- epilogue: this group's half of the output channels
             mbar_wait(d_full, (uint32_t)(it & 1));
@@ -385,23 +421,67 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 TmemLd<HALF>::ld(d_tmem + (uint32_t)(j * 2 * COUT + COUT), r[j][1]);
             }
             tmem_ld_wait();
-            tc_fence_before();               // the accumulators may be overwritten once every warp has arrived
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d_empty);
             const int b = (int)(tile / C::TILES), t = (int)(tile % C::TILES);
             const size_t pix = (size_t)(t * C::TH + prow) * C::WO + ox;
-            const size_t chan0 = ((size_t)b * COUT + wg * HALF) * (C::HO * C::WO) + pix;
-            float* yp = a.y + chan0;
-            const float* sp = a.skip ? a.skip + chan0 : nullptr;
+            if constexpr (!C::FUSE) {
+                tc_fence_before();           // the accumulators may be overwritten once every warp has arrived
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty);
+                const size_t chan0 = ((size_t)b * COUT + wg * HALF) * (C::HO * C::WO) + pix;
+                float* yp = a.y + chan0;
+                const float* sp = a.skip ? a.skip + chan0 : nullptr;
 #pragma unroll
-            for (int c = 0; c < HALF; ++c) {
-                float val = __uint_as_float(r[0][0][c]) + __uint_as_float(r[0][1][c]);
-                if constexpr (C::NACC == 2)
-                    val += __uint_as_float(r[1][0][c]) + __uint_as_float(r[1][1][c]);
-                val += bias_r[c];
-                if (sp) val += __ldg(sp + (size_t)c * (C::HO * C::WO));
-                if (a.out_relu) val = fmaxf(val, 0.f);
-                yp[(size_t)c * (C::HO * C::WO)] = val;
+                for (int c = 0; c < HALF; ++c) {
+                    float val = __uint_as_float(r[0][0][c]) + __uint_as_float(r[0][1][c]);
+                    if constexpr (C::NACC == 2)
+                        val += __uint_as_float(r[1][0][c]) + __uint_as_float(r[1][1][c]);
+                    val += bias_r[c];
+                    if (sp) val += __ldg(sp + (size_t)c * (C::HO * C::WO));
+                    if (a.out_relu) val = fmaxf(val, 0.f);
+                    yp[(size_t)c * (C::HO * C::WO)] = val;
+                }
+            } else {
+                // relu(conv3x3 + bias) for this group's 16 middle channels -> hi / lo -> A operand of the 1x1 in A buffer 0
+                // (every MMA of this tile has completed: d_full), columns [16 wg, 16 wg + 16) of hi [0, 32) and lo [32, 64)
+                {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float h = fmaxf(__uint_as_float(r[0][0][c]) + __uint_as_float(r[0][1][c]) + bias_r[c], 0.f);
+                        hi[c] = (__float_as_uint(h) + 0x1000u) & 0xFFFFE000u;
+                        lo[c] = __float_as_uint(h - __uint_as_float(hi[c]));
+                    }
+                    tmem_st16(lane_base + (uint32_t)(wg * 16), hi);
+                    tmem_st16(lane_base + (uint32_t)(C::K2 + wg * 16), lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a2_full);
+                // skip connection: the block input at this pixel is the centre tap of the input tile (raw, no ReLU)
+                constexpr int H2 = C::COUT2 / 2;
+                float xin[H2];
+#pragma unroll
+                for (int c = 0; c < H2; ++c) xin[c] = tin[((wg * H2 + c) * C::RIN + prow + 1) * W + ox];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(in_empty + 8u * stage);
+                mbar_wait(d2_full, (uint32_t)(it & 1));
+                tc_fence_after();
+                uint32_t m2[H2], s2[H2];
+                const uint32_t d2 = lane_base + (uint32_t)C::D_COL + (uint32_t)(wg * H2);
+                TmemLd<H2>::ld(d2, m2);
+                TmemLd<H2>::ld(d2 + (uint32_t)C::COUT2, s2);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty);
+                float* yp = a.y + ((size_t)b * C::COUT2 + wg * H2) * (C::HO * C::WO) + pix;
+#pragma unroll
+                for (int c = 0; c < H2; ++c) {
+                    // (no ReLU here: out_relu named the one between the two convolutions, applied above)
+                    yp[(size_t)c * (C::HO * C::WO)] =
+                        __uint_as_float(m2[c]) + __uint_as_float(s2[c]) + __ldg(a.bias2 + wg * H2 + c) + xin[c];
+                }
             }
         }
     }
@@ -462,7 +542,7 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DMB_CHECK(r == CUDA_SUCCESS, "conv_tm: cuTensorMapEncodeTiled failed (%d)", (int)r);
     TmKArgs k{};
-    k.wtm = a.wtm; k.bias = a.bias; k.y = a.y; k.skip = a.skip;
+    k.wtm = a.wtm; k.bias = a.bias; k.y = a.y; k.skip = a.skip; k.bias2 = a.bias2;
     k.ntiles = (int64_t)a.B * C::TILES;
     k.in_relu = a.in_relu; k.out_relu = a.out_relu;
     { const char* e = getenv("DMB_TM_DBG"); k.dbg = e ? atoi(e) : 0; }
@@ -518,6 +598,11 @@ int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
     if (a.ks == 4 && a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 64>>(a, st);
     if (a.ks == 4) return launch_tm<TM<4, 2, 16, 16, 32>>(a, st);
     if (a.ks == 3 && a.Cout == 16) return launch_tm<TM<3, 1, 16, 16, 16>>(a, st);
+    if (a.ks == 3 && a.bias2) {
+        DMB_CHECK(!a.skip && a.out_relu, "conv_tm: the fused residual layer takes its skip from the input tile and "
+                  "applies ReLU between the two convolutions");
+        return launch_tm<TM<3, 1, 16, 32, 16, true>>(a, st);
+    }
     if (a.ks == 3) return launch_tm<TM<3, 1, 16, 32, 16>>(a, st);
     return launch_tm<TM<1, 1, 32, 16, 16>>(a, st);
 }

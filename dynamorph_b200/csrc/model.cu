@@ -47,7 +47,7 @@ struct Builder {
     int conv(const std::string& key, int cin, int cout, int ks, int stride, bool transposed) {
         ConvL c{};
         c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.transposed = transposed; c.bn = -1;
-        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1;
         c.w_off = take_param(key + ".weight", (int64_t)cin * cout * ks * ks);
         c.b_off = take_param(key + ".bias", cout);
         c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
@@ -63,7 +63,7 @@ struct Builder {
         ConvL c{};
         c.cin = cin; c.cout = cmid; c.cmid = cmid; c.ks = 4; c.stride = 2; c.composite = 1; c.bn = -1;
         c.bias_classes = 1;
-        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1;
         c.w0_off = take_param(key0 + ".weight", (int64_t)cmid * cin);
         c.b0_off = take_param(key0 + ".bias", cmid);
         c.w_off = take_param(key1 + ".weight", (int64_t)cmid * cmid * 16);
@@ -186,7 +186,20 @@ int build_layout(const dmb_model* m, Layout& L) {
         };
         if (m->arch == DMB_ARCH_Z16) { want(L.e2, H / 2, W / 2); want(L.e3, H / 4, W / 4); want(L.e4, H / 8, W / 8); }
         else want(L.e2, H / 2, W / 2);
-        for (const ResL& r : L.enc_res) { want(r.a, L.lh, L.lw); want(r.b, L.lh, L.lw); }
+        for (const ResL& r : L.enc_res) {
+            ConvL& ca = L.convs[r.a];
+            const ConvL& cb = L.convs[r.b];
+            const bool fuse = conv_tm_supported(ca.cin, ca.cout, ca.ks, ca.stride, L.lh, L.lw) && ca.ks == 3 &&
+                              ca.cout == 32 && conv_tm_supported(cb.cin, cb.cout, cb.ks, cb.stride, L.lh, L.lw);
+            if (fuse) {      // one image: the 3x3's tiles, then the 1x1's (conv_tm.cu FUSE)
+                ca.ptm_off = B.take_packed(conv_tm_weight_floats(ca.cin, ca.cout, ca.ks) +
+                                           conv_tm_weight_floats(cb.cin, cb.cout, cb.ks));
+                ca.ptm_tail = r.b;
+            } else {
+                want(r.a, L.lh, L.lw);
+            }
+            want(r.b, L.lh, L.lw);
+        }
     }
     L.pzero_off = B.take_packed(L.max_c);
     L.n_params = B.p; L.n_bnbuf = B.bb; L.n_packed = B.pk;
@@ -389,13 +402,18 @@ int64_t wino_min_batch() {
 
 // Smallest batch that takes the tensor-memory-operand kernels (persistent CTAs; tiles = batch x 2..8).  DMB_TM=0 switches
 // them off, DMB_TM_MIN_B overrides the threshold.
-constexpr bool TM_DEFAULT_ON = false;      // flipped once the kernels are validated on the GPU
+constexpr bool TM_DEFAULT_ON = true;
 int64_t tm_min_batch() {
     const char* sw = getenv("DMB_TM");
     const bool on = sw ? (sw[0] != '0') : TM_DEFAULT_ON;
     if (!on) return INT64_MAX;
     const char* e = getenv("DMB_TM_MIN_B");
     return e ? atoll(e) : 256;
+}
+
+bool tm_fuse_enabled() {
+    const char* e = getenv("DMB_TM_FUSE");
+    return !(e && e[0] == '0');
 }
 
 // conv (or convT) layer `ci`: in -> out, optional ReLU on load; in BN modes gathers statistics and
@@ -494,7 +512,17 @@ int run_res(Ctx& c, const std::vector<ResL>& res, std::vector<float*>& ra, std::
         const bool last = (i + 1 == res.size());
         float* dst = (last && final_out) ? final_out : hs[i];
         Act a1, b1;
-        if (c.mode == DMB_BN_EVAL && wino_fused_ok(c, res[i], h, H, W)) {
+        if (c.mode == DMB_BN_EVAL && c.L.convs[res[i].a].ptm_tail == res[i].b && !h.s && c.B >= tm_min_batch() && tm_fuse_enabled()) {
+            // whole residual layer in ONE tensor-core kernel: 3x3 -> ReLU -> 1x1 -> + skip (conv_tm.cu, FUSE)
+            const ConvL& la = c.L.convs[res[i].a];
+            const ConvL& lb = c.L.convs[res[i].b];
+            ConvTmArgs a{};
+            a.x = h.p; a.wtm = c.packed + la.ptm_off; a.bias = c.packed + la.pb_off; a.y = dst; a.skip = nullptr;
+            a.B = (int)c.B; a.Cin = la.cin; a.H = H; a.W = W; a.Cout = la.cout; a.ks = la.ks; a.stride = la.stride;
+            a.in_relu = 1; a.out_relu = 1; a.bias2 = c.packed + lb.pb_off;
+            DMB_TRY(conv_tm(a, c.st));
+            h = Act(); h.p = dst;
+        } else if (c.mode == DMB_BN_EVAL && wino_fused_ok(c, res[i], h, H, W)) {
             // conv3x3 (Winograd, tensor cores) -> ReLU -> conv1x1 + skip in ONE kernel (conv_wino_tc.cu, FUSE)
             const ConvL& la = c.L.convs[res[i].a];
             const ConvL& lb = c.L.convs[res[i].b];
@@ -1318,6 +1346,25 @@ int dmb_conv2d_tm(const float* x, const float* w_packed, const float* bias, floa
     a.x = x; a.wtm = scratch; a.bias = bias; a.y = y; a.skip = skip;
     a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
     a.in_relu = in_relu; a.out_relu = out_relu;
+    return conv_tm(a, st);
+}
+
+int dmb_residual_layer_tm_scratch_floats(int64_t* floats) {
+    DMB_CHECK(floats != nullptr, "dmb_residual_layer_tm_scratch_floats: null output");
+    *floats = conv_tm_weight_floats(16, 32, 3) + conv_tm_weight_floats(32, 16, 1);
+    return 0;
+}
+
+int dmb_residual_layer_tm(const float* x, const float* w1_packed, const float* bias1, const float* w2_packed,
+                          const float* bias2, float* y, int64_t batch, float* scratch, void* stream) {
+    DMB_CHECK(x && w1_packed && bias1 && w2_packed && bias2 && y && scratch, "dmb_residual_layer_tm: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    DMB_TRY(pack_tm_weights(w1_packed, scratch, 16, 32, 3, st));
+    DMB_TRY(pack_tm_weights(w2_packed, scratch + conv_tm_weight_floats(16, 32, 3), 32, 16, 1, st));
+    ConvTmArgs a{};
+    a.x = x; a.wtm = scratch; a.bias = bias1; a.y = y; a.skip = nullptr; a.bias2 = bias2;
+    a.B = (int)batch; a.Cin = 16; a.H = 16; a.W = 16; a.Cout = 32; a.ks = 3; a.stride = 1;
+    a.in_relu = 1; a.out_relu = 1;
     return conv_tm(a, st);
 }
 

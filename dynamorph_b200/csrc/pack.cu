@@ -166,7 +166,14 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
     }
     if (bn_mode == DMB_BN_EVAL) {                // [b_hi; b_lo] operand images for conv_tm.cu
         for (const ConvL& c : L.convs)
-            if (c.ptm_off >= 0) DMB_TRY(pack_tm_weights(packed + c.pw_off, packed + c.ptm_off, c.cin, c.cout, c.ks, st));
+            if (c.ptm_off >= 0) {
+                DMB_TRY(pack_tm_weights(packed + c.pw_off, packed + c.ptm_off, c.cin, c.cout, c.ks, st));
+                if (c.ptm_tail >= 0) {
+                    const ConvL& t = L.convs[c.ptm_tail];
+                    DMB_TRY(pack_tm_weights(packed + t.pw_off, packed + c.ptm_off + conv_tm_weight_floats(c.cin, c.cout, c.ks),
+                                            t.cin, t.cout, t.ks, st));
+                }
+            }
     }
     if (L.tc && bn_mode == DMB_BN_EVAL) {        // split, swizzled tiles of the folded weights for conv_tc.cu
         for (const ConvL& c : L.convs)

@@ -181,6 +181,13 @@ int dmb_conv2d_tm_scratch_floats(int32_t cin, int32_t cout, int32_t ksize, int64
 int dmb_conv2d_tm(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
                   int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, int32_t in_relu,
                   const float* skip, int32_t out_relu, float* scratch, void* stream);
+/* One whole ResidualBlock layer of the default configuration at the 16x16 latent (vq_vae.py:203-209, :222-225, eval mode
+ * with BatchNorm folded): y = x + conv1x1(relu(conv3x3(relu(x)) + bias1)) + bias2 in ONE tensor-core kernel; the 1x1 is a
+ * second GEMM whose activation operand is written to tensor memory by the first one's epilogue.  x, y (B,16,16,16);
+ * w1_packed [16][3][3][32]; w2_packed [32][1][1][16]; scratch: dmb_residual_layer_tm_scratch_floats() floats.        */
+int dmb_residual_layer_tm_scratch_floats(int64_t* floats);
+int dmb_residual_layer_tm(const float* x, const float* w1_packed, const float* bias1, const float* w2_packed,
+                          const float* bias2, float* y, int64_t batch, float* scratch, void* stream);
 /* nn.ConvTranspose2d(k=4, stride=2, padding=1) forward; w_packed is [Cin][4][4][Cout].        */
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,

@@ -65,3 +65,23 @@ for name, cin, H, cout, ks, s, in_relu, out_relu, with_skip in LAYERS:
     print(f"{name:30s} B={B}: tmem {ms_tm:7.3f} ms ({2 * macs * B / ms_tm / 1e9:6.1f} TFLOP/s fp32-equiv) err {e_tm:.2e} | "
           f"cuda-core {ms_cc:7.3f} ms ({2 * macs * B / ms_cc / 1e9:6.1f}) err {e_cc:.2e} | speed-up {ms_cc / ms_tm:.2f}x",
           flush=True)
+
+# ---- fused residual layer: y = x + conv1x1(relu(conv3x3(relu(x)) + b1)) + b2 in one kernel, against the two-kernel chain
+g = torch.Generator(device=dev).manual_seed(7)
+x = torch.randn(B, 16, 16, 16, device=dev, generator=g)
+w1 = torch.randn(32, 16, 3, 3, device=dev, generator=g) * 0.1
+b1 = torch.randn(32, device=dev, generator=g) * 0.1
+w2 = torch.randn(16, 32, 1, 1, device=dev, generator=g) * 0.1
+b2 = torch.randn(16, device=dev, generator=g) * 0.1
+w1p, w2p = w1.permute(1, 2, 3, 0).contiguous().reshape(-1), w2.permute(1, 2, 3, 0).contiguous().reshape(-1)
+n = C.c_int64()
+call("dmb_residual_layer_tm_scratch_floats", C.byref(n))
+scratch = torch.zeros(n.value, device=dev)
+y_f = torch.empty(B, 16, 16, 16, device=dev)
+f_fused = lambda: call("dmb_residual_layer_tm", ptr(x), ptr(w1p), ptr(b1), ptr(w2p), ptr(b2), ptr(y_f), B, ptr(scratch), st)
+ms_f = time_it(f_fused)
+sel = torch.cat([torch.arange(32), torch.arange(B - 32, B)]).to(dev)
+xd = x[sel].double()
+ref = xd + F.conv2d(F.conv2d(xd.relu(), w1.double(), b1.double(), padding=1).relu(), w2.double(), b2.double())
+err = float((y_f[sel].double() - ref).abs().max() / ref.abs().max())
+print(f"fused residual layer (3x3 16->32, ReLU, 1x1 32->16, +skip) B={B}: {ms_f:.3f} ms, err {err:.2e}", flush=True)

@@ -619,6 +619,17 @@ int run_encoder_tc(Ctx& c, const float* x, float* zb_out) {
     return 0;
 }
 
+// Sub-batch (patches) of the head -> enc.4 pair in EVAL mode, 0 = whole batch at once (the default).  Measured on B200
+// (profiles/README.md, round 2): DMB_ENC_SUBBATCH=256 cuts the step's DRAM traffic from 625 to 443 KB per patch (the head
+// output never reaches HBM) but the 64 short dependent launches per 8192 patches cost more than the traffic saves
+// (4.94 -> 3.59 M patches/s), so it is opt-in.
+int64_t enc_subbatch(int64_t B) {
+    const char* e = getenv("DMB_ENC_SUBBATCH");
+    const int64_t sb = e ? atoll(e) : 0;
+    if (sb <= 0 || B < 4 * sb) return 0;
+    return sb;
+}
+
 // encoder: x -> z_before (written to zb_out unless the final merge is handed to `fuse`)
 int run_encoder(Ctx& c, const float* x, float* zb_out, Pending* fuse) {
     const Layout& L = c.L;
@@ -629,8 +640,30 @@ int run_encoder(Ctx& c, const float* x, float* zb_out, Pending* fuse) {
     Act in; in.p = x;
     Act a1, a2, a3, a4, out;
     if (m.arch == DMB_ARCH_Z16) {
-        DMB_TRY(run_conv(c, L.e1, in, false, H, W, c.w.y1, nullptr, ev, &a1));
-        DMB_TRY(run_conv(c, L.e2, a1, !ev, H / 2, W / 2, c.w.y2, nullptr, ev, &a2));
+        const int64_t SB = ev ? enc_subbatch(c.B) : 0;
+        if (SB > 0) {
+            // The head's output (h/2 x H/2 x W/2 floats per patch, as large as the input) is the biggest tensor of the
+            // step and is read exactly once, by the next layer.  The two layers therefore walk the batch in sub-batches
+            // whose head output fits the 126 MB L2 and alternate between two slots: the consumer reads it from L2 and
+            // the slot is overwritten while its lines are still resident, so it never has to reach HBM.
+            const size_t x_per = (size_t)m.num_inputs * H * W;
+            const size_t y1_per = (size_t)(m.num_hiddens / 2) * (H / 2) * (W / 2);
+            const size_t y2_per = (size_t)m.num_hiddens * (H / 4) * (W / 4);
+            int slot = 0;
+            for (int64_t b0 = 0; b0 < c.B; b0 += SB, slot ^= 1) {
+                const int64_t n = (c.B - b0 < SB) ? c.B - b0 : SB;
+                Ctx cs{c.L, c.packed, c.w, n, c.mode, c.bnbuf, c.st, c.sync};
+                Act xin, o1, o2;
+                xin.p = x + (size_t)b0 * x_per;
+                float* y1s = c.w.y1 + (size_t)slot * SB * y1_per;
+                DMB_TRY(run_conv(cs, L.e1, xin, false, H, W, y1s, nullptr, true, &o1));
+                DMB_TRY(run_conv(cs, L.e2, o1, false, H / 2, W / 2, c.w.y2 + (size_t)b0 * y2_per, nullptr, true, &o2));
+            }
+            a2 = Act(); a2.p = c.w.y2;
+        } else {
+            DMB_TRY(run_conv(c, L.e1, in, false, H, W, c.w.y1, nullptr, ev, &a1));
+            DMB_TRY(run_conv(c, L.e2, a1, !ev, H / 2, W / 2, c.w.y2, nullptr, ev, &a2));
+        }
         DMB_TRY(run_conv(c, L.e3, a2, !ev, H / 4, W / 4, c.w.y3, nullptr, ev, &a3));
         float* y4 = (L.enc_res.empty() && zb_out && ev) ? zb_out : c.w.y4;
         DMB_TRY(run_conv(c, L.e4, a3, !ev, H / 8, W / 8, y4, nullptr, false, &a4));

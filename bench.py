@@ -439,6 +439,35 @@ def parity_sample(model, x_dev, zb_rows, idx_rows, k, raw=None, seed=0):
     return res
 
 
+def pca_table(dev, hbm_peak):
+    """the PCA projection of the latents (run_dim_reduction.py:86 `pca.transform`), 65,536 latent
+    rows x 4096 -> 32 components resident on the device: the tcgen05 form (3xTF32 1x1 convolution, csrc/pca.cu ->
+    conv_tc.cu) beside the fp32 CUDA-core GEMM.  The op reads each latent row once: HBM is its roof."""
+    import ctypes as C
+    from dynamorph_b200._lib import call, ptr
+    n, l, k = 65536, 4096, 32
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(n, l, device=dev, generator=g)
+    comp = torch.randn(k, l, device=dev, generator=g) / 64.0
+    mean = torch.randn(l, device=dev, generator=g) * 0.1
+    out_tc, out_cc = torch.empty(n, k, device=dev), torch.empty(n, k, device=dev)
+    nf = C.c_int64()
+    call("dmb_pca_transform_scratch_floats", n, l, C.byref(nf))
+    scratch = torch.empty(nf.value, device=dev)
+    f_tc = lambda: call("dmb_pca_transform_tc", ptr(x), n, l, ptr(mean), ptr(comp), k, None, ptr(out_tc), ptr(scratch), st)
+    f_cc = lambda: call("dmb_pca_transform", ptr(x), n, l, ptr(mean), ptr(comp), k, None, ptr(out_cc), st)
+    res = {"rows": n, "latent_len": l, "components": k}
+    for tag, fn in (("tcgen05", f_tc), ("cuda_core", f_cc)):
+        fn(); torch.cuda.synchronize()
+        ms = time_events(fn, 3)
+        res[tag] = {"ms": ms, "rows_per_s": n / (ms * 1e-3), "gbs": n * l * 4 / ms / 1e6, "hbm_frac": n * l * 4 / ms / 1e6 / hbm_peak}
+    ref = (x[:2048].double() - mean.double()) @ comp.double().T
+    res["tcgen05"]["max_err_of_max"] = float((out_tc[:2048].double() - ref).abs().max() / ref.abs().max())
+    res["cuda_core"]["max_err_of_max"] = float((out_cc[:2048].double() - ref).abs().max() / ref.abs().max())
+    return res
+
+
 def wide_config_table(dev, bf16_peak):
     """BASELINE.json configs[3] (64-wide, 512 codes): eval-mode encode at batch 1024 on the tcgen05 path
     (csrc/conv_tc.cu 3xTF32 convs + csrc/vq_tc.cu tensor-core code search) and, for comparison, with both switched
@@ -758,6 +787,10 @@ def run_ours(args):
             except Exception:
                 bf16 = 1590.0
             line["wide_config"] = wide_config_table(dev, bf16)
+            try:
+                line["pca_projection"] = pca_table(dev, hbm_peak)
+            except Exception as ex:
+                line["pca_projection"] = {"unavailable": repr(ex)[:200]}
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cores)     # the CPU baseline gets every host core back
             v, cores, sec = cpu_reference_rate(1024, 256, 2)

@@ -166,10 +166,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // FUSE_ (3x3, 16 -> 32 only): the rest of a ResidualBlock layer rides on the same tile -- ReLU, the 1x1 convolution back
 // to COUT2 = 16 channels as a second small GEMM (its A operand is the first GEMM's activated output, split and stored
 // to tensor memory by the epilogue warps), bias and the skip connection (vq_vae.py:203-209, :222-225).
-template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false>
+template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false, bool INRELU_ = false>
 struct TM {
     static constexpr int KS = KS_, S = S_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
     static constexpr bool FUSE = FUSE_;
+    static constexpr bool INRELU = INRELU_;                  // ReLU on load, compiled in (a run-time flag left 16
+                                                             // predicated FMNMX per chunk in the layers without it)
     static constexpr int COUT2 = 16;                         // FUSE: output channels of the 1x1
     static constexpr int K2 = COUT;                          // FUSE: its reduction length
     static constexpr int NROWS2 = 2 * COUT2;
@@ -200,6 +202,12 @@ struct TM {
     // resident CTA: reading them back (LDTM, 64 B/clk per SM) is what a third and fourth would cost.
     static constexpr int NACC = (NCH >= 2 && cpow2(D_COL + 2 * 2 * COUT) <= cpow2(D_COL + 2 * COUT)) ? 2 : 1;
     static constexpr int TMEM_COLS = cpow2(D_COL + NACC * 2 * COUT);
+    // Two accumulator sets where they fit: the epilogue of tile t then runs AFTER this warp group's first chunk of tile
+    // t+1 (ncu: 30 % of the stall samples sat on the wait for the tile's last MMAs in front of the epilogue)
+    // (only where each warp group still has a chunk to build AFTER its deferred epilogue: the tile's accumulator cannot
+    // then complete -- and the single d_full barrier cannot run two phases ahead of a waiting group -- before that wait)
+    static constexpr bool DBUF = !FUSE && NCH >= 4 && (D_COL + 2 * NACC * 2 * COUT <= TMEM_COLS);
+    static constexpr int D_SET = NACC * 2 * COUT;
     static constexpr int CTAS = (TMEM_COLS <= 256) ? 2 : 1;  // per SM
     static constexpr int SMEM_BUDGET = (CTAS == 2 ? 110 : 200) * 1024;
     static constexpr int NSTAGE_RAW = (SMEM_BUDGET - B_FLOATS * 4 - 2048) / ((IN_BYTES + 127) & ~127);
@@ -293,8 +301,10 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
         uint32_t nuse0 = 0, nuse1 = 0;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-            // the epilogue of the previous tile (both warp groups) has read the accumulators
-            if (it > 0) mbar_wait_warp_sleep(d_empty, (uint32_t)((it - 1) & 1));
+            // the epilogue (both warp groups) of the tile that last used this accumulator set has read it
+            constexpr int DIST = C::DBUF ? 2 : 1;
+            if (it >= DIST) mbar_wait_warp_sleep(d_empty, (uint32_t)((it - DIST) & 1));
+            const uint32_t d_set = d_tmem + (C::DBUF ? (uint32_t)((it & 1) * C::D_SET) : 0u);
 #pragma unroll
             for (int ch = 0; ch < C::NCH; ++ch) {
                 const uint32_t buf = (uint32_t)(ch & 1);
@@ -303,7 +313,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 if (buf) ++nuse1; else ++nuse0;
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + buf * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
-                const uint32_t dacc = d_tmem + (uint32_t)((ch % C::NACC) * 2 * COUT);
+                const uint32_t dacc = d_set + (uint32_t)((ch % C::NACC) * 2 * COUT);
 #pragma unroll
                 for (int s = 0; s < KC / 8; ++s) {
                     const int kg = ch * KC + 8 * s;
@@ -343,77 +353,72 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
 #pragma unroll
         for (int c = 0; c < HALF; ++c) bias_r[c] = __ldg(a.bias + wg * HALF + c);
         uint32_t my_n = 0;                                   // chunks this group has produced (uses of its A buffer)
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-            const int stage = it % C::NSTAGE;
-            mbar_wait(in_full + 8u * stage, (uint32_t)((it / C::NSTAGE) & 1));
-            const float* tin = reinterpret_cast<const float*>(stage0 + (size_t)stage * C::STAGE_BYTES);
-#pragma unroll 1
-            for (int ch = wg; ch < C::NCH; ch += 2, ++my_n) {
-                // gather first (shared memory only), then wait for the buffer: the MMAs of this group's previous chunk
-                // overlap the loads
-                float v[KC];
-                const int ky = ch / C::CPR, ci0 = (ch % C::CPR) * C::CPC;
-                const float* rp = tin + ((size_t)ci0 * C::RIN + prow * S + ky) * W + S * ox;
-                if (a.dbg & 4) {
-#pragma unroll
-                    for (int j = 0; j < KC; ++j) v[j] = 0.f;
-                }
-#pragma unroll
-                for (int ci = 0; ci < C::CPC; ++ci) {
-                    if (a.dbg & 4) break;
-                    if constexpr (KS == 4) {
-                        float2 f = *reinterpret_cast<const float2*>(rp + ci * C::RIN * W);
-                        if (a.in_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-                        const float up = __shfl_up_sync(0xffffffffu, f.y, 1), dn = __shfl_down_sync(0xffffffffu, f.x, 1);
-                        v[ci * 4 + 0] = left ? 0.f : up;
-                        v[ci * 4 + 1] = f.x;
-                        v[ci * 4 + 2] = f.y;
-                        v[ci * 4 + 3] = right ? 0.f : dn;
-                    } else if constexpr (KS == 3) {
-                        float f = rp[ci * C::RIN * W];
-                        if (a.in_relu) f = fmaxf(f, 0.f);
-                        const float up = __shfl_up_sync(0xffffffffu, f, 1), dn = __shfl_down_sync(0xffffffffu, f, 1);
-                        v[ci * 3 + 0] = left ? 0.f : up;
-                        v[ci * 3 + 1] = f;
-                        v[ci * 3 + 2] = right ? 0.f : dn;
-                    } else {
-                        float f = rp[ci * C::RIN * W];
-                        if (a.in_relu) f = fmaxf(f, 0.f);
-                        v[ci] = f;
-                    }
-                }
-                if (my_n > 0) mbar_wait(a_empty + 8u * wg, (my_n - 1) & 1u);
-                tc_fence_after();
-                const uint32_t a_hi = lane_base + (uint32_t)wg * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
-#pragma unroll
-                for (int j0 = 0; j0 < KC; j0 += 16) {
-                    if (a.dbg & 8) break;
-                    // hi = x rounded to TF32 on the bit pattern (cvt.rna.tf32 compiles to a five-instruction sequence),
-                    // lo = x - hi exactly; the tensor core drops the 13 low bits of lo
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        hi[j] = (__float_as_uint(v[j0 + j]) + 0x1000u) & 0xFFFFE000u;
-                        lo[j] = __float_as_uint(v[j0 + j] - __uint_as_float(hi[j]));
-                    }
-                    tmem_st16(a_hi + (uint32_t)j0, hi);
-                    tmem_st16(a_lo + (uint32_t)j0, lo);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + 8u * wg);
-            }
-            if constexpr (!C::FUSE) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(in_empty + 8u * stage);  // this warp is done with the input stage
-            }
 
-            // ---- epilogue: this group's half of the output channels
+        // gather + split + tensor-memory store of chunk `ch` of the tile staged at `tin`
+        auto produce = [&](const float* tin, int ch) {
+            // gather first (shared memory only), then wait for the buffer: the MMAs of this group's previous chunk
+            // overlap the loads
+            float v[KC];
+            const int ky = ch / C::CPR, ci0 = (ch % C::CPR) * C::CPC;
+            const float* rp = tin + ((size_t)ci0 * C::RIN + prow * S + ky) * W + S * ox;
+            if (a.dbg & 4) {
+#pragma unroll
+                for (int j = 0; j < KC; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int ci = 0; ci < C::CPC; ++ci) {
+                if (a.dbg & 4) break;
+                if constexpr (KS == 4) {
+                    float2 f = *reinterpret_cast<const float2*>(rp + ci * C::RIN * W);
+                    if constexpr (C::INRELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                    const float up = __shfl_up_sync(0xffffffffu, f.y, 1), dn = __shfl_down_sync(0xffffffffu, f.x, 1);
+                    v[ci * 4 + 0] = left ? 0.f : up;
+                    v[ci * 4 + 1] = f.x;
+                    v[ci * 4 + 2] = f.y;
+                    v[ci * 4 + 3] = right ? 0.f : dn;
+                } else if constexpr (KS == 3) {
+                    float f = rp[ci * C::RIN * W];
+                    if constexpr (C::INRELU) f = fmaxf(f, 0.f);
+                    const float up = __shfl_up_sync(0xffffffffu, f, 1), dn = __shfl_down_sync(0xffffffffu, f, 1);
+                    v[ci * 3 + 0] = left ? 0.f : up;
+                    v[ci * 3 + 1] = f;
+                    v[ci * 3 + 2] = right ? 0.f : dn;
+                } else {
+                    float f = rp[ci * C::RIN * W];
+                    if constexpr (C::INRELU) f = fmaxf(f, 0.f);
+                    v[ci] = f;
+                }
+            }
+            if (my_n > 0) mbar_wait(a_empty + 8u * wg, (my_n - 1) & 1u);
+            tc_fence_after();
+            const uint32_t a_hi = lane_base + (uint32_t)wg * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
+#pragma unroll
+            for (int j0 = 0; j0 < KC; j0 += 16) {
+                if (a.dbg & 8) break;
+                // hi = x rounded to TF32 on the bit pattern (cvt.rna.tf32 compiles to a five-instruction sequence),
+                // lo = x - hi exactly; the tensor core drops the 13 low bits of lo
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    hi[j] = (__float_as_uint(v[j0 + j]) + 0x1000u) & 0xFFFFE000u;
+                    lo[j] = __float_as_uint(v[j0 + j] - __uint_as_float(hi[j]));
+                }
+                tmem_st16(a_hi + (uint32_t)j0, hi);
+                tmem_st16(a_lo + (uint32_t)j0, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + 8u * wg);
+            ++my_n;
+        };
+
+        // epilogue of tile `tile` (the it-th of this CTA): this group's half of the output channels
+        auto epilogue = [&](int64_t tile, int it, const float* tin, int stage) {
             mbar_wait(d_full, (uint32_t)(it & 1));
             tc_fence_after();
-            const uint32_t d_tmem = lane_base + (uint32_t)C::D_COL + (uint32_t)(wg * HALF);
+            const uint32_t d_tmem = lane_base + (uint32_t)C::D_COL + (uint32_t)(wg * HALF) +
+                                    (C::DBUF ? (uint32_t)((it & 1) * C::D_SET) : 0u);
             uint32_t r[C::NACC][2][HALF];
 #pragma unroll
             for (int j = 0; j < C::NACC; ++j) {
@@ -483,6 +488,36 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                         __uint_as_float(m2[c]) + __uint_as_float(s2[c]) + __ldg(a.bias2 + wg * H2 + c) + xin[c];
                 }
             }
+        };
+
+        int it = 0;
+        int64_t prev_tile = -1;
+        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+            const int stage = it % C::NSTAGE;
+            mbar_wait(in_full + 8u * stage, (uint32_t)((it / C::NSTAGE) & 1));
+            const float* tin = reinterpret_cast<const float*>(stage0 + (size_t)stage * C::STAGE_BYTES);
+            if constexpr (C::DBUF) {
+                // this group's first chunk of the tile lets the MMA warp start on it; the previous tile's epilogue
+                // (its MMAs have had a whole chunk to drain) comes next, then the remaining chunks
+                if (wg < C::NCH) produce(tin, wg);
+                if (prev_tile >= 0) epilogue(prev_tile, it - 1, nullptr, 0);
+#pragma unroll 1
+                for (int ch = wg + 2; ch < C::NCH; ch += 2) produce(tin, ch);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(in_empty + 8u * stage);  // this warp is done with the input stage
+                prev_tile = tile;
+            } else {
+#pragma unroll 1
+                for (int ch = wg; ch < C::NCH; ch += 2) produce(tin, ch);
+                if constexpr (!C::FUSE) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(in_empty + 8u * stage);
+                }
+                epilogue(tile, it, tin, stage);
+            }
+        }
+        if constexpr (C::DBUF) {
+            if (prev_tile >= 0) epilogue(prev_tile, it - 1, nullptr, 0);
         }
     }
     tc_fence_before();
@@ -595,15 +630,19 @@ int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
     DMB_CHECK(!(reinterpret_cast<uintptr_t>(a.x) & 15) && !(reinterpret_cast<uintptr_t>(a.wtm) & 15),
               "conv_tm: x and the weight image must be 16-byte aligned");
     DMB_CHECK(a.B > 0, "conv_tm: empty batch");
+    if (a.ks == 3 && a.Cout == 32) {
+        // the residual block's 3x3: ReLU on load compiled in or out; with bias2 the whole layer is fused
+        if (a.bias2) {
+            DMB_CHECK(!a.skip && a.out_relu && a.in_relu, "conv_tm: the fused residual layer applies ReLU on load and "
+                      "between the two convolutions and takes its skip from the input tile");
+            return launch_tm<TM<3, 1, 16, 32, 16, true, true>>(a, st);
+        }
+        return a.in_relu ? launch_tm<TM<3, 1, 16, 32, 16, false, true>>(a, st) : launch_tm<TM<3, 1, 16, 32, 16>>(a, st);
+    }
+    DMB_CHECK(!a.in_relu && !a.bias2, "conv_tm: ReLU on load / the fused tail exist for the 3x3 16 -> 32 layer only");
     if (a.ks == 4 && a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 64>>(a, st);
     if (a.ks == 4) return launch_tm<TM<4, 2, 16, 16, 32>>(a, st);
-    if (a.ks == 3 && a.Cout == 16) return launch_tm<TM<3, 1, 16, 16, 16>>(a, st);
-    if (a.ks == 3 && a.bias2) {
-        DMB_CHECK(!a.skip && a.out_relu, "conv_tm: the fused residual layer takes its skip from the input tile and "
-                  "applies ReLU between the two convolutions");
-        return launch_tm<TM<3, 1, 16, 32, 16, true>>(a, st);
-    }
-    if (a.ks == 3) return launch_tm<TM<3, 1, 16, 32, 16>>(a, st);
+    if (a.ks == 3) return launch_tm<TM<3, 1, 16, 16, 16>>(a, st);
     return launch_tm<TM<1, 1, 32, 16, 16>>(a, st);
 }
 

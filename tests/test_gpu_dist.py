@@ -59,7 +59,15 @@ def _run(fn, world, *args):
     for r in res:
         if isinstance(r, tuple) and r and r[0] == "error":
             raise AssertionError(r[2])
-    return [r[1] for r in sorted(res, key=lambda t: t[0])]
+    def revive(o):
+        if isinstance(o, np.ndarray):
+            return torch.from_numpy(o)
+        if isinstance(o, dict):
+            return {k: revive(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return type(o)(revive(v) for v in o)
+        return o
+    return [revive(r[1]) for r in sorted(res, key=lambda t: t[0])]
 
 
 def _batch(case, per_rank, world):
@@ -78,8 +86,9 @@ def _train_rank(rank, world, case, per_rank, steps, sync_bn, use_graph):
     losses = []
     for _ in range(steps):
         losses.append(tr.step(x).cpu().tolist())
-    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
-    return losses, sd, tr.grad.cpu().clone()
+    # numpy, not tensors: a tensor put on a multiprocessing queue travels as a shared-memory handle that dies with the rank
+    sd = {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}
+    return losses, sd, tr.grad.cpu().numpy().copy()
 
 
 def _flat(grads, keys):
@@ -170,7 +179,7 @@ def _encode_rank(rank, world, n):
     x = O.synthetic_patches(n, 55)
     a, b = shard_range(n, rank, world)
     _, _, idx = m.encode_latents(x[a:b].cuda(rank), "eval")
-    return gather_code_indices(idx, n, 64).cpu()
+    return gather_code_indices(idx, n, 64).cpu().numpy().copy()
 
 
 def test_two_rank_encode_sharding_and_index_gather():

@@ -134,15 +134,17 @@ class FusedTrainer:
         torch.cuda.synchronize()
         for dst, src in zip(live, snap):
             dst.copy_(src)
+        # (an explicit capture stream of THIS device: torch.cuda.graph's default one is created once, on whichever device
+        # was current first, and a capture through it on another GPU records nothing)
         g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
+        with torch.cuda.graph(g1, stream=side):
             self._fwd_bwd(st)
             if self.world == 1:
                 self._adam()
         g2 = None
         if self.world > 1:
             g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
+            with torch.cuda.graph(g2, stream=side):
                 self._adam()
         st.graphs = (g1, g2)
 
@@ -209,7 +211,7 @@ class FusedTrainer:
                     for dst, src in zip(live, snap):
                         dst.copy_(src)
                     st.fwd_graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(st.fwd_graph):
+                    with torch.cuda.graph(st.fwd_graph, stream=side):
                         self._forward(st)
                 st.fwd_graph.replay()
             elif self.sync_bn:

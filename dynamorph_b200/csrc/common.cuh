@@ -159,7 +159,17 @@ struct ConvTmArgs {
     // relu?(x)) + bias)) + bias2; the weight image then holds the 1x1's image (pack_tm_weights(w2, ., 32, 16, 1)) right
     // behind the 3x3's; out_relu here names the ReLU BETWEEN the two convolutions and must be set, skip must be null
     const float* bias2;
+    // train-mode BatchNorm around the layer (bn != 0; DMB_BN_PER_SAMPLE / DMB_BN_BATCH): the producer's pending affine
+    // relu?(x * in_scale[c] + in_shift[c]) ([Cin] or [B][Cin] tables, nullptr = identity) is applied on load, y receives
+    // the raw output and `stats` one (sum, sum of squares) double pair per (patch, tile, channel), conv_tm_bands() tiles
+    // per patch -- the layout bn_finalize reads.  skip / out_relu / bias2 must be unset.
+    int bn;
+    const float* in_scale;
+    const float* in_shift;
+    int in_per_sample;
+    double* stats;
 };
+int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W);     // statistics rows per patch (0: unsupported)
 bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);
 int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);

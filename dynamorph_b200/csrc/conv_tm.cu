@@ -166,8 +166,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // FUSE_ (3x3, 16 -> 32 only): the rest of a ResidualBlock layer rides on the same tile -- ReLU, the 1x1 convolution back
 // to COUT2 = 16 channels as a second small GEMM (its A operand is the first GEMM's activated output, split and stored
 // to tensor memory by the epilogue warps), bias and the skip connection (vq_vae.py:203-209, :222-225).
-template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false, bool INRELU_ = false>
+// BN_ (train-mode BatchNorm around the layer, DMB_BN_PER_SAMPLE / DMB_BN_BATCH): the producer's pending affine + ReLU is
+// applied to every gathered value (relu?(x * scale[c] + shift[c]), tables per channel or per patch and channel; rows
+// outside the image stay zero), the layer's raw output is stored, and the epilogue leaves one (sum, sum of squares)
+// partial per (patch, tile, channel) for bn_finalize -- the contract of conv_tma.cuh / conv_fwd.cu.
+template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false, bool INRELU_ = false, bool BN_ = false>
 struct TM {
+    static constexpr bool BN = BN_;
     static constexpr int KS = KS_, S = S_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
     static constexpr bool FUSE = FUSE_;
     static constexpr bool INRELU = INRELU_;                  // ReLU on load, compiled in (a run-time flag left 16
@@ -213,7 +218,7 @@ struct TM {
     static constexpr int NSTAGE_RAW = (SMEM_BUDGET - B_FLOATS * 4 - 2048) / ((IN_BYTES + 127) & ~127);
     static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
     static constexpr int STAGE_BYTES = (IN_BYTES + 127) & ~127;
-    static constexpr size_t SMEM = 1024 + (size_t)B_FLOATS * 4 + (size_t)NSTAGE * STAGE_BYTES + 256;
+    static constexpr size_t SMEM = 1024 + (size_t)B_FLOATS * 4 + (size_t)NSTAGE * STAGE_BYTES + 256 + 1024;  // + barriers + stat_red
     static constexpr int HALF = COUT / 2;                    // output channels per epilogue warp group
     static_assert(128 % WO == 0 && HO % TH == 0, "a tile is 128 consecutive output pixels of one patch");
     static_assert(WO <= 32 && 32 % WO == 0, "a warp covers whole output rows (shuffle neighbours)");
@@ -225,6 +230,7 @@ struct TM {
     static_assert((W * 4) % 16 == 0 && W <= 256 && RIN <= 256 && CIN <= 256, "TMA box");
     static_assert(!FUSE || (KS == 3 && COUT == 32 && CIN == COUT2 && NACC == 1 && A_COLS >= 2 * K2),
                   "the fused tail is the 3x3 16 -> 32 -> 1x1 -> 16 residual layer");
+    static_assert(!BN || (!FUSE && !INRELU), "BatchNorm form: ReLU on load is a run-time flag of the transform");
 };
 
 struct TmKArgs {
@@ -233,6 +239,10 @@ struct TmKArgs {
     float* y;               // (B, Cout, Ho, Wo)
     const float* skip;      // (B, Cout, Ho, Wo) or nullptr
     const float* bias2;     // FUSE: bias of the 1x1 [16]
+    const float* in_scale;  // BN: pending affine of the input, [Cin] or [B][Cin] (nullptr = identity)
+    const float* in_shift;
+    int in_per_sample;
+    double* stats;          // BN: [B][TILES][Cout][2] partial (sum, sum of squares) per tile
     int64_t ntiles;
     int in_relu, out_relu;
     int dbg;                // DMB_TM_DBG skip experiments (results are wrong): 1 no a_lo*b_hi MMAs, 2 no a_hi MMAs,
@@ -257,6 +267,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
     const uint32_t a_empty = a_full + 16u, d_full = a_empty + 16u, d_empty = d_full + 8u;
     const uint32_t a2_full = d_empty + 8u, d2_full = a2_full + 8u;
     uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 8);
+    [[maybe_unused]] float* stat_red = reinterpret_cast<float*>(bars + 32);      // 1 KB behind the 256-byte barrier block
     const uint32_t slot = smem_u32(slot_mem);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -354,13 +365,26 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
         for (int c = 0; c < HALF; ++c) bias_r[c] = __ldg(a.bias + wg * HALF + c);
         uint32_t my_n = 0;                                   // chunks this group has produced (uses of its A buffer)
 
-        // gather + split + tensor-memory store of chunk `ch` of the tile staged at `tin`
-        auto produce = [&](const float* tin, int ch) {
+        // gather + split + tensor-memory store of chunk `ch` of the tile staged at `tin` (tile = patch b, rows from row0)
+        auto produce = [&](const float* tin, int ch, int b = 0, int row0 = 0) {
             // gather first (shared memory only), then wait for the buffer: the MMAs of this group's previous chunk
             // overlap the loads
             float v[KC];
             const int ky = ch / C::CPR, ci0 = (ch % C::CPR) * C::CPC;
             const float* rp = tin + ((size_t)ci0 * C::RIN + prow * S + ky) * W + S * ox;
+            // BN: affine + ReLU of the producer on every value; an input row outside the image contributes zeros (the TMA
+            // zero fill would otherwise turn into `shift`), the left / right border columns are zeroed below as always
+            [[maybe_unused]] const float* tsc = nullptr;
+            [[maybe_unused]] const float* tsh = nullptr;
+            [[maybe_unused]] bool row_ok = true;
+            [[maybe_unused]] float xf_lo = 0.f;
+            if constexpr (C::BN) {
+                const size_t tb = (a.in_per_sample ? (size_t)b * CIN : 0) + ci0;
+                tsc = a.in_scale ? a.in_scale + tb : nullptr;
+                tsh = a.in_scale ? a.in_shift + tb : nullptr;
+                row_ok = (unsigned)(row0 + prow * S + ky) < (unsigned)C::H;
+                xf_lo = a.in_relu ? 0.f : -INFINITY;
+            }
             if (a.dbg & 4) {
 #pragma unroll
                 for (int j = 0; j < KC; ++j) v[j] = 0.f;
@@ -368,9 +392,15 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
 #pragma unroll
             for (int ci = 0; ci < C::CPC; ++ci) {
                 if (a.dbg & 4) break;
+                [[maybe_unused]] float sc = 1.f, sh = 0.f;
+                if constexpr (C::BN) {
+                    if (tsc) { sc = __ldg(tsc + ci); sh = __ldg(tsh + ci); }
+                    if (!row_ok) { sc = 0.f; sh = 0.f; }
+                }
                 if constexpr (KS == 4) {
                     float2 f = *reinterpret_cast<const float2*>(rp + ci * C::RIN * W);
                     if constexpr (C::INRELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                    if constexpr (C::BN) { f.x = fmaxf(fmaf(f.x, sc, sh), xf_lo); f.y = fmaxf(fmaf(f.y, sc, sh), xf_lo); }
                     const float up = __shfl_up_sync(0xffffffffu, f.y, 1), dn = __shfl_down_sync(0xffffffffu, f.x, 1);
                     v[ci * 4 + 0] = left ? 0.f : up;
                     v[ci * 4 + 1] = f.x;
@@ -379,6 +409,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 } else if constexpr (KS == 3) {
                     float f = rp[ci * C::RIN * W];
                     if constexpr (C::INRELU) f = fmaxf(f, 0.f);
+                    if constexpr (C::BN) f = fmaxf(fmaf(f, sc, sh), xf_lo);
                     const float up = __shfl_up_sync(0xffffffffu, f, 1), dn = __shfl_down_sync(0xffffffffu, f, 1);
                     v[ci * 3 + 0] = left ? 0.f : up;
                     v[ci * 3 + 1] = f;
@@ -386,6 +417,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 } else {
                     float f = rp[ci * C::RIN * W];
                     if constexpr (C::INRELU) f = fmaxf(f, 0.f);
+                    if constexpr (C::BN) f = fmaxf(fmaf(f, sc, sh), xf_lo);
                     v[ci] = f;
                 }
             }
@@ -435,6 +467,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 const size_t chan0 = ((size_t)b * COUT + wg * HALF) * (C::HO * C::WO) + pix;
                 float* yp = a.y + chan0;
                 const float* sp = a.skip ? a.skip + chan0 : nullptr;
+                [[maybe_unused]] float ssum[HALF], ssq[HALF];
 #pragma unroll
                 for (int c = 0; c < HALF; ++c) {
                     float val = __uint_as_float(r[0][0][c]) + __uint_as_float(r[0][1][c]);
@@ -444,6 +477,37 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                     if (sp) val += __ldg(sp + (size_t)c * (C::HO * C::WO));
                     if (a.out_relu) val = fmaxf(val, 0.f);
                     yp[(size_t)c * (C::HO * C::WO)] = val;
+                    if constexpr (C::BN) { ssum[c] = val; ssq[c] = val * val; }
+                }
+                if constexpr (C::BN) {
+                    // (sum, sum of squares) over the tile's 128 pixels per channel: lane tree inside each warp (fixed
+                    // order), the four warp sums of a group through shared memory, one double2 per channel
+                    if (a.stats) {
+#pragma unroll
+                        for (int c = 0; c < HALF; ++c) {
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], o);
+                                ssq[c] += __shfl_xor_sync(0xffffffffu, ssq[c], o);
+                            }
+                        }
+                        float2* red = reinterpret_cast<float2*>(stat_red) + (size_t)(wg * 4 + q) * HALF;
+                        if (lane == 0) {
+#pragma unroll
+                            for (int c = 0; c < HALF; ++c) red[c] = make_float2(ssum[c], ssq[c]);
+                        }
+                        // named barrier per warp group (ids 1, 2): the four warps of the group meet, nobody else
+                        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory");
+                        if (q == 0 && lane < HALF) {
+                            const float2* rr = reinterpret_cast<const float2*>(stat_red) + (size_t)(wg * 4) * HALF + lane;
+                            double s = 0.0, qq = 0.0;
+#pragma unroll
+                            for (int w4 = 0; w4 < 4; ++w4) { s += (double)rr[w4 * HALF].x; qq += (double)rr[w4 * HALF].y; }
+                            double* dst = a.stats + ((((size_t)b * C::TILES + t) * COUT) + wg * HALF + lane) * 2;
+                            dst[0] = s; dst[1] = qq;
+                        }
+                        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory");     // stat_red is reused by the next tile
+                    }
                 }
             } else {
                 // relu(conv3x3 + bias) for this group's 16 middle channels -> hi / lo -> A operand of the 1x1 in A buffer 0
@@ -496,19 +560,20 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
             const int stage = it % C::NSTAGE;
             mbar_wait(in_full + 8u * stage, (uint32_t)((it / C::NSTAGE) & 1));
             const float* tin = reinterpret_cast<const float*>(stage0 + (size_t)stage * C::STAGE_BYTES);
+            const int tb = (int)(tile / C::TILES), trow0 = (int)(tile % C::TILES) * C::TH * S - C::PAD;
             if constexpr (C::DBUF) {
                 // this group's first chunk of the tile lets the MMA warp start on it; the previous tile's epilogue
                 // (its MMAs have had a whole chunk to drain) comes next, then the remaining chunks
-                if (wg < C::NCH) produce(tin, wg);
+                if (wg < C::NCH) produce(tin, wg, tb, trow0);
                 if (prev_tile >= 0) epilogue(prev_tile, it - 1, nullptr, 0);
 #pragma unroll 1
-                for (int ch = wg + 2; ch < C::NCH; ch += 2) produce(tin, ch);
+                for (int ch = wg + 2; ch < C::NCH; ch += 2) produce(tin, ch, tb, trow0);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(in_empty + 8u * stage);  // this warp is done with the input stage
                 prev_tile = tile;
             } else {
 #pragma unroll 1
-                for (int ch = wg; ch < C::NCH; ch += 2) produce(tin, ch);
+                for (int ch = wg; ch < C::NCH; ch += 2) produce(tin, ch, tb, trow0);
                 if constexpr (!C::FUSE) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(in_empty + 8u * stage);
@@ -578,6 +643,7 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     DMB_CHECK(r == CUDA_SUCCESS, "conv_tm: cuTensorMapEncodeTiled failed (%d)", (int)r);
     TmKArgs k{};
     k.wtm = a.wtm; k.bias = a.bias; k.y = a.y; k.skip = a.skip; k.bias2 = a.bias2;
+    k.in_scale = a.in_scale; k.in_shift = a.in_shift; k.in_per_sample = a.in_per_sample; k.stats = a.stats;
     k.ntiles = (int64_t)a.B * C::TILES;
     k.in_relu = a.in_relu; k.out_relu = a.out_relu;
     { const char* e = getenv("DMB_TM_DBG"); k.dbg = e ? atoi(e) : 0; }
@@ -611,6 +677,11 @@ bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W) {
            (ks == 1 && stride == 1 && cin == 32 && cout == 16 && W == 16);
 }
 
+int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W) {
+    if (!conv_tm_supported(cin, cout, ks, stride, H, W)) return 0;
+    return (H / stride) * (W / stride) / 128;       // tiles of 128 output pixels per patch
+}
+
 int64_t conv_tm_weight_floats(int cin, int cout, int ks) {
     const int K = ks * ks * cin;
     return (int64_t)((K + 31) / 32) * 2 * cout * 32;
@@ -630,6 +701,17 @@ int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
     DMB_CHECK(!(reinterpret_cast<uintptr_t>(a.x) & 15) && !(reinterpret_cast<uintptr_t>(a.wtm) & 15),
               "conv_tm: x and the weight image must be 16-byte aligned");
     DMB_CHECK(a.B > 0, "conv_tm: empty batch");
+    if (a.bn) {
+        // train-mode BatchNorm around the layer: transform on load, raw output, statistics partials
+        DMB_CHECK(!a.bias2 && !a.skip && !a.out_relu, "conv_tm: the BatchNorm form stores the raw convolution output");
+        DMB_CHECK((a.in_scale == nullptr) == (a.in_shift == nullptr), "conv_tm: scale / shift come together");
+        if (a.ks == 4 && a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 64, false, false, true>>(a, st);
+        if (a.ks == 4) return launch_tm<TM<4, 2, 16, 16, 32, false, false, true>>(a, st);
+        if (a.ks == 3 && a.Cout == 16) return launch_tm<TM<3, 1, 16, 16, 16, false, false, true>>(a, st);
+        if (a.ks == 3) return launch_tm<TM<3, 1, 16, 32, 16, false, false, true>>(a, st);
+        return launch_tm<TM<1, 1, 32, 16, 16, false, false, true>>(a, st);
+    }
+    DMB_CHECK(!a.in_scale && !a.stats, "conv_tm: a pending affine / statistics need the BatchNorm form (bn = 1)");
     if (a.ks == 3 && a.Cout == 32) {
         // the residual block's 3x3: ReLU on load compiled in or out; with bias2 the whole layer is fused
         if (a.bias2) {

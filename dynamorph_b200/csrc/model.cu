@@ -18,6 +18,24 @@ bool pdl_enabled() {
     static const bool on = []() { const char* e = getenv("DMB_PDL"); return !(e && e[0] == '0'); }();
     return on;
 }
+// Tensor-memory-operand kernels (conv_tm.cu): smallest batch that takes them (persistent CTAs; tiles = batch x 2..8).
+// DMB_TM=0 switches them off, DMB_TM_MIN_B overrides the threshold.
+constexpr bool TM_DEFAULT_ON = true;
+int64_t tm_min_batch() {
+    const char* sw = getenv("DMB_TM");
+    const bool on = sw ? (sw[0] != '0') : TM_DEFAULT_ON;
+    if (!on) return INT64_MAX;
+    const char* e = getenv("DMB_TM_MIN_B");
+    return e ? atoll(e) : 256;
+}
+// ... and their train-mode-BatchNorm form, taken for per-patch statistics (bulk encoding with the as-written process_VAE
+// semantics).  The training step (BATCH) keeps the CUDA-core kernels: its batches are a few hundred patches.
+bool tm_bn_mode(int bn_mode, int64_t B) {
+    const char* e = getenv("DMB_TM_BN");
+    if (e && e[0] == '0') return false;
+    return bn_mode == DMB_BN_PER_SAMPLE && B >= tm_min_batch();
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -283,6 +301,9 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
                 (void)enc_side;
                 Ho = L.lh; Wo = L.lw; nb = conv_fwd_bands(c.ks, c.stride, c.cin, c.cout, (int)Ho, (int)Wo, true, B);
             }
+            if (c.ptm_off >= 0 && tm_bn_mode(bn_mode, B) && !c.transposed &&
+                conv_tm_supported(c.cin, c.cout, c.ks, c.stride, (int)Ho * c.stride, (int)Wo * c.stride))
+                nb = conv_tm_bands(c.cin, c.cout, c.ks, c.stride, (int)Ho * c.stride, (int)Wo * c.stride);
             DMB_CHECK(nb > 0, "no launch plan for conv %zu", ci);
             BnWs& b = w.bn[c.bn];
             const int64_t rows = (bn_mode == DMB_BN_PER_SAMPLE) ? B : 1;
@@ -400,17 +421,6 @@ int64_t wino_min_batch() {
     return e ? atoll(e) : 512;
 }
 
-// Smallest batch that takes the tensor-memory-operand kernels (persistent CTAs; tiles = batch x 2..8).  DMB_TM=0 switches
-// them off, DMB_TM_MIN_B overrides the threshold.
-constexpr bool TM_DEFAULT_ON = true;
-int64_t tm_min_batch() {
-    const char* sw = getenv("DMB_TM");
-    const bool on = sw ? (sw[0] != '0') : TM_DEFAULT_ON;
-    if (!on) return INT64_MAX;
-    const char* e = getenv("DMB_TM_MIN_B");
-    return e ? atoll(e) : 256;
-}
-
 bool tm_fuse_enabled() {
     const char* e = getenv("DMB_TM_FUSE");
     return !(e && e[0] == '0');
@@ -433,6 +443,18 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout;
         DMB_TRY(convt_fwd(a, c.st));
         Ho = 2 * H; Wo = 2 * W;
+    } else if (bn_live && l.ptm_off >= 0 && !skip && tm_bn_mode(c.mode, c.B) &&
+               conv_tm_supported(l.cin, l.cout, l.ks, l.stride, H, W)) {
+        // per-patch statistics: the same tensor-core kernel with the producer's affine + ReLU on load and the
+        // statistics partials in the epilogue (conv_tm.cu, BN form)
+        ConvTmArgs a{};
+        a.x = in.p; a.wtm = c.packed + l.ptm_off; a.bias = c.packed + l.pb_off; a.y = out;
+        a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.ks = l.ks; a.stride = l.stride;
+        a.bn = 1; a.in_scale = in.s; a.in_shift = in.t; a.in_per_sample = c.per_sample(); a.in_relu = in_relu;
+        a.stats = bw->part;
+        DMB_CHECK(bw->nbands == conv_tm_bands(l.cin, l.cout, l.ks, l.stride, H, W), "statistics layout of conv %d", ci);
+        DMB_TRY(conv_tm(a, c.st));
+        Ho = H / l.stride; Wo = W / l.stride;
     } else if (c.mode == DMB_BN_EVAL && l.ptm_off >= 0 && !in.s && c.B >= tm_min_batch() &&
                conv_tm_supported(l.cin, l.cout, l.ks, l.stride, H, W)) {
         // thin layers of the default configuration: tcgen05 with the activation operand in tensor memory (conv_tm.cu)

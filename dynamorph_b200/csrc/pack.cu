@@ -164,7 +164,7 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
         for (const ConvL& c : L.convs)
             if (c.pwn_off >= 0) DMB_TRY(pack_wino_weights(packed + c.pw_off, packed + c.pwn_off, c.cin, c.cout, st));
     }
-    if (bn_mode == DMB_BN_EVAL) {                // [b_hi; b_lo] operand images for conv_tm.cu
+    {                                            // [b_hi; b_lo] operand images for conv_tm.cu (every mode: folded or raw)
         for (const ConvL& c : L.convs)
             if (c.ptm_off >= 0) {
                 DMB_TRY(pack_tm_weights(packed + c.pw_off, packed + c.ptm_off, c.cin, c.cout, c.ks, st));

@@ -1404,6 +1404,24 @@ int dmb_conv2d_tm(const float* x, const float* w_packed, const float* bias, floa
     return conv_tm(a, st);
 }
 
+int dmb_conv2d_tm_bn(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                     int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, const float* in_scale,
+                     const float* in_shift, int32_t in_per_sample, int32_t in_relu, double* stats, int32_t* bands,
+                     float* scratch, void* stream) {
+    DMB_CHECK(x && w_packed && bias && y && scratch, "dmb_conv2d_tm_bn: null pointer");
+    DMB_CHECK(conv_tm_supported(cin, cout, ksize, stride, h, w), "dmb_conv2d_tm_bn: layer %dx%d s%d %d->%d @%dx%d is not one "
+              "of the thin encoder shapes this kernel is built for", ksize, ksize, stride, cin, cout, h, w);
+    if (bands) *bands = conv_tm_bands(cin, cout, ksize, stride, h, w);
+    cudaStream_t st = (cudaStream_t)stream;
+    DMB_TRY(pack_tm_weights(w_packed, scratch, cin, cout, ksize, st));
+    ConvTmArgs a{};
+    a.x = x; a.wtm = scratch; a.bias = bias; a.y = y;
+    a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
+    a.bn = 1; a.in_scale = in_scale; a.in_shift = in_shift; a.in_per_sample = in_per_sample; a.in_relu = in_relu;
+    a.stats = stats;
+    return conv_tm(a, st);
+}
+
 int dmb_residual_layer_tm_scratch_floats(int64_t* floats) {
     DMB_CHECK(floats != nullptr, "dmb_residual_layer_tm_scratch_floats: null output");
     *floats = conv_tm_weight_floats(16, 32, 3) + conv_tm_weight_floats(32, 16, 1);

@@ -181,6 +181,14 @@ int dmb_conv2d_tm_scratch_floats(int32_t cin, int32_t cout, int32_t ksize, int64
 int dmb_conv2d_tm(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
                   int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, int32_t in_relu,
                   const float* skip, int32_t out_relu, float* scratch, void* stream);
+/* The same layers with a train-mode BatchNorm on either side (DMB_BN_PER_SAMPLE / DMB_BN_BATCH): the producer's pending
+ * affine relu?(x * in_scale[c] + in_shift[c]) ([Cin] tables, or [B][Cin] with in_per_sample) is applied on load (NULL =
+ * identity), y receives the raw convolution output, and `stats` (may be NULL) one (sum, sum of squares) double pair per
+ * (patch, tile of 128 output pixels, channel): [B][*bands][Cout][2], the layout bn_finalize reads.                    */
+int dmb_conv2d_tm_bn(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                     int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, const float* in_scale,
+                     const float* in_shift, int32_t in_per_sample, int32_t in_relu, double* stats, int32_t* bands,
+                     float* scratch, void* stream);
 /* One whole ResidualBlock layer of the default configuration at the 16x16 latent (vq_vae.py:203-209, :222-225, eval mode
  * with BatchNorm folded): y = x + conv1x1(relu(conv3x3(relu(x)) + bias1)) + bias2 in ONE tensor-core kernel; the 1x1 is a
  * second GEMM whose activation operand is written to tensor memory by the first one's epilogue.  x, y (B,16,16,16);

@@ -1,0 +1,138 @@
+"""-m gpu: the thin-channel tensor-core convolutions with the activation operand in tensor memory (csrc/conv_tm.cu:
+tcgen05.mma with A in TMEM, 3xTF32 split in registers) through the layer-level C ABI (dmb_conv2d_tm, dmb_conv2d_tm_bn,
+dmb_residual_layer_tm), against torch's CPU float64 conv2d on the same seeded inputs -- the arithmetic of the reference's
+nn.Conv2d layers at the default widths (HiddenStateExtractor/vq_vae.py:280-289, :203-209, :222-225).  Tolerance 2e-6 of
+max|y| (measured 1.3e-7 .. 4.9e-7; the path-level bar in BASELINE.json is 1e-4)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (ksize, stride, cin, cout, input width): every layer of the default VQ_VAE / VQ_VAE_z16 encoder behind the head
+SHAPES = [(4, 2, 8, 16, 64), (4, 2, 16, 16, 32), (3, 1, 16, 16, 16), (3, 1, 16, 32, 16), (1, 1, 32, 16, 16)]
+TOL = 2e-6
+
+
+def _inputs(shape, B, seed=0):
+    ks, stride, cin, cout, W = shape
+    g = torch.Generator(device="cuda").manual_seed(ks * 1000 + cin * 10 + cout + B + seed)
+    x = torch.randn(B, cin, W, W, device="cuda", generator=g)
+    w = torch.randn(cout, cin, ks, ks, device="cuda", generator=g) * (cin * ks * ks) ** -0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    return x, w, bias, g
+
+
+def _scratch(cin, cout, ks):
+    from dynamorph_b200._lib import call
+    n = C.c_int64()
+    call("dmb_conv2d_tm_scratch_floats", cin, cout, ks, C.byref(n))
+    return torch.zeros(n.value, device="cuda")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ref(x, w, bias, ks, stride, in_relu=False, skip=None, out_relu=False):
+    x = x.double().cpu()
+    if in_relu:
+        x = x.relu()
+    y = F.conv2d(x, w.double().cpu(), bias.double().cpu(), stride=stride, padding=0 if ks == 1 else 1)
+    if skip is not None:
+        y = y + skip.double().cpu()
+    return y.relu() if out_relu else y
+
+
+def _err(y, ref):
+    return float((y.double().cpu() - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "k%ds%d_%dto%d_w%d" % s)
+@pytest.mark.parametrize("B", [1, 3, 300])
+def test_tm_conv_matches_torch(shape, B):
+    """Plain, and with everything the eval-mode schedule asks of the layer (ReLU on load for the residual 3x3, skip for
+    the 1x1, ReLU on store).  B = 1 and 3: fewer tiles than persistent CTAs; B = 300: every CTA loops and wraps."""
+    from dynamorph_b200._lib import call, ptr
+    ks, stride, cin, cout, W = shape
+    x, w, bias, g = _inputs(shape, B)
+    wp = w.permute(1, 2, 3, 0).contiguous()
+    scratch = _scratch(cin, cout, ks)
+    y = torch.empty(B, cout, W // stride, W // stride, device="cuda")
+    call("dmb_conv2d_tm", ptr(x), ptr(wp), ptr(bias), ptr(y), B, cin, W, W, cout, ks, stride, 0, None, 0, ptr(scratch), _stream())
+    assert _err(y, _ref(x, w, bias, ks, stride)) < TOL
+    in_relu = int(ks == 3 and cout == 32)
+    skip = torch.randn(B, cout, W // stride, W // stride, device="cuda", generator=g) if ks == 1 else None
+    call("dmb_conv2d_tm", ptr(x), ptr(wp), ptr(bias), ptr(y), B, cin, W, W, cout, ks, stride, in_relu, ptr(skip), 1,
+         ptr(scratch), _stream())
+    assert _err(y, _ref(x, w, bias, ks, stride, bool(in_relu), skip, True)) < TOL
+
+
+@pytest.mark.parametrize("B", [1, 5, 300])
+def test_tm_fused_residual_layer(B):
+    """y = x + conv1x1(relu(conv3x3(relu(x)) + b1)) + b2 in ONE kernel (two chained GEMMs, the second one's A operand
+    written to tensor memory by the first one's epilogue) == the two-convolution chain in float64."""
+    from dynamorph_b200._lib import call, ptr
+    g = torch.Generator(device="cuda").manual_seed(40 + B)
+    x = torch.randn(B, 16, 16, 16, device="cuda", generator=g)
+    w1 = torch.randn(32, 16, 3, 3, device="cuda", generator=g) / 12
+    b1 = torch.randn(32, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(16, 32, 1, 1, device="cuda", generator=g) / 6
+    b2 = torch.randn(16, device="cuda", generator=g) * 0.1
+    n = C.c_int64()
+    call("dmb_residual_layer_tm_scratch_floats", C.byref(n))
+    scratch = torch.zeros(n.value, device="cuda")
+    y = torch.empty_like(x)
+    call("dmb_residual_layer_tm", ptr(x), ptr(w1.permute(1, 2, 3, 0).contiguous()), ptr(b1),
+         ptr(w2.permute(1, 2, 3, 0).contiguous()), ptr(b2), ptr(y), B, ptr(scratch), _stream())
+    xd = x.double().cpu()
+    ref = xd + F.conv2d(F.conv2d(xd.relu(), w1.double().cpu(), b1.double().cpu(), padding=1).relu(), w2.double().cpu(),
+                        b2.double().cpu())
+    assert _err(y, ref) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "k%ds%d_%dto%d_w%d" % s)
+@pytest.mark.parametrize("per_sample,in_relu", [(True, True), (False, True), (True, False)])
+def test_tm_conv_batchnorm_form(shape, per_sample, in_relu):
+    """Train-mode BatchNorm around the layer: relu?(x * scale + shift) applied on load (per patch and channel, or per
+    channel; zero padding must stay zero although shift != 0), raw output stored, (sum, sum of squares) partials per
+    (patch, tile, channel) whose fold equals the float64 sums of the output."""
+    from dynamorph_b200._lib import call, ptr
+    ks, stride, cin, cout, W = shape
+    B = 7
+    x, w, bias, g = _inputs(shape, B, seed=5)
+    rows = B if per_sample else 1
+    sc = torch.rand(rows, cin, device="cuda", generator=g) + 0.5
+    sh = torch.randn(rows, cin, device="cuda", generator=g) * 0.5
+    wp = w.permute(1, 2, 3, 0).contiguous()
+    scratch = _scratch(cin, cout, ks)
+    Ho = W // stride
+    y = torch.empty(B, cout, Ho, Ho, device="cuda")
+    bands = C.c_int32()
+    stats = torch.full((B * 8 * cout * 2,), float("nan"), dtype=torch.float64, device="cuda")
+    call("dmb_conv2d_tm_bn", ptr(x), ptr(wp), ptr(bias), ptr(y), B, cin, W, W, cout, ks, stride, ptr(sc), ptr(sh),
+         int(per_sample), int(in_relu), ptr(stats), C.byref(bands), ptr(scratch), _stream())
+    torch.cuda.synchronize()
+    assert bands.value == Ho * Ho // 128
+    xt = x.double().cpu() * sc.double().cpu().reshape(rows, cin, 1, 1) + sh.double().cpu().reshape(rows, cin, 1, 1)
+    if in_relu:
+        xt = xt.relu()
+    ref = F.conv2d(xt, w.double().cpu(), bias.double().cpu(), stride=stride, padding=0 if ks == 1 else 1)
+    assert _err(y, ref) < TOL
+    part = stats[:B * bands.value * cout * 2].reshape(B, bands.value, cout, 2).cpu()
+    got = part.sum(1)                                            # per (patch, channel)
+    yd = y.double().cpu()
+    assert torch.allclose(got[..., 0], yd.sum((2, 3)), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(got[..., 1], (yd * yd).sum((2, 3)), rtol=1e-5, atol=1e-4)
+
+
+def test_tm_rejects_other_shapes():
+    from dynamorph_b200._lib import DmbError, call, ptr
+    x = torch.zeros(1, 8, 32, 32, device="cuda")
+    w = torch.zeros(8 * 16 * 16, device="cuda")
+    b = torch.zeros(16, device="cuda")
+    y = torch.zeros(1, 16, 16, 16, device="cuda")
+    with pytest.raises(DmbError, match="thin encoder shapes"):
+        call("dmb_conv2d_tm", ptr(x), ptr(w), ptr(b), ptr(y), 1, 8, 32, 32, 16, 4, 2, 0, None, 0, ptr(w), _stream())

@@ -161,7 +161,7 @@ struct ConvTmArgs {
     const float* bias2;
     // train-mode BatchNorm around the layer (bn != 0; DMB_BN_PER_SAMPLE / DMB_BN_BATCH): the producer's pending affine
     // relu?(x * in_scale[c] + in_shift[c]) ([Cin] or [B][Cin] tables, nullptr = identity) is applied on load, y receives
-    // the raw output and `stats` one (sum, sum of squares) double pair per (patch, tile, channel), conv_tm_bands() tiles
+    // the raw output and `stats` one (sum, sum of squares) double pair per (patch, warp of 32 pixels, channel), conv_tm_bands() rows
     // per patch -- the layout bn_finalize reads.  skip / out_relu / bias2 must be unset.
     int bn;
     const float* in_scale;

@@ -242,7 +242,7 @@ struct TmKArgs {
     const float* in_scale;  // BN: pending affine of the input, [Cin] or [B][Cin] (nullptr = identity)
     const float* in_shift;
     int in_per_sample;
-    double* stats;          // BN: [B][TILES][Cout][2] partial (sum, sum of squares) per tile
+    double* stats;          // BN: [B][TILES*4][Cout][2] partial (sum, sum of squares) per warp (32 pixels)
     int64_t ntiles;
     int in_relu, out_relu;
     int dbg;                // DMB_TM_DBG skip experiments (results are wrong): 1 no a_lo*b_hi MMAs, 2 no a_hi MMAs,
@@ -395,6 +395,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                 [[maybe_unused]] float sc = 1.f, sh = 0.f;
                 if constexpr (C::BN) {
                     if (tsc) { sc = __ldg(tsc + ci); sh = __ldg(tsh + ci); }
+                    // (selects, not a branch: rows of one warp can differ and the shuffles below are full-mask)
                     if (!row_ok) { sc = 0.f; sh = 0.f; }
                 }
                 if constexpr (KS == 4) {
@@ -480,33 +481,43 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                     if constexpr (C::BN) { ssum[c] = val; ssq[c] = val * val; }
                 }
                 if constexpr (C::BN) {
-                    // (sum, sum of squares) over the tile's 128 pixels per channel: lane tree inside each warp (fixed
-                    // order), the four warp sums of a group through shared memory, one double2 per channel
+                    // (sum, sum of squares) of this WARP's 32 pixels per channel, one partial row per warp (the four
+                    // quadrants of a tile are four rows of the [B][TILES*4][Cout][2] partials: no shared memory, no
+                    // barrier between the warps).  Recursive halving: at each of the first log2(HALF) steps a lane keeps
+                    // half of the channels it holds and adds its partner's values for them, then plain butterflies --
+                    // 9 (HALF = 8) or 16 (HALF = 16) shuffles per quantity instead of 5 per channel; fixed order.
                     if (a.stats) {
+                        int held = HALF;
+                        int chan = 0;
 #pragma unroll
-                        for (int c = 0; c < HALF; ++c) {
+                        for (int o = 16; o > 0; o >>= 1) {
+                            if (held > 1) {
+                                const int half = held >> 1;
+                                const bool upper = (lane & o) != 0;
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], o);
-                                ssq[c] += __shfl_xor_sync(0xffffffffu, ssq[c], o);
+                                for (int i = 0; i < HALF / 2; ++i) {
+                                    if (i < half) {
+                                        const float send_s = upper ? ssum[i] : ssum[i + half];
+                                        const float send_q = upper ? ssq[i] : ssq[i + half];
+                                        const float keep_s = upper ? ssum[i + half] : ssum[i];
+                                        const float keep_q = upper ? ssq[i + half] : ssq[i];
+                                        ssum[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, o);
+                                        ssq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, o);
+                                    }
+                                }
+                                chan += upper ? half : 0;
+                                held = half;
+                            } else {
+                                ssum[0] += __shfl_xor_sync(0xffffffffu, ssum[0], o);
+                                ssq[0] += __shfl_xor_sync(0xffffffffu, ssq[0], o);
                             }
                         }
-                        float2* red = reinterpret_cast<float2*>(stat_red) + (size_t)(wg * 4 + q) * HALF;
-                        if (lane == 0) {
-#pragma unroll
-                            for (int c = 0; c < HALF; ++c) red[c] = make_float2(ssum[c], ssq[c]);
+                        // lanes whose low bits (those of the plain butterfly steps) are zero publish their channel
+                        constexpr int PLAIN = (HALF == 8) ? 3 : 1;      // mask of the butterfly-only lane bits
+                        if ((lane & PLAIN) == 0) {
+                            double* dst = a.stats + ((((size_t)b * (C::TILES * 4) + t * 4 + q) * COUT) + wg * HALF + chan) * 2;
+                            dst[0] = (double)ssum[0]; dst[1] = (double)ssq[0];
                         }
-                        // named barrier per warp group (ids 1, 2): the four warps of the group meet, nobody else
-                        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory");
-                        if (q == 0 && lane < HALF) {
-                            const float2* rr = reinterpret_cast<const float2*>(stat_red) + (size_t)(wg * 4) * HALF + lane;
-                            double s = 0.0, qq = 0.0;
-#pragma unroll
-                            for (int w4 = 0; w4 < 4; ++w4) { s += (double)rr[w4 * HALF].x; qq += (double)rr[w4 * HALF].y; }
-                            double* dst = a.stats + ((((size_t)b * C::TILES + t) * COUT) + wg * HALF + lane) * 2;
-                            dst[0] = s; dst[1] = qq;
-                        }
-                        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + wg) : "memory");     // stat_red is reused by the next tile
                     }
                 }
             } else {
@@ -679,7 +690,7 @@ bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W) {
 
 int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W) {
     if (!conv_tm_supported(cin, cout, ks, stride, H, W)) return 0;
-    return (H / stride) * (W / stride) / 128;       // tiles of 128 output pixels per patch
+    return (H / stride) * (W / stride) / 32;        // one partial row per warp: 32 output pixels
 }
 
 int64_t conv_tm_weight_floats(int cin, int cout, int ks) {

@@ -184,7 +184,7 @@ int dmb_conv2d_tm(const float* x, const float* w_packed, const float* bias, floa
 /* The same layers with a train-mode BatchNorm on either side (DMB_BN_PER_SAMPLE / DMB_BN_BATCH): the producer's pending
  * affine relu?(x * in_scale[c] + in_shift[c]) ([Cin] tables, or [B][Cin] with in_per_sample) is applied on load (NULL =
  * identity), y receives the raw convolution output, and `stats` (may be NULL) one (sum, sum of squares) double pair per
- * (patch, tile of 128 output pixels, channel): [B][*bands][Cout][2], the layout bn_finalize reads.                    */
+ * (patch, warp of 32 output pixels, channel): [B][*bands][Cout][2], the layout bn_finalize reads.                    */
 int dmb_conv2d_tm_bn(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
                      int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, const float* in_scale,
                      const float* in_shift, int32_t in_per_sample, int32_t in_relu, double* stats, int32_t* bands,

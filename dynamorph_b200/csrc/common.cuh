@@ -173,6 +173,9 @@ int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W);     // s
 bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);
 int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);
+constexpr int TM_PACK_MAX = 16;
+struct TmPackJob { const float* w; float* out; int cin, cout, ks; };
+int pack_tm_weights_multi(const TmPackJob* jobs, int n, cudaStream_t st);      // all layers of a model in one launch
 int conv_tm(const ConvTmArgs& a, cudaStream_t st);
 
 // transposed 4x4 stride-2 pad-1 convolution, forward (convt_fwd.cu)
@@ -219,6 +222,10 @@ struct WgradArgs {
 };
 int wgrad_partial_floats(const WgradArgs& a, int* ncta);
 int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStream_t st);
+// TMA-fed specialisation for the default-width layers (wgrad_tma.cu): both return 1 when they do not take the call;
+// they write the same per-CTA partial layout, which wgrad() folds with the same reduction kernel
+int wgrad_tma_plan(const WgradArgs& a, int* ncta, int* out_floats);
+int wgrad_tma(const WgradArgs& a, int* ncta, int* out_floats, cudaStream_t st);
 int composite_chain(const float* dweff, const float* w0, const float* b0, const float* w1, int ni, int cm,
                     float* dw0, float* db0, float* dw1, float* db1, cudaStream_t st);
 
@@ -275,6 +282,29 @@ struct AffineAddArgs {
     int64_t B; int C; int HW;
 };
 int affine_add(const AffineAddArgs& a, cudaStream_t st);
+
+// The z16 decoder's tail in the training step (dec_tail.cu): conv1x1 CM -> NI at full resolution + the reconstruction
+// loss in one streaming kernel; loss gradient + the 1x1's data / weight / bias gradients + the previous layer's bias
+// gradient in another.
+struct DecTailArgs {
+    int64_t B; int cm, ni, hw;
+    const float* t3;       // (B, CM, H, W) post-ReLU input of the 1x1
+    const float* x;        // (B, NI, H, W) the batch
+    const float* mask; int mask_c; const float* cvar;
+    const float* w;        // packed [CM][NI]
+    const float* bias;     // [NI] (forward)
+    float* decoded;        // forward: out, backward: in
+    double* loss_sum;      // forward: += sum of the weighted squared error
+    float* g_t3;           // backward: gradient at t3 (ReLU gate applied)
+    float scale;           // backward: grad_scale * weight_recon / numel(decoded)
+    double* partials;      // backward: dec_tail_partial_doubles() scratch
+    unsigned* ticket;      // backward: zero on entry (reset on exit)
+    float* dw; float* db; float* db_prev;      // (NI, CM), (NI), (CM)
+};
+bool dec_tail_supported(int cm, int ni, int hw);
+int64_t dec_tail_partial_doubles(int64_t B, int hw, int cm, int ni);
+int dec_tail_forward(const DecTailArgs& a, cudaStream_t st);
+int dec_tail_backward(const DecTailArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------
 // vector quantiser (vq.cu)

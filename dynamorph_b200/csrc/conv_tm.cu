@@ -628,6 +628,33 @@ __global__ void pack_tm_kernel(const float* __restrict__ w, float* __restrict__ 
     }
 }
 
+// the same for every layer of a model in ONE launch (blockIdx.y = layer): a training step re-packs every step
+struct PackTmJobs { int n; TmPackJob j[TM_PACK_MAX]; };
+__global__ void pack_tm_multi_kernel(const PackTmJobs jobs) {
+    pdl_wait();
+    const TmPackJob& jb = jobs.j[blockIdx.y];
+    const float* __restrict__ w = jb.w;
+    float* __restrict__ out = jb.out;
+    const int cin = jb.cin, cout = jb.cout, ks = jb.ks;
+    const int KC = ks * cin, K = ks * KC, NT = (K + 31) / 32, NR = 2 * cout;
+    const int total = NT * 32 * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / cout, co = i - k * cout;
+        float hi = 0.f, lo = 0.f;
+        if (k < K) {
+            const int ky = k / KC, r = k - ky * KC, ci = r / ks, kx = r - ci * ks;
+            const float wv = __ldg(w + ((size_t)(ci * ks + ky) * ks + kx) * cout + co);
+            hi = __uint_as_float(tf32_rna_bits(wv));
+            lo = wv - hi;
+        }
+        const int tile = k >> 5, q = (k & 31) >> 2, e = k & 3;
+        const size_t tb = (size_t)tile * NR * 32;
+        out[tb + (size_t)co * 32 + (((q ^ (co & 7)) << 2) | e)] = hi;
+        const int n2 = cout + co;
+        out[tb + (size_t)n2 * 32 + (((q ^ (n2 & 7)) << 2) | e)] = lo;
+    }
+}
+
 PFN_cuTensorMapEncodeTiled tm_encoder() {
     static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
         void* p = nullptr;
@@ -703,6 +730,23 @@ int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks
     DMB_LAUNCH((pack_tm_kernel), (total + 255) / 256, 256, 0, st, w_packed, out, cin, cout, ks);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
+    return 0;
+}
+
+int pack_tm_weights_multi(const TmPackJob* jobs, int n, cudaStream_t st) {
+    for (int i0 = 0; i0 < n; i0 += TM_PACK_MAX) {
+        PackTmJobs pj{};
+        pj.n = (n - i0 < TM_PACK_MAX) ? n - i0 : TM_PACK_MAX;
+        int most = 0;
+        for (int i = 0; i < pj.n; ++i) {
+            pj.j[i] = jobs[i0 + i];
+            const int total = ((pj.j[i].ks * pj.j[i].ks * pj.j[i].cin + 31) / 32) * 32 * pj.j[i].cout;
+            if (total > most) most = total;
+        }
+        DMB_LAUNCH((pack_tm_multi_kernel), dim3((most + 255) / 256, pj.n), 256, 0, st, pj);
+        DMB_CUDA(cudaGetLastError());
+        DMB_LAUNCHED(1);
+    }
     return 0;
 }
 

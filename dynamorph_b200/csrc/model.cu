@@ -724,7 +724,14 @@ int run_vq(Ctx& c, const float* codebook, const float* z, const Pending* pre, fl
     return vq_forward(a, c.st);
 }
 
-int run_decoder(Ctx& c, const float* za, float* decoded) {
+// The fused decoder tail of the training step (dec_tail.cu); DMB_DEC_TAIL=0 keeps the separate launches.
+bool dec_tail_on(const dmb_model& m) {
+    const char* e = getenv("DMB_DEC_TAIL");
+    if (e && e[0] == '0') return false;
+    return m.arch == DMB_ARCH_Z16 && dec_tail_supported(m.num_hiddens / 4, m.num_inputs, m.height * m.width);
+}
+
+int run_decoder(Ctx& c, const float* za, float* decoded, bool skip_tail = false) {
     const Layout& L = c.L;
     const dmb_model& m = L.m;
     const bool ev = c.mode == DMB_BN_EVAL;
@@ -735,7 +742,7 @@ int run_decoder(Ctx& c, const float* za, float* decoded) {
         DMB_TRY(run_conv(c, L.d0, in, false, L.lh, L.lw, c.w.t1, nullptr, true, &a1));
         DMB_TRY(run_conv(c, L.d1, a1, false, 2 * L.lh, 2 * L.lw, c.w.t2, nullptr, true, &a2));
         DMB_TRY(run_conv(c, L.d2, a2, false, 4 * L.lh, 4 * L.lw, c.w.t3, nullptr, true, &a3));
-        DMB_TRY(run_conv(c, L.d3, a3, false, 8 * L.lh, 8 * L.lw, decoded, nullptr, false, &o));
+        if (!skip_tail) DMB_TRY(run_conv(c, L.d3, a3, false, 8 * L.lh, 8 * L.lw, decoded, nullptr, false, &o));
     } else {
         DMB_CHECK(c.w.t1, "decoder needs a workspace carved with keep_activations=1");
         Act h;
@@ -1064,14 +1071,32 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
     const int h = m.num_hiddens, h2 = h / 2, h4 = h / 4;
     int nb = 0;
 
-    // 0. reconstruction-loss gradient
-    DMB_TRY(recon_grad(c, x, mask, mask_c, cvar, decoded, grad_scale * m.weight_recon));
-    // 1-4. decoder (no BatchNorm): dec.6 conv1x1, dec.4 / dec.2 / dec.0 ConvT
     Act t3; t3.p = w.t3; Act t2; t2.p = w.t2; Act t1; t1.p = w.t1; Act za; za.p = w.za;
-    GradT G; G.g = w.gd;
-    DMB_TRY(B.wgrad_layer(L.d3, G, t3, false, H, W, true));
-    DMB_TRY(B.dgrad_layer(L.d3, G, H, W, w.g_t3, &t3, nullptr, w.bias_part, nullptr, &nb));
-    DMB_TRY(sum_partials(w.bias_part, (int)c.B, nb, h4, grads + L.convs[L.d2].b_off, st));
+    GradT G;
+    if (dec_tail_on(m)) {
+        // 0-1. reconstruction-loss gradient, dec.6 (1x1) weight / bias / data gradients and dec.4's bias gradient in
+        // one pass over the full-resolution tensors (the loss gradient itself is never stored)
+        const ConvL& l = L.convs[L.d3];
+        DecTailArgs t{};
+        t.B = c.B; t.cm = l.cin; t.ni = l.cout; t.hw = H * W;
+        t.t3 = w.t3; t.x = x; t.mask = mask; t.mask_c = mask_c; t.cvar = cvar; t.w = c.packed + l.pw_off;
+        t.decoded = const_cast<float*>(decoded); t.g_t3 = w.g_t3;
+        t.scale = grad_scale * m.weight_recon / (float)(c.B * (int64_t)m.num_inputs * H * W);
+        DMB_CHECK(dec_tail_partial_doubles(c.B, H * W, t.cm, t.ni) <= (int64_t)c.B * (H / 2) * (L.max_c > 2 ? L.max_c : 2) * 2,
+                  "decoder tail: partial scratch too small");
+        t.partials = w.bias_part; t.ticket = reinterpret_cast<unsigned*>(w.recon_sum + 2);
+        t.dw = grads + l.w_off; t.db = grads + l.b_off; t.db_prev = grads + L.convs[L.d2].b_off;
+        DMB_TRY(dec_tail_backward(t, st));
+    } else {
+        // 0. reconstruction-loss gradient
+        DMB_TRY(recon_grad(c, x, mask, mask_c, cvar, decoded, grad_scale * m.weight_recon));
+        // 1. dec.6 conv1x1
+        G.g = w.gd;
+        DMB_TRY(B.wgrad_layer(L.d3, G, t3, false, H, W, true));
+        DMB_TRY(B.dgrad_layer(L.d3, G, H, W, w.g_t3, &t3, nullptr, w.bias_part, nullptr, &nb));
+        DMB_TRY(sum_partials(w.bias_part, (int)c.B, nb, h4, grads + L.convs[L.d2].b_off, st));
+    }
+    // 2-4. decoder (no BatchNorm): dec.4 / dec.2 / dec.0 ConvT
     G = GradT(); G.g = w.g_t3;
     DMB_TRY(B.wgrad_layer(L.d2, G, t2, false, H / 2, W / 2, false));
     DMB_TRY(B.dgrad_layer(L.d2, G, H / 2, W / 2, w.g_t2, &t2, nullptr, w.bias_part, nullptr, &nb));
@@ -1441,6 +1466,39 @@ int dmb_residual_layer_tm(const float* x, const float* w1_packed, const float* b
     return conv_tm(a, st);
 }
 
+static void wgrad_args(WgradArgs& a, const float* x, const float* gy, int64_t batch, int32_t cin, int32_t h, int32_t w,
+                       int32_t cout, int32_t ksize, int32_t stride) {
+    a.x = x; a.g = gy; a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
+    a.Ho = h / stride; a.Wo = w / stride;
+}
+
+int dmb_conv2d_weight_grad_scratch_floats(int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout, int32_t ksize,
+                                          int32_t stride, int64_t* floats) {
+    DMB_CHECK(floats && batch > 0 && stride > 0, "dmb_conv2d_weight_grad_scratch_floats: bad arguments");
+    WgradArgs a{};
+    wgrad_args(a, nullptr, nullptr, batch, cin, h, w, cout, ksize, stride);
+    int ncta = 0;
+    const int pf = wgrad_partial_floats(a, &ncta);
+    DMB_CHECK(pf > 0, "dmb_conv2d_weight_grad: unsupported layer %dx%d s%d %d->%d", ksize, ksize, stride, cin, cout);
+    *floats = (int64_t)pf * ncta;
+    return 0;
+}
+
+int dmb_conv2d_weight_grad(const float* x, const float* gy, float* dw, float* db, int64_t batch, int32_t cin, int32_t h,
+                           int32_t w, int32_t cout, int32_t ksize, int32_t stride, const float* x_scale,
+                           const float* x_shift, int32_t x_relu, const float* y_raw, const float* ga, const float* gb,
+                           const float* gc, float* scratch, void* stream) {
+    DMB_CHECK(x && gy && dw && scratch && batch > 0, "dmb_conv2d_weight_grad: null pointer / empty batch");
+    DMB_CHECK((x_scale == nullptr) == (x_shift == nullptr), "dmb_conv2d_weight_grad: x_scale / x_shift come together");
+    DMB_CHECK((ga == nullptr) == (gc == nullptr) && (y_raw == nullptr) == (gb == nullptr) && (ga || !y_raw),
+              "dmb_conv2d_weight_grad: ga / gc come together, y_raw / gb come together and need ga");
+    WgradArgs a{};
+    wgrad_args(a, x, gy, batch, cin, h, w, cout, ksize, stride);
+    a.xs = x_scale; a.xt = x_shift; a.x_relu = x_relu; a.y = y_raw; a.ga = ga; a.gb = gb; a.gc = gc;
+    a.partials = scratch;
+    return wgrad(a, dw, db, nullptr, (cudaStream_t)stream);
+}
+
 int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const float* bias, float* y,
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,
                                  const float* in_scale, const float* in_shift, int32_t in_per_sample,
@@ -1552,9 +1610,20 @@ static int train_forward_impl(const dmb_model* m, const float* packed, const flo
     DMB_CUDA(cudaMemsetAsync(w.recon_sum, 0, sizeof(double) * 4, st));
     DMB_TRY(run_vq(c, params + L.codebook_off, w.zb, &pend, w.zb, w.za, w.idx, w.vq_stats));
     DMB_TRY(dmb_vq_finalize(w.vq_stats, L.D, m->num_embeddings, m->commitment_cost, w.scalars, stream));
-    DMB_TRY(run_decoder(c, w.za, decoded));
-    DMB_TRY(dmb_recon_loss(decoded, x, mask, mask_channels, channel_var, batch, m->num_inputs,
-                           m->height * m->width, w.recon_sum, stream));
+    if (dec_tail_on(*m)) {
+        // dec.6 (1x1) and the reconstruction loss in one pass over the full-resolution tensors
+        DMB_TRY(run_decoder(c, w.za, decoded, true));
+        const ConvL& l = L.convs[L.d3];
+        DecTailArgs t{};
+        t.B = batch; t.cm = l.cin; t.ni = l.cout; t.hw = m->height * m->width;
+        t.t3 = w.t3; t.x = x; t.mask = mask; t.mask_c = mask_channels; t.cvar = channel_var;
+        t.w = packed + l.pw_off; t.bias = packed + l.pb_off; t.decoded = decoded; t.loss_sum = w.recon_sum;
+        DMB_TRY(dec_tail_forward(t, st));
+    } else {
+        DMB_TRY(run_decoder(c, w.za, decoded));
+        DMB_TRY(dmb_recon_loss(decoded, x, mask, mask_channels, channel_var, batch, m->num_inputs,
+                               m->height * m->width, w.recon_sum, stream));
+    }
     const bool z32 = m->arch == DMB_ARCH_Z32;
     if (tm) {
         // pair similarities on z_before (vq_vae.py:325, vae.py:322) or, for VQ_VAE_z32, on z_after (vae.py:444)

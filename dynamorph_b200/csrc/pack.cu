@@ -165,15 +165,17 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
             if (c.pwn_off >= 0) DMB_TRY(pack_wino_weights(packed + c.pw_off, packed + c.pwn_off, c.cin, c.cout, st));
     }
     {                                            // [b_hi; b_lo] operand images for conv_tm.cu (every mode: folded or raw)
+        std::vector<TmPackJob> jobs;
         for (const ConvL& c : L.convs)
             if (c.ptm_off >= 0) {
-                DMB_TRY(pack_tm_weights(packed + c.pw_off, packed + c.ptm_off, c.cin, c.cout, c.ks, st));
+                jobs.push_back(TmPackJob{packed + c.pw_off, packed + c.ptm_off, c.cin, c.cout, c.ks});
                 if (c.ptm_tail >= 0) {
                     const ConvL& t = L.convs[c.ptm_tail];
-                    DMB_TRY(pack_tm_weights(packed + t.pw_off, packed + c.ptm_off + conv_tm_weight_floats(c.cin, c.cout, c.ks),
-                                            t.cin, t.cout, t.ks, st));
+                    jobs.push_back(TmPackJob{packed + t.pw_off, packed + c.ptm_off + conv_tm_weight_floats(c.cin, c.cout, c.ks),
+                                             t.cin, t.cout, t.ks});
                 }
             }
+        if (!jobs.empty()) DMB_TRY(pack_tm_weights_multi(jobs.data(), (int)jobs.size(), st));
     }
     if (L.tc && bn_mode == DMB_BN_EVAL) {        // split, swizzled tiles of the folded weights for conv_tc.cu
         for (const ConvL& c : L.convs)

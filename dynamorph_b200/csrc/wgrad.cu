@@ -364,6 +364,10 @@ __global__ void composite_chain_kernel(const float* __restrict__ dweff, const fl
 }  // namespace
 
 int wgrad_partial_floats(const WgradArgs& a, int* ncta) {
+    {
+        int n = 0, of = 0;
+        if (wgrad_tma_plan(a, &n, &of) == 0) { if (ncta) *ncta = n; return of; }
+    }
     WgK k;
     if (plan(a, k)) return -1;
     int n = 148 * 2;
@@ -378,6 +382,18 @@ int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStrea
     DMB_CHECK((a.ks == 1 && a.stride == 1) || (a.ks == 3 && a.stride == 1) || (a.ks == 4 && a.stride == 2),
               "wgrad: unsupported kernel %d stride %d", a.ks, a.stride);
     DMB_CHECK(a.Wo % 4 == 0 && a.W % 4 == 0, "wgrad: widths must be multiples of 4");
+    {
+        int n = 0, of = 0;
+        const int rc = wgrad_tma(a, &n, &of, st);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            const int cin_eff = a.Cin + (a.ones_channel ? 1 : 0);
+            DMB_LAUNCH((wgrad_reduce_kernel), (of + 31) / 32, 1024, 0, st, a.partials, n, of, cin_eff, a.Cout, a.ks, dw, db, packed_out);
+            DMB_CUDA(cudaGetLastError());
+            DMB_LAUNCHED(1);
+            return 0;
+        }
+    }
     WgK k;
     const int rc = plan(a, k);
     DMB_CHECK(rc == 0, "wgrad: no plan (Cout=%d Cin=%d): %d", a.Cout, a.Cin, rc);

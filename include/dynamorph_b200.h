@@ -201,6 +201,20 @@ int dmb_conv_transpose2d_forward(const float* x, const float* w_packed, const fl
                                  int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout,
                                  const float* in_scale, const float* in_shift, int32_t in_per_sample,
                                  int32_t in_relu, int32_t out_relu, void* stream);
+/* Weight and bias gradient of one Conv2d (autograd of F.conv2d w.r.t. weight / bias, run_training.py:406):
+ *   dw[co][ci][ky][kx] = sum_{b,oy,ox} gy'[b][co][oy][ox] * act[b][ci][S*oy - P + ky][S*ox - P + kx],  db[co] = sum gy'
+ * with the transforms the training step folds into the loads:  act = relu?(x * x_scale[c] + x_shift[c])  (the producer's
+ * BatchNorm + ReLU; NULL = identity) and  gy' = gy * ga[c] + y_raw * gb[c] + gc[c]  (the BatchNorm backward of the layer's
+ * own BatchNorm; ga NULL = plain gy, y_raw/gb NULL = affine only).  ksize/stride: (1,1) (3,1) (4,2), padding 1 unless 1x1.
+ * dw (Cout, Cin, k, k) and db (Cout, may be NULL) in the torch layout.  The default-width layer shapes on 128x128 patches
+ * run the TMA-fed kernel (csrc/wgrad_tma.cu), everything else the generic one (csrc/wgrad.cu); both are deterministic.
+ * scratch: dmb_conv2d_weight_grad_scratch_floats() floats.                                                              */
+int dmb_conv2d_weight_grad_scratch_floats(int64_t batch, int32_t cin, int32_t h, int32_t w, int32_t cout, int32_t ksize,
+                                          int32_t stride, int64_t* floats);
+int dmb_conv2d_weight_grad(const float* x, const float* gy, float* dw, float* db, int64_t batch, int32_t cin, int32_t h,
+                           int32_t w, int32_t cout, int32_t ksize, int32_t stride, const float* x_scale,
+                           const float* x_shift, int32_t x_relu, const float* y_raw, const float* ga, const float* gb,
+                           const float* gc, float* scratch, void* stream);
 /* Launch a register-resident FMA loop (16 chains x iters per thread) and report the FLOPs it
  * performs in *flops_out_host; the caller times it with CUDA events to get the FP32 roof.    */
 int dmb_bench_fp32_fma(int32_t blocks, int32_t threads, int32_t iters, float* scratch,

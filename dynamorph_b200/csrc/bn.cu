@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) bn_finalize_batch_kernel(const BnFinalize
     pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[8][2];
     const int c = blockIdx.x;
-    const int n = a.B * a.nbands;
+    const int n = a.rows > 0 ? a.rows : a.B * a.nbands;
     double s = 0.0, q = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) {
         const double2 v = *reinterpret_cast<const double2*>(a.partials + ((size_t)i * a.C + c) * 2);
@@ -138,7 +138,8 @@ __global__ void affine_add_kernel(const AffineAddArgs a, int64_t total4) {
 }  // namespace
 
 int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
-    if (!a.per_sample && (int64_t)a.B * a.nbands >= 64) {
+    DMB_CHECK(a.rows == 0 || !a.per_sample, "bn_finalize: a row count belongs to whole-batch statistics");
+    if (!a.per_sample && (a.rows > 0 || (int64_t)a.B * a.nbands >= 64)) {
         DMB_LAUNCH((bn_finalize_batch_kernel), a.C, 256, 0, st, a);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_batch_kernel(const BnBwdA
     pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
     __shared__ double red[8][2];
     const int c = blockIdx.x;
-    const int n = a.B * a.nbands;
+    const int n = a.rows > 0 ? a.rows : a.B * a.nbands;
     double sg = 0.0, sgy = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) {
         const double2 v = *reinterpret_cast<const double2*>(a.partials + ((size_t)i * a.C + c) * 2);
@@ -280,7 +281,8 @@ __global__ void sum_partials_kernel(const double* partials, int n, int C, float*
 }  // namespace
 
 int bn_backward_finalize(const BnBwdArgs& a, cudaStream_t st) {
-    if (!a.per_sample && (int64_t)a.B * a.nbands >= 64) {
+    DMB_CHECK(a.rows == 0 || !a.per_sample, "bn_backward_finalize: a row count belongs to whole-batch statistics");
+    if (!a.per_sample && (a.rows > 0 || (int64_t)a.B * a.nbands >= 64)) {
         DMB_LAUNCH((bn_bwd_finalize_batch_kernel), a.C, 256, 0, st, a);
         DMB_CUDA(cudaGetLastError());
         DMB_LAUNCHED(1);

@@ -168,7 +168,13 @@ struct ConvTmArgs {
     const float* in_shift;
     int in_per_sample;
     double* stats;
+    // whole-batch statistics (DMB_BN_BATCH): every warp of the persistent CTAs adds up the partials of its tiles and
+    // `stats` receives *stat_rows = 4 * grid <= TM_BATCH_ROWS_MAX rows of [Cout][2] (fixed order: deterministic)
+    int stats_batch;
+    int* stat_rows;
 };
+constexpr int TM_MAX_SMS = 192;
+constexpr int TM_BATCH_ROWS_MAX = 4 * 2 * TM_MAX_SMS;
 int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W);     // statistics rows per patch (0: unsupported)
 bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);
@@ -238,6 +244,7 @@ int composite_chain(const float* dweff, const float* w0, const float* b0, const 
 struct BnFinalizeArgs {
     const double* partials;  // [B][nbands][C][2]
     int B, nbands, C;
+    int rows;                // BATCH mode: number of partial rows when it is not B * nbands (0 = B * nbands)
     int64_t count_per_sample;  // Ho*Wo
     int per_sample;
     const float* gamma;
@@ -257,6 +264,7 @@ int bn_finalize(const BnFinalizeArgs& a, cudaStream_t st);
 struct BnBwdArgs {
     const double* partials;  // [B][nbands][C][2]
     int B, nbands, C;
+    int rows;                // BATCH mode: number of partial rows when it is not B * nbands (0 = B * nbands)
     int64_t count_per_sample;
     int per_sample;
     const float* gamma;

@@ -243,6 +243,8 @@ struct TmKArgs {
     const float* in_shift;
     int in_per_sample;
     double* stats;          // BN: [B][TILES*4][Cout][2] partial (sum, sum of squares) per warp (32 pixels)
+    int stats_batch;        // BN: whole-batch statistics -- every warp adds up its tiles' partials and leaves ONE row at
+                            // the end: [gridDim.x * 4][Cout][2]
     int64_t ntiles;
     int in_relu, out_relu;
     int dbg;                // DMB_TM_DBG skip experiments (results are wrong): 1 no a_lo*b_hi MMAs, 2 no a_hi MMAs,
@@ -364,6 +366,8 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
 #pragma unroll
         for (int c = 0; c < HALF; ++c) bias_r[c] = __ldg(a.bias + wg * HALF + c);
         uint32_t my_n = 0;                                   // chunks this group has produced (uses of its A buffer)
+        [[maybe_unused]] double acc_s = 0.0, acc_q = 0.0;    // BN, stats_batch: this lane's channel over all tiles of the CTA
+        [[maybe_unused]] int acc_chan = 0;
 
         // gather + split + tensor-memory store of chunk `ch` of the tile staged at `tin` (tile = patch b, rows from row0)
         auto produce = [&](const float* tin, int ch, int b = 0, int row0 = 0) {
@@ -514,7 +518,9 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                         }
                         // lanes whose low bits (those of the plain butterfly steps) are zero publish their channel
                         constexpr int PLAIN = (HALF == 8) ? 3 : 1;      // mask of the butterfly-only lane bits
-                        if ((lane & PLAIN) == 0) {
+                        if (a.stats_batch) {
+                            acc_s += (double)ssum[0]; acc_q += (double)ssq[0]; acc_chan = chan;
+                        } else if ((lane & PLAIN) == 0) {
                             double* dst = a.stats + ((((size_t)b * (C::TILES * 4) + t * 4 + q) * COUT) + wg * HALF + chan) * 2;
                             dst[0] = (double)ssum[0]; dst[1] = (double)ssq[0];
                         }
@@ -594,6 +600,13 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
         }
         if constexpr (C::DBUF) {
             if (prev_tile >= 0) epilogue(prev_tile, it - 1, nullptr, 0);
+        }
+        if constexpr (C::BN) {
+            constexpr int PLAIN = (HALF == 8) ? 3 : 1;
+            if (a.stats && a.stats_batch && (lane & PLAIN) == 0) {       // (every CTA of the grid has at least one tile)
+                double* dst = a.stats + (((size_t)blockIdx.x * 4 + q) * COUT + wg * HALF + acc_chan) * 2;
+                dst[0] = acc_s; dst[1] = acc_q;
+            }
         }
     }
     tc_fence_before();
@@ -682,6 +695,7 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     TmKArgs k{};
     k.wtm = a.wtm; k.bias = a.bias; k.y = a.y; k.skip = a.skip; k.bias2 = a.bias2;
     k.in_scale = a.in_scale; k.in_shift = a.in_shift; k.in_per_sample = a.in_per_sample; k.stats = a.stats;
+    k.stats_batch = a.stats_batch;
     k.ntiles = (int64_t)a.B * C::TILES;
     k.in_relu = a.in_relu; k.out_relu = a.out_relu;
     { const char* e = getenv("DMB_TM_DBG"); k.dbg = e ? atoi(e) : 0; }
@@ -696,8 +710,10 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     }
     int sms = 148;
     DMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sms > TM_MAX_SMS) sms = TM_MAX_SMS;
     const int64_t grid = std::min<int64_t>(k.ntiles, (int64_t)sms * C::CTAS);
     DMB_CHECK(grid > 0, "conv_tm: empty launch");
+    if (a.stat_rows) *a.stat_rows = (int)grid * 4;
     DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);

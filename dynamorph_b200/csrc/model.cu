@@ -28,12 +28,17 @@ int64_t tm_min_batch() {
     const char* e = getenv("DMB_TM_MIN_B");
     return e ? atoll(e) : 256;
 }
-// ... and their train-mode-BatchNorm form, taken for per-patch statistics (bulk encoding with the as-written process_VAE
-// semantics).  The training step (BATCH) keeps the CUDA-core kernels: its batches are a few hundred patches.
+// ... and their train-mode-BatchNorm form: per-patch statistics (bulk encoding with the as-written process_VAE semantics)
+// and whole-batch statistics (the training step, from the same batch size: 256 patches are 512 .. 8192 tiles for the 296
+// persistent CTAs).  DMB_TM_BN=0 switches both off, DMB_TM_BN_BATCH=0 the training form only.
 bool tm_bn_mode(int bn_mode, int64_t B) {
     const char* e = getenv("DMB_TM_BN");
     if (e && e[0] == '0') return false;
-    return bn_mode == DMB_BN_PER_SAMPLE && B >= tm_min_batch();
+    if (bn_mode == DMB_BN_BATCH) {
+        const char* eb = getenv("DMB_TM_BN_BATCH");
+        if (eb && eb[0] == '0') return false;
+    }
+    return (bn_mode == DMB_BN_PER_SAMPLE || bn_mode == DMB_BN_BATCH) && B >= tm_min_batch();
 }
 
 void set_error(const char* fmt, ...) {
@@ -309,7 +314,9 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             const int64_t rows = (bn_mode == DMB_BN_PER_SAMPLE) ? B : 1;
             b.nbands = nb;
             b.count = Ho * Wo;
-            b.part = bp.take<double>(B * nb * c.cout * 2);
+            // (whole-batch statistics of the tensor-memory kernels: one row per warp of the persistent grid)
+            const int64_t part_rows = (B * nb > TM_BATCH_ROWS_MAX) ? B * nb : TM_BATCH_ROWS_MAX;
+            b.part = bp.take<double>(part_rows * c.cout * 2);
             b.scale = bp.take<float>(rows * c.cout);
             b.shift = bp.take<float>(rows * c.cout);
             b.mean = bp.take<float>(rows * c.cout);
@@ -434,6 +441,7 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
     const bool bn_live = (l.bn >= 0 && c.mode != DMB_BN_EVAL);
     BnWs* bw = bn_live ? &c.w.bn[l.bn] : nullptr;
     int Ho, Wo;
+    int stat_rows = 0;      // whole-batch statistics: rows of partials when that is not B * nbands
     if (l.transposed) {
         ConvTFwdArgs a{};
         a.x = in.p; a.y = out; a.w = c.packed + l.pw_off; a.bias = c.packed + l.pb_off;
@@ -452,8 +460,10 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.ks = l.ks; a.stride = l.stride;
         a.bn = 1; a.in_scale = in.s; a.in_shift = in.t; a.in_per_sample = c.per_sample(); a.in_relu = in_relu;
         a.stats = bw->part;
+        a.stats_batch = c.per_sample() ? 0 : 1; a.stat_rows = &stat_rows;
         DMB_CHECK(bw->nbands == conv_tm_bands(l.cin, l.cout, l.ks, l.stride, H, W), "statistics layout of conv %d", ci);
         DMB_TRY(conv_tm(a, c.st));
+        if (c.per_sample()) stat_rows = 0;
         Ho = H / l.stride; Wo = W / l.stride;
     } else if (c.mode == DMB_BN_EVAL && l.ptm_off >= 0 && !in.s && c.B >= tm_min_batch() &&
                conv_tm_supported(l.cin, l.cout, l.ks, l.stride, H, W)) {
@@ -490,10 +500,11 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
     if (bn_live) {
         const BnL& b = c.L.bns[l.bn];
         BnFinalizeArgs f{};
-        f.partials = bw->part; f.B = (int)c.B; f.nbands = bw->nbands; f.C = l.cout;
+        f.partials = bw->part; f.B = (int)c.B; f.nbands = bw->nbands; f.C = l.cout; f.rows = stat_rows;
         f.count_per_sample = (int64_t)Ho * Wo;
         if (c.synced()) {          // statistics of the GLOBAL batch: one row of summed partials, global element count
-            DMB_TRY(c.exchange(bw->part, c.B * bw->nbands, l.cout, bw->gsum));
+            DMB_TRY(c.exchange(bw->part, stat_rows > 0 ? stat_rows : c.B * bw->nbands, l.cout, bw->gsum));
+            f.rows = 0;
             f.partials = bw->gsum; f.B = 1; f.nbands = 1;
             f.count_per_sample = (int64_t)Ho * Wo * c.B * c.sync->world;
         }

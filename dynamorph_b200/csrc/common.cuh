@@ -172,11 +172,21 @@ struct ConvTmArgs {
     // `stats` receives *stat_rows = 4 * grid <= TM_BATCH_ROWS_MAX rows of [Cout][2] (fixed order: deterministic)
     int stats_batch;
     int* stat_rows;
+    // data-gradient form (dg != 0; training step, whole-batch statistics; shapes: conv_tm_dg_supported): plain input x (the
+    // gradient at the layer's output), wtm = image of the data-gradient weights, epilogue
+    //   o = acc + bias;  o *= [mask_src * mask_s[c] + mask_t[c] > 0];  o += skip;  store;  stats: (sum o, sum o * stat_src)
+    // or (sum o, sum o^2) without stat_src -- the contract of conv_fwd's data-gradient extras
+    int dg;
+    const float* mask_src;
+    const float* mask_s;
+    const float* mask_t;
+    const float* stat_src;
 };
 constexpr int TM_MAX_SMS = 192;
 constexpr int TM_BATCH_ROWS_MAX = 4 * 2 * TM_MAX_SMS;
 int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W);     // statistics rows per patch (0: unsupported)
 bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
+bool conv_tm_dg_supported(int cin, int cout, int ks, int stride, int H, int W);
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);
 int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);
 constexpr int TM_PACK_MAX = 16;

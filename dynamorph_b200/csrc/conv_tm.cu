@@ -170,9 +170,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // applied to every gathered value (relu?(x * scale[c] + shift[c]), tables per channel or per patch and channel; rows
 // outside the image stay zero), the layer's raw output is stored, and the epilogue leaves one (sum, sum of squares)
 // partial per (patch, tile, channel) for bn_finalize -- the contract of conv_tma.cuh / conv_fwd.cu.
-template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false, bool INRELU_ = false, bool BN_ = false>
+// DG_ (data gradient of a training step, whole-batch statistics): plain input (the gradient at the layer's output, any
+// BatchNorm-backward transform already applied), and the epilogue of the CUDA-core data-gradient kernels (conv_fwd.cu):
+// ReLU gate of the layer back-propagated into ([mask_src * mask_s[c] + mask_t[c] > 0]), skip gradient, store, and the
+// next BatchNorm backward's sums (sum o, sum o * stat_src) -- or (sum o, sum o^2) for a bias gradient -- per CTA.
+template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false, bool INRELU_ = false, bool BN_ = false,
+          bool DG_ = false>
 struct TM {
     static constexpr bool BN = BN_;
+    static constexpr bool DG = DG_;
+    static constexpr bool STATS = BN_ || DG_;
     static constexpr int KS = KS_, S = S_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
     static constexpr bool FUSE = FUSE_;
     static constexpr bool INRELU = INRELU_;                  // ReLU on load, compiled in (a run-time flag left 16
@@ -231,6 +238,7 @@ struct TM {
     static_assert(!FUSE || (KS == 3 && COUT == 32 && CIN == COUT2 && NACC == 1 && A_COLS >= 2 * K2),
                   "the fused tail is the 3x3 16 -> 32 -> 1x1 -> 16 residual layer");
     static_assert(!BN || (!FUSE && !INRELU), "BatchNorm form: ReLU on load is a run-time flag of the transform");
+    static_assert(!DG || (!FUSE && !INRELU && !BN), "data-gradient form: plain input");
 };
 
 struct TmKArgs {
@@ -250,10 +258,18 @@ struct TmKArgs {
     int dbg;                // DMB_TM_DBG skip experiments (results are wrong): 1 no a_lo*b_hi MMAs, 2 no a_hi MMAs,
                             // 4 no gather (zeros), 8 no split / tensor-memory stores
 };
+// extras of the data-gradient form: a separate kernel parameter (growing TmKArgs by as little as 16 bytes changed the
+// register allocation of EVERY variant: 0 -> 28..116 bytes of spills in the plain forward kernels)
+struct TmDgArgs {
+    const float* mask_src;  // (B, Cout, Ho, Wo) or nullptr
+    const float* mask_s;    // its affine [Cout] (nullptr = identity)
+    const float* mask_t;
+    const float* stat_src;  // (B, Cout, Ho, Wo) or nullptr
+};
 
 template <class C>
 __global__ void __launch_bounds__(TM_THREADS, C::CTAS)
-conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
+conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const TmDgArgs dg) {
     constexpr int KS = C::KS, S = C::S, CIN = C::CIN, COUT = C::COUT, W = C::W, KC = C::KC, HALF = C::HALF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -479,12 +495,24 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
                     if constexpr (C::NACC == 2)
                         val += __uint_as_float(r[1][0][c]) + __uint_as_float(r[1][1][c]);
                     val += bias_r[c];
+                    if constexpr (C::DG) {
+                        if (dg.mask_src) {
+                            float mv = __ldg(dg.mask_src + chan0 + (size_t)c * (C::HO * C::WO));
+                            if (dg.mask_s) mv = fmaf(mv, __ldg(dg.mask_s + wg * HALF + c), __ldg(dg.mask_t + wg * HALF + c));
+                            if (!(mv > 0.f)) val = 0.f;
+                        }
+                    }
                     if (sp) val += __ldg(sp + (size_t)c * (C::HO * C::WO));
                     if (a.out_relu) val = fmaxf(val, 0.f);
                     yp[(size_t)c * (C::HO * C::WO)] = val;
-                    if constexpr (C::BN) { ssum[c] = val; ssq[c] = val * val; }
+                    if constexpr (C::STATS) {
+                        ssum[c] = val; ssq[c] = val * val;
+                        if constexpr (C::DG) {
+                            if (dg.stat_src) ssq[c] = val * __ldg(dg.stat_src + chan0 + (size_t)c * (C::HO * C::WO));
+                        }
+                    }
                 }
-                if constexpr (C::BN) {
+                if constexpr (C::STATS) {
                     // (sum, sum of squares) of this WARP's 32 pixels per channel, one partial row per warp (the four
                     // quadrants of a tile are four rows of the [B][TILES*4][Cout][2] partials: no shared memory, no
                     // barrier between the warps).  Recursive halving: at each of the first log2(HALF) steps a lane keeps
@@ -601,7 +629,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a) {
         if constexpr (C::DBUF) {
             if (prev_tile >= 0) epilogue(prev_tile, it - 1, nullptr, 0);
         }
-        if constexpr (C::BN) {
+        if constexpr (C::STATS) {
             constexpr int PLAIN = (HALF == 8) ? 3 : 1;
             if (a.stats && a.stats_batch && (lane & PLAIN) == 0) {       // (every CTA of the grid has at least one tile)
                 double* dst = a.stats + (((size_t)blockIdx.x * 4 + q) * COUT + wg * HALF + acc_chan) * 2;
@@ -696,6 +724,7 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     k.wtm = a.wtm; k.bias = a.bias; k.y = a.y; k.skip = a.skip; k.bias2 = a.bias2;
     k.in_scale = a.in_scale; k.in_shift = a.in_shift; k.in_per_sample = a.in_per_sample; k.stats = a.stats;
     k.stats_batch = a.stats_batch;
+    TmDgArgs d{a.mask_src, a.mask_s, a.mask_t, a.stat_src};
     k.ntiles = (int64_t)a.B * C::TILES;
     k.in_relu = a.in_relu; k.out_relu = a.out_relu;
     { const char* e = getenv("DMB_TM_DBG"); k.dbg = e ? atoi(e) : 0; }
@@ -714,7 +743,7 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     const int64_t grid = std::min<int64_t>(k.ntiles, (int64_t)sms * C::CTAS);
     DMB_CHECK(grid > 0, "conv_tm: empty launch");
     if (a.stat_rows) *a.stat_rows = (int)grid * 4;
-    DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k);
+    DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k, d);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -729,6 +758,18 @@ bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W) {
            (ks == 3 && stride == 1 && cin == 16 && cout == 16 && W == 16) ||
            (ks == 3 && stride == 1 && cin == 16 && cout == 32 && W == 16) ||
            (ks == 1 && stride == 1 && cin == 32 && cout == 16 && W == 16);
+}
+
+// shapes of the data-gradient form, named by the data-gradient convolution's own (cin, cout): the default model's
+// residual 1x1 (16 -> 32) and 3x3 (32 -> 16), enc.10 (16 -> 16) and the stride-2 convolutions that back-propagate through
+// the decoder's ConvTranspose2d 16 -> 8 (at 64 x 64) and 16 -> 16 (at 32 x 32)
+bool conv_tm_dg_supported(int cin, int cout, int ks, int stride, int H, int W) {
+    if (H != W) return false;
+    return (ks == 1 && stride == 1 && cin == 16 && cout == 32 && W == 16) ||
+           (ks == 3 && stride == 1 && cin == 32 && cout == 16 && W == 16) ||
+           (ks == 3 && stride == 1 && cin == 16 && cout == 16 && W == 16) ||
+           (ks == 4 && stride == 2 && cin == 8 && cout == 16 && W == 64) ||
+           (ks == 4 && stride == 2 && cin == 16 && cout == 16 && W == 32);
 }
 
 int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W) {
@@ -767,11 +808,25 @@ int pack_tm_weights_multi(const TmPackJob* jobs, int n, cudaStream_t st) {
 }
 
 int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
-    DMB_CHECK(conv_tm_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W), "conv_tm: unsupported layer %dx%d s%d %d->%d @%dx%d",
-              a.ks, a.ks, a.stride, a.Cin, a.Cout, a.H, a.W);
+    DMB_CHECK(a.dg ? conv_tm_dg_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W)
+                   : conv_tm_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W),
+              "conv_tm: unsupported layer %dx%d s%d %d->%d @%dx%d", a.ks, a.ks, a.stride, a.Cin, a.Cout, a.H, a.W);
     DMB_CHECK(!(reinterpret_cast<uintptr_t>(a.x) & 15) && !(reinterpret_cast<uintptr_t>(a.wtm) & 15),
               "conv_tm: x and the weight image must be 16-byte aligned");
     DMB_CHECK(a.B > 0, "conv_tm: empty batch");
+    if (a.dg) {
+        // data gradient of a training step: plain input, gate / skip / BatchNorm-backward sums in the epilogue
+        DMB_CHECK(!a.bn && !a.bias2 && !a.in_relu && !a.out_relu && !a.in_scale, "conv_tm: the data-gradient form takes a plain input");
+        DMB_CHECK((a.mask_s == nullptr) == (a.mask_t == nullptr) && (a.mask_src || !a.mask_s), "conv_tm: mask affine without a mask");
+        DMB_CHECK(!a.stats || (a.stats_batch && a.stat_rows), "conv_tm: the data-gradient form leaves whole-batch sums");
+        DMB_CHECK(a.stats || !a.stat_src, "conv_tm: stat_src without stats");
+        if (a.ks == 1) return launch_tm<TM<1, 1, 16, 32, 16, false, false, false, true>>(a, st);
+        if (a.ks == 3 && a.Cin == 32) return launch_tm<TM<3, 1, 32, 16, 16, false, false, false, true>>(a, st);
+        if (a.ks == 3) return launch_tm<TM<3, 1, 16, 16, 16, false, false, false, true>>(a, st);
+        if (a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 64, false, false, false, true>>(a, st);
+        return launch_tm<TM<4, 2, 16, 16, 32, false, false, false, true>>(a, st);
+    }
+    DMB_CHECK(!a.mask_src && !a.stat_src, "conv_tm: gate / stat_src belong to the data-gradient form (dg = 1)");
     if (a.bn) {
         // train-mode BatchNorm around the layer: transform on load, raw output, statistics partials
         DMB_CHECK(!a.bias2 && !a.skip && !a.out_relu, "conv_tm: the BatchNorm form stores the raw convolution output");

@@ -70,7 +70,7 @@ struct Builder {
     int conv(const std::string& key, int cin, int cout, int ks, int stride, bool transposed) {
         ConvL c{};
         c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.transposed = transposed; c.bn = -1;
-        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1; c.pdtm_off = -1;
         c.w_off = take_param(key + ".weight", (int64_t)cin * cout * ks * ks);
         c.b_off = take_param(key + ".bias", cout);
         c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
@@ -86,7 +86,7 @@ struct Builder {
         ConvL c{};
         c.cin = cin; c.cout = cmid; c.cmid = cmid; c.ks = 4; c.stride = 2; c.composite = 1; c.bn = -1;
         c.bias_classes = 1;
-        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1; c.pdtm_off = -1;
         c.w0_off = take_param(key0 + ".weight", (int64_t)cmid * cin);
         c.b0_off = take_param(key0 + ".bias", cmid);
         c.w_off = take_param(key1 + ".weight", (int64_t)cmid * cmid * 16);
@@ -223,6 +223,23 @@ int build_layout(const dmb_model* m, Layout& L) {
             }
             want(r.b, L.lh, L.lw);
         }
+        // ... and of the training step's data-gradient convolutions that have a tensor-memory form: stride-1 layers at the
+        // latent resolution (channels swapped, taps flipped: pdw_off) and the stride-2 convolutions that back-propagate
+        // through a ConvTranspose2d
+        auto want_dg = [&](int ci, int hh, int ww) {      // hh x ww: the layer's INPUT map
+            if (ci < 0) return;
+            ConvL& c = L.convs[ci];
+            if (c.pdw_off < 0 || c.composite) return;
+            bool ok;
+            if (c.transposed) ok = conv_tm_dg_supported(c.cout, c.cin, 4, 2, 2 * hh, 2 * ww);
+            else ok = c.stride == 1 && conv_tm_dg_supported(c.cout, c.cin, c.ks, 1, hh, ww);
+            if (ok) c.pdtm_off = B.take_packed(conv_tm_weight_floats(c.cout, c.cin, c.ks));
+        };
+        if (m->arch == DMB_ARCH_Z16) {
+            want_dg(L.e4, H / 8, W / 8);
+            want_dg(L.d0, L.lh, L.lw); want_dg(L.d1, 2 * L.lh, 2 * L.lw); want_dg(L.d2, 4 * L.lh, 4 * L.lw);
+        }
+        for (const ResL& r : L.enc_res) { want_dg(r.a, L.lh, L.lw); want_dg(r.b, L.lh, L.lw); }
     }
     L.pzero_off = B.take_packed(L.max_c);
     L.n_params = B.p; L.n_bnbuf = B.bb; L.n_packed = B.pk;
@@ -336,7 +353,8 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             const int64_t hmax = (m.arch == DMB_ARCH_Z16 && (int)ci == L.e1) ? H / 2 :
                                  (((int)ci == L.e2 && m.arch == DMB_ARCH_Z16) ? H / 4 :
                                  ((m.arch == DMB_ARCH_Z32 && ((int)ci == L.e1 || (int)ci == L.d0)) ? H / 2 : L.lh));
-            b.part = bp.take<double>(B * hmax * c.cout * 2);
+            const int64_t prow = (B * hmax > TM_BATCH_ROWS_MAX) ? B * hmax : TM_BATCH_ROWS_MAX;
+            b.part = bp.take<double>(prow * c.cout * 2);
             b.A = bp.take<float>(rows * c.cout);
             b.Bc = bp.take<float>(rows * c.cout);
             b.Cc = bp.take<float>(rows * c.cout);
@@ -364,7 +382,10 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             w.g_dra.push_back(bp.take<float>(B * rh * lat));
             w.g_dh.push_back(bp.take<float>(B * h * lat));
         }
-        w.bias_part = bp.take<double>(B * (H / 2) * (size_t)(L.max_c > 2 ? L.max_c : 2) * 2);
+        {
+            const int64_t prow = (B * (H / 2) > TM_BATCH_ROWS_MAX) ? B * (H / 2) : TM_BATCH_ROWS_MAX;
+            w.bias_part = bp.take<double>(prow * (size_t)(L.max_c > 2 ? L.max_c : 2) * 2);
+        }
         size_t maxw = 0;
         for (const ConvL& c : L.convs) {
             const size_t f = (size_t)(c.cin + 1) * c.ks * c.ks * c.cout + c.cout + (size_t)c.cin;
@@ -426,6 +447,11 @@ int64_t wino_min_batch() {
     if (off && off[0] == '0') return INT64_MAX;
     const char* e = getenv("DMB_WINO_MIN_B");
     return e ? atoll(e) : 512;
+}
+
+bool tm_dg_enabled() {      // data-gradient form of the tensor-memory kernels in the training step (DMB_TM_DG=0: off)
+    const char* e = getenv("DMB_TM_DG");
+    return !(e && e[0] == '0');
 }
 
 bool tm_fuse_enabled() {
@@ -880,6 +906,7 @@ struct Bwd {
     cudaStream_t st;
     SideStream* side = nullptr;
     bool forked = false;
+    int stat_rows = 0;      // rows of partial sums the LAST dgrad_layer call left when that is not B * nbands (conv_tm.cu)
     bool ps() const { return c.per_sample(); }
     int L_lat_h() const { return c.L.lh; }
     int L_lat_w() const { return c.L.lw; }
@@ -937,6 +964,31 @@ struct Bwd {
         const float* wd = c.packed + l.pdw_off;
         const float* zero = c.packed + c.L.pzero_off;
         const bool up = (!l.transposed && l.stride == 2);      // conv stride 2 -> transposed-conv kernel
+        stat_rows = 0;
+        if (l.pdtm_off >= 0 && !ps() && tm_dg_enabled() && c.B >= tm_min_batch() &&
+            (!G.A || (c.w.g_tmp && H == L_lat_h() && W == L_lat_w() && !l.transposed))) {
+            // tensor cores, activation operand in tensor memory (conv_tm.cu, data-gradient form).  A BatchNorm-backward
+            // gradient  A*g + Bc*y + Cc  is materialised first (one small elementwise launch at the latent resolution).
+            ConvTmArgs a{};
+            a.x = G.g;
+            a.Cin = l.cout; a.Cout = l.cin; a.B = (int)c.B;
+            if (l.transposed) { a.ks = 4; a.stride = 2; a.H = 2 * H; a.W = 2 * W; }
+            else { a.ks = l.ks; a.stride = 1; a.H = H; a.W = W; }
+            if (G.A) {
+                AffineAddArgs aa{};
+                aa.a = G.g; aa.sa = G.A; aa.ta = G.Cc; aa.b = G.y; aa.sb = G.Bc; aa.tb = zero;
+                aa.per_sample = 0; aa.out = c.w.g_tmp; aa.B = c.B; aa.C = a.Cin; aa.HW = a.H * a.W;
+                DMB_TRY(affine_add(aa, st));
+                a.x = c.w.g_tmp;
+            }
+            a.wtm = c.packed + l.pdtm_off; a.bias = zero; a.y = gout; a.skip = skip; a.dg = 1;
+            if (gate) { a.mask_src = gate->p; a.mask_s = gate->s; a.mask_t = gate->t; }
+            a.stats = stats; a.stat_src = stat_src; a.stats_batch = 1; a.stat_rows = &stat_rows;
+            if (nbands) *nbands = 0;
+            DMB_TRY(conv_tm(a, st));
+            if (!stats) stat_rows = 0;
+            return 0;
+        }
         if (up) {
             ConvTFwdArgs a{};
             a.x = G.g; a.x2 = G.y; a.in_scale = G.A; a.in_b = G.Bc; a.in_shift = G.Cc; a.in_per_sample = ps();
@@ -985,8 +1037,10 @@ struct Bwd {
         BnWs& bw = c.w.bn[l.bn];
         BnBwdArgs a{};
         a.partials = bb.part; a.B = (int)c.B; a.nbands = nbands; a.C = l.cout; a.count_per_sample = count;
+        a.rows = stat_rows;      // (set by the dgrad_layer call that left these sums)
         if (c.synced()) {
-            DMB_TRY(c.exchange(bb.part, c.B * nbands, l.cout, bb.gsum));
+            DMB_TRY(c.exchange(bb.part, stat_rows > 0 ? stat_rows : c.B * nbands, l.cout, bb.gsum));
+            a.rows = 0;
             a.partials = bb.gsum; a.B = 1; a.nbands = 1; a.count_per_sample = count * c.B * c.sync->world;
             a.grad_div = c.sync->world;
         }
@@ -1111,11 +1165,13 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
     G = GradT(); G.g = w.g_t3;
     DMB_TRY(B.wgrad_layer(L.d2, G, t2, false, H / 2, W / 2, false));
     DMB_TRY(B.dgrad_layer(L.d2, G, H / 2, W / 2, w.g_t2, &t2, nullptr, w.bias_part, nullptr, &nb));
-    DMB_TRY(sum_partials(w.bias_part, (int)c.B, nb, h4, grads + L.convs[L.d1].b_off, st));
+    DMB_TRY(sum_partials(w.bias_part, B.stat_rows > 0 ? 1 : (int)c.B, B.stat_rows > 0 ? B.stat_rows : nb, h4,
+                         grads + L.convs[L.d1].b_off, st));
     G = GradT(); G.g = w.g_t2;
     DMB_TRY(B.wgrad_layer(L.d1, G, t1, false, H / 4, W / 4, false));
     DMB_TRY(B.dgrad_layer(L.d1, G, H / 4, W / 4, w.g_t1, &t1, nullptr, w.bias_part, nullptr, &nb));
-    DMB_TRY(sum_partials(w.bias_part, (int)c.B, nb, h2, grads + L.convs[L.d0].b_off, st));
+    DMB_TRY(sum_partials(w.bias_part, B.stat_rows > 0 ? 1 : (int)c.B, B.stat_rows > 0 ? B.stat_rows : nb, h2,
+                         grads + L.convs[L.d0].b_off, st));
     G = GradT(); G.g = w.g_t1;
     DMB_TRY(B.wgrad_layer(L.d0, G, za, false, lh, lw, false));
     DMB_TRY(B.dgrad_layer(L.d0, G, lh, lw, w.g_za, nullptr, nullptr, nullptr, nullptr, nullptr));
@@ -1455,6 +1511,33 @@ int dmb_conv2d_tm_bn(const float* x, const float* w_packed, const float* bias, f
     a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
     a.bn = 1; a.in_scale = in_scale; a.in_shift = in_shift; a.in_per_sample = in_per_sample; a.in_relu = in_relu;
     a.stats = stats;
+    return conv_tm(a, st);
+}
+
+int dmb_conv2d_tm_batch_stat_rows(int32_t* rows) {
+    DMB_CHECK(rows != nullptr, "dmb_conv2d_tm_batch_stat_rows: null output");
+    *rows = TM_BATCH_ROWS_MAX;
+    return 0;
+}
+
+int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64_t batch, int32_t cin, int32_t h, int32_t w,
+                        int32_t cout, int32_t ksize, int32_t stride, const float* mask_src, const float* mask_scale,
+                        const float* mask_shift, const float* skip, double* stats, const float* stat_src,
+                        int32_t* stat_rows, float* scratch, void* stream) {
+    DMB_CHECK(gy && w_packed && gx && scratch, "dmb_conv2d_tm_dgrad: null pointer");
+    DMB_CHECK(conv_tm_dg_supported(cin, cout, ksize, stride, h, w), "dmb_conv2d_tm_dgrad: %dx%d s%d %d->%d @%dx%d is not one "
+              "of the data-gradient shapes this kernel is built for", ksize, ksize, stride, cin, cout, h, w);
+    DMB_CHECK(!stats || stat_rows, "dmb_conv2d_tm_dgrad: stats needs stat_rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    DMB_TRY(pack_tm_weights(w_packed, scratch, cin, cout, ksize, st));
+    const int64_t wf = (conv_tm_weight_floats(cin, cout, ksize) + 63) & ~63ll;
+    float* zero = scratch + wf;
+    DMB_CUDA(cudaMemsetAsync(zero, 0, sizeof(float) * cout, st));
+    ConvTmArgs a{};
+    a.x = gy; a.wtm = scratch; a.bias = zero; a.y = gx; a.skip = skip;
+    a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
+    a.dg = 1; a.mask_src = mask_src; a.mask_s = mask_scale; a.mask_t = mask_shift;
+    a.stats = stats; a.stat_src = stat_src; a.stats_batch = 1; a.stat_rows = stat_rows;
     return conv_tm(a, st);
 }
 

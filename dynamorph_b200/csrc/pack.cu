@@ -175,6 +175,10 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
                                              t.cin, t.cout, t.ks});
                 }
             }
+        if (bn_mode != DMB_BN_EVAL)             // training: images of the data-gradient weights (channels swapped)
+            for (const ConvL& c : L.convs)
+                if (c.pdtm_off >= 0)
+                    jobs.push_back(TmPackJob{packed + c.pdw_off, packed + c.pdtm_off, c.cout, c.cin, c.ks});
         if (!jobs.empty()) DMB_TRY(pack_tm_weights_multi(jobs.data(), (int)jobs.size(), st));
     }
     if (L.tc && bn_mode == DMB_BN_EVAL) {        // split, swizzled tiles of the folded weights for conv_tc.cu

@@ -189,6 +189,22 @@ int dmb_conv2d_tm_bn(const float* x, const float* w_packed, const float* bias, f
                      int32_t h, int32_t w, int32_t cout, int32_t ksize, int32_t stride, const float* in_scale,
                      const float* in_shift, int32_t in_per_sample, int32_t in_relu, double* stats, int32_t* bands,
                      float* scratch, void* stream);
+/* Data gradient of a training step on the same kernel (whole-batch BatchNorm; autograd of F.conv2d w.r.t. its input,
+ * run_training.py:406): gx = conv(gy) with the data-gradient weights w_packed [Cin][k][k][Cout] (Cin = channels of gy;
+ * stride-1 layers: the layer's weight with channels swapped and taps flipped; a ConvTranspose2d back-propagates through
+ * the 4x4 stride-2 convolution of its own taps), then the epilogue of the CUDA-core data-gradient kernels:
+ *   gx *= [mask_src * mask_scale[c] + mask_shift[c] > 0]   (ReLU gate of the producer; NULL = none, scale NULL = identity)
+ *   gx += skip                                              (NULL = none)
+ *   stats (may be NULL): per-CTA partial (sum gx, sum gx * stat_src) -- (sum gx, sum gx^2) without stat_src -- as
+ *   *stat_rows rows of [Cout][2] doubles (at most dmb_conv2d_tm_batch_stat_rows() rows), the input of the next
+ *   BatchNorm backward / bias gradient.
+ * Shapes (cin -> cout of THIS convolution): 1x1 16 -> 32 @16, 3x3 32 -> 16 @16, 3x3 16 -> 16 @16, 4x4 s2 8 -> 16 @64,
+ * 4x4 s2 16 -> 16 @32.  scratch: dmb_conv2d_tm_scratch_floats(cin, cout, k) rounded up to 64, + cout floats.          */
+int dmb_conv2d_tm_batch_stat_rows(int32_t* rows);
+int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64_t batch, int32_t cin, int32_t h, int32_t w,
+                        int32_t cout, int32_t ksize, int32_t stride, const float* mask_src, const float* mask_scale,
+                        const float* mask_shift, const float* skip, double* stats, const float* stat_src,
+                        int32_t* stat_rows, float* scratch, void* stream);
 /* One whole ResidualBlock layer of the default configuration at the 16x16 latent (vq_vae.py:203-209, :222-225, eval mode
  * with BatchNorm folded): y = x + conv1x1(relu(conv3x3(relu(x)) + bias1)) + bias2 in ONE tensor-core kernel; the 1x1 is a
  * second GEMM whose activation operand is written to tensor memory by the first one's epilogue.  x, y (B,16,16,16);

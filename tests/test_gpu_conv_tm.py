@@ -136,3 +136,54 @@ def test_tm_rejects_other_shapes():
     y = torch.zeros(1, 16, 16, 16, device="cuda")
     with pytest.raises(DmbError, match="thin encoder shapes"):
         call("dmb_conv2d_tm", ptr(x), ptr(w), ptr(b), ptr(y), 1, 8, 32, 32, 16, 4, 2, 0, None, 0, ptr(w), _stream())
+
+
+# (ksize, stride, cin, cout, input width) of the data-gradient convolutions: residual 1x1 / 3x3, enc.10, and the stride-2
+# convolutions that back-propagate through the decoder's ConvTranspose2d layers
+DG_SHAPES = [(1, 1, 16, 32, 16), (3, 1, 32, 16, 16), (3, 1, 16, 16, 16), (4, 2, 8, 16, 64), (4, 2, 16, 16, 32)]
+
+
+@pytest.mark.parametrize("shape", DG_SHAPES, ids=lambda s: "k%ds%d_%dto%d_w%d" % s)
+@pytest.mark.parametrize("B,extras", [(2, False), (5, True), (300, True)])
+def test_tm_conv_data_gradient_form(shape, B, extras):
+    """The training step's data-gradient form: plain gradient in, then gate by the producer's ReLU
+    ([mask_src * s + t > 0]), skip gradient, and per-CTA partial sums (sum gx, sum gx * stat_src) whose fold equals the
+    float64 sums -- the epilogue contract of the CUDA-core data-gradient kernels (csrc/conv_fwd.cu)."""
+    from dynamorph_b200._lib import call, ptr
+    ks, stride, cin, cout, W = shape
+    gy, w, _, g = _inputs(shape, B, seed=11)
+    wp = w.permute(1, 2, 3, 0).contiguous()
+    n = C.c_int64()
+    call("dmb_conv2d_tm_scratch_floats", cin, cout, ks, C.byref(n))
+    scratch = torch.zeros(((n.value + 63) // 64) * 64 + cout, device="cuda")
+    Ho = W // stride
+    gx = torch.empty(B, cout, Ho, Ho, device="cuda")
+    zero = torch.zeros(cout, device="cuda")
+    ref = _ref(gy, w, zero, ks, stride)
+    rows_max = C.c_int32()
+    call("dmb_conv2d_tm_batch_stat_rows", C.byref(rows_max))
+    if not extras:
+        call("dmb_conv2d_tm_dgrad", ptr(gy), ptr(wp), ptr(gx), B, cin, W, W, cout, ks, stride, None, None, None, None,
+             None, None, None, ptr(scratch), _stream())
+        assert _err(gx, ref) < TOL
+        return
+    mask_src = torch.randn(B, cout, Ho, Ho, device="cuda", generator=g)
+    ms = torch.rand(cout, device="cuda", generator=g) + 0.5
+    mt = torch.randn(cout, device="cuda", generator=g) * 0.3
+    skip = torch.randn(B, cout, Ho, Ho, device="cuda", generator=g)
+    src = torch.randn(B, cout, Ho, Ho, device="cuda", generator=g)
+    gate = ((mask_src * ms.reshape(1, -1, 1, 1) + mt.reshape(1, -1, 1, 1)) > 0).double().cpu()
+    ref = ref * gate + skip.double().cpu()
+    for stat_src in (src, None):
+        stats = torch.full((rows_max.value * cout * 2,), float("nan"), dtype=torch.float64, device="cuda")
+        rows = C.c_int32()
+        call("dmb_conv2d_tm_dgrad", ptr(gy), ptr(wp), ptr(gx), B, cin, W, W, cout, ks, stride, ptr(mask_src), ptr(ms),
+             ptr(mt), ptr(skip), ptr(stats), ptr(stat_src), C.byref(rows), ptr(scratch), _stream())
+        torch.cuda.synchronize()
+        assert _err(gx, ref) < TOL
+        assert 0 < rows.value <= rows_max.value and rows.value % 4 == 0
+        got = stats[:rows.value * cout * 2].reshape(rows.value, cout, 2).sum(0).cpu()
+        gd = gx.double().cpu()
+        other = src.double().cpu() if stat_src is not None else gd
+        assert torch.allclose(got[:, 0], gd.sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(got[:, 1], (gd * other).sum((0, 2, 3)), rtol=1e-5, atol=1e-3)

@@ -356,5 +356,7 @@ int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx,
                       float g_loss_scale, float beta, int64_t batch, int d, int p, int k, float* grad_z,
                       float* grad_codebook, double* stats, const float* stat_src, float* scratch, int scratch_rows,
                       cudaStream_t st);
+int vq_codebook_grad_only(const float* z, const float* codebook, const int32_t* idx, float g_loss_scale, int64_t batch,
+                          int d, int p, int k, float* grad_codebook, float* scratch, int scratch_rows, cudaStream_t st);
 
 }  // namespace dmb

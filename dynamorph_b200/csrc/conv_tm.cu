@@ -495,9 +495,11 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                     if constexpr (C::NACC == 2)
                         val += __uint_as_float(r[1][0][c]) + __uint_as_float(r[1][1][c]);
                     val += bias_r[c];
+                    [[maybe_unused]] float mraw = 0.f;
                     if constexpr (C::DG) {
                         if (dg.mask_src) {
                             float mv = __ldg(dg.mask_src + chan0 + (size_t)c * (C::HO * C::WO));
+                            mraw = mv;
                             if (dg.mask_s) mv = fmaf(mv, __ldg(dg.mask_s + wg * HALF + c), __ldg(dg.mask_t + wg * HALF + c));
                             if (!(mv > 0.f)) val = 0.f;
                         }
@@ -508,7 +510,10 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                     if constexpr (C::STATS) {
                         ssum[c] = val; ssq[c] = val * val;
                         if constexpr (C::DG) {
-                            if (dg.stat_src) ssq[c] = val * __ldg(dg.stat_src + chan0 + (size_t)c * (C::HO * C::WO));
+                            // (the BatchNorm whose backward sums these are is usually the one whose output gates: one load)
+                            if (dg.stat_src)
+                                ssq[c] = val * (dg.stat_src == dg.mask_src ? mraw
+                                                                           : __ldg(dg.stat_src + chan0 + (size_t)c * (C::HO * C::WO)));
                         }
                     }
                 }
@@ -762,13 +767,14 @@ bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W) {
 
 // shapes of the data-gradient form, named by the data-gradient convolution's own (cin, cout): the default model's
 // residual 1x1 (16 -> 32) and 3x3 (32 -> 16), enc.10 (16 -> 16) and the stride-2 convolutions that back-propagate through
-// the decoder's ConvTranspose2d 16 -> 8 (at 64 x 64) and 16 -> 16 (at 32 x 32)
+// a ConvTranspose2d 16 -> 8 (output 64 x 64 or 32 x 32: the default decoder's first layer) and 16 -> 16 (output 32 x 32)
 bool conv_tm_dg_supported(int cin, int cout, int ks, int stride, int H, int W) {
     if (H != W) return false;
     return (ks == 1 && stride == 1 && cin == 16 && cout == 32 && W == 16) ||
            (ks == 3 && stride == 1 && cin == 32 && cout == 16 && W == 16) ||
            (ks == 3 && stride == 1 && cin == 16 && cout == 16 && W == 16) ||
            (ks == 4 && stride == 2 && cin == 8 && cout == 16 && W == 64) ||
+           (ks == 4 && stride == 2 && cin == 8 && cout == 16 && W == 32) ||
            (ks == 4 && stride == 2 && cin == 16 && cout == 16 && W == 32);
 }
 
@@ -823,7 +829,8 @@ int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
         if (a.ks == 1) return launch_tm<TM<1, 1, 16, 32, 16, false, false, false, true>>(a, st);
         if (a.ks == 3 && a.Cin == 32) return launch_tm<TM<3, 1, 32, 16, 16, false, false, false, true>>(a, st);
         if (a.ks == 3) return launch_tm<TM<3, 1, 16, 16, 16, false, false, false, true>>(a, st);
-        if (a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 64, false, false, false, true>>(a, st);
+        if (a.Cin == 8 && a.W == 64) return launch_tm<TM<4, 2, 8, 16, 64, false, false, false, true>>(a, st);
+        if (a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 32, false, false, false, true>>(a, st);
         return launch_tm<TM<4, 2, 16, 16, 32, false, false, false, true>>(a, st);
     }
     DMB_CHECK(!a.mask_src && !a.stat_src, "conv_tm: gate / stat_src belong to the data-gradient form (dg = 1)");

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) dec_tail_forward_kernel(const TailArgs a)
 }
 
 template <int CM, int NI>
-__global__ void __launch_bounds__(256) dec_tail_backward_kernel(const TailArgs a) {
+__global__ void __launch_bounds__(256, (CM <= 4) ? 4 : 1) dec_tail_backward_kernel(const TailArgs a) {
     pdl_wait();
     constexpr int NV = NI * CM + NI + CM;
     __shared__ double red[8][NV];
@@ -100,48 +100,57 @@ __global__ void __launch_bounds__(256) dec_tail_backward_kernel(const TailArgs a
 #pragma unroll
         for (int c = 0; c < CM; ++c) w[c][o] = __ldg(a.w + c * NI + o);
     }
-    double sums[NV];
+    // per-thread partial sums in float (a thread adds a few dozen products; the cross-thread tree below is double)
+    float sums[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) sums[j] = 0.0;
+    for (int j = 0; j < NV; ++j) sums[j] = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.quads; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = i / a.hw4;
         const int64_t q = i - b * a.hw4;
-        float4 gd[NI];
+        // every load of the iteration is issued before the first use (one DRAM round trip per quad, not two)
+        float4 d[NI], v[NI], mk[NI], t[CM];
 #pragma unroll
         for (int o = 0; o < NI; ++o) {
             const int64_t pi = (b * NI + o) * a.hw4 + q;
-            const float4 d = ld4(a.decoded, pi), v = ld4(a.x, pi);
-            float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (a.mask) mk = ld4(a.mask, (a.mask_c == 1) ? (b * a.hw4 + q) : pi);
+            d[o] = ld4(a.decoded, pi); v[o] = ld4(a.x, pi);
+            mk[o] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (a.mask) mk[o] = ld4(a.mask, (a.mask_c == 1) ? (b * a.hw4 + q) : pi);
+        }
+#pragma unroll
+        for (int c = 0; c < CM; ++c) t[c] = ld4(a.t3, (b * CM + c) * a.hw4 + q);      // post-ReLU: relu'(.) = (t > 0)
+        float4 gd[NI];
+#pragma unroll
+        for (int o = 0; o < NI; ++o) {
             // d/d dec of  scale * sum ((dec*m - x*m)^2 / cv)  =  scale * 2 (dec*m - x*m) m / cv
-            gd[o].x = k2[o] * (d.x * mk.x - v.x * mk.x) * mk.x; gd[o].y = k2[o] * (d.y * mk.y - v.y * mk.y) * mk.y;
-            gd[o].z = k2[o] * (d.z * mk.z - v.z * mk.z) * mk.z; gd[o].w = k2[o] * (d.w * mk.w - v.w * mk.w) * mk.w;
-            sums[NI * CM + o] += (double)((gd[o].x + gd[o].y) + (gd[o].z + gd[o].w));
+            gd[o].x = k2[o] * (d[o].x * mk[o].x - v[o].x * mk[o].x) * mk[o].x;
+            gd[o].y = k2[o] * (d[o].y * mk[o].y - v[o].y * mk[o].y) * mk[o].y;
+            gd[o].z = k2[o] * (d[o].z * mk[o].z - v[o].z * mk[o].z) * mk[o].z;
+            gd[o].w = k2[o] * (d[o].w * mk[o].w - v[o].w * mk[o].w) * mk[o].w;
+            sums[NI * CM + o] += (gd[o].x + gd[o].y) + (gd[o].z + gd[o].w);
         }
 #pragma unroll
         for (int c = 0; c < CM; ++c) {
             const int64_t pi = (b * CM + c) * a.hw4 + q;
-            const float4 t = ld4(a.t3, pi);                  // post-ReLU: relu'(.) = (t > 0)
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int o = 0; o < NI; ++o) {
                 g.x = fmaf(w[c][o], gd[o].x, g.x); g.y = fmaf(w[c][o], gd[o].y, g.y);
                 g.z = fmaf(w[c][o], gd[o].z, g.z); g.w = fmaf(w[c][o], gd[o].w, g.w);
-                sums[o * CM + c] += (double)(fmaf(gd[o].x, t.x, gd[o].y * t.y) + fmaf(gd[o].z, t.z, gd[o].w * t.w));
+                sums[o * CM + c] += fmaf(gd[o].x, t[c].x, gd[o].y * t[c].y) + fmaf(gd[o].z, t[c].z, gd[o].w * t[c].w);
             }
-            if (!(t.x > 0.f)) g.x = 0.f;
-            if (!(t.y > 0.f)) g.y = 0.f;
-            if (!(t.z > 0.f)) g.z = 0.f;
-            if (!(t.w > 0.f)) g.w = 0.f;
+            if (!(t[c].x > 0.f)) g.x = 0.f;
+            if (!(t[c].y > 0.f)) g.y = 0.f;
+            if (!(t[c].z > 0.f)) g.z = 0.f;
+            if (!(t[c].w > 0.f)) g.w = 0.f;
             reinterpret_cast<float4*>(a.g_t3)[pi] = g;
-            sums[NI * CM + NI + c] += (double)((g.x + g.y) + (g.z + g.w));
+            sums[NI * CM + NI + c] += (g.x + g.y) + (g.z + g.w);
         }
     }
     // warp tree (fixed order) -> eight warp rows -> one row per CTA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-        double s = sums[j];
+        double s = (double)sums[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) red[warp][j] = s;

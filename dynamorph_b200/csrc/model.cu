@@ -1138,6 +1138,13 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
 
     Act t3; t3.p = w.t3; Act t2; t2.p = w.t2; Act t1; t1.p = w.t1; Act za; za.p = w.za;
     GradT G;
+    {   // the codebook gradient needs nothing but the forward's z_before and indices: first job of the side stream,
+        // beside the decoder's data-gradient chain
+        cudaStream_t sw;
+        DMB_TRY(B.wgrad_stream(&sw));
+        DMB_TRY(vq_codebook_grad_only(w.zb, params + L.codebook_off, w.idx, grad_scale * m.weight_commitment, c.B, h,
+                                      lh * lw, m.num_embeddings, grads + L.codebook_off, w.vq_part, w.vq_part_rows, sw));
+    }
     if (dec_tail_on(m)) {
         // 0-1. reconstruction-loss gradient, dec.6 (1x1) weight / bias / data gradients and dec.4's bias gradient in
         // one pass over the full-resolution tensors (the loss gradient itself is never stored)
@@ -1183,7 +1190,7 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
     {
         const ConvL& lb = L.convs[L.enc_res[nres - 1].b];
         DMB_TRY(vq_backward_stats(w.zb, params + L.codebook_off, w.idx, w.g_za, g_tm, grad_scale * m.weight_commitment,
-                                  m.commitment_cost, c.B, h, P, m.num_embeddings, w.g_zb, grads + L.codebook_off,
+                                  m.commitment_cost, c.B, h, P, m.num_embeddings, w.g_zb, nullptr,
                                   w.bnb[lb.bn].part, w.erb[nres - 1], w.vq_part, w.vq_part_rows, st));
     }
     // 6. residual layers, last to first

@@ -295,25 +295,36 @@ __global__ void __launch_bounds__(128) vq_backward_kernel(
     const int k = live ? idx[n] : 0;
     const size_t base = (size_t)b * d * p + pos;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = 0; c < d; ++c) {
-        float gz = 0.f, sy = 0.f;
-        if (live) {
-            const float zv = __ldg(z + base + (size_t)c * p);
-            const float q = __ldg(cb + (size_t)k * d + c);
-            float g = g_zst ? __ldg(g_zst + base + (size_t)c * p) : 0.f;
-            if (g_extra) g += __ldg(g_extra + base + (size_t)c * p);
-            gz = g + coef * beta * (zv - q);
-            if (grad_z) grad_z[base + (size_t)c * p] = gz;
-            if (stats) sy = gz * __ldg(stat_src + base + (size_t)c * p);
-        }
-        if (stats) {
-            float s = gz;
+    // eight channels at a time: all of their loads are issued before the first use (the one-channel loop was a chain of
+    // DRAM round trips: 28 us for 4 MB at batch 256)
+    for (int c0 = 0; c0 < d; c0 += 8) {
+        float zv[8], q[8], g[8], sv[8];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const bool on = live && c < d;
+            const size_t o = base + (size_t)c * p;
+            zv[j] = on ? __ldg(z + o) : 0.f;
+            q[j] = on ? __ldg(cb + (size_t)k * d + c) : 0.f;
+            g[j] = (on && g_zst) ? __ldg(g_zst + o) : 0.f;
+            if (on && g_extra) g[j] += __ldg(g_extra + o);
+            sv[j] = (on && stats) ? __ldg(stat_src + o) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            if (c >= d) break;
+            const float gz = live ? g[j] + coef * beta * (zv[j] - q[j]) : 0.f;
+            if (live && grad_z) grad_z[base + (size_t)c * p] = gz;
+            if (stats) {
+                float s = gz, sy = gz * sv[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                }
+                if (lane == 0) { red[c][warp][0] = s; red[c][warp][1] = sy; }
             }
-            if (lane == 0) { red[c][warp][0] = s; red[c][warp][1] = sy; }
         }
     }
     if (stats) {
@@ -454,6 +465,13 @@ int vq_backward_stats(const float* z, const float* codebook, const int32_t* idx,
         DMB_TRY(vq_codebook_grad(z, codebook, idx, nullptr, g_loss_scale, total, d, p, k, grad_codebook, scratch,
                                  scratch_rows, st));
     return 0;
+}
+// the codebook gradient alone (the training step runs it beside the data-gradient chain, on the weight-gradient stream)
+int vq_codebook_grad_only(const float* z, const float* codebook, const int32_t* idx, float g_loss_scale, int64_t batch,
+                          int d, int p, int k, float* grad_codebook, float* scratch, int scratch_rows, cudaStream_t st) {
+    DMB_CHECK(d <= VQB_MAXD, "vq backward: embedding_dim %d > %d", d, VQB_MAXD);
+    return vq_codebook_grad(z, codebook, idx, nullptr, g_loss_scale, batch * p, d, p, k, grad_codebook, scratch,
+                            scratch_rows, st);
 }
 }  // namespace dmb
 

@@ -198,8 +198,8 @@ int dmb_conv2d_tm_bn(const float* x, const float* w_packed, const float* bias, f
  *   stats (may be NULL): per-CTA partial (sum gx, sum gx * stat_src) -- (sum gx, sum gx^2) without stat_src -- as
  *   *stat_rows rows of [Cout][2] doubles (at most dmb_conv2d_tm_batch_stat_rows() rows), the input of the next
  *   BatchNorm backward / bias gradient.
- * Shapes (cin -> cout of THIS convolution): 1x1 16 -> 32 @16, 3x3 32 -> 16 @16, 3x3 16 -> 16 @16, 4x4 s2 8 -> 16 @64,
- * 4x4 s2 16 -> 16 @32.  scratch: dmb_conv2d_tm_scratch_floats(cin, cout, k) rounded up to 64, + cout floats.          */
+ * Shapes (cin -> cout of THIS convolution): 1x1 16 -> 32 @16, 3x3 32 -> 16 @16, 3x3 16 -> 16 @16, 4x4 s2 8 -> 16 @64 and
+ * @32, 4x4 s2 16 -> 16 @32.  scratch: dmb_conv2d_tm_scratch_floats(cin, cout, k) rounded up to 64, + cout floats.          */
 int dmb_conv2d_tm_batch_stat_rows(int32_t* rows);
 int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64_t batch, int32_t cin, int32_t h, int32_t w,
                         int32_t cout, int32_t ksize, int32_t stride, const float* mask_src, const float* mask_scale,

@@ -140,7 +140,8 @@ def test_tm_rejects_other_shapes():
 
 # (ksize, stride, cin, cout, input width) of the data-gradient convolutions: residual 1x1 / 3x3, enc.10, and the stride-2
 # convolutions that back-propagate through the decoder's ConvTranspose2d layers
-DG_SHAPES = [(1, 1, 16, 32, 16), (3, 1, 32, 16, 16), (3, 1, 16, 16, 16), (4, 2, 8, 16, 64), (4, 2, 16, 16, 32)]
+DG_SHAPES = [(1, 1, 16, 32, 16), (3, 1, 32, 16, 16), (3, 1, 16, 16, 16), (4, 2, 8, 16, 64), (4, 2, 8, 16, 32),
+             (4, 2, 16, 16, 32)]
 
 
 @pytest.mark.parametrize("shape", DG_SHAPES, ids=lambda s: "k%ds%d_%dto%d_w%d" % s)

@@ -181,12 +181,19 @@ struct ConvTmArgs {
     const float* mask_s;
     const float* mask_t;
     const float* stat_src;
+    // ... with the BatchNorm backward in front of the layer applied on load (shapes: conv_tm_dg_dual):
+    //   x := in_a[c] * x + in_b[c] * x2 + in_c[c]   ([Cin] tables; x2 = the raw activation, same shape as x)
+    const float* x2;
+    const float* in_a;
+    const float* in_b;
+    const float* in_c;
 };
 constexpr int TM_MAX_SMS = 192;
 constexpr int TM_BATCH_ROWS_MAX = 4 * 2 * TM_MAX_SMS;
 int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W);     // statistics rows per patch (0: unsupported)
 bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
 bool conv_tm_dg_supported(int cin, int cout, int ks, int stride, int H, int W);
+bool conv_tm_dg_dual(int cin, int cout, int ks, int stride, int H, int W);
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);
 int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);
 constexpr int TM_PACK_MAX = 16;

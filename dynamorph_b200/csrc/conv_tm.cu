@@ -161,6 +161,12 @@ template <> struct TmemLd<16> {
             : "r"(taddr) : "memory");
     }
 };
+template <> struct TmemLd<32> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t* v) {
+        TmemLd<16>::ld(taddr, v);
+        TmemLd<16>::ld(taddr + 16u, v + 16);
+    }
+};
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // FUSE_ (3x3, 16 -> 32 only): the rest of a ResidualBlock layer rides on the same tile -- ReLU, the 1x1 convolution back
@@ -174,11 +180,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // BatchNorm-backward transform already applied), and the epilogue of the CUDA-core data-gradient kernels (conv_fwd.cu):
 // ReLU gate of the layer back-propagated into ([mask_src * mask_s[c] + mask_t[c] > 0]), skip gradient, store, and the
 // next BatchNorm backward's sums (sum o, sum o * stat_src) -- or (sum o, sum o^2) for a bias gradient -- per CTA.
+// DUAL_ (with DG_): the BatchNorm backward in front of the layer is applied on load,  x = A[c]*g + Bc[c]*y + Cc[c]  with g
+// and the raw activation y staged side by side (two TMA boxes per stage) -- otherwise the caller materialises it.
+// CT_: a ConvTranspose2d(4x4, stride 2, padding 1) CIN -> COUT/4 written as the 3x3 stride-1 convolution it is on the
+// INPUT grid: output pixel (2y + py, 2x + px) only sees input pixels (y + dy, x + dx) with dy in {-1, 0} (py = 0) or
+// {0, 1} (py = 1), so the four output phases are 4 * Cout "channels" n = (2 py + px) * Cout + co of one 3x3 kernel whose
+// unused taps are zero (pack_tm image with ct = 1); the epilogue scatters them (pixel shuffle): warp group = py, a
+// thread stores the px pair of its input pixel as one float2.  Statistics rows: one per (CTA, quadrant, py).
 template <int KS_, int S_, int CIN_, int COUT_, int WIN_, bool FUSE_ = false, bool INRELU_ = false, bool BN_ = false,
-          bool DG_ = false>
+          bool DG_ = false, bool DUAL_ = false, bool CT_ = false>
 struct TM {
+    static constexpr bool CT = CT_;
+    static constexpr int CT_C = COUT_ / 4;                   // CT: output channels of the transposed convolution
     static constexpr bool BN = BN_;
     static constexpr bool DG = DG_;
+    static constexpr bool DUAL = DUAL_;
     static constexpr bool STATS = BN_ || DG_;
     static constexpr int KS = KS_, S = S_, CIN = CIN_, COUT = COUT_, W = WIN_, H = WIN_;
     static constexpr bool FUSE = FUSE_;
@@ -212,7 +228,7 @@ struct TM {
     // 1.2e-6 for the FFMA kernels).  Chunk ky therefore accumulates into accumulator ky % NACC and the epilogue adds the
     // partial sums in round-to-nearest fp32.  Two accumulators where tensor memory allows it without losing the second
     // resident CTA: reading them back (LDTM, 64 B/clk per SM) is what a third and fourth would cost.
-    static constexpr int NACC = (NCH >= 2 && cpow2(D_COL + 2 * 2 * COUT) <= cpow2(D_COL + 2 * COUT)) ? 2 : 1;
+    static constexpr int NACC = (NCH >= 2 && COUT <= 32 && cpow2(D_COL + 2 * 2 * COUT) <= cpow2(D_COL + 2 * COUT)) ? 2 : 1;
     static constexpr int TMEM_COLS = cpow2(D_COL + NACC * 2 * COUT);
     // Two accumulator sets where they fit: the epilogue of tile t then runs AFTER this warp group's first chunk of tile
     // t+1 (ncu: 30 % of the stall samples sat on the wait for the tile's last MMAs in front of the epilogue)
@@ -222,15 +238,18 @@ struct TM {
     static constexpr int D_SET = NACC * 2 * COUT;
     static constexpr int CTAS = (TMEM_COLS <= 256) ? 2 : 1;  // per SM
     static constexpr int SMEM_BUDGET = (CTAS == 2 ? 110 : 200) * 1024;
-    static constexpr int NSTAGE_RAW = (SMEM_BUDGET - B_FLOATS * 4 - 2048) / ((IN_BYTES + 127) & ~127);
+    static constexpr int STAGE_BYTES = (((DUAL ? 2 : 1) * IN_BYTES) + 127) & ~127;
+    static constexpr int NSTAGE_RAW = (SMEM_BUDGET - B_FLOATS * 4 - 2048) / STAGE_BYTES;
     static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
-    static constexpr int STAGE_BYTES = (IN_BYTES + 127) & ~127;
     static constexpr size_t SMEM = 1024 + (size_t)B_FLOATS * 4 + (size_t)NSTAGE * STAGE_BYTES + 256 + 1024;  // + barriers + stat_red
     static constexpr int HALF = COUT / 2;                    // output channels per epilogue warp group
+    static constexpr int NS = CT ? CT_C : HALF;              // statistics channels a thread holds
+    static constexpr int STAT_ROWS = CT ? 8 : 4;             // whole-batch statistics rows per CTA
     static_assert(128 % WO == 0 && HO % TH == 0, "a tile is 128 consecutive output pixels of one patch");
     static_assert(WO <= 32 && 32 % WO == 0, "a warp covers whole output rows (shuffle neighbours)");
     static_assert(KC % 16 == 0 && KC <= 48 && CIN % CPC == 0, "chunk = 16..48 k values");
-    static_assert(COUT == 16 || COUT == 32, "N = Cout and 2*Cout must be legal MMA widths");
+    static_assert(COUT == 16 || COUT == 32 || (CT && COUT == 64), "N = Cout and 2*Cout must be legal MMA widths");
+    static_assert(!CT || (KS == 3 && S == 1 && !FUSE && !BN && !INRELU), "transposed form: 3x3 on the input grid");
     static_assert((NROWS * 128) % 1024 == 0, "operand tiles stay 1024-byte aligned");
     static_assert(TMEM_COLS <= 512 && NSTAGE >= 2, "resources");
     static_assert((KS == 1 && S == 1) || (KS == 3 && S == 1) || (KS == 4 && S == 2), "unsupported kernel");
@@ -239,6 +258,7 @@ struct TM {
                   "the fused tail is the 3x3 16 -> 32 -> 1x1 -> 16 residual layer");
     static_assert(!BN || (!FUSE && !INRELU), "BatchNorm form: ReLU on load is a run-time flag of the transform");
     static_assert(!DG || (!FUSE && !INRELU && !BN), "data-gradient form: plain input");
+    static_assert(!DUAL || (DG && KS != 4 && IN_BYTES % 128 == 0), "dual-tensor load: data-gradient form, stride 1");
 };
 
 struct TmKArgs {
@@ -265,11 +285,15 @@ struct TmDgArgs {
     const float* mask_s;    // its affine [Cout] (nullptr = identity)
     const float* mask_t;
     const float* stat_src;  // (B, Cout, Ho, Wo) or nullptr
+    const float* in_a;      // DUAL: x = in_a[c] * g + in_b[c] * y + in_c[c] per input channel (nullptr: g alone, one box)
+    const float* in_b;
+    const float* in_c;
 };
 
 template <class C>
 __global__ void __launch_bounds__(TM_THREADS, C::CTAS)
-conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const TmDgArgs dg) {
+conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const TmDgArgs dg,
+               const __grid_constant__ CUtensorMap tmap2) {
     constexpr int KS = C::KS, S = C::S, CIN = C::CIN, COUT = C::COUT, W = C::W, KC = C::KC, HALF = C::HALF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -319,6 +343,15 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                 if (n > 0) mbar_wait_sleep(in_empty + 8u * stage, (uint32_t)((n - 1) & 1));
                 const int b = (int)(tile / C::TILES), t = (int)(tile % C::TILES);
                 const uint32_t bar = in_full + 8u * stage;
+                if constexpr (C::DUAL) {
+                    const bool dual = dg.in_a != nullptr;
+                    mbar_expect_tx(bar, (uint32_t)(dual ? 2 * C::IN_BYTES : C::IN_BYTES));
+                    tma_load_4d(stage0_u + (uint32_t)(stage * C::STAGE_BYTES), &tmap, bar, 0, t * C::TH * S - C::PAD, b, 0);
+                    if (dual)
+                        tma_load_4d(stage0_u + (uint32_t)(stage * C::STAGE_BYTES + C::IN_BYTES), &tmap2, bar, 0,
+                                    t * C::TH * S - C::PAD, b, 0);
+                    continue;
+                }
                 mbar_expect_tx(bar, (uint32_t)C::IN_BYTES);
                 tma_load_4d(stage0_u + (uint32_t)(stage * C::STAGE_BYTES), &tmap, bar, 0, t * C::TH * S - C::PAD, b, 0);
             }
@@ -380,7 +413,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
         const bool left = (ox == 0), right = (ox == C::WO - 1);
         float bias_r[HALF];
 #pragma unroll
-        for (int c = 0; c < HALF; ++c) bias_r[c] = __ldg(a.bias + wg * HALF + c);
+        for (int c = 0; c < HALF; ++c) bias_r[c] = __ldg(a.bias + (C::CT ? c % C::CT_C : wg * HALF + c));
         uint32_t my_n = 0;                                   // chunks this group has produced (uses of its A buffer)
         [[maybe_unused]] double acc_s = 0.0, acc_q = 0.0;    // BN, stats_batch: this lane's channel over all tiles of the CTA
         [[maybe_unused]] int acc_chan = 0;
@@ -404,6 +437,11 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                 tsh = a.in_scale ? a.in_shift + tb : nullptr;
                 row_ok = (unsigned)(row0 + prow * S + ky) < (unsigned)C::H;
                 xf_lo = a.in_relu ? 0.f : -INFINITY;
+            }
+            [[maybe_unused]] bool dual = false;
+            if constexpr (C::DUAL) {
+                dual = dg.in_a != nullptr;
+                row_ok = (unsigned)(row0 + prow * S + ky) < (unsigned)C::H;
             }
             if (a.dbg & 4) {
 #pragma unroll
@@ -431,6 +469,13 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                     float f = rp[ci * C::RIN * W];
                     if constexpr (C::INRELU) f = fmaxf(f, 0.f);
                     if constexpr (C::BN) f = fmaxf(fmaf(f, sc, sh), xf_lo);
+                    if constexpr (C::DUAL) {
+                        if (dual) {      // BatchNorm backward on load; rows outside the image stay zero
+                            float ca = __ldg(dg.in_a + ci0 + ci), cb = __ldg(dg.in_b + ci0 + ci), cc = __ldg(dg.in_c + ci0 + ci);
+                            if (!row_ok) { ca = 0.f; cb = 0.f; cc = 0.f; }
+                            f = fmaf(f, ca, fmaf(rp[C::IN_FLOATS + ci * C::RIN * W], cb, cc));
+                        }
+                    }
                     const float up = __shfl_up_sync(0xffffffffu, f, 1), dn = __shfl_down_sync(0xffffffffu, f, 1);
                     v[ci * 3 + 0] = left ? 0.f : up;
                     v[ci * 3 + 1] = f;
@@ -439,6 +484,11 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                     float f = rp[ci * C::RIN * W];
                     if constexpr (C::INRELU) f = fmaxf(f, 0.f);
                     if constexpr (C::BN) f = fmaxf(fmaf(f, sc, sh), xf_lo);
+                    if constexpr (C::DUAL) {
+                        if (dual)
+                            f = fmaf(f, __ldg(dg.in_a + ci0 + ci),
+                                     fmaf(rp[C::IN_FLOATS + ci * C::RIN * W], __ldg(dg.in_b + ci0 + ci), __ldg(dg.in_c + ci0 + ci)));
+                    }
                     v[ci] = f;
                 }
             }
@@ -485,16 +535,52 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                 tc_fence_before();           // the accumulators may be overwritten once every warp has arrived
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty);
-                const size_t chan0 = ((size_t)b * COUT + wg * HALF) * (C::HO * C::WO) + pix;
-                float* yp = a.y + chan0;
-                const float* sp = a.skip ? a.skip + chan0 : nullptr;
-                [[maybe_unused]] float ssum[HALF], ssq[HALF];
-#pragma unroll
-                for (int c = 0; c < HALF; ++c) {
+                [[maybe_unused]] float ssum[C::NS], ssq[C::NS];
+                auto accv = [&](int c) {
                     float val = __uint_as_float(r[0][0][c]) + __uint_as_float(r[0][1][c]);
                     if constexpr (C::NACC == 2)
                         val += __uint_as_float(r[1][0][c]) + __uint_as_float(r[1][1][c]);
-                    val += bias_r[c];
+                    return val + bias_r[c];
+                };
+                if constexpr (C::CT) {
+                    // pixel shuffle: this group's columns are n = wg*HALF + px*CT_C + co  ->  output (co, 2y + wg, 2x + px)
+                    constexpr int CT_C = C::CT_C;
+                    constexpr size_t PLANE = (size_t)4 * C::HO * C::WO;
+                    const size_t o0 = (((size_t)b * CT_C) * (2 * C::HO) + 2 * (t * C::TH + prow) + wg) * (2 * C::WO) + 2 * ox;
+#pragma unroll
+                    for (int co = 0; co < CT_C; ++co) {
+                        float v0 = accv(co), v1 = accv(CT_C + co);
+                        [[maybe_unused]] float2 mraw = make_float2(0.f, 0.f);
+                        if constexpr (C::DG) {
+                            if (dg.mask_src) {
+                                mraw = __ldg(reinterpret_cast<const float2*>(dg.mask_src + o0 + co * PLANE));
+                                float m0 = mraw.x, m1 = mraw.y;
+                                if (dg.mask_s) {
+                                    const float ms = __ldg(dg.mask_s + co), mt = __ldg(dg.mask_t + co);
+                                    m0 = fmaf(m0, ms, mt); m1 = fmaf(m1, ms, mt);
+                                }
+                                if (!(m0 > 0.f)) v0 = 0.f;
+                                if (!(m1 > 0.f)) v1 = 0.f;
+                            }
+                        }
+                        if (a.out_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                        *reinterpret_cast<float2*>(a.y + o0 + co * PLANE) = make_float2(v0, v1);
+                        if constexpr (C::STATS) {
+                            ssum[co] = v0 + v1; ssq[co] = fmaf(v0, v0, v1 * v1);
+                            if (dg.stat_src) {
+                                const float2 sv = (dg.stat_src == dg.mask_src)
+                                                      ? mraw : __ldg(reinterpret_cast<const float2*>(dg.stat_src + o0 + co * PLANE));
+                                ssq[co] = fmaf(v0, sv.x, v1 * sv.y);
+                            }
+                        }
+                    }
+                } else {
+                const size_t chan0 = ((size_t)b * COUT + wg * HALF) * (C::HO * C::WO) + pix;
+                float* yp = a.y + chan0;
+                const float* sp = a.skip ? a.skip + chan0 : nullptr;
+#pragma unroll
+                for (int c = 0; c < HALF; ++c) {
+                    float val = accv(c);
                     [[maybe_unused]] float mraw = 0.f;
                     if constexpr (C::DG) {
                         if (dg.mask_src) {
@@ -517,6 +603,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                         }
                     }
                 }
+                }
                 if constexpr (C::STATS) {
                     // (sum, sum of squares) of this WARP's 32 pixels per channel, one partial row per warp (the four
                     // quadrants of a tile are four rows of the [B][TILES*4][Cout][2] partials: no shared memory, no
@@ -524,7 +611,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                     // half of the channels it holds and adds its partner's values for them, then plain butterflies --
                     // 9 (HALF = 8) or 16 (HALF = 16) shuffles per quantity instead of 5 per channel; fixed order.
                     if (a.stats) {
-                        int held = HALF;
+                        int held = C::NS;
                         int chan = 0;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) {
@@ -532,7 +619,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                                 const int half = held >> 1;
                                 const bool upper = (lane & o) != 0;
 #pragma unroll
-                                for (int i = 0; i < HALF / 2; ++i) {
+                                for (int i = 0; i < (C::NS + 1) / 2; ++i) {
                                     if (i < half) {
                                         const float send_s = upper ? ssum[i] : ssum[i + half];
                                         const float send_q = upper ? ssq[i] : ssq[i + half];
@@ -550,7 +637,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                             }
                         }
                         // lanes whose low bits (those of the plain butterfly steps) are zero publish their channel
-                        constexpr int PLAIN = (HALF == 8) ? 3 : 1;      // mask of the butterfly-only lane bits
+                        constexpr int PLAIN = 32 / C::NS - 1;            // mask of the butterfly-only lane bits
                         if (a.stats_batch) {
                             acc_s += (double)ssum[0]; acc_q += (double)ssq[0]; acc_chan = chan;
                         } else if ((lane & PLAIN) == 0) {
@@ -635,9 +722,10 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
             if (prev_tile >= 0) epilogue(prev_tile, it - 1, nullptr, 0);
         }
         if constexpr (C::STATS) {
-            constexpr int PLAIN = (HALF == 8) ? 3 : 1;
+            constexpr int PLAIN = 32 / C::NS - 1;
             if (a.stats && a.stats_batch && (lane & PLAIN) == 0) {       // (every CTA of the grid has at least one tile)
-                double* dst = a.stats + (((size_t)blockIdx.x * 4 + q) * COUT + wg * HALF + acc_chan) * 2;
+                double* dst = C::CT ? a.stats + ((((size_t)blockIdx.x * 4 + q) * 2 + wg) * C::CT_C + acc_chan) * 2
+                                    : a.stats + (((size_t)blockIdx.x * 4 + q) * COUT + wg * HALF + acc_chan) * 2;
                 dst[0] = acc_s; dst[1] = acc_q;
             }
         }
@@ -729,7 +817,19 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     k.wtm = a.wtm; k.bias = a.bias; k.y = a.y; k.skip = a.skip; k.bias2 = a.bias2;
     k.in_scale = a.in_scale; k.in_shift = a.in_shift; k.in_per_sample = a.in_per_sample; k.stats = a.stats;
     k.stats_batch = a.stats_batch;
-    TmDgArgs d{a.mask_src, a.mask_s, a.mask_t, a.stat_src};
+    TmDgArgs d{a.mask_src, a.mask_s, a.mask_t, a.stat_src, a.in_a, a.in_b, a.in_c};
+    CUtensorMap map2 = map;
+    if constexpr (C::DUAL) {
+        if (a.in_a) {
+            DMB_CHECK(a.x2 && a.in_b && a.in_c && !(reinterpret_cast<uintptr_t>(a.x2) & 15), "conv_tm: the dual-tensor load needs x2 (16-byte aligned) and all three coefficient tables");
+            const CUresult r2 = enc(&map2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.x2), gdim, gstr, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            DMB_CHECK(r2 == CUDA_SUCCESS, "conv_tm: cuTensorMapEncodeTiled failed (%d)", (int)r2);
+        }
+    } else {
+        DMB_CHECK(!a.in_a, "conv_tm: this layer shape has no dual-tensor load (materialise the BatchNorm-backward gradient)");
+    }
     k.ntiles = (int64_t)a.B * C::TILES;
     k.in_relu = a.in_relu; k.out_relu = a.out_relu;
     { const char* e = getenv("DMB_TM_DBG"); k.dbg = e ? atoi(e) : 0; }
@@ -747,8 +847,8 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     if (sms > TM_MAX_SMS) sms = TM_MAX_SMS;
     const int64_t grid = std::min<int64_t>(k.ntiles, (int64_t)sms * C::CTAS);
     DMB_CHECK(grid > 0, "conv_tm: empty launch");
-    if (a.stat_rows) *a.stat_rows = (int)grid * 4;
-    DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k, d);
+    if (a.stat_rows) *a.stat_rows = (int)grid * C::STAT_ROWS;
+    DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k, d, map2);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;
@@ -776,6 +876,11 @@ bool conv_tm_dg_supported(int cin, int cout, int ks, int stride, int H, int W) {
            (ks == 4 && stride == 2 && cin == 8 && cout == 16 && W == 64) ||
            (ks == 4 && stride == 2 && cin == 8 && cout == 16 && W == 32) ||
            (ks == 4 && stride == 2 && cin == 16 && cout == 16 && W == 32);
+}
+
+// ... of which these apply a BatchNorm backward on load (x2 / in_a / in_b / in_c)
+bool conv_tm_dg_dual(int cin, int cout, int ks, int stride, int H, int W) {
+    return conv_tm_dg_supported(cin, cout, ks, stride, H, W) && stride == 1 && !(ks == 3 && cin == 32);
 }
 
 int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W) {
@@ -826,9 +931,9 @@ int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
         DMB_CHECK((a.mask_s == nullptr) == (a.mask_t == nullptr) && (a.mask_src || !a.mask_s), "conv_tm: mask affine without a mask");
         DMB_CHECK(!a.stats || (a.stats_batch && a.stat_rows), "conv_tm: the data-gradient form leaves whole-batch sums");
         DMB_CHECK(a.stats || !a.stat_src, "conv_tm: stat_src without stats");
-        if (a.ks == 1) return launch_tm<TM<1, 1, 16, 32, 16, false, false, false, true>>(a, st);
+        if (a.ks == 1) return launch_tm<TM<1, 1, 16, 32, 16, false, false, false, true, true>>(a, st);
         if (a.ks == 3 && a.Cin == 32) return launch_tm<TM<3, 1, 32, 16, 16, false, false, false, true>>(a, st);
-        if (a.ks == 3) return launch_tm<TM<3, 1, 16, 16, 16, false, false, false, true>>(a, st);
+        if (a.ks == 3) return launch_tm<TM<3, 1, 16, 16, 16, false, false, false, true, true>>(a, st);
         if (a.Cin == 8 && a.W == 64) return launch_tm<TM<4, 2, 8, 16, 64, false, false, false, true>>(a, st);
         if (a.Cin == 8) return launch_tm<TM<4, 2, 8, 16, 32, false, false, false, true>>(a, st);
         return launch_tm<TM<4, 2, 16, 16, 32, false, false, false, true>>(a, st);

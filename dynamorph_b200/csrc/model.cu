@@ -974,7 +974,9 @@ struct Bwd {
             a.Cin = l.cout; a.Cout = l.cin; a.B = (int)c.B;
             if (l.transposed) { a.ks = 4; a.stride = 2; a.H = 2 * H; a.W = 2 * W; }
             else { a.ks = l.ks; a.stride = 1; a.H = H; a.W = W; }
-            if (G.A) {
+            if (G.A && conv_tm_dg_dual(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W)) {
+                a.x2 = G.y; a.in_a = G.A; a.in_b = G.Bc; a.in_c = G.Cc;       // BatchNorm backward applied on load
+            } else if (G.A) {
                 AffineAddArgs aa{};
                 aa.a = G.g; aa.sa = G.A; aa.ta = G.Cc; aa.b = G.y; aa.sb = G.Bc; aa.tb = zero;
                 aa.per_sample = 0; aa.out = c.w.g_tmp; aa.B = c.B; aa.C = a.Cin; aa.HW = a.H * a.W;
@@ -1528,13 +1530,18 @@ int dmb_conv2d_tm_batch_stat_rows(int32_t* rows) {
 }
 
 int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64_t batch, int32_t cin, int32_t h, int32_t w,
-                        int32_t cout, int32_t ksize, int32_t stride, const float* mask_src, const float* mask_scale,
+                        int32_t cout, int32_t ksize, int32_t stride, const float* y_raw, const float* ga, const float* gb,
+                        const float* gc, const float* mask_src, const float* mask_scale,
                         const float* mask_shift, const float* skip, double* stats, const float* stat_src,
                         int32_t* stat_rows, float* scratch, void* stream) {
     DMB_CHECK(gy && w_packed && gx && scratch, "dmb_conv2d_tm_dgrad: null pointer");
     DMB_CHECK(conv_tm_dg_supported(cin, cout, ksize, stride, h, w), "dmb_conv2d_tm_dgrad: %dx%d s%d %d->%d @%dx%d is not one "
               "of the data-gradient shapes this kernel is built for", ksize, ksize, stride, cin, cout, h, w);
     DMB_CHECK(!stats || stat_rows, "dmb_conv2d_tm_dgrad: stats needs stat_rows");
+    DMB_CHECK((ga != nullptr) == (y_raw != nullptr) && (ga != nullptr) == (gb != nullptr) && (ga != nullptr) == (gc != nullptr),
+              "dmb_conv2d_tm_dgrad: y_raw / ga / gb / gc come together");
+    DMB_CHECK(!ga || conv_tm_dg_dual(cin, cout, ksize, stride, h, w), "dmb_conv2d_tm_dgrad: this shape has no BatchNorm-"
+              "backward transform on load");
     cudaStream_t st = (cudaStream_t)stream;
     DMB_TRY(pack_tm_weights(w_packed, scratch, cin, cout, ksize, st));
     const int64_t wf = (conv_tm_weight_floats(cin, cout, ksize) + 63) & ~63ll;
@@ -1545,6 +1552,7 @@ int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64
     a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = ksize; a.stride = stride;
     a.dg = 1; a.mask_src = mask_src; a.mask_s = mask_scale; a.mask_t = mask_shift;
     a.stats = stats; a.stat_src = stat_src; a.stats_batch = 1; a.stat_rows = stat_rows;
+    a.x2 = y_raw; a.in_a = ga; a.in_b = gb; a.in_c = gc;
     return conv_tm(a, st);
 }
 

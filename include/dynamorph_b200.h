@@ -198,11 +198,14 @@ int dmb_conv2d_tm_bn(const float* x, const float* w_packed, const float* bias, f
  *   stats (may be NULL): per-CTA partial (sum gx, sum gx * stat_src) -- (sum gx, sum gx^2) without stat_src -- as
  *   *stat_rows rows of [Cout][2] doubles (at most dmb_conv2d_tm_batch_stat_rows() rows), the input of the next
  *   BatchNorm backward / bias gradient.
+ * y_raw / ga / gb / gc (all or none; stride-1 shapes except 3x3 32 -> 16): the BatchNorm backward in front of the layer
+ * applied on load, gy' = ga[c] * gy + gb[c] * y_raw + gc[c] (both tensors staged by TMA side by side).
  * Shapes (cin -> cout of THIS convolution): 1x1 16 -> 32 @16, 3x3 32 -> 16 @16, 3x3 16 -> 16 @16, 4x4 s2 8 -> 16 @64 and
  * @32, 4x4 s2 16 -> 16 @32.  scratch: dmb_conv2d_tm_scratch_floats(cin, cout, k) rounded up to 64, + cout floats.          */
 int dmb_conv2d_tm_batch_stat_rows(int32_t* rows);
 int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64_t batch, int32_t cin, int32_t h, int32_t w,
-                        int32_t cout, int32_t ksize, int32_t stride, const float* mask_src, const float* mask_scale,
+                        int32_t cout, int32_t ksize, int32_t stride, const float* y_raw, const float* ga, const float* gb,
+                        const float* gc, const float* mask_src, const float* mask_scale,
                         const float* mask_shift, const float* skip, double* stats, const float* stat_src,
                         int32_t* stat_rows, float* scratch, void* stream);
 /* One whole ResidualBlock layer of the default configuration at the 16x16 latent (vq_vae.py:203-209, :222-225, eval mode

@@ -17,15 +17,15 @@ calibrate(m, synthetic_patches(32, 1, dev))
 m.train()
 tr = FusedTrainer(m, lr=0.0, use_graph=False)      # lr 0: parameters never move
 x = synthetic_patches(B, 7, dev)
-tr._prepare(x, None)
-tr._static["x"].copy_(x)
+st = tr._plan(x, None)
+tr._load(st, x, None, None)
 ref = None
 bad = {}
 names = [(k, o, n) for k, o, n in tr.eng.param_slices()] if hasattr(tr.eng, "param_slices") else None
 for r in range(reps):
-    tr._fwd_bwd()
+    tr._fwd_bwd(st)
     torch.cuda.synchronize()
-    g = tr.grad.clone(); l = tr.losses.clone(); d = tr._static["decoded"].clone()
+    g = tr.grad.clone(); l = tr.losses.clone(); d = st.decoded.clone()
     if ref is None:
         ref = (g, l, d)
         continue

@@ -165,9 +165,19 @@ def test_tm_conv_data_gradient_form(shape, B, extras):
     call("dmb_conv2d_tm_batch_stat_rows", C.byref(rows_max))
     if not extras:
         call("dmb_conv2d_tm_dgrad", ptr(gy), ptr(wp), ptr(gx), B, cin, W, W, cout, ks, stride, None, None, None, None,
-             None, None, None, ptr(scratch), _stream())
+             None, None, None, None, None, None, None, ptr(scratch), _stream())
         assert _err(gx, ref) < TOL
         return
+    dual = stride == 1 and not (ks == 3 and cin == 32)       # BatchNorm backward applied on load
+    y_raw = ga = gb = gc = None
+    if dual:
+        y_raw = torch.randn(B, cin, W, W, device="cuda", generator=g)
+        ga = torch.rand(cin, device="cuda", generator=g) + 0.5
+        gb = torch.randn(cin, device="cuda", generator=g) * 0.3
+        gc = torch.randn(cin, device="cuda", generator=g) * 0.3
+        gt = (gy.double() * ga.double().reshape(1, -1, 1, 1) + y_raw.double() * gb.double().reshape(1, -1, 1, 1)
+              + gc.double().reshape(1, -1, 1, 1))
+        ref = _ref(gt, w, zero, ks, stride)
     mask_src = torch.randn(B, cout, Ho, Ho, device="cuda", generator=g)
     ms = torch.rand(cout, device="cuda", generator=g) + 0.5
     mt = torch.randn(cout, device="cuda", generator=g) * 0.3
@@ -178,8 +188,9 @@ def test_tm_conv_data_gradient_form(shape, B, extras):
     for stat_src in (src, None):
         stats = torch.full((rows_max.value * cout * 2,), float("nan"), dtype=torch.float64, device="cuda")
         rows = C.c_int32()
-        call("dmb_conv2d_tm_dgrad", ptr(gy), ptr(wp), ptr(gx), B, cin, W, W, cout, ks, stride, ptr(mask_src), ptr(ms),
-             ptr(mt), ptr(skip), ptr(stats), ptr(stat_src), C.byref(rows), ptr(scratch), _stream())
+        call("dmb_conv2d_tm_dgrad", ptr(gy), ptr(wp), ptr(gx), B, cin, W, W, cout, ks, stride, ptr(y_raw), ptr(ga), ptr(gb),
+             ptr(gc), ptr(mask_src), ptr(ms), ptr(mt), ptr(skip), ptr(stats), ptr(stat_src), C.byref(rows), ptr(scratch),
+             _stream())
         torch.cuda.synchronize()
         assert _err(gx, ref) < TOL
         assert 0 < rows.value <= rows_max.value and rows.value % 4 == 0

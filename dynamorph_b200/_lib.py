@@ -74,6 +74,8 @@ SIGNATURES = {
     "dmb_conv2d_tm_batch_stat_rows": [C.POINTER(_I32)],
     "dmb_conv2d_tm_dgrad": [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             C.POINTER(_I32), _P, _P],
+    "dmb_conv_transpose2d_tm": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                C.POINTER(_I32), _P, _P],
     "dmb_residual_layer_tm_scratch_floats": [C.POINTER(_I64)],
     "dmb_residual_layer_tm": [_P, _P, _P, _P, _P, _P, _I64, _P, _P],
     "dmb_conv2d_weight_grad_scratch_floats": [_I64, _I32, _I32, _I32, _I32, _I32, _I32, C.POINTER(_I64)],

@@ -187,6 +187,10 @@ struct ConvTmArgs {
     const float* in_a;
     const float* in_b;
     const float* in_c;
+    // transposed form (ct != 0): ConvTranspose2d(4x4, stride 2, padding 1) Cin -> Cout, x (B, Cin, H, W) -> y (B, Cout, 2H,
+    // 2W); wtm = pack_tm_weights_ct image; plain (bias + optional ReLU on store) or with dg = 1 (gate / sums / dual load;
+    // statistics rows: 8 per CTA).  Shapes: conv_tm_ct_supported.
+    int ct;
 };
 constexpr int TM_MAX_SMS = 192;
 constexpr int TM_BATCH_ROWS_MAX = 4 * 2 * TM_MAX_SMS;
@@ -194,10 +198,12 @@ int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W);     // s
 bool conv_tm_supported(int cin, int cout, int ks, int stride, int H, int W);
 bool conv_tm_dg_supported(int cin, int cout, int ks, int stride, int H, int W);
 bool conv_tm_dg_dual(int cin, int cout, int ks, int stride, int H, int W);
+bool conv_tm_ct_supported(int cin, int cout, int H, int W, bool dg);
+int pack_tm_weights_ct(const float* w_packed, float* out, int cin, int cout, cudaStream_t st);   // image: conv_tm_weight_floats(cin, 4*cout, 3)
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);
 int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);
 constexpr int TM_PACK_MAX = 16;
-struct TmPackJob { const float* w; float* out; int cin, cout, ks; };
+struct TmPackJob { const float* w; float* out; int cin, cout, ks; int ct; };      // ct: transposed form (w = [Cin][4][4][Cout])
 int pack_tm_weights_multi(const TmPackJob* jobs, int n, cudaStream_t st);      // all layers of a model in one launch
 int conv_tm(const ConvTmArgs& a, cudaStream_t st);
 

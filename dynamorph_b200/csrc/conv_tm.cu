@@ -691,10 +691,33 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
             }
         };
 
+        // DG: the epilogue reads the gate (and skip) tensor at the tile's output pixels -- cold lines whose DRAM latency
+        // nothing hid (the gather warps ARE the epilogue warps: +14 .. +30 us per launch at batch 256).  Each thread
+        // therefore asks for one or two of the tile's lines in L2 before it starts on the tile.
+        [[maybe_unused]] auto prefetch_out = [&](const float* base, int64_t tile) {
+            const int b = (int)(tile / C::TILES), t = (int)(tile % C::TILES);
+            constexpr int LPC = C::CT ? 16 : 4;                                  // 128-byte lines per channel and tile
+            constexpr int NL = (C::CT ? C::CT_C : COUT) * LPC;
+            const int me = warp * 32 + lane;
+#pragma unroll
+            for (int l0 = 0; l0 < NL; l0 += 256) {
+                const int l = l0 + me;
+                if (l < NL) {
+                    const int ch = l / LPC, seg = l % LPC;
+                    const float* p = C::CT ? base + ((size_t)b * C::CT_C + ch) * (4 * C::HO * C::WO) + (size_t)t * 512 + seg * 32
+                                           : base + ((size_t)b * COUT + ch) * (C::HO * C::WO) + (size_t)t * 128 + seg * 32;
+                    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+                }
+            }
+        };
         int it = 0;
         int64_t prev_tile = -1;
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
             const int stage = it % C::NSTAGE;
+            if constexpr (C::DG) {
+                if (dg.mask_src) prefetch_out(dg.mask_src, tile);
+                if (a.skip) prefetch_out(a.skip, tile);
+            }
             mbar_wait(in_full + 8u * stage, (uint32_t)((it / C::NSTAGE) & 1));
             const float* tin = reinterpret_cast<const float*>(stage0 + (size_t)stage * C::STAGE_BYTES);
             const int tb = (int)(tile / C::TILES), trow0 = (int)(tile % C::TILES) * C::TH * S - C::PAD;
@@ -769,7 +792,9 @@ __global__ void pack_tm_multi_kernel(const PackTmJobs jobs) {
     const TmPackJob& jb = jobs.j[blockIdx.y];
     const float* __restrict__ w = jb.w;
     float* __restrict__ out = jb.out;
-    const int cin = jb.cin, cout = jb.cout, ks = jb.ks;
+    // ct: the source is a transposed convolution's [Cin][4][4][Cout]; the image is that of the 3x3 convolution over the
+    // input grid with 4 * Cout phase channels n = (2 py + px) * Cout + co (conv_tm.cu, CT form)
+    const int cin = jb.cin, ks = jb.ct ? 3 : jb.ks, cout = jb.ct ? 4 * jb.cout : jb.cout;
     const int KC = ks * cin, K = ks * KC, NT = (K + 31) / 32, NR = 2 * cout;
     const int total = NT * 32 * cout;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -777,7 +802,16 @@ __global__ void pack_tm_multi_kernel(const PackTmJobs jobs) {
         float hi = 0.f, lo = 0.f;
         if (k < K) {
             const int ky = k / KC, r = k - ky * KC, ci = r / ks, kx = r - ci * ks;
-            const float wv = __ldg(w + ((size_t)(ci * ks + ky) * ks + kx) * cout + co);
+            float wv;
+            if (jb.ct) {
+                const int ph = co / jb.cout, c = co - ph * jb.cout, py = ph >> 1, px = ph & 1;
+                // output row 2y + py takes input row y + (ky - 1) through tap  py + 1 - 2 (ky - 1)  of the 4x4 kernel
+                const int ty = py + 3 - 2 * ky, tx = px + 3 - 2 * kx;
+                const bool on = (ky - 1 == -1 + py || ky - 1 == py) && (kx - 1 == -1 + px || kx - 1 == px);
+                wv = on ? __ldg(w + ((size_t)(ci * 4 + ty) * 4 + tx) * jb.cout + c) : 0.f;
+            } else {
+                wv = __ldg(w + ((size_t)(ci * ks + ky) * ks + kx) * cout + co);
+            }
             hi = __uint_as_float(tf32_rna_bits(wv));
             lo = wv - hi;
         }
@@ -878,6 +912,14 @@ bool conv_tm_dg_supported(int cin, int cout, int ks, int stride, int H, int W) {
            (ks == 4 && stride == 2 && cin == 16 && cout == 16 && W == 32);
 }
 
+// transposed form (ConvTranspose2d 4x4 s2 p1, cin -> cout, input H x W): the default decoder's first layer (plain: bias,
+// ReLU on store) and the data gradients of the encoder's stride-2 convolutions 16 -> 16 @32 and 8 -> 16 @64 (dg)
+bool conv_tm_ct_supported(int cin, int cout, int H, int W, bool dg) {
+    if (H != W) return false;
+    if (!dg) return cin == 16 && cout == 8 && W == 16;
+    return (cin == 16 && cout == 16 && W == 16) || (cin == 16 && cout == 8 && W == 32);
+}
+
 // ... of which these apply a BatchNorm backward on load (x2 / in_a / in_b / in_c)
 bool conv_tm_dg_dual(int cin, int cout, int ks, int stride, int H, int W) {
     return conv_tm_dg_supported(cin, cout, ks, stride, H, W) && stride == 1 && !(ks == 3 && cin == 32);
@@ -891,6 +933,11 @@ int conv_tm_bands(int cin, int cout, int ks, int stride, int H, int W) {
 int64_t conv_tm_weight_floats(int cin, int cout, int ks) {
     const int K = ks * ks * cin;
     return (int64_t)((K + 31) / 32) * 2 * cout * 32;
+}
+
+int pack_tm_weights_ct(const float* w_packed, float* out, int cin, int cout, cudaStream_t st) {
+    TmPackJob j{w_packed, out, cin, cout, 4, 1};
+    return pack_tm_weights_multi(&j, 1, st);
 }
 
 int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st) {
@@ -908,7 +955,8 @@ int pack_tm_weights_multi(const TmPackJob* jobs, int n, cudaStream_t st) {
         int most = 0;
         for (int i = 0; i < pj.n; ++i) {
             pj.j[i] = jobs[i0 + i];
-            const int total = ((pj.j[i].ks * pj.j[i].ks * pj.j[i].cin + 31) / 32) * 32 * pj.j[i].cout;
+            const int total = pj.j[i].ct ? ((9 * pj.j[i].cin + 31) / 32) * 32 * 4 * pj.j[i].cout
+                                         : ((pj.j[i].ks * pj.j[i].ks * pj.j[i].cin + 31) / 32) * 32 * pj.j[i].cout;
             if (total > most) most = total;
         }
         DMB_LAUNCH((pack_tm_multi_kernel), dim3((most + 255) / 256, pj.n), 256, 0, st, pj);
@@ -919,12 +967,29 @@ int pack_tm_weights_multi(const TmPackJob* jobs, int n, cudaStream_t st) {
 }
 
 int conv_tm(const ConvTmArgs& a, cudaStream_t st) {
-    DMB_CHECK(a.dg ? conv_tm_dg_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W)
-                   : conv_tm_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W),
-              "conv_tm: unsupported layer %dx%d s%d %d->%d @%dx%d", a.ks, a.ks, a.stride, a.Cin, a.Cout, a.H, a.W);
     DMB_CHECK(!(reinterpret_cast<uintptr_t>(a.x) & 15) && !(reinterpret_cast<uintptr_t>(a.wtm) & 15),
               "conv_tm: x and the weight image must be 16-byte aligned");
     DMB_CHECK(a.B > 0, "conv_tm: empty batch");
+    if (a.ct) {
+        // ConvTranspose2d 4x4 s2 p1 as a 3x3 convolution on the input grid + pixel shuffle
+        DMB_CHECK(conv_tm_ct_supported(a.Cin, a.Cout, a.H, a.W, a.dg != 0), "conv_tm: unsupported transposed layer %d->%d @%dx%d%s",
+                  a.Cin, a.Cout, a.H, a.W, a.dg ? " (data gradient)" : "");
+        DMB_CHECK(!a.bn && !a.bias2 && !a.in_relu && !a.in_scale && !a.skip, "conv_tm: the transposed form takes a plain input and no skip");
+        DMB_CHECK(!(reinterpret_cast<uintptr_t>(a.y) & 7), "conv_tm: y must be 8-byte aligned");
+        if (!a.dg) {
+            DMB_CHECK(!a.mask_src && !a.stat_src && !a.stats && !a.in_a, "conv_tm: gate / sums belong to the data-gradient form");
+            return launch_tm<TM<3, 1, 16, 32, 16, false, false, false, false, false, true>>(a, st);
+        }
+        DMB_CHECK(!a.out_relu, "conv_tm: no ReLU on store in the data-gradient form");
+        DMB_CHECK((a.mask_s == nullptr) == (a.mask_t == nullptr) && (a.mask_src || !a.mask_s), "conv_tm: mask affine without a mask");
+        DMB_CHECK(!a.stats || (a.stats_batch && a.stat_rows), "conv_tm: the data-gradient form leaves whole-batch sums");
+        DMB_CHECK(a.stats || !a.stat_src, "conv_tm: stat_src without stats");
+        if (a.Cout == 16) return launch_tm<TM<3, 1, 16, 64, 16, false, false, false, true, true, true>>(a, st);
+        return launch_tm<TM<3, 1, 16, 32, 32, false, false, false, true, true, true>>(a, st);
+    }
+    DMB_CHECK(a.dg ? conv_tm_dg_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W)
+                   : conv_tm_supported(a.Cin, a.Cout, a.ks, a.stride, a.H, a.W),
+              "conv_tm: unsupported layer %dx%d s%d %d->%d @%dx%d", a.ks, a.ks, a.stride, a.Cin, a.Cout, a.H, a.W);
     if (a.dg) {
         // data gradient of a training step: plain input, gate / skip / BatchNorm-backward sums in the epilogue
         DMB_CHECK(!a.bn && !a.bias2 && !a.in_relu && !a.out_relu && !a.in_scale, "conv_tm: the data-gradient form takes a plain input");

@@ -70,7 +70,7 @@ struct Builder {
     int conv(const std::string& key, int cin, int cout, int ks, int stride, bool transposed) {
         ConvL c{};
         c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.transposed = transposed; c.bn = -1;
-        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1; c.pdtm_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1; c.pdtm_off = -1; c.pctm_off = -1;
         c.w_off = take_param(key + ".weight", (int64_t)cin * cout * ks * ks);
         c.b_off = take_param(key + ".bias", cout);
         c.pw_off = take_packed((int64_t)cin * cout * ks * ks);
@@ -86,7 +86,7 @@ struct Builder {
         ConvL c{};
         c.cin = cin; c.cout = cmid; c.cmid = cmid; c.ks = 4; c.stride = 2; c.composite = 1; c.bn = -1;
         c.bias_classes = 1;
-        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1; c.pdtm_off = -1;
+        c.ptc_off = -1; c.pwn_off = -1; c.ptm_off = -1; c.ptm_tail = -1; c.pdtm_off = -1; c.pctm_off = -1;
         c.w0_off = take_param(key0 + ".weight", (int64_t)cmid * cin);
         c.b0_off = take_param(key0 + ".bias", cmid);
         c.w_off = take_param(key1 + ".weight", (int64_t)cmid * cmid * 16);
@@ -230,12 +230,26 @@ int build_layout(const dmb_model* m, Layout& L) {
             if (ci < 0) return;
             ConvL& c = L.convs[ci];
             if (c.pdw_off < 0 || c.composite) return;
+            if (!c.transposed && c.stride == 2) {
+                // the data gradient of a stride-2 convolution is a transposed convolution cout -> cin over its output map
+                if (c.ks == 4 && conv_tm_ct_supported(c.cout, c.cin, hh / 2, ww / 2, true))
+                    c.pdtm_off = B.take_packed(conv_tm_weight_floats(c.cout, 4 * c.cin, 3));
+                return;
+            }
             bool ok;
             if (c.transposed) ok = conv_tm_dg_supported(c.cout, c.cin, 4, 2, 2 * hh, 2 * ww);
             else ok = c.stride == 1 && conv_tm_dg_supported(c.cout, c.cin, c.ks, 1, hh, ww);
             if (ok) c.pdtm_off = B.take_packed(conv_tm_weight_floats(c.cout, c.cin, c.ks));
         };
+        auto want_ct = [&](int ci, int hh, int ww) {      // forward of a ConvTranspose2d in the transposed form
+            if (ci < 0) return;
+            ConvL& c = L.convs[ci];
+            if (c.transposed && c.ks == 4 && c.bn < 0 && conv_tm_ct_supported(c.cin, c.cout, hh, ww, false))
+                c.pctm_off = B.take_packed(conv_tm_weight_floats(c.cin, 4 * c.cout, 3));
+        };
         if (m->arch == DMB_ARCH_Z16) {
+            want_ct(L.d0, L.lh, L.lw);
+            want_dg(L.e2, H / 2, W / 2); want_dg(L.e3, H / 4, W / 4);
             want_dg(L.e4, H / 8, W / 8);
             want_dg(L.d0, L.lh, L.lw); want_dg(L.d1, 2 * L.lh, 2 * L.lw); want_dg(L.d2, 4 * L.lh, 4 * L.lw);
         }
@@ -353,7 +367,7 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             const int64_t hmax = (m.arch == DMB_ARCH_Z16 && (int)ci == L.e1) ? H / 2 :
                                  (((int)ci == L.e2 && m.arch == DMB_ARCH_Z16) ? H / 4 :
                                  ((m.arch == DMB_ARCH_Z32 && ((int)ci == L.e1 || (int)ci == L.d0)) ? H / 2 : L.lh));
-            const int64_t prow = (B * hmax > TM_BATCH_ROWS_MAX) ? B * hmax : TM_BATCH_ROWS_MAX;
+            const int64_t prow = (B * hmax > 2 * TM_BATCH_ROWS_MAX) ? B * hmax : 2 * TM_BATCH_ROWS_MAX;   // (transposed form: 8 rows per CTA)
             b.part = bp.take<double>(prow * c.cout * 2);
             b.A = bp.take<float>(rows * c.cout);
             b.Bc = bp.take<float>(rows * c.cout);
@@ -454,6 +468,11 @@ bool tm_dg_enabled() {      // data-gradient form of the tensor-memory kernels i
     return !(e && e[0] == '0');
 }
 
+bool tm_ct_enabled() {      // transposed form of the tensor-memory kernels (DMB_TM_CT=0: off)
+    const char* e = getenv("DMB_TM_CT");
+    return !(e && e[0] == '0');
+}
+
 bool tm_fuse_enabled() {
     const char* e = getenv("DMB_TM_FUSE");
     return !(e && e[0] == '0');
@@ -468,7 +487,16 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
     BnWs* bw = bn_live ? &c.w.bn[l.bn] : nullptr;
     int Ho, Wo;
     int stat_rows = 0;      // whole-batch statistics: rows of partials when that is not B * nbands
-    if (l.transposed) {
+    if (l.transposed && l.pctm_off >= 0 && !bn_live && !in.s && !in_relu && tm_ct_enabled() && c.B >= tm_min_batch() &&
+        conv_tm_ct_supported(l.cin, l.cout, H, W, false)) {
+        // ConvTranspose2d on the tensor cores: 3x3 on the input grid + pixel shuffle (conv_tm.cu, CT form)
+        ConvTmArgs a{};
+        a.x = in.p; a.wtm = c.packed + l.pctm_off; a.bias = c.packed + l.pb_off; a.y = out;
+        a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.ks = 4; a.stride = 2;
+        a.ct = 1; a.out_relu = out_relu;
+        DMB_TRY(conv_tm(a, c.st));
+        Ho = 2 * H; Wo = 2 * W;
+    } else if (l.transposed) {
         ConvTFwdArgs a{};
         a.x = in.p; a.y = out; a.w = c.packed + l.pw_off; a.bias = c.packed + l.pb_off;
         a.in_scale = in.s; a.in_shift = in.t; a.in_per_sample = c.per_sample(); a.in_relu = in_relu;
@@ -965,7 +993,23 @@ struct Bwd {
         const float* zero = c.packed + c.L.pzero_off;
         const bool up = (!l.transposed && l.stride == 2);      // conv stride 2 -> transposed-conv kernel
         stat_rows = 0;
-        if (l.pdtm_off >= 0 && !ps() && tm_dg_enabled() && c.B >= tm_min_batch() &&
+        if (up && l.pdtm_off >= 0 && !ps() && tm_dg_enabled() && tm_ct_enabled() && c.B >= tm_min_batch() && !skip &&
+            conv_tm_ct_supported(l.cout, l.cin, H / 2, W / 2, true)) {
+            // stride-2 convolution: its data gradient is a transposed convolution over the output map -- tensor cores,
+            // BatchNorm backward applied on load, gate and the next BatchNorm backward's sums in the epilogue
+            ConvTmArgs a{};
+            a.x = G.g; a.wtm = c.packed + l.pdtm_off; a.bias = zero; a.y = gout;
+            a.B = (int)c.B; a.Cin = l.cout; a.Cout = l.cin; a.H = H / 2; a.W = W / 2; a.ks = 4; a.stride = 2;
+            a.ct = 1; a.dg = 1;
+            if (G.A) { a.x2 = G.y; a.in_a = G.A; a.in_b = G.Bc; a.in_c = G.Cc; }
+            if (gate) { a.mask_src = gate->p; a.mask_s = gate->s; a.mask_t = gate->t; }
+            a.stats = stats; a.stat_src = stat_src; a.stats_batch = 1; a.stat_rows = &stat_rows;
+            if (nbands) *nbands = 0;
+            DMB_TRY(conv_tm(a, st));
+            if (!stats) stat_rows = 0;
+            return 0;
+        }
+        if (!up && l.pdtm_off >= 0 && !ps() && tm_dg_enabled() && c.B >= tm_min_batch() &&
             (!G.A || (c.w.g_tmp && H == L_lat_h() && W == L_lat_w() && !l.transposed))) {
             // tensor cores, activation operand in tensor memory (conv_tm.cu, data-gradient form).  A BatchNorm-backward
             // gradient  A*g + Bc*y + Cc  is materialised first (one small elementwise launch at the latent resolution).
@@ -1553,6 +1597,34 @@ int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64
     a.dg = 1; a.mask_src = mask_src; a.mask_s = mask_scale; a.mask_t = mask_shift;
     a.stats = stats; a.stat_src = stat_src; a.stats_batch = 1; a.stat_rows = stat_rows;
     a.x2 = y_raw; a.in_a = ga; a.in_b = gb; a.in_c = gc;
+    return conv_tm(a, st);
+}
+
+int dmb_conv_transpose2d_tm(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                            int32_t h, int32_t w, int32_t cout, int32_t out_relu, int32_t data_gradient, const float* y_raw,
+                            const float* ga, const float* gb, const float* gc, const float* mask_src,
+                            const float* mask_scale, const float* mask_shift, double* stats, const float* stat_src,
+                            int32_t* stat_rows, float* scratch, void* stream) {
+    DMB_CHECK(x && w_packed && y && scratch, "dmb_conv_transpose2d_tm: null pointer");
+    DMB_CHECK(conv_tm_ct_supported(cin, cout, h, w, data_gradient != 0), "dmb_conv_transpose2d_tm: %d->%d @%dx%d%s is not one of "
+              "the shapes this kernel is built for", cin, cout, h, w, data_gradient ? " (data gradient)" : "");
+    DMB_CHECK(data_gradient || (!y_raw && !ga && !gb && !gc && !mask_src && !mask_scale && !mask_shift && !stats && !stat_src),
+              "dmb_conv_transpose2d_tm: the BatchNorm-backward load, gate and sums belong to the data-gradient form");
+    DMB_CHECK((ga != nullptr) == (y_raw != nullptr) && (ga != nullptr) == (gb != nullptr) && (ga != nullptr) == (gc != nullptr),
+              "dmb_conv_transpose2d_tm: y_raw / ga / gb / gc come together");
+    DMB_CHECK(!stats || stat_rows, "dmb_conv_transpose2d_tm: stats needs stat_rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    DMB_TRY(pack_tm_weights_ct(w_packed, scratch, cin, cout, st));
+    const int64_t wf = (conv_tm_weight_floats(cin, 4 * cout, 3) + 63) & ~63ll;
+    float* zero = scratch + wf;
+    if (!bias) DMB_CUDA(cudaMemsetAsync(zero, 0, sizeof(float) * cout, st));
+    ConvTmArgs a{};
+    a.x = x; a.wtm = scratch; a.bias = bias ? bias : zero; a.y = y;
+    a.B = (int)batch; a.Cin = cin; a.H = h; a.W = w; a.Cout = cout; a.ks = 4; a.stride = 2;
+    a.ct = 1; a.dg = data_gradient ? 1 : 0; a.out_relu = out_relu;
+    a.x2 = y_raw; a.in_a = ga; a.in_b = gb; a.in_c = gc;
+    a.mask_src = mask_src; a.mask_s = mask_scale; a.mask_t = mask_shift;
+    a.stats = stats; a.stat_src = stat_src; a.stats_batch = stats ? 1 : 0; a.stat_rows = stat_rows;
     return conv_tm(a, st);
 }
 

@@ -29,6 +29,7 @@ struct ConvL {
     int64_t ptm_off;             // [b_hi; b_lo] operand image of the EVAL-folded weights for conv_tm.cu or -1
     int ptm_tail;                // conv whose image follows this one's (the 1x1 of a fused residual layer) or -1
     int64_t pdtm_off;            // conv_tm.cu image of the data-gradient weights (training step) or -1
+    int64_t pctm_off;            // ConvTranspose2d: conv_tm.cu image of the transposed form (3x3 on the input grid) or -1
 };
 
 struct Entry { std::string key; int which; int64_t off, numel; };

@@ -175,10 +175,16 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
                                              t.cin, t.cout, t.ks});
                 }
             }
+        for (const ConvL& c : L.convs)          // ConvTranspose2d layers in the transposed form
+            if (c.pctm_off >= 0) jobs.push_back(TmPackJob{packed + c.pw_off, packed + c.pctm_off, c.cin, c.cout, 4, 1});
         if (bn_mode != DMB_BN_EVAL)             // training: images of the data-gradient weights (channels swapped)
             for (const ConvL& c : L.convs)
-                if (c.pdtm_off >= 0)
-                    jobs.push_back(TmPackJob{packed + c.pdw_off, packed + c.pdtm_off, c.cout, c.cin, c.ks});
+                if (c.pdtm_off >= 0) {
+                    if (!c.transposed && c.stride == 2)      // data gradient = transposed convolution cout -> cin
+                        jobs.push_back(TmPackJob{packed + c.pdw_off, packed + c.pdtm_off, c.cout, c.cin, 4, 1});
+                    else
+                        jobs.push_back(TmPackJob{packed + c.pdw_off, packed + c.pdtm_off, c.cout, c.cin, c.ks, 0});
+                }
         if (!jobs.empty()) DMB_TRY(pack_tm_weights_multi(jobs.data(), (int)jobs.size(), st));
     }
     if (L.tc && bn_mode == DMB_BN_EVAL) {        // split, swizzled tiles of the folded weights for conv_tc.cu

@@ -208,6 +208,20 @@ int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64
                         const float* gc, const float* mask_src, const float* mask_scale,
                         const float* mask_shift, const float* skip, double* stats, const float* stat_src,
                         int32_t* stat_rows, float* scratch, void* stream);
+/* nn.ConvTranspose2d(cin, cout, 4, stride 2, padding 1) (vq_vae.py:292-296) on the same kernel: the layer is the 3x3
+ * convolution it amounts to on the INPUT grid with 4*cout phase channels (unused taps zero) followed by a pixel shuffle
+ * in the epilogue.  x (B, cin, h, w) -> y (B, cout, 2h, 2w); w_packed [cin][4][4][cout]; bias [cout] (NULL = none).
+ *   data_gradient = 0: bias, optional ReLU on store.  Shape: 16 -> 8 @16 (the default decoder's first layer).
+ *   data_gradient = 1: the data gradient of a stride-2 nn.Conv2d(cout -> cin, 4, 2, 1) of the training step
+ *     (w_packed = that layer's weight as [its Cout][4][4][its Cin]), with the extras of dmb_conv2d_tm_dgrad: BatchNorm
+ *     backward on load (y_raw / ga / gb / gc), ReLU gate, per-CTA sums (8 rows per CTA: at most twice
+ *     dmb_conv2d_tm_batch_stat_rows()).  Shapes: 16 -> 16 @16 (enc.7) and 16 -> 8 @32 (enc.4).
+ * scratch: dmb_conv2d_tm_scratch_floats(cin, 4*cout, 3) rounded up to 64, + cout floats.                            */
+int dmb_conv_transpose2d_tm(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,
+                            int32_t h, int32_t w, int32_t cout, int32_t out_relu, int32_t data_gradient, const float* y_raw,
+                            const float* ga, const float* gb, const float* gc, const float* mask_src,
+                            const float* mask_scale, const float* mask_shift, double* stats, const float* stat_src,
+                            int32_t* stat_rows, float* scratch, void* stream);
 /* One whole ResidualBlock layer of the default configuration at the 16x16 latent (vq_vae.py:203-209, :222-225, eval mode
  * with BatchNorm folded): y = x + conv1x1(relu(conv3x3(relu(x)) + bias1)) + bias2 in ONE tensor-core kernel; the 1x1 is a
  * second GEMM whose activation operand is written to tensor memory by the first one's epilogue.  x, y (B,16,16,16);

@@ -199,3 +199,64 @@ def test_tm_conv_data_gradient_form(shape, B, extras):
         other = src.double().cpu() if stat_src is not None else gd
         assert torch.allclose(got[:, 0], gd.sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
         assert torch.allclose(got[:, 1], (gd * other).sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
+
+
+# transposed form: (cin, cout, input width, data_gradient)
+CT_SHAPES = [(16, 8, 16, False), (16, 16, 16, True), (16, 8, 32, True)]
+
+
+@pytest.mark.parametrize("shape", CT_SHAPES, ids=lambda s: "%dto%d_w%d_%s" % (s[0], s[1], s[2], "dg" if s[3] else "fwd"))
+@pytest.mark.parametrize("B", [1, 5, 300])
+def test_tm_conv_transpose_form(shape, B):
+    """nn.ConvTranspose2d(4, 2, 1) as a 3x3 convolution on the input grid + pixel shuffle: the forward layer (bias, ReLU on
+    store) and the data gradient of a stride-2 convolution (BatchNorm backward on load, gate, per-CTA sums) against
+    torch's float64 conv_transpose2d."""
+    from dynamorph_b200._lib import call, ptr
+    cin, cout, W, dgrad = shape
+    g = torch.Generator(device="cuda").manual_seed(cin * 100 + cout + W + B)
+    x = torch.randn(B, cin, W, W, device="cuda", generator=g)
+    w = torch.randn(cin, cout, 4, 4, device="cuda", generator=g) * (cin * 4) ** -0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    wp = w.permute(0, 2, 3, 1).contiguous()                     # [cin][4][4][cout]
+    n = C.c_int64()
+    call("dmb_conv2d_tm_scratch_floats", cin, 4 * cout, 3, C.byref(n))
+    scratch = torch.zeros(((n.value + 63) // 64) * 64 + cout, device="cuda")
+    y = torch.full((B, cout, 2 * W, 2 * W), float("nan"), device="cuda")
+    if not dgrad:
+        for relu in (0, 1):
+            call("dmb_conv_transpose2d_tm", ptr(x), ptr(wp), ptr(bias), ptr(y), B, cin, W, W, cout, relu, 0, None, None, None,
+                 None, None, None, None, None, None, None, ptr(scratch), _stream())
+            ref = F.conv_transpose2d(x.double().cpu(), w.double().cpu(), bias.double().cpu(), stride=2, padding=1)
+            assert _err(y, ref.relu() if relu else ref) < TOL
+        return
+    y_raw = torch.randn(B, cin, W, W, device="cuda", generator=g)
+    ga = torch.rand(cin, device="cuda", generator=g) + 0.5
+    gb = torch.randn(cin, device="cuda", generator=g) * 0.3
+    gc = torch.randn(cin, device="cuda", generator=g) * 0.3
+    mask_src = torch.randn(B, cout, 2 * W, 2 * W, device="cuda", generator=g)
+    ms = torch.rand(cout, device="cuda", generator=g) + 0.5
+    mt = torch.randn(cout, device="cuda", generator=g) * 0.3
+    src = torch.randn(B, cout, 2 * W, 2 * W, device="cuda", generator=g)
+    # plain data gradient first
+    call("dmb_conv_transpose2d_tm", ptr(x), ptr(wp), None, ptr(y), B, cin, W, W, cout, 0, 1, None, None, None, None, None,
+         None, None, None, None, None, ptr(scratch), _stream())
+    assert _err(y, F.conv_transpose2d(x.double().cpu(), w.double().cpu(), None, stride=2, padding=1)) < TOL
+    xt = (x.double() * ga.double().reshape(1, -1, 1, 1) + y_raw.double() * gb.double().reshape(1, -1, 1, 1)
+          + gc.double().reshape(1, -1, 1, 1)).cpu()
+    gate = ((mask_src * ms.reshape(1, -1, 1, 1) + mt.reshape(1, -1, 1, 1)) > 0).double().cpu()
+    ref = F.conv_transpose2d(xt, w.double().cpu(), None, stride=2, padding=1) * gate
+    rows_max = C.c_int32()
+    call("dmb_conv2d_tm_batch_stat_rows", C.byref(rows_max))
+    for stat_src in (mask_src, src, None):
+        stats = torch.full((2 * rows_max.value * cout * 2,), float("nan"), dtype=torch.float64, device="cuda")
+        rows = C.c_int32()
+        call("dmb_conv_transpose2d_tm", ptr(x), ptr(wp), None, ptr(y), B, cin, W, W, cout, 0, 1, ptr(y_raw), ptr(ga), ptr(gb),
+             ptr(gc), ptr(mask_src), ptr(ms), ptr(mt), ptr(stats), ptr(stat_src), C.byref(rows), ptr(scratch), _stream())
+        torch.cuda.synchronize()
+        assert _err(y, ref) < TOL
+        assert 0 < rows.value <= 2 * rows_max.value and rows.value % 8 == 0
+        got = stats[:rows.value * cout * 2].reshape(rows.value, cout, 2).sum(0).cpu()
+        gd = y.double().cpu()
+        other = stat_src.double().cpu() if stat_src is not None else gd
+        assert torch.allclose(got[:, 0], gd.sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(got[:, 1], (gd * other).sum((0, 2, 3)), rtol=1e-5, atol=1e-3)

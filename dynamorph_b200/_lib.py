@@ -71,6 +71,7 @@ SIGNATURES = {
     "dmb_conv2d_tm_scratch_floats": [_I32, _I32, _I32, C.POINTER(_I64)],
     "dmb_conv2d_tm": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P],
     "dmb_conv2d_tm_bn": [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, C.POINTER(_I32), _P, _P],
+    "dmb_bn_count_batch": [_P, _I32, _P],
     "dmb_conv2d_tm_batch_stat_rows": [C.POINTER(_I32)],
     "dmb_conv2d_tm_dgrad": [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             C.POINTER(_I32), _P, _P],

@@ -32,6 +32,12 @@ __global__ void adam_tick_kernel(int* step, float* bc, float b1, float b2) {
     bc[0] = (float)(1.0 - pow((double)b1, (double)t));
     bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
 }
+// BatchNorm2d.num_batches_tracked += 1 for every BatchNorm of the model (one int64 each, flat)
+__global__ void bn_count_kernel(long long* nbt, int n) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nbt[i] += 1;
+}
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                                 const float* __restrict__ bc, float gscale) {
@@ -105,6 +111,15 @@ int dmb_adam_step_dev(float* params, const float* grads, float* exp_avg, float* 
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     DMB_LAUNCH((dmb::adam_dev_kernel), (unsigned)blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc_dev, grad_scale);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+int dmb_bn_count_batch(int64_t* num_batches_tracked, int32_t n, void* stream) {
+    DMB_CHECK(num_batches_tracked || n == 0, "dmb_bn_count_batch: null pointer");
+    if (n <= 0) return 0;
+    DMB_LAUNCH((dmb::bn_count_kernel), (n + 63) / 64, 64, 0, (cudaStream_t)stream, reinterpret_cast<long long*>(num_batches_tracked), n);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -198,10 +198,21 @@ class Engine:
             return BN_MODES[override]
         return BN_BATCH if self.module.training else BN_EVAL
 
+    def _count_batch(self):
+        """num_batches_tracked += 1 of every BatchNorm (one small launch of the library on the current stream, so that a
+        captured training step holds no ATen kernel)."""
+        t = self._flat_nbt
+        if t is None or t.numel() == 0:
+            return
+        if t.is_cuda:
+            call("dmb_bn_count_batch", ptr(t), t.numel(), _stream())
+        else:
+            t += 1
+
     def _bump_num_batches_tracked(self):
         self._bn_dirty += 1
         if self._flat_nbt is not None and len(self.bn_modules()):
-            self._flat_nbt += 1
+            self._count_batch()
 
     # ---------------------------------------------------------------- ops
     def encoder_forward(self, x: torch.Tensor, bn_mode: Optional[str] = None) -> torch.Tensor:

@@ -62,7 +62,7 @@ class SyncBNStep:
                    ptr(st.cv), B, tm, C.byref(self.desc), ptr(st.decoded), ptr(tr.losses),
                    ptr(eng._flat_bn) if update_running else None, ptr(st.ws), st.nws, _stream())
         if update_running:
-            eng._flat_nbt += 1
+            eng._count_batch()
 
     def backward(self, st):
         tr, eng = self.tr, self.tr.eng

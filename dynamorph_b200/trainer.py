@@ -59,7 +59,7 @@ class FusedTrainer:
              ptr(st.cv), B, tm, ptr(st.decoded), ptr(self.losses), ptr(eng._flat_bn) if update_running else None,
              ptr(st.ws), st.nws, _stream())
         if update_running:
-            eng._flat_nbt += 1
+            eng._count_batch()
 
     def _backward(self, st: _Plan):
         eng = self.eng

@@ -368,6 +368,9 @@ int dmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 int dmb_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, int32_t* step_dev, float* bc_dev,
                       float grad_scale, void* stream);
+/* nn.BatchNorm2d.num_batches_tracked += 1 of a train-mode forward (torch/nn/modules/batchnorm.py; the reference's
+ * model(batch) at run_training.py:404) for the n BatchNorm layers of the model, kept as n consecutive int64.        */
+int dmb_bn_count_batch(int64_t* num_batches_tracked, int32_t n, void* stream);
 
 /* ---- input staging (pipeline/train_utils.py:252-274) -------------------------------- */
 /* zscore_patch: per patch and channel (x - mean) / (std + DBL_EPSILON), float64 or

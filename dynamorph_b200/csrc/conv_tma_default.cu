@@ -9,7 +9,9 @@ namespace {
     X(4, 2, 2, 8, 128) X(4, 2, 8, 16, 64) X(4, 2, 16, 16, 32) X(3, 1, 16, 16, 16) X(3, 1, 16, 32, 16)              \
     X(1, 1, 32, 16, 16) X(3, 1, 16, 32, 32) X(1, 1, 32, 16, 32)                                                    \
     /* data gradients of the residual block (training backward): channel counts swapped */                        \
-    X(3, 1, 32, 16, 16) X(1, 1, 16, 32, 16) X(3, 1, 32, 16, 32) X(1, 1, 16, 32, 32)
+    X(3, 1, 32, 16, 16) X(1, 1, 16, 32, 16) X(3, 1, 32, 16, 32) X(1, 1, 16, 32, 32)                                \
+    /* data gradient of the decoder's second ConvTranspose2d (8 -> 4): stride-2 convolution 4 -> 8 over its output */  \
+    X(4, 2, 4, 8, 64)
 
 // everything but the dual-tensor transform on load (x2 / in_b: BatchNorm backward folded into the load of a data
 // gradient) -- callers materialise that gradient first when they want this kernel (csrc/model.cu:dgrad_layer)

@@ -673,6 +673,17 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         train[tb] = {"ms": float(t[0]), "batch_per_gpu": tb, "global_batch": tb * world,
                      "patches_per_s": tb * world / (float(t[0]) * 1e-3), "total_loss_after": float(tl.tolist()[2])}
+        if tb == 256:
+            # kernels of the library in ONE step (counted on an eager replica of the same step; the timed steps above are
+            # graph replays of exactly these launches)
+            eager = FusedTrainer(tmodel, lr=1e-4, use_graph=False)
+            eager.step(xt)
+            torch.cuda.synchronize()
+            lib.dmb_launch_count(1)
+            eager.step(xt)
+            torch.cuda.synchronize()
+            train[tb]["launches_per_step"] = int(lib.dmb_launch_count(0))
+            del eager
         del trainer, tmodel
     # the reference's own API for the same step (run_one_batch: autograd + optimiser.step + 1 host sync), N = 1 only
     eager_ms = None
@@ -729,6 +740,7 @@ def run_ours(args):
                        "what": "forward + backward + one flat-gradient NCCL allreduce (N>1) + fused Adam, CUDA-graph replay "
                                "(trainer.FusedTrainer); per-rank BatchNorm statistics",
                        "total_loss_after": train[256]["total_loss_after"],
+                       "launches_per_step": train[256].get("launches_per_step"),
                        "batch_512_per_gpu": train[512],
                        "run_one_batch_ms": eager_ms,
                        "run_one_batch_note": "the reference's own step API (run_training.run_one_batch: autograd + "

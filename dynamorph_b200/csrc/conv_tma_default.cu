@@ -62,9 +62,16 @@ int launch_xf(const ConvFwdArgs& a, cudaStream_t st) {
     return launch_tma<TC<KS, S, CI, CO, WIN, WC, 0, false, COT>>(a, st);
 }
 
+// Four output channels (below the 8-channel tile): the stride-2 convolution 4 -> 4 over 128x128 maps, i.e. the data
+// gradient of the decoder's last ConvTranspose2d (4 -> 4) -- 4-channel tiling only
+bool is_44(int ks, int stride, int Cin, int Cout, int H, int W) {
+    return ks == 4 && stride == 2 && Cin == 4 && Cout == 4 && H == 128 && W == 128;
+}
+
 }  // namespace
 
 int conv_tma_bands_default(int ks, int stride, int Cin, int Cout, int H, int W, int64_t /*B*/) {
+    if (is_44(ks, stride, Cin, Cout, H, W)) return TC<4, 2, 4, 4, 128, false, 0, false, 4>::NBANDS;
 #define X(KS, S, CI, CO, WIN)                                                                        \
     if (ks == KS && stride == S && Cin == CI && Cout == CO && W == WIN && H == WIN)                  \
         return TC<KS, S, CI, CO, WIN, false>::NBANDS;     /* identical for the 4-channel tiling (static_assert below) */
@@ -76,6 +83,7 @@ int conv_tma_bands_default(int ks, int stride, int Cin, int Cout, int H, int W, 
 // Returns 1 if the call was not taken, 0 on success, <0 on error.
 int conv_tma_default(const ConvFwdArgs& a, cudaStream_t st) {
     if (!tma_plain(a) || a.out_nhwc) return 1;
+    if (is_44(a.ks, a.stride, a.Cin, a.Cout, a.H, a.W)) return launch_xf<4, 2, 4, 4, 128, false, 4>(a, st);
 #define X(KS, S, CI, CO, WIN)                                                                        \
     if (a.ks == KS && a.stride == S && a.Cin == CI && a.Cout == CO && a.W == WIN && a.H == WIN) {   \
         if (small_launch<KS, S, CI, CO, WIN>(a.B)) return launch_xf<KS, S, CI, CO, WIN, false, 4>(a, st); \

@@ -250,7 +250,13 @@ struct WgradArgs {
     float* partials;        // scratch: wgrad_partial_floats() floats per CTA x *ncta
 };
 int wgrad_partial_floats(const WgradArgs& a, int* ncta);
-int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStream_t st);
+// With a queue the fold of the per-CTA partials is NOT launched: the job is appended and wgrad_reduce_flush() folds every
+// queued layer in ONE launch (the partial regions must then stay untouched until the flush: one region per layer).
+struct WgReduceJob { const float* partials; int ncta, out_floats, cin_eff, cout, ks; float* dw; float* db; float* packed_out; int block0; };
+constexpr int WG_REDUCE_MAX = 24;
+struct WgReduceQueue { int n = 0; int blocks = 0; WgReduceJob j[WG_REDUCE_MAX]; };
+int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStream_t st, WgReduceQueue* q = nullptr);
+int wgrad_reduce_flush(WgReduceQueue& q, cudaStream_t st);
 // TMA-fed specialisation for the default-width layers (wgrad_tma.cu): both return 1 when they do not take the call;
 // they write the same per-CTA partial layout, which wgrad() folds with the same reduction kernel
 int wgrad_tma_plan(const WgradArgs& a, int* ncta, int* out_floats);

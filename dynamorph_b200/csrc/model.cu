@@ -405,7 +405,22 @@ int carve_workspace(const Layout& L, int64_t B, int bn_mode, int keep, void* bas
             const size_t f = (size_t)(c.cin + 1) * c.ks * c.ks * c.cout + c.cout + (size_t)c.cin;
             if (f > maxw) maxw = f;
         }
-        w.wg_part_floats = maxw * 148 * 2;
+        // Opt-in (DMB_WG_QUEUE=1): one region of per-CTA partials per layer (the default widths: ~30 MB) and the folds of a
+        // step in TWO launches (everything before the head, then the head) instead of one per layer: 79 -> 69 launches per
+        // step, but measured slower as a CUDA-graph replay (0.858 against 0.850 ms at batch 256; eager: 0.844 against 0.854)
+        // -- the big fold sits in the tail where only the weight-gradient stream still works.
+        size_t sumw = 0;
+        for (const ConvL& c : L.convs) {
+            const size_t f = (size_t)(c.cin + 1) * c.ks * c.ks * c.cout + c.cout + (size_t)c.cin;
+            sumw += (f + 63) & ~(size_t)63;
+        }
+        w.wg_queue = false;
+        {
+            const char* e = getenv("DMB_WG_QUEUE");
+            if (e && e[0] == '1')
+                w.wg_queue = (int)L.convs.size() + 1 <= WG_REDUCE_MAX && sumw * 148 * 2 * sizeof(float) <= ((size_t)64 << 20);
+        }
+        w.wg_part_floats = (w.wg_queue ? sumw : maxw) * 148 * 2;
         w.wg_part = bp.take<float>(w.wg_part_floats);
         w.dweff = bp.take<float>((size_t)(m.num_inputs + 1) * 16 * h2 + h2 + 16);
         w.vq_part_rows = (int)((B * lat + 255) / 256 < 296 ? (B * lat + 255) / 256 : 296);
@@ -935,7 +950,29 @@ struct Bwd {
     SideStream* side = nullptr;
     bool forked = false;
     int stat_rows = 0;      // rows of partial sums the LAST dgrad_layer call left when that is not B * nbands (conv_tm.cu)
+    WgReduceQueue rq;       // folds of the weight-gradient partials, launched once (flush_wgrad) when wg_queue
+    size_t wg_off = 0;
     bool ps() const { return c.per_sample(); }
+    // scratch for the next weight-gradient launch (need floats) and the queue its fold goes to (nullptr: fold at once)
+    int wgrad_scratch(size_t need, float** part, WgReduceQueue** q) {
+        if (c.w.wg_queue) {
+            DMB_CHECK(wg_off + need <= c.w.wg_part_floats, "wgrad scratch too small (queued folds)");
+            *part = c.w.wg_part + wg_off;
+            wg_off += (need + 63) & ~(size_t)63;
+            *q = &rq;
+        } else {
+            DMB_CHECK(need <= c.w.wg_part_floats, "wgrad scratch too small");
+            *part = c.w.wg_part;
+            *q = nullptr;
+        }
+        return 0;
+    }
+    int flush_wgrad() {     // on the stream the weight gradients run on
+        if (rq.n == 0) return 0;
+        cudaStream_t sw = side ? side->s : st;
+        if (side && !forked) DMB_TRY(wgrad_stream(&sw));
+        return wgrad_reduce_flush(rq, sw);
+    }
     int L_lat_h() const { return c.L.lh; }
     int L_lat_w() const { return c.L.lw; }
     // stream for the next weight-gradient launch: the side stream once it has seen everything issued so far
@@ -976,11 +1013,13 @@ struct Bwd {
         }
         int ncta = 0;
         const int pf = wgrad_partial_floats(a, &ncta);
-        DMB_CHECK(pf > 0 && (size_t)pf * ncta <= c.w.wg_part_floats, "wgrad scratch too small for layer %d", li);
+        DMB_CHECK(pf > 0, "no weight-gradient plan for layer %d", li);
+        WgReduceQueue* q = nullptr;
+        DMB_TRY(wgrad_scratch((size_t)pf * ncta, &a.partials, &q));
         float* db = (with_bias && !l.transposed) ? grads + l.b_off : nullptr;
         cudaStream_t sw;
         DMB_TRY(wgrad_stream(&sw));
-        return wgrad(a, grads + l.w_off, db, nullptr, sw);
+        return wgrad(a, grads + l.w_off, db, nullptr, sw, q);
     }
 
     // data gradient of conv layer li: G (at the layer's output, Ho x Wo) -> gout (at its input, H x W), gated by
@@ -1261,6 +1300,8 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
     Act y1a; y1a.p = w.y1; y1a.s = w.bn[L.convs[L.e1].bn].scale; y1a.t = w.bn[L.convs[L.e1].bn].shift;
     DMB_TRY(B.wgrad_layer(L.e2, G2, y1a, true, H / 2, W / 2, true));
     DMB_TRY(B.dgrad_layer(L.e2, G2, H / 2, W / 2, w.g_y1, &y1a, nullptr, w.bnb[L.convs[L.e1].bn].part, w.y1, &nb));
+    // (fold every layer queued so far while the head's inputs are still being produced: the last fold is then the head's alone)
+    DMB_TRY(B.flush_wgrad());
     // 10. composite head (enc.0 1x1 + enc.1 4x4 s2) behind enc.2 BN: gradient of the effective conv, then chain rule
     DMB_TRY(B.bn_bwd(L.e1, nb, (int64_t)(H / 2) * (W / 2), &G1, w.g_y1, w.y1));
     {
@@ -1272,13 +1313,17 @@ int run_backward_z16(Ctx& c, const float* params, const float* x, const float* m
         a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.Ho = H / 2; a.Wo = W / 2;
         int ncta = 0;
         const int pf = wgrad_partial_floats(a, &ncta);
-        DMB_CHECK(pf > 0 && (size_t)pf * ncta <= w.wg_part_floats, "wgrad scratch too small for the head");
+        DMB_CHECK(pf > 0, "no weight-gradient plan for the head");
+        WgReduceQueue* q = nullptr;
+        DMB_TRY(B.wgrad_scratch((size_t)pf * ncta, &a.partials, &q));
         cudaStream_t sw;
         DMB_TRY(B.wgrad_stream(&sw));
-        DMB_TRY(wgrad(a, nullptr, nullptr, w.dweff, sw));
+        DMB_TRY(wgrad(a, nullptr, nullptr, w.dweff, sw, q));
+        DMB_TRY(B.flush_wgrad());        // every layer's partials -> gradients, one launch
         DMB_TRY(composite_chain(w.dweff, params + l.w0_off, params + l.b0_off, params + l.w_off, l.cin, l.cmid,
                                 grads + l.w0_off, grads + l.b0_off, grads + l.w_off, grads + l.b_off, sw));
     }
+    DMB_TRY(B.flush_wgrad());
     return B.join();
 }
 
@@ -1347,6 +1392,7 @@ int run_backward_z32(Ctx& c, const float* params, const float* x, const float* m
     DMB_TRY(B.bn_bwd(L.e1, nb, (int64_t)(H / 2) * (W / 2), &G1, w.g_y1, w.y1));
     Act xin; xin.p = x;
     DMB_TRY(B.wgrad_layer(L.e1, G1, xin, false, H, W, true));
+    DMB_TRY(B.flush_wgrad());
     return B.join();
 }
 

@@ -85,6 +85,7 @@ struct Workspace {
     float* vq_part = nullptr;              // codebook-gradient partials [vq_part_rows][K][D]
     int vq_part_rows = 0;
     size_t wg_part_floats = 0;
+    bool wg_queue = false;                 // wg_part holds one region per layer: the folds are queued and launched once
     double* vq_stats = nullptr;            // [2+K]
     double* recon_sum = nullptr;           // [1]
     float* scalars = nullptr;              // [8] vq loss, perplexity, ..., [4] time-matching loss

@@ -322,6 +322,40 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
     dw[((size_t)co * cin_eff + ci) * nt + tap] = s;      // (Cout, Cin, kh, kw) of the wgrad problem
 }
 
+// the same for every queued layer in ONE launch: a block finds its job from its index (jobs hold their first block)
+__global__ void __launch_bounds__(1024) wgrad_reduce_multi_kernel(const WgReduceQueue q) {
+    pdl_wait();
+    __shared__ float red[32][33];
+    int ji = 0;
+    while (ji + 1 < q.n && (int)blockIdx.x >= q.j[ji + 1].block0) ++ji;
+    const WgReduceJob& jb = q.j[ji];
+    const float* __restrict__ partials = jb.partials;
+    const int ncta = jb.ncta, out_floats = jb.out_floats;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int e = ((int)blockIdx.x - jb.block0) * 32 + lane;
+    float s = 0.f;
+    if (e < out_floats) {
+        const int per = (ncta + 31) / 32;
+        const int c0 = grp * per, c1 = min(ncta, c0 + per);
+        for (int c = c0; c < c1; ++c) s += partials[(size_t)c * out_floats + e];
+    }
+    red[grp][lane] = s;
+    __syncthreads();
+    if (grp != 0 || e >= out_floats) return;
+    s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) s += red[g][lane];
+    if (jb.packed_out) { jb.packed_out[e] = s; return; }
+    const int nt = jb.ks * jb.ks;
+    const int nw = jb.cin_eff * nt * jb.cout;
+    if (e >= nw) { if (jb.db) jb.db[e - nw] = s; return; }
+    const int co = e % jb.cout;
+    const int t = e / jb.cout;
+    const int tap = t % nt;
+    const int ci = t / nt;
+    jb.dw[((size_t)co * jb.cin_eff + ci) * nt + tap] = s;
+}
+
 // composite head: chain rule from the effective (ni+1)-channel 4x4 conv to enc.0 / enc.1 parameters
 __global__ void composite_chain_kernel(const float* __restrict__ dweff, const float* __restrict__ w0,
                                        const float* __restrict__ b0, const float* __restrict__ w1, int ni, int cm,
@@ -378,7 +412,34 @@ int wgrad_partial_floats(const WgradArgs& a, int* ncta) {
 
 // dw: torch-layout weight gradient (Cout_w, Cin_w, k, k) of the *wgrad problem* (for a ConvTranspose2d the
 // caller swaps the tensors so that this IS the (Cin_T, Cout_T, k, k) layout); db may be nullptr.
-int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStream_t st) {
+namespace {
+// fold now, or append to the queue
+int reduce_or_queue(const float* partials, int ncta, int of, int cin_eff, int cout, int ks, float* dw, float* db,
+                    float* packed_out, cudaStream_t st, WgReduceQueue* q) {
+    if (q) {
+        DMB_CHECK(q->n < WG_REDUCE_MAX, "wgrad: reduce queue full");
+        WgReduceJob& j = q->j[q->n++];
+        j = WgReduceJob{partials, ncta, of, cin_eff, cout, ks, dw, db, packed_out, q->blocks};
+        q->blocks += (of + 31) / 32;
+        return 0;
+    }
+    DMB_LAUNCH((wgrad_reduce_kernel), (of + 31) / 32, 1024, 0, st, partials, ncta, of, cin_eff, cout, ks, dw, db, packed_out);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+}  // namespace
+
+int wgrad_reduce_flush(WgReduceQueue& q, cudaStream_t st) {
+    if (q.n == 0) return 0;
+    DMB_LAUNCH((wgrad_reduce_multi_kernel), q.blocks, 1024, 0, st, q);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    q.n = 0; q.blocks = 0;
+    return 0;
+}
+
+int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStream_t st, WgReduceQueue* q) {
     DMB_CHECK((a.ks == 1 && a.stride == 1) || (a.ks == 3 && a.stride == 1) || (a.ks == 4 && a.stride == 2),
               "wgrad: unsupported kernel %d stride %d", a.ks, a.stride);
     DMB_CHECK(a.Wo % 4 == 0 && a.W % 4 == 0, "wgrad: widths must be multiples of 4");
@@ -388,10 +449,7 @@ int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStrea
         if (rc < 0) return rc;
         if (rc == 0) {
             const int cin_eff = a.Cin + (a.ones_channel ? 1 : 0);
-            DMB_LAUNCH((wgrad_reduce_kernel), (of + 31) / 32, 1024, 0, st, a.partials, n, of, cin_eff, a.Cout, a.ks, dw, db, packed_out);
-            DMB_CUDA(cudaGetLastError());
-            DMB_LAUNCHED(1);
-            return 0;
+            return reduce_or_queue(a.partials, n, of, cin_eff, a.Cout, a.ks, dw, db, packed_out, st, q);
         }
     }
     WgK k;
@@ -408,11 +466,7 @@ int wgrad(const WgradArgs& a, float* dw, float* db, float* packed_out, cudaStrea
         else if (a.ks == 3) DMB_TRY((launch<3, 1, 2>(k, ncta, st)));
         else DMB_TRY((launch<4, 2, 2>(k, ncta, st)));
     }
-    const int blocks = (k.out_floats + 31) / 32;
-    DMB_LAUNCH((wgrad_reduce_kernel), blocks, 1024, 0, st, a.partials, ncta, k.out_floats, k.cin_eff, a.Cout, a.ks, dw, db, packed_out);
-    DMB_CUDA(cudaGetLastError());
-    DMB_LAUNCHED(1);
-    return 0;
+    return reduce_or_queue(a.partials, ncta, k.out_floats, k.cin_eff, a.Cout, a.ks, dw, db, packed_out, st, q);
 }
 
 int composite_chain(const float* dweff, const float* w0, const float* b0, const float* w1, int ni, int cm,

@@ -338,6 +338,15 @@ struct DecTailArgs {
     unsigned* ticket;      // backward: zero on entry (reset on exit)
     float* dw; float* db; float* db_prev;      // (NI, CM), (NI), (CM)
 };
+// ... with dec.4 (ConvTranspose2d ci -> cm, 4x4 s2 p1, + ReLU) in front of the forward tail: t2 -> t3, decoded, loss
+struct DecTail2Args {
+    int64_t B; int ci, cm, ni, hi, wi;      // hi x wi: the maps of t2 (t3 / decoded / x are 2hi x 2wi)
+    const float* t2; const float* w4; const float* b4; float* t3;
+    const float* x; const float* mask; int mask_c; const float* cvar;
+    const float* w6; const float* b6; float* decoded; double* loss_sum;
+};
+bool dec_tail2_supported(int ci, int cm, int ni, int hi, int wi);
+int dec_tail2_forward(const DecTail2Args& a, cudaStream_t st);
 bool dec_tail_supported(int cm, int ni, int hw);
 int64_t dec_tail_partial_doubles(int64_t B, int hw, int cm, int ni);
 int dec_tail_forward(const DecTailArgs& a, cudaStream_t st);

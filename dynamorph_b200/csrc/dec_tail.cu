@@ -87,6 +87,125 @@ __global__ void __launch_bounds__(256) dec_tail_forward_kernel(const TailArgs a)
     }
 }
 
+// dec.4 (ConvTranspose2d CI -> CM, 4x4 stride 2 padding 1, + ReLU) fused in front of the forward tail: t2 -> t3 (stored:
+// the backward pass needs it), decoded and the loss in ONE pass -- t3 (the largest tensor of the step, 262 KB per patch)
+// is written once and never read back by the forward (vq_vae.py:296-298, :322).
+//   out[co][2y+py][2x+px] = b[co] + sum_ci sum_{dy in {py-1, py}} sum_{dx in {px-1, px}} in[ci][y+dy][x+dx] * w[ci][ky][kx][co]
+//   with ky = py + 1 - 2 dy, kx = px + 1 - 2 dx.
+// A thread owns input pixel (y, x) and output row parity py: the px pair of output pixels for all CM channels (float2
+// stores, a warp = 32 consecutive x = 256 contiguous bytes per channel); py is warp-uniform, so the weight reads are
+// 16-byte shared-memory broadcasts.
+struct Tail2Args {
+    const float* t2;       // (B, CI, Hi, Wi) post-ReLU input of dec.4
+    const float* w4;       // dec.4 packed [CI][4][4][CM]
+    const float* b4;       // [CM]
+    float* t3;             // (B, CM, 2Hi, 2Wi) out (post-ReLU)
+    const float* x; const float* mask; int mask_c; const float* cvar;
+    const float* w6;       // dec.6 packed [CM][NI]
+    const float* b6;       // [NI]
+    float* decoded;
+    double* loss_sum;
+    int64_t items;         // B * Hi * 2 * Wi
+    int hi, wi;            // powers of two: item -> (b, y, py, x) by shifts (64-bit div / mod by run-time values cost more
+    int lh, lw;            // instructions than the 144 FMAs of an item)
+};
+
+template <int CI, int CM, int NI>
+__global__ void __launch_bounds__(256, 4) dec_tail2_forward_kernel(const Tail2Args a) {
+    static_assert(CM == 4, "one float4 of output channels per tap");
+    pdl_wait();
+    __shared__ float4 w4s[CI * 16];
+    __shared__ double red[8];
+    for (int i = threadIdx.x; i < CI * 16; i += 256) w4s[i] = __ldg(reinterpret_cast<const float4*>(a.w4) + i);
+    float w6[CM][NI], b6[NI], cv[NI];
+#pragma unroll
+    for (int o = 0; o < NI; ++o) {
+        b6[o] = __ldg(a.b6 + o); cv[o] = __ldg(a.cvar + o);
+#pragma unroll
+        for (int c = 0; c < CM; ++c) w6[c][o] = __ldg(a.w6 + c * NI + o);
+    }
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b4));
+    __syncthreads();
+    const int wi = a.wi, hi = a.hi, wo = 2 * wi;
+    const size_t in_plane = (size_t)hi * wi, out_plane = 4 * in_plane;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < a.items; i += (int64_t)gridDim.x * 256) {
+        const int x = (int)(i & (wi - 1));
+        int64_t r = i >> a.lw;
+        const int py = (int)(r & 1); r >>= 1;
+        const int y = (int)(r & (hi - 1));
+        const int64_t b = r >> a.lh;
+        // the 2 x 3 input window of every channel: rows y + py - 1, y + py; columns x - 1, x, x + 1 (zero outside)
+        float v[CI][2][3];
+        const float* ip = a.t2 + (size_t)b * CI * in_plane;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int yy = y + py - 1 + d;
+            const bool rok = (unsigned)yy < (unsigned)hi;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int xx = x - 1 + e;
+                const bool ok = rok && (unsigned)xx < (unsigned)wi;
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) v[ci][d][e] = ok ? __ldg(ip + ci * in_plane + (size_t)yy * wi + xx) : 0.f;
+            }
+        }
+        const size_t opix = (size_t)(2 * y + py) * wo + 2 * x;
+        // the batch (and mask) values of this pixel pair: issued before the arithmetic, used after it
+        float2 xv[NI], mk[NI];
+#pragma unroll
+        for (int o = 0; o < NI; ++o) {
+            const size_t pi = ((size_t)b * NI + o) * out_plane + opix;
+            xv[o] = __ldg(reinterpret_cast<const float2*>(a.x + pi));
+            mk[o] = make_float2(1.f, 1.f);
+            if (a.mask) mk[o] = __ldg(reinterpret_cast<const float2*>(a.mask + ((a.mask_c == 1) ? (size_t)b * out_plane + opix : pi)));
+        }
+        float4 o0 = b4, o1 = b4;                 // px = 0, 1
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int ky = py + 3 - 2 * (py + d);           // dy = py - 1 + d  ->  ky = py + 1 - 2 dy
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    // px = 0: dx = -1 + e (columns x-1, x), kx = 3 - 2e;  px = 1: dx = e (columns x, x+1), kx = 2 - 2e
+                    const float4 wa = w4s[(ci * 4 + ky) * 4 + (3 - 2 * e)];
+                    const float4 wb = w4s[(ci * 4 + ky) * 4 + (2 - 2 * e)];
+                    const float va = v[ci][d][e], vb = v[ci][d][e + 1];
+                    o0.x = fmaf(va, wa.x, o0.x); o0.y = fmaf(va, wa.y, o0.y); o0.z = fmaf(va, wa.z, o0.z); o0.w = fmaf(va, wa.w, o0.w);
+                    o1.x = fmaf(vb, wb.x, o1.x); o1.y = fmaf(vb, wb.y, o1.y); o1.z = fmaf(vb, wb.z, o1.z); o1.w = fmaf(vb, wb.w, o1.w);
+                }
+            }
+        const float t0[CM] = {fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f)};
+        const float t1[CM] = {fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f)};
+        float* tp = a.t3 + (size_t)b * CM * out_plane + opix;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) *reinterpret_cast<float2*>(tp + c * out_plane) = make_float2(t0[c], t1[c]);
+        float part = 0.f;
+#pragma unroll
+        for (int o = 0; o < NI; ++o) {
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CM; ++c) { d0 = fmaf(w6[c][o], t0[c], d0); d1 = fmaf(w6[c][o], t1[c], d1); }
+            d0 += b6[o]; d1 += b6[o];
+            const size_t pi = ((size_t)b * NI + o) * out_plane + opix;
+            *reinterpret_cast<float2*>(a.decoded + pi) = make_float2(d0, d1);
+            const float e0 = d0 * mk[o].x - xv[o].x * mk[o].x, e1 = d1 * mk[o].y - xv[o].y * mk[o].y;
+            part += (e0 * e0) / cv[o] + (e1 * e1) / cv[o];
+        }
+        acc += (double)part;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int wq = 0; wq < 8; ++wq) s += red[wq];
+        atomicAdd(a.loss_sum, s);
+    }
+}
+
 template <int CM, int NI>
 __global__ void __launch_bounds__(256, (CM <= 4) ? 4 : 1) dec_tail_backward_kernel(const TailArgs a) {
     pdl_wait();
@@ -227,6 +346,28 @@ int dec_tail_forward(const DecTailArgs& d, cudaStream_t st) {
     a.t3 = d.t3; a.x = d.x; a.mask = d.mask; a.mask_c = d.mask_c; a.cvar = d.cvar; a.w = d.w; a.bias = d.bias;
     a.decoded = d.decoded; a.loss_sum = d.loss_sum; a.quads = d.B * (int64_t)(d.hw / 4); a.hw4 = d.hw / 4;
     return d.cm == 4 ? launch_tail<4, 2>(a, false, st) : launch_tail<16, 2>(a, false, st);
+}
+
+bool dec_tail2_supported(int ci, int cm, int ni, int hi, int wi) {
+    return ci == 4 && cm == 4 && ni == 2 && wi >= 32 && (wi & (wi - 1)) == 0 && hi > 0 && (hi & (hi - 1)) == 0;
+}
+
+int dec_tail2_forward(const DecTail2Args& d, cudaStream_t st) {
+    DMB_CHECK(dec_tail2_supported(d.ci, d.cm, d.ni, d.hi, d.wi), "dec_tail2: unsupported shape %d -> %d -> %d @%dx%d", d.ci, d.cm,
+              d.ni, d.hi, d.wi);
+    DMB_CHECK(!(reinterpret_cast<uintptr_t>(d.w4) & 15) && !(reinterpret_cast<uintptr_t>(d.b4) & 15), "dec_tail2: weights must be 16-byte aligned");
+    Tail2Args a{};
+    a.t2 = d.t2; a.w4 = d.w4; a.b4 = d.b4; a.t3 = d.t3; a.x = d.x; a.mask = d.mask; a.mask_c = d.mask_c; a.cvar = d.cvar;
+    a.w6 = d.w6; a.b6 = d.b6; a.decoded = d.decoded; a.loss_sum = d.loss_sum;
+    a.items = d.B * (int64_t)d.hi * 2 * d.wi; a.hi = d.hi; a.wi = d.wi;
+    for (a.lh = 0; (1 << a.lh) < d.hi; ++a.lh) {}
+    for (a.lw = 0; (1 << a.lw) < d.wi; ++a.lw) {}
+    int64_t blocks = (a.items + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;       // one resident wave (4 CTAs per SM), grid-stride
+    DMB_LAUNCH((dec_tail2_forward_kernel<4, 4, 2>), (unsigned)blocks, 256, 0, st, a);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
 }
 
 int dec_tail_backward(const DecTailArgs& d, cudaStream_t st) {

@@ -811,7 +811,18 @@ bool dec_tail_on(const dmb_model& m) {
     return m.arch == DMB_ARCH_Z16 && dec_tail_supported(m.num_hiddens / 4, m.num_inputs, m.height * m.width);
 }
 
-int run_decoder(Ctx& c, const float* za, float* decoded, bool skip_tail = false) {
+// ... with dec.4 in front of it as well (dec_tail2_forward); DMB_DEC_TAIL2=0 keeps dec.4 a separate launch.
+bool dec_tail2_on(const Layout& L) {
+    const char* e = getenv("DMB_DEC_TAIL2");
+    if (e && e[0] == '0') return false;
+    const dmb_model& m = L.m;
+    if (!dec_tail_on(m)) return false;
+    const ConvL& l4 = L.convs[L.d2];
+    const ConvL& l6 = L.convs[L.d3];
+    return l4.transposed && l4.ks == 4 && dec_tail2_supported(l4.cin, l4.cout, l6.cout, 4 * L.lh, 4 * L.lw);
+}
+
+int run_decoder(Ctx& c, const float* za, float* decoded, bool skip_tail = false, bool skip_d2 = false) {
     const Layout& L = c.L;
     const dmb_model& m = L.m;
     const bool ev = c.mode == DMB_BN_EVAL;
@@ -821,7 +832,7 @@ int run_decoder(Ctx& c, const float* za, float* decoded, bool skip_tail = false)
         DMB_CHECK(c.w.t1 && c.w.t2 && c.w.t3, "decoder needs a workspace carved with keep_activations=1");
         DMB_TRY(run_conv(c, L.d0, in, false, L.lh, L.lw, c.w.t1, nullptr, true, &a1));
         DMB_TRY(run_conv(c, L.d1, a1, false, 2 * L.lh, 2 * L.lw, c.w.t2, nullptr, true, &a2));
-        DMB_TRY(run_conv(c, L.d2, a2, false, 4 * L.lh, 4 * L.lw, c.w.t3, nullptr, true, &a3));
+        if (!skip_d2) DMB_TRY(run_conv(c, L.d2, a2, false, 4 * L.lh, 4 * L.lw, c.w.t3, nullptr, true, &a3));
         if (!skip_tail) DMB_TRY(run_conv(c, L.d3, a3, false, 8 * L.lh, 8 * L.lw, decoded, nullptr, false, &o));
     } else {
         DMB_CHECK(c.w.t1, "decoder needs a workspace carved with keep_activations=1");
@@ -1837,7 +1848,18 @@ static int train_forward_impl(const dmb_model* m, const float* packed, const flo
     DMB_CUDA(cudaMemsetAsync(w.recon_sum, 0, sizeof(double) * 4, st));
     DMB_TRY(run_vq(c, params + L.codebook_off, w.zb, &pend, w.zb, w.za, w.idx, w.vq_stats));
     DMB_TRY(dmb_vq_finalize(w.vq_stats, L.D, m->num_embeddings, m->commitment_cost, w.scalars, stream));
-    if (dec_tail_on(*m)) {
+    if (dec_tail2_on(L)) {
+        // dec.4 (ConvTranspose2d + ReLU), dec.6 (1x1) and the reconstruction loss in one pass: t3 is written once
+        DMB_TRY(run_decoder(c, w.za, decoded, true, true));
+        const ConvL& l4 = L.convs[L.d2];
+        const ConvL& l6 = L.convs[L.d3];
+        DecTail2Args t{};
+        t.B = batch; t.ci = l4.cin; t.cm = l4.cout; t.ni = l6.cout; t.hi = 4 * L.lh; t.wi = 4 * L.lw;
+        t.t2 = w.t2; t.w4 = packed + l4.pw_off; t.b4 = packed + l4.pb_off; t.t3 = w.t3;
+        t.x = x; t.mask = mask; t.mask_c = mask_channels; t.cvar = channel_var;
+        t.w6 = packed + l6.pw_off; t.b6 = packed + l6.pb_off; t.decoded = decoded; t.loss_sum = w.recon_sum;
+        DMB_TRY(dec_tail2_forward(t, st));
+    } else if (dec_tail_on(*m)) {
         // dec.6 (1x1) and the reconstruction loss in one pass over the full-resolution tensors
         DMB_TRY(run_decoder(c, w.za, decoded, true));
         const ConvL& l = L.convs[L.d3];

@@ -503,6 +503,17 @@ def wide_config_table(dev, bf16_peak):
             os.environ.pop(k, None)
         # MACs that run on the tensor cores (every conv behind the head + the code search), x3 passes for the convs
         row["tensor_core"]["speedup_vs_cuda_core"] = row["cuda_core"]["ms"] / row["tensor_core"]["ms"]
+        # the training step of the same configuration at the same batch (forward + backward + Adam, graph replay); these
+        # widths train on the CUDA-core kernels
+        from dynamorph_b200.trainer import FusedTrainer
+        m.train()
+        tr = FusedTrainer(m, lr=1e-4, use_graph=True)
+        for _ in range(3):
+            tr.step(x)
+        torch.cuda.synchronize()
+        tms = time_events(lambda: tr.step(x), 3)
+        row["train_step"] = {"ms": tms, "batch": B, "patches_per_s": B / (tms * 1e-3), "path": "cuda_core"}
+        del tr
         out[name] = row
         del m
         torch.cuda.empty_cache()

@@ -169,7 +169,7 @@ struct ConvTmArgs {
     int in_per_sample;
     double* stats;
     // whole-batch statistics (DMB_BN_BATCH): every warp of the persistent CTAs adds up the partials of its tiles and
-    // `stats` receives *stat_rows = 4 * grid <= TM_BATCH_ROWS_MAX rows of [Cout][2] (fixed order: deterministic)
+    // `stats` receives *stat_rows = grid <= TM_BATCH_ROWS_MAX rows of [Cout][2], one per CTA (fixed order: deterministic)
     int stats_batch;
     int* stat_rows;
     // data-gradient form (dg != 0; training step, whole-batch statistics; shapes: conv_tm_dg_supported): plain input x (the
@@ -189,7 +189,7 @@ struct ConvTmArgs {
     const float* in_c;
     // transposed form (ct != 0): ConvTranspose2d(4x4, stride 2, padding 1) Cin -> Cout, x (B, Cin, H, W) -> y (B, Cout, 2H,
     // 2W); wtm = pack_tm_weights_ct image; plain (bias + optional ReLU on store) or with dg = 1 (gate / sums / dual load;
-    // statistics rows: 8 per CTA).  Shapes: conv_tm_ct_supported.
+    // statistics rows: one per CTA, [Cout][2]).  Shapes: conv_tm_ct_supported.
     int ct;
 };
 constexpr int TM_MAX_SMS = 192;

@@ -241,10 +241,13 @@ struct TM {
     static constexpr int STAGE_BYTES = (((DUAL ? 2 : 1) * IN_BYTES) + 127) & ~127;
     static constexpr int NSTAGE_RAW = (SMEM_BUDGET - B_FLOATS * 4 - 2048) / STAGE_BYTES;
     static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
-    static constexpr size_t SMEM = 1024 + (size_t)B_FLOATS * 4 + (size_t)NSTAGE * STAGE_BYTES + 256 + 1024;  // + barriers + stat_red
+    static constexpr size_t SMEM = 1024 + (size_t)B_FLOATS * 4 + (size_t)NSTAGE * STAGE_BYTES + 256 + 2048;  // + barriers + stat_red
     static constexpr int HALF = COUT / 2;                    // output channels per epilogue warp group
     static constexpr int NS = CT ? CT_C : HALF;              // statistics channels a thread holds
-    static constexpr int STAT_ROWS = CT ? 8 : 4;             // whole-batch statistics rows per CTA
+    static constexpr int WARP_ROWS = CT ? 8 : 4;             // whole-batch statistics: warp rows folded into ONE row per CTA
+    static constexpr int CS = CT ? CT_C : COUT;              // channels of a statistics row
+    static constexpr int STAT_ROWS = 1;                      // whole-batch statistics rows per CTA
+    static_assert(WARP_ROWS * CS * 16 <= 2048, "the CTA's statistics fold fits its shared-memory slot");
     static_assert(128 % WO == 0 && HO % TH == 0, "a tile is 128 consecutive output pixels of one patch");
     static_assert(WO <= 32 && 32 % WO == 0, "a warp covers whole output rows (shuffle neighbours)");
     static_assert(KC % 16 == 0 && KC <= 48 && CIN % CPC == 0, "chunk = 16..48 k values");
@@ -309,7 +312,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
     const uint32_t a_empty = a_full + 16u, d_full = a_empty + 16u, d_empty = d_full + 8u;
     const uint32_t a2_full = d_empty + 8u, d2_full = a2_full + 8u;
     uint32_t* slot_mem = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 8);
-    [[maybe_unused]] float* stat_red = reinterpret_cast<float*>(bars + 32);      // 1 KB behind the 256-byte barrier block
+    [[maybe_unused]] double2* stat_red = reinterpret_cast<double2*>(bars + 32);  // 2 KB behind the 256-byte barrier block
     const uint32_t slot = smem_u32(slot_mem);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -745,16 +748,24 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
             if (prev_tile >= 0) epilogue(prev_tile, it - 1, nullptr, 0);
         }
         if constexpr (C::STATS) {
+            // whole-batch statistics: the warps' sums meet in shared memory ([quadrant (x py)][channel]) ...
             constexpr int PLAIN = 32 / C::NS - 1;
-            if (a.stats && a.stats_batch && (lane & PLAIN) == 0) {       // (every CTA of the grid has at least one tile)
-                double* dst = C::CT ? a.stats + ((((size_t)blockIdx.x * 4 + q) * 2 + wg) * C::CT_C + acc_chan) * 2
-                                    : a.stats + (((size_t)blockIdx.x * 4 + q) * COUT + wg * HALF + acc_chan) * 2;
-                dst[0] = acc_s; dst[1] = acc_q;
-            }
+            if (a.stats && a.stats_batch && (lane & PLAIN) == 0)         // (every CTA of the grid has at least one tile)
+                stat_red[C::CT ? (q * 2 + wg) * C::CS + acc_chan : q * C::CS + wg * HALF + acc_chan] = make_double2(acc_s, acc_q);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (C::STATS) {
+        // ... and leave ONE row per CTA, added in a fixed order (296 rows per launch for the finalize kernel to fold)
+        if (a.stats && a.stats_batch && tid < C::CS) {
+            double s = 0.0, q2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < C::WARP_ROWS; ++r) { const double2 v = stat_red[r * C::CS + tid]; s += v.x; q2 += v.y; }
+            double* dst = a.stats + ((size_t)blockIdx.x * C::CS + tid) * 2;
+            dst[0] = s; dst[1] = q2;
+        }
+    }
     if (warp == 8) {
         __syncwarp();
         tmem_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);

@@ -214,7 +214,7 @@ int dmb_conv2d_tm_dgrad(const float* gy, const float* w_packed, float* gx, int64
  *   data_gradient = 0: bias, optional ReLU on store.  Shape: 16 -> 8 @16 (the default decoder's first layer).
  *   data_gradient = 1: the data gradient of a stride-2 nn.Conv2d(cout -> cin, 4, 2, 1) of the training step
  *     (w_packed = that layer's weight as [its Cout][4][4][its Cin]), with the extras of dmb_conv2d_tm_dgrad: BatchNorm
- *     backward on load (y_raw / ga / gb / gc), ReLU gate, per-CTA sums (8 rows per CTA: at most twice
+ *     backward on load (y_raw / ga / gb / gc), ReLU gate, per-CTA sums (one row per CTA, at most
  *     dmb_conv2d_tm_batch_stat_rows()).  Shapes: 16 -> 16 @16 (enc.7) and 16 -> 8 @32 (enc.4).
  * scratch: dmb_conv2d_tm_scratch_floats(cin, 4*cout, 3) rounded up to 64, + cout floats.                            */
 int dmb_conv_transpose2d_tm(const float* x, const float* w_packed, const float* bias, float* y, int64_t batch, int32_t cin,

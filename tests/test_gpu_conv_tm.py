@@ -193,7 +193,7 @@ def test_tm_conv_data_gradient_form(shape, B, extras):
              _stream())
         torch.cuda.synchronize()
         assert _err(gx, ref) < TOL
-        assert 0 < rows.value <= rows_max.value and rows.value % 4 == 0
+        assert 0 < rows.value <= rows_max.value                   # one row per persistent CTA
         got = stats[:rows.value * cout * 2].reshape(rows.value, cout, 2).sum(0).cpu()
         gd = gx.double().cpu()
         other = src.double().cpu() if stat_src is not None else gd
@@ -254,7 +254,7 @@ def test_tm_conv_transpose_form(shape, B):
              ptr(gc), ptr(mask_src), ptr(ms), ptr(mt), ptr(stats), ptr(stat_src), C.byref(rows), ptr(scratch), _stream())
         torch.cuda.synchronize()
         assert _err(y, ref) < TOL
-        assert 0 < rows.value <= 2 * rows_max.value and rows.value % 8 == 0
+        assert 0 < rows.value <= rows_max.value                   # one row per persistent CTA
         got = stats[:rows.value * cout * 2].reshape(rows.value, cout, 2).sum(0).cpu()
         gd = y.double().cpu()
         other = stat_src.double().cpu() if stat_src is not None else gd

@@ -146,6 +146,18 @@ int64_t conv_wino_weight_floats(int cin, int cout);
 int pack_wino_weights(const float* w_packed, float* out, int cin, int cout, cudaStream_t st);
 int conv_wino(const ConvWinoArgs& a, cudaStream_t st);
 
+// Whole-batch statistics of conv_tm.cu finalised INSIDE the producing kernel: the last CTA to finish (ticket counter)
+// folds the per-CTA rows in a fixed order and does what bn_finalize (mode 1) / bn_backward_finalize (mode 2) would have
+// done in a launch of their own.  ticket: one zeroed unsigned in device memory, left zero again.
+struct TmFinArgs {
+    unsigned* ticket;
+    int mode;                // 0 none, 1 BatchNorm forward (scale / shift / running statistics), 2 BatchNorm backward (A, Bc, Cc, dgamma, dbeta)
+    double cnt;              // elements per channel (pixels x batch)
+    const float* gamma; const float* beta; float eps, momentum;
+    float* scale; float* shift; float* running_mean; float* running_var; float* save_mean; float* save_invstd;   // mode 1
+    const float* mean; const float* invstd; float* A; float* Bc; float* Cc; float* dgamma; float* dbeta;         // mode 2
+};
+
 // thin-channel convolutions on tcgen05 with the activation operand in tensor memory (conv_tm.cu); EVAL mode, NCHW in/out
 struct ConvTmArgs {
     const float* x;         // (B, Cin, H, W) NCHW
@@ -191,6 +203,7 @@ struct ConvTmArgs {
     // 2W); wtm = pack_tm_weights_ct image; plain (bias + optional ReLU on store) or with dg = 1 (gate / sums / dual load;
     // statistics rows: one per CTA, [Cout][2]).  Shapes: conv_tm_ct_supported.
     int ct;
+    const TmFinArgs* fin;   // whole-batch statistics finalised in the kernel (nullptr: rows only)
 };
 constexpr int TM_MAX_SMS = 192;
 constexpr int TM_BATCH_ROWS_MAX = 4 * 2 * TM_MAX_SMS;

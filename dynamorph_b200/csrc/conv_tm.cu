@@ -296,7 +296,7 @@ struct TmDgArgs {
 template <class C>
 __global__ void __launch_bounds__(TM_THREADS, C::CTAS)
 conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const TmDgArgs dg,
-               const __grid_constant__ CUtensorMap tmap2) {
+               const __grid_constant__ CUtensorMap tmap2, const TmFinArgs fin) {
     constexpr int KS = C::KS, S = C::S, CIN = C::CIN, COUT = C::COUT, W = C::W, KC = C::KC, HALF = C::HALF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -757,13 +757,80 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
     tc_fence_before();
     __syncthreads();
     if constexpr (C::STATS) {
-        // ... and leave ONE row per CTA, added in a fixed order (296 rows per launch for the finalize kernel to fold)
-        if (a.stats && a.stats_batch && tid < C::CS) {
+        // ... and leave ONE row per CTA, added in a fixed order (296 rows per launch for the finalize to fold).  The two
+        // helper warps do it: they have no output stores in flight, so their __threadfence below is cheap.
+        const bool rows_on = a.stats && a.stats_batch;
+        if (rows_on && tid >= 256 && tid - 256 < C::CS) {
+            const int c = tid - 256;
             double s = 0.0, q2 = 0.0;
 #pragma unroll
-            for (int r = 0; r < C::WARP_ROWS; ++r) { const double2 v = stat_red[r * C::CS + tid]; s += v.x; q2 += v.y; }
-            double* dst = a.stats + ((size_t)blockIdx.x * C::CS + tid) * 2;
+            for (int r = 0; r < C::WARP_ROWS; ++r) { const double2 v = stat_red[r * C::CS + c]; s += v.x; q2 += v.y; }
+            double* dst = a.stats + ((size_t)blockIdx.x * C::CS + c) * 2;
             dst[0] = s; dst[1] = q2;
+            if (fin.mode != 0) __threadfence();
+        }
+        if (fin.mode != 0 && rows_on) {
+            // the last CTA to get here folds every CTA's row and finalises the BatchNorm (no launch of its own, no wait
+            // for SM room beside the weight-gradient stream); fixed order: group g adds rows g, g + G, ..., then the groups
+            __shared__ bool last;
+            __syncthreads();
+            if (tid == 256) last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1);
+            __syncthreads();
+            if (last) {
+                __threadfence();
+                constexpr int G = 256 / C::CS;
+                double2* part = reinterpret_cast<double2*>(stage0);          // [G][CS]: the input stages are free by now
+                if (tid < 256) {
+                    const int c = tid % C::CS, g = tid / C::CS;
+                    double s = 0.0, q2 = 0.0;
+                    const double2* rows = reinterpret_cast<const double2*>(a.stats) + c;
+                    const int n = (int)gridDim.x;
+                    for (int r0 = g; r0 < n; r0 += 8 * G) {                  // eight independent loads in flight
+                        double2 v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int r = r0 + j * G;
+                            v[j] = r < n ? __ldcg(rows + (size_t)r * C::CS) : make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { s += v[j].x; q2 += v[j].y; }
+                    }
+                    part[g * C::CS + c] = make_double2(s, q2);
+                }
+                __syncthreads();
+                if (tid < C::CS) {
+                    const int c = tid;
+                    double s = 0.0, q2 = 0.0;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) { const double2 v = part[g * C::CS + c]; s += v.x; q2 += v.y; }
+                    if (fin.mode == 1) {             // bn_finalize_batch_kernel
+                        const double mean = s / fin.cnt;
+                        double var = q2 / fin.cnt - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const float invstd = (float)(1.0 / sqrt(var + (double)fin.eps));
+                        const float sc = fin.gamma[c] * invstd;
+                        fin.scale[c] = sc;
+                        fin.shift[c] = fin.beta[c] - (float)mean * sc;
+                        if (fin.save_mean) { fin.save_mean[c] = (float)mean; fin.save_invstd[c] = invstd; }
+                        if (fin.running_mean) {
+                            const double unbiased = fin.cnt > 1.0 ? var * fin.cnt / (fin.cnt - 1.0) : var;
+                            fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mean;
+                            fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unbiased;
+                        }
+                    } else {                         // bn_bwd_finalize_batch_kernel: s = sum g, q2 = sum g * y
+                        const double N = fin.cnt;
+                        const double mu = fin.mean[c], is = fin.invstd[c], gm = fin.gamma[c];
+                        const double dbeta = s;
+                        const double dgamma = is * (q2 - mu * s);
+                        fin.A[c] = (float)(gm * is);
+                        fin.Bc[c] = (float)(-gm * is * is * dgamma / N);
+                        fin.Cc[c] = (float)(-gm * is * dbeta / N + gm * is * is * mu * dgamma / N);
+                        fin.dgamma[c] = (float)dgamma;
+                        fin.dbeta[c] = (float)dbeta;
+                    }
+                }
+                if (tid == 0) *fin.ticket = 0u;
+            }
         }
     }
     if (warp == 8) {
@@ -893,7 +960,16 @@ int launch_tm(const ConvTmArgs& a, cudaStream_t st) {
     const int64_t grid = std::min<int64_t>(k.ntiles, (int64_t)sms * C::CTAS);
     DMB_CHECK(grid > 0, "conv_tm: empty launch");
     if (a.stat_rows) *a.stat_rows = (int)grid * C::STAT_ROWS;
-    DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k, d, map2);
+    TmFinArgs fin{};
+    if (a.fin) {
+        if constexpr (C::STATS) {
+            DMB_CHECK(a.fin->ticket && a.stats && a.stats_batch && (a.fin->mode == 1 || a.fin->mode == 2), "conv_tm: the in-kernel finalize needs a ticket and whole-batch statistics");
+            fin = *a.fin;
+        } else {
+            DMB_CHECK(false, "conv_tm: this form leaves no statistics to finalise");
+        }
+    }
+    DMB_LAUNCH((kern), (unsigned)grid, TM_THREADS, C::SMEM, st, map, k, d, map2, fin);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

@@ -457,7 +457,17 @@ struct Ctx {
     float* bnbuf;      // running stats to update in BATCH mode (may be null)
     cudaStream_t st;
     const dmb_sync_bn* sync = nullptr;     // synchronised BatchNorm across data-parallel ranks (BATCH mode only)
+    unsigned* fin_ticket = nullptr;        // zeroed counter: whole-batch BatchNorm finalised inside conv_tm.cu (training step)
     bool per_sample() const { return mode == DMB_BN_PER_SAMPLE; }
+    // Opt-in (DMB_TM_FIN=1): the last CTA of a conv_tm launch finalises the BatchNorm it left sums for, instead of a
+    // bn_finalize / bn_backward_finalize launch (68 instead of 79 launches per step).  Measured slower at batch 256: the
+    // serial fold of 296 rows by one CTA (fence, ticket, one or two L2 round trips, the fold) adds 4-5 us to every
+    // producing kernel, a separate finalize launch under programmatic dependent launch costs 3-4 (0.827 against 0.820 ms).
+    bool fin_in_kernel() const {
+        if (!fin_ticket || mode != DMB_BN_BATCH || synced()) return false;
+        const char* e = getenv("DMB_TM_FIN");
+        return e && e[0] == '1';
+    }
     bool synced() const { return sync && sync->world > 1 && sync->allreduce && mode == DMB_BN_BATCH; }
     // fold the per-CTA partials of one BatchNorm into [C][2] doubles and sum those across the ranks
     int exchange(const double* partials, int64_t rows, int C, double* gsum) const {
@@ -502,6 +512,7 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
     BnWs* bw = bn_live ? &c.w.bn[l.bn] : nullptr;
     int Ho, Wo;
     int stat_rows = 0;      // whole-batch statistics: rows of partials when that is not B * nbands
+    bool fin_done = false;  // ... already finalised inside the producing kernel
     if (l.transposed && l.pctm_off >= 0 && !bn_live && !in.s && !in_relu && tm_ct_enabled() && c.B >= tm_min_batch() &&
         conv_tm_ct_supported(l.cin, l.cout, H, W, false)) {
         // ConvTranspose2d on the tensor cores: 3x3 on the input grid + pixel shuffle (conv_tm.cu, CT form)
@@ -531,6 +542,20 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         a.stats = bw->part;
         a.stats_batch = c.per_sample() ? 0 : 1; a.stat_rows = &stat_rows;
         DMB_CHECK(bw->nbands == conv_tm_bands(l.cin, l.cout, l.ks, l.stride, H, W), "statistics layout of conv %d", ci);
+        TmFinArgs fin{};
+        if (c.fin_in_kernel()) {     // the last CTA finalises the BatchNorm: no bn_finalize launch below
+            const BnL& b = c.L.bns[l.bn];
+            fin.ticket = c.fin_ticket; fin.mode = 1;
+            fin.cnt = (double)(H / l.stride) * (W / l.stride) * (double)c.B;
+            fin.gamma = c.packed + b.pg_off; fin.beta = c.packed + b.pb_off;
+            fin.eps = c.L.m.bn_eps; fin.momentum = c.L.m.bn_momentum;
+            fin.scale = bw->scale; fin.shift = bw->shift;
+            fin.running_mean = c.bnbuf ? c.bnbuf + b.rm_off : nullptr;
+            fin.running_var = c.bnbuf ? c.bnbuf + b.rv_off : nullptr;
+            fin.save_mean = bw->mean; fin.save_invstd = bw->invstd;
+            a.fin = &fin;
+            fin_done = true;
+        }
         DMB_TRY(conv_tm(a, c.st));
         if (c.per_sample()) stat_rows = 0;
         Ho = H / l.stride; Wo = W / l.stride;
@@ -566,7 +591,9 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         Ho = a.Ho; Wo = a.Wo;
     }
     if (result) { result->p = out; result->s = nullptr; result->t = nullptr; }
-    if (bn_live) {
+    if (bn_live && fin_done) {
+        if (result) { result->s = bw->scale; result->t = bw->shift; }
+    } else if (bn_live) {
         const BnL& b = c.L.bns[l.bn];
         BnFinalizeArgs f{};
         f.partials = bw->part; f.B = (int)c.B; f.nbands = bw->nbands; f.C = l.cout; f.rows = stat_rows;
@@ -961,9 +988,28 @@ struct Bwd {
     SideStream* side = nullptr;
     bool forked = false;
     int stat_rows = 0;      // rows of partial sums the LAST dgrad_layer call left when that is not B * nbands (conv_tm.cu)
+    int fin_bn = -1;        // BatchNorm whose backward the LAST dgrad_layer call finalised inside its kernel (-1: none)
     WgReduceQueue rq;       // folds of the weight-gradient partials, launched once (flush_wgrad) when wg_queue
     size_t wg_off = 0;
     bool ps() const { return c.per_sample(); }
+    // in-kernel BatchNorm-backward finalize for the sums a data-gradient kernel leaves in `stats` (a bnb[].part)
+    bool fill_fin(double* stats, int64_t count, TmFinArgs& fin) {
+        fin_bn = -1;
+        if (!stats || !c.fin_in_kernel()) return false;
+        int bn = -1;
+        for (size_t j = 0; j < c.w.bnb.size(); ++j)
+            if (c.w.bnb[j].part == stats) bn = (int)j;
+        if (bn < 0) return false;          // (bias_part: a plain sum, folded by sum_partials)
+        const BnL& b = c.L.bns[bn];
+        Workspace::BnB& bb = c.w.bnb[bn];
+        BnWs& bw = c.w.bn[bn];
+        fin = TmFinArgs{};
+        fin.ticket = c.fin_ticket; fin.mode = 2; fin.cnt = (double)count * (double)c.B;
+        fin.gamma = c.packed + b.pg_off; fin.mean = bw.mean; fin.invstd = bw.invstd;
+        fin.A = bb.A; fin.Bc = bb.Bc; fin.Cc = bb.Cc; fin.dgamma = grads + b.g_off; fin.dbeta = grads + b.b_off;
+        fin_bn = bn;
+        return true;
+    }
     // scratch for the next weight-gradient launch (need floats) and the queue its fold goes to (nullptr: fold at once)
     int wgrad_scratch(size_t need, float** part, WgReduceQueue** q) {
         if (c.w.wg_queue) {
@@ -1043,6 +1089,7 @@ struct Bwd {
         const float* zero = c.packed + c.L.pzero_off;
         const bool up = (!l.transposed && l.stride == 2);      // conv stride 2 -> transposed-conv kernel
         stat_rows = 0;
+        fin_bn = -1;
         if (up && l.pdtm_off >= 0 && !ps() && tm_dg_enabled() && tm_ct_enabled() && c.B >= tm_min_batch() && !skip &&
             conv_tm_ct_supported(l.cout, l.cin, H / 2, W / 2, true)) {
             // stride-2 convolution: its data gradient is a transposed convolution over the output map -- tensor cores,
@@ -1055,6 +1102,8 @@ struct Bwd {
             if (gate) { a.mask_src = gate->p; a.mask_s = gate->s; a.mask_t = gate->t; }
             a.stats = stats; a.stat_src = stat_src; a.stats_batch = 1; a.stat_rows = &stat_rows;
             if (nbands) *nbands = 0;
+            TmFinArgs fin{};
+            if (fill_fin(stats, (int64_t)H * W, fin)) a.fin = &fin;
             DMB_TRY(conv_tm(a, st));
             if (!stats) stat_rows = 0;
             return 0;
@@ -1081,6 +1130,8 @@ struct Bwd {
             if (gate) { a.mask_src = gate->p; a.mask_s = gate->s; a.mask_t = gate->t; }
             a.stats = stats; a.stat_src = stat_src; a.stats_batch = 1; a.stat_rows = &stat_rows;
             if (nbands) *nbands = 0;
+            TmFinArgs fin{};
+            if (fill_fin(stats, (int64_t)a.H / a.stride * (a.W / a.stride), fin)) a.fin = &fin;
             DMB_TRY(conv_tm(a, st));
             if (!stats) stat_rows = 0;
             return 0;
@@ -1131,6 +1182,11 @@ struct Bwd {
         const BnL& b = c.L.bns[l.bn];
         Workspace::BnB& bb = c.w.bnb[l.bn];
         BnWs& bw = c.w.bn[l.bn];
+        if (fin_bn == l.bn) {      // the kernel that left these sums finalised them too
+            fin_bn = -1;
+            G->g = g; G->y = y; G->A = bb.A; G->Bc = bb.Bc; G->Cc = bb.Cc;
+            return 0;
+        }
         BnBwdArgs a{};
         a.partials = bb.part; a.B = (int)c.B; a.nbands = nbands; a.C = l.cout; a.count_per_sample = count;
         a.rows = stat_rows;      // (set by the dgrad_layer call that left these sums)
@@ -1843,9 +1899,10 @@ static int train_forward_impl(const dmb_model* m, const float* packed, const flo
     cudaStream_t st = (cudaStream_t)stream;
     Ctx c{L, packed, w, batch, DMB_BN_BATCH, bnbuf_inout, st, sync};
     Pending pend;
-    DMB_TRY(run_encoder(c, x, w.zb, &pend));
     DMB_CUDA(cudaMemsetAsync(w.vq_stats, 0, sizeof(double) * (2 + m->num_embeddings), st));
     DMB_CUDA(cudaMemsetAsync(w.recon_sum, 0, sizeof(double) * 4, st));
+    c.fin_ticket = reinterpret_cast<unsigned*>(w.recon_sum + 3);       // zeroed above; every user leaves it zero
+    DMB_TRY(run_encoder(c, x, w.zb, &pend));
     DMB_TRY(run_vq(c, params + L.codebook_off, w.zb, &pend, w.zb, w.za, w.idx, w.vq_stats));
     DMB_TRY(dmb_vq_finalize(w.vq_stats, L.D, m->num_embeddings, m->commitment_cost, w.scalars, stream));
     if (dec_tail2_on(L)) {
@@ -1925,6 +1982,7 @@ int dmb_train_backward_sync(const dmb_model* m, const float* packed, const float
     DMB_CHECK(packed && params && x && channel_var && decoded && grads, "dmb_train_backward: null pointer");
     DMB_TRY(prep(m, batch, DMB_BN_BATCH, 1, workspace, workspace_bytes, L, w));
     Ctx c{L, packed, w, batch, DMB_BN_BATCH, nullptr, (cudaStream_t)stream, sync};
+    c.fin_ticket = reinterpret_cast<unsigned*>(w.recon_sum + 3);       // zeroed by the forward pass, left zero by every user
     const float* g_tm = nullptr;
     if (tm) {
         // d(weight * tm_loss)/dz; z_after is a straight-through copy of z_before, so either source feeds dL/dz_before

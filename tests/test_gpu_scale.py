@@ -237,7 +237,8 @@ def test_train_step_dispatch_variants_agree_at_a_ragged_batch(monkeypatch):
     """Batch 259 (tile counts that are no multiple of the persistent grid) through the default dispatch -- forward, data
     gradients and the first ConvTranspose2d on the tensor-memory kernels -- against the CUDA-core kernels of round 1
     (DMB_TM_BN_BATCH / DMB_TM_DG / DMB_TM_CT / DMB_DEC_TAIL2 = 0), against the opt-in queued weight-gradient folds
-    (DMB_WG_QUEUE=1) and against the decoder tail without dec.4 fused in (DMB_DEC_TAIL2=0):
+    (DMB_WG_QUEUE=1), against the decoder tail without dec.4 fused in (DMB_DEC_TAIL2=0) and against the opt-in
+    BatchNorm finalize inside the producing kernel (DMB_TM_FIN=1):
     losses agree to fp32 round-off and every gradient tensor to 5e-3 of its largest entry (different round-off flips a
     few ReLU gates at near-ties, a discrete change that grows towards the first layers: measured 1e-3 at enc.0; the
     fp64-referenced envelope of test_c2_train_step_batch_256 is the parity statement, this one guards the ragged loops)."""
@@ -248,7 +249,7 @@ def test_train_step_dispatch_variants_agree_at_a_ragged_batch(monkeypatch):
     x = O.synthetic_patches(B, 77).cuda()
 
     def run(env):
-        for k in ("DMB_TM_BN_BATCH", "DMB_TM_DG", "DMB_TM_CT", "DMB_WG_QUEUE", "DMB_DEC_TAIL2"):
+        for k in ("DMB_TM_BN_BATCH", "DMB_TM_DG", "DMB_TM_CT", "DMB_WG_QUEUE", "DMB_DEC_TAIL2", "DMB_TM_FIN"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -263,7 +264,7 @@ def test_train_step_dispatch_variants_agree_at_a_ragged_batch(monkeypatch):
 
     g0, l0, views = run({})
     for env in ({"DMB_TM_BN_BATCH": "0", "DMB_TM_DG": "0", "DMB_TM_CT": "0", "DMB_DEC_TAIL2": "0"}, {"DMB_WG_QUEUE": "1"},
-                {"DMB_DEC_TAIL2": "0"}):
+                {"DMB_DEC_TAIL2": "0"}, {"DMB_TM_FIN": "1"}):
         g1, l1, _ = run(env)
         assert torch.allclose(l0[:5], l1[:5], rtol=2e-5, atol=1e-7), (env, l0, l1)
         for name, off, n in views:

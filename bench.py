@@ -408,6 +408,39 @@ def pcie_h2d_peak(dev, barrier=None):
     return best
 
 
+def pcie_duplex_peak(dev, barrier=None):
+    """What the end-to-end step actually asks of the host link: device -> pinned host alone, and host -> device WHILE
+    device -> host runs (256 MB in, 132 MB out: the byte ratio of the raw-input step), every rank at the same time.
+    Returns (d2h_alone, h2d_duplex, d2h_duplex) in GB/s for this rank, best of 3."""
+    n_in, n_out = 64 << 20, 33 << 20
+    h_in = torch.empty(n_in, dtype=torch.float32, pin_memory=True)
+    d_in = torch.empty(n_in, dtype=torch.float32, device=dev)
+    h_out = torch.empty(n_out, dtype=torch.float32, pin_memory=True)
+    d_out = torch.empty(n_out, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = [0.0, 0.0, 0.0]
+    for _ in range(3):
+        if barrier is not None:
+            barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        best[0] = max(best[0], n_out * 4 / (time.perf_counter() - t0) / 1e9)
+        if barrier is not None:
+            barrier()
+        torch.cuda.synchronize()
+        a0, a1, b0, b1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        with torch.cuda.stream(s1):
+            a0.record(s1); d_in.copy_(h_in, non_blocking=True); a1.record(s1)
+        with torch.cuda.stream(s2):
+            b0.record(s2); h_out.copy_(d_out, non_blocking=True); b1.record(s2)
+        torch.cuda.synchronize()
+        best[1] = max(best[1], n_in * 4 / (a0.elapsed_time(a1) * 1e-3) / 1e9)
+        best[2] = max(best[2], n_out * 4 / (b0.elapsed_time(b1) * 1e-3) / 1e9)
+    return best
+
+
 def parity_sample(model, x_dev, zb_rows, idx_rows, k, raw=None, seed=0):
     """Oracle parity of `k` patches spread over a timed batch (first / last 16 + random rows): z_before within 1e-4
     relative, code indices equal except where the oracle's best / second-best gap is below 1e-6 relative (the bar of
@@ -653,6 +686,10 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
     h2d_peak_total = float(tt[0])
+    tt = torch.tensor(pcie_duplex_peak(dev, barrier), device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+    d2h_alone_total, h2d_duplex_total, d2h_duplex_total = (float(v) for v in tt)
 
     # ---- parity of the TIMED device path: 256 patches spread over the timed batch against the oracle
     step("eval")
@@ -743,6 +780,12 @@ def run_ours(args):
                          "h2d_gbs_peak_all_ranks_measured": h2d_peak_total,
                          "frac": e2e16_value * (x16.numel() * 2 / ne) / 1e9 / h2d_peak_total,
                          "frac_float32": e2e_value * (x_host.numel() * 4 / ne) / 1e9 / h2d_peak_total,
+                         "d2h_gbs_peak_all_ranks_measured": d2h_alone_total,
+                         "duplex": {"h2d_gbs": h2d_duplex_total, "d2h_gbs": d2h_duplex_total,
+                                    "d2h_gbs_achieved_all_ranks": e2e16_value * (d2h / ne) / 1e9,
+                                    "frac_h2d": e2e16_value * (x16.numel() * 2 / ne) / 1e9 / max(h2d_duplex_total, 1e-9),
+                                    "note": "both directions at once, 256 MB in / 132 MB out per rank (the byte ratio of "
+                                            "the raw-input step), every rank at the same time: the link as the step uses it"},
                          "note": "peak = pinned host->device copies issued by all ranks at the same time (256 MB each, "
                                  "best of 5), summed; the end-to-end step is bound by it"}},
         "gpu_launches": int(launches),

@@ -798,7 +798,9 @@ def run_ours(args):
                        "batch_512_per_gpu": train[512],
                        "run_one_batch_ms": eager_ms,
                        "run_one_batch_note": "the reference's own step API (run_training.run_one_batch: autograd + "
-                                             "optimizer.step + zero_grad + one host read-back), batch 256, wall clock"},
+                                             "optimizer.step + zero_grad + one host read-back), batch 256, wall clock; "
+                                             "forward and backward are CUDA-graph replays from the second call of a "
+                                             "batch geometry on (dynamorph_b200/autograd.py)"},
         "per_sample_bn": {"value": world * chunk / (ms_ps * 1e-3), "unit": "patches/s", "ms_per_step": ms_ps,
                           "note": "as-written process_VAE semantics (train-mode BN, batch 1) at batch speed"},
     }

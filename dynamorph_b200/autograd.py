@@ -46,6 +46,54 @@ class VQFunction(torch.autograd.Function):
         return gz, gcb, None
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Graph replay behind the eager API.  `model(batch)` + `total_loss.backward()` is what the reference's run_one_batch does
+# every step (run_training.py:404-406); the library's forward and backward are ~80 launches each way, issued from the
+# host every call.  From the second call with the same batch geometry on, both are CUDA-graph replays over static buffers
+# (the plan machinery of trainer.FusedTrainer): the inputs are copied in, the outputs cloned out, autograd still routes the
+# gradient of total_loss.  DMB_EAGER_GRAPH=0 keeps every call eager.
+# ---------------------------------------------------------------------------------------------------------------------
+def _eager_graphs_enabled() -> bool:
+    import os
+    return os.environ.get("DMB_EAGER_GRAPH", "1") != "0"
+
+
+def _eager_plan(model, x, mask, time_matching_mat):
+    """The captured (forward graph, backward graph) pair for this batch geometry, or None (first call of a geometry,
+    capture in progress elsewhere, disabled)."""
+    if not _eager_graphs_enabled() or torch.cuda.is_current_stream_capturing():
+        return None
+    eng = model._engine
+    key = (tuple(x.shape), None if mask is None else tuple(mask.shape), time_matching_mat is not None,
+           eng._flat.data_ptr(), x.device.index)
+    seen = model.__dict__.setdefault("_eager_seen", {})
+    if key not in seen:
+        if len(seen) >= 8:
+            seen.pop(next(iter(seen)))
+        seen[key] = None                      # first call of this geometry runs eagerly (lazy initialisation, warm-up)
+        return None
+    if seen[key] is None:
+        from .trainer import FusedTrainer
+        tr = model.__dict__.get("_eager_tr")
+        if tr is None or tr.eng is not eng or tr.eng._flat.data_ptr() != eng._flat.data_ptr():
+            tr = model.__dict__["_eager_tr"] = FusedTrainer(model, lr=0.0, use_graph=False)
+            tr.world, tr.sync_bn = 1, False
+        with torch.cuda.device(x.device):
+            st = tr._plan(x, mask, time_matching_mat)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf, stream=side):
+                tr._forward(st)
+            with torch.cuda.graph(gb, stream=side):
+                tr._backward(st)
+            # (capture records, it does not run: the counters / flags _forward touched on the host are put back)
+        seen[key] = {"tr": tr, "st": st, "gf": gf, "gb": gb, "n": 0}
+    return seen[key]
+
+
 class TrainStepFunction(torch.autograd.Function):
     """Whole-model forward (train-mode BatchNorm) with the gradient of `total_loss` w.r.t. every
     trainable tensor computed by the fused backward schedule (dmb_train_forward / dmb_train_backward)."""
@@ -57,6 +105,30 @@ class TrainStepFunction(torch.autograd.Function):
         eng = model._engine
         x = _require_cuda(inputs.detach(), "inputs")
         B, Cin, H, W = x.shape
+        if batch_mask is not None:
+            _m = _require_cuda(batch_mask.detach(), "batch_mask")
+            if _m.shape[0] != B or tuple(_m.shape[2:]) != (H, W) or _m.shape[1] not in (1, Cin):
+                batch_mask = _m.expand(B, Cin, H, W).contiguous()
+        if time_matching_mat is not None and tuple(time_matching_mat.shape) != (B, B):
+            raise AssertionError("sim_mat.shape == time_matching_mat.shape")      # vq_vae.py:329
+        gp = _eager_plan(model, x, None if batch_mask is None else batch_mask.detach(), time_matching_mat)
+        if gp is not None:
+            tr, st = gp["tr"], gp["st"]
+            with torch.cuda.device(x.device):
+                tr._load(st, x, None if batch_mask is None else batch_mask.detach(), time_matching_mat)
+                gp["gf"].replay()
+            gp["n"] += 1
+            eng._bn_dirty += 1
+            ctx.graph_plan, ctx.graph_n = gp, gp["n"]
+            ctx.model = model
+            ctx.set_materialize_grads(False)
+            decoded = st.decoded.clone()
+            losses = tr.losses.clone()
+            ctx.mark_non_differentiable(decoded)
+            recon, commit, total, ppl, tml = losses[0], losses[1], losses[2], losses[3], losses[4]
+            ctx.mark_non_differentiable(ppl)
+            return decoded, recon, commit, total, ppl, tml
+        ctx.graph_plan = None
         s = eng.spec(H, W)
         packed = eng.packed(BN_BATCH, H, W)
         ws, n = eng.workspace(s, B, BN_BATCH, 1)
@@ -99,6 +171,18 @@ class TrainStepFunction(torch.autograd.Function):
                                       "commitment_loss are reported values of the fused step)")
         if g_total is None:
             return (None,) * (4 + len(eng.trainable()))
+        if ctx.graph_plan is not None:
+            gp = ctx.graph_plan
+            if gp["n"] != ctx.graph_n:
+                raise RuntimeError("dynamorph_b200: the activation workspace was reused by another call before "
+                                   "backward(); call backward() right after the forward of the same batch")
+            with torch.cuda.device(gp["st"].x.device):
+                gp["gb"].replay()
+            flat_g = gp["tr"].grad.clone()
+            flat_g.mul_(g_total)
+            eng.last_flat_grad = flat_g
+            grads = tuple(flat_g[off:off + n].view(p.shape) if p.requires_grad else None for p, off, n in eng._views)
+            return (None, None, None, None) + grads
         if eng.workspace_token() != ctx.ws_token:
             raise RuntimeError("dynamorph_b200: the activation workspace was reused by another call before "
                                "backward(); call backward() right after the forward of the same batch")

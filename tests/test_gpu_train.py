@@ -265,3 +265,46 @@ def test_device_augmentation_matches_reference_loop(shape):
     assert got.data_ptr() == xg.data_ptr()          # transformed in place, like the reference
     assert torch.equal(got.cpu(), ref)
     assert after_ref == after_got
+
+
+@pytest.mark.parametrize("name", ["vqvae_default", "z16_masked"])
+def test_eager_api_graph_replay_is_the_eager_step(name, U, monkeypatch):
+    """`model(batch)` + `total_loss.backward()` replays captured CUDA graphs from the second call of a batch geometry on
+    (dynamorph_b200/autograd.py).  Same kernels, same order: five run_one_batch steps end with bit-identical parameters,
+    running statistics and loss curves with and without the graphs (DMB_EAGER_GRAPH=0)."""
+    from dynamorph_b200.run_training import run_one_batch
+    from dynamorph_b200.optim import FusedAdam
+    g = Golden(name)
+    x = g.t("x_train").cuda()
+    results = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DMB_EAGER_GRAPH", flag)
+        m = U.model_from_state(g.state()).train()
+        opt = FusedAdam(m, lr=1e-3)
+        tl = {}
+        for _ in range(5):
+            m, tl = run_one_batch(m, x.clone(), tl, model_kwargs={"batch_mask": _mask(g)}, optimizer=opt, transform=None,
+                                  training=True)
+        assert ("_eager_tr" in m.__dict__) == (flag == "1")           # the graphs were (not) built
+        results.append((tl, {k: v.detach().clone() for k, v in m.state_dict().items()}))
+    (tl1, sd1), (tl0, sd0) = results
+    assert tl1["total_loss"] == tl0["total_loss"] and tl1["perplexity"] == tl0["perplexity"]
+    for k in sd0:
+        assert torch.equal(sd1[k], sd0[k]), k
+
+
+def test_eager_api_backward_after_another_forward_raises(U):
+    """The activations of a forward live in one workspace per batch geometry: backward() after ANOTHER forward of the same
+    geometry must fail loudly, graph replay or not (third call on: replayed graphs)."""
+    g = Golden("vqvae_default")
+    m = U.model_from_state(g.state()).train()
+    x = g.t("x_train").cuda()
+    for _ in range(2):
+        m(x)[1]["total_loss"].backward()
+        m.zero_grad()
+    _, d1 = m(x)
+    _, d2 = m(x)
+    with pytest.raises(RuntimeError, match="reused by another call"):
+        d1["total_loss"].backward()
+    d2["total_loss"].backward()
+    assert all(p.grad is not None for p in m.parameters() if p.requires_grad)

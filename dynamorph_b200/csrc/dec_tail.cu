@@ -92,9 +92,9 @@ __global__ void __launch_bounds__(256) dec_tail_forward_kernel(const TailArgs a)
 // is written once and never read back by the forward (vq_vae.py:296-298, :322).
 //   out[co][2y+py][2x+px] = b[co] + sum_ci sum_{dy in {py-1, py}} sum_{dx in {px-1, px}} in[ci][y+dy][x+dx] * w[ci][ky][kx][co]
 //   with ky = py + 1 - 2 dy, kx = px + 1 - 2 dx.
-// A thread owns input pixel (y, x) and output row parity py: the px pair of output pixels for all CM channels (float2
-// stores, a warp = 32 consecutive x = 256 contiguous bytes per channel); py is warp-uniform, so the weight reads are
-// 16-byte shared-memory broadcasts.
+// A thread owns two adjacent input pixels and output row parity py: four consecutive output pixels for all CM channels
+// (float4 stores, a warp = 64 consecutive x = 512 contiguous bytes per channel); py is warp-uniform, so the weight reads
+// are 16-byte shared-memory broadcasts.
 struct Tail2Args {
     const float* t2;       // (B, CI, Hi, Wi) post-ReLU input of dec.4
     const float* w4;       // dec.4 packed [CI][4][4][CM]
@@ -111,8 +111,11 @@ struct Tail2Args {
 };
 
 template <int CI, int CM, int NI>
-__global__ void __launch_bounds__(256, 4) dec_tail2_forward_kernel(const Tail2Args a) {
+__global__ void __launch_bounds__(256, 3) dec_tail2_forward_kernel(const Tail2Args a) {
     static_assert(CM == 4, "one float4 of output channels per tap");
+    // A thread owns TWO adjacent input pixels (x0, x0 + 1) and one output row parity: four consecutive output pixels
+    // per channel = one float4 store; the 2 x 4 input window is one 8-byte and two 4-byte loads per row and channel, and
+    // every weight read serves both pixels (the one-pixel form spent 518 instructions per item for 144 FMAs).
     pdl_wait();
     __shared__ float4 w4s[CI * 16];
     __shared__ double red[8];
@@ -126,72 +129,88 @@ __global__ void __launch_bounds__(256, 4) dec_tail2_forward_kernel(const Tail2Ar
     }
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b4));
     __syncthreads();
-    const int wi = a.wi, hi = a.hi, wo = 2 * wi;
+    const int wi = a.wi, hi = a.hi, wo = 2 * wi, wh = wi >> 1;
     const size_t in_plane = (size_t)hi * wi, out_plane = 4 * in_plane;
+    const int64_t items = a.items >> 1;
     double acc = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < a.items; i += (int64_t)gridDim.x * 256) {
-        const int x = (int)(i & (wi - 1));
-        int64_t r = i >> a.lw;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < items; i += (int64_t)gridDim.x * 256) {
+        const int x0 = 2 * (int)(i & (wh - 1));
+        int64_t r = i >> (a.lw - 1);
         const int py = (int)(r & 1); r >>= 1;
         const int y = (int)(r & (hi - 1));
         const int64_t b = r >> a.lh;
-        // the 2 x 3 input window of every channel: rows y + py - 1, y + py; columns x - 1, x, x + 1 (zero outside)
-        float v[CI][2][3];
+        // rows y + py - 1, y + py; columns x0 - 1 .. x0 + 2 (zero outside the map)
+        float v[CI][2][4];
         const float* ip = a.t2 + (size_t)b * CI * in_plane;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
             const int yy = y + py - 1 + d;
             const bool rok = (unsigned)yy < (unsigned)hi;
+            const bool lok = rok && x0 > 0, hok = rok && x0 + 2 < wi;
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                const int xx = x - 1 + e;
-                const bool ok = rok && (unsigned)xx < (unsigned)wi;
-#pragma unroll
-                for (int ci = 0; ci < CI; ++ci) v[ci][d][e] = ok ? __ldg(ip + ci * in_plane + (size_t)yy * wi + xx) : 0.f;
+            for (int ci = 0; ci < CI; ++ci) {
+                const float* rp = ip + ci * in_plane + (size_t)(rok ? yy : 0) * wi + x0;
+                const float2 m = rok ? __ldg(reinterpret_cast<const float2*>(rp)) : make_float2(0.f, 0.f);
+                v[ci][d][0] = lok ? __ldg(rp - 1) : 0.f;
+                v[ci][d][1] = m.x; v[ci][d][2] = m.y;
+                v[ci][d][3] = hok ? __ldg(rp + 2) : 0.f;
             }
         }
-        const size_t opix = (size_t)(2 * y + py) * wo + 2 * x;
-        // the batch (and mask) values of this pixel pair: issued before the arithmetic, used after it
-        float2 xv[NI], mk[NI];
+        const size_t opix = (size_t)(2 * y + py) * wo + 2 * x0;
+        float4 xv[NI], mk[NI];
 #pragma unroll
         for (int o = 0; o < NI; ++o) {
             const size_t pi = ((size_t)b * NI + o) * out_plane + opix;
-            xv[o] = __ldg(reinterpret_cast<const float2*>(a.x + pi));
-            mk[o] = make_float2(1.f, 1.f);
-            if (a.mask) mk[o] = __ldg(reinterpret_cast<const float2*>(a.mask + ((a.mask_c == 1) ? (size_t)b * out_plane + opix : pi)));
+            xv[o] = __ldg(reinterpret_cast<const float4*>(a.x + pi));
+            mk[o] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (a.mask) mk[o] = __ldg(reinterpret_cast<const float4*>(a.mask + ((a.mask_c == 1) ? (size_t)b * out_plane + opix : pi)));
         }
-        float4 o0 = b4, o1 = b4;                 // px = 0, 1
+        // o[q]: output pixel 2 x0 + q (q = 2 j + px for input pixel x0 + j), four channels each
+        float4 o[4] = {b4, b4, b4, b4};
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
-                const int ky = py + 3 - 2 * (py + d);           // dy = py - 1 + d  ->  ky = py + 1 - 2 dy
+                const int ky = 3 - py - 2 * d;                  // dy = py - 1 + d  ->  ky = py + 1 - 2 dy
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    // px = 0: dx = -1 + e (columns x-1, x), kx = 3 - 2e;  px = 1: dx = e (columns x, x+1), kx = 2 - 2e
+                    // px = 0: dx = -1 + e, kx = 3 - 2e;  px = 1: dx = e, kx = 2 - 2e
                     const float4 wa = w4s[(ci * 4 + ky) * 4 + (3 - 2 * e)];
                     const float4 wb = w4s[(ci * 4 + ky) * 4 + (2 - 2 * e)];
-                    const float va = v[ci][d][e], vb = v[ci][d][e + 1];
-                    o0.x = fmaf(va, wa.x, o0.x); o0.y = fmaf(va, wa.y, o0.y); o0.z = fmaf(va, wa.z, o0.z); o0.w = fmaf(va, wa.w, o0.w);
-                    o1.x = fmaf(vb, wb.x, o1.x); o1.y = fmaf(vb, wb.y, o1.y); o1.z = fmaf(vb, wb.z, o1.z); o1.w = fmaf(vb, wb.w, o1.w);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float va = v[ci][d][j + e], vb = v[ci][d][j + e + 1];
+                        float4& oa = o[2 * j];
+                        float4& ob = o[2 * j + 1];
+                        oa.x = fmaf(va, wa.x, oa.x); oa.y = fmaf(va, wa.y, oa.y); oa.z = fmaf(va, wa.z, oa.z); oa.w = fmaf(va, wa.w, oa.w);
+                        ob.x = fmaf(vb, wb.x, ob.x); ob.y = fmaf(vb, wb.y, ob.y); ob.z = fmaf(vb, wb.z, ob.z); ob.w = fmaf(vb, wb.w, ob.w);
+                    }
                 }
             }
-        const float t0[CM] = {fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f)};
-        const float t1[CM] = {fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f)};
+        float t[CM][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            t[0][q] = fmaxf(o[q].x, 0.f); t[1][q] = fmaxf(o[q].y, 0.f); t[2][q] = fmaxf(o[q].z, 0.f); t[3][q] = fmaxf(o[q].w, 0.f);
+        }
         float* tp = a.t3 + (size_t)b * CM * out_plane + opix;
 #pragma unroll
-        for (int c = 0; c < CM; ++c) *reinterpret_cast<float2*>(tp + c * out_plane) = make_float2(t0[c], t1[c]);
+        for (int c = 0; c < CM; ++c) *reinterpret_cast<float4*>(tp + c * out_plane) = make_float4(t[c][0], t[c][1], t[c][2], t[c][3]);
         float part = 0.f;
 #pragma unroll
-        for (int o = 0; o < NI; ++o) {
-            float d0 = 0.f, d1 = 0.f;
+        for (int oc = 0; oc < NI; ++oc) {
+            float dv[4];
 #pragma unroll
-            for (int c = 0; c < CM; ++c) { d0 = fmaf(w6[c][o], t0[c], d0); d1 = fmaf(w6[c][o], t1[c], d1); }
-            d0 += b6[o]; d1 += b6[o];
-            const size_t pi = ((size_t)b * NI + o) * out_plane + opix;
-            *reinterpret_cast<float2*>(a.decoded + pi) = make_float2(d0, d1);
-            const float e0 = d0 * mk[o].x - xv[o].x * mk[o].x, e1 = d1 * mk[o].y - xv[o].y * mk[o].y;
-            part += (e0 * e0) / cv[o] + (e1 * e1) / cv[o];
+            for (int q = 0; q < 4; ++q) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < CM; ++c) s = fmaf(w6[c][oc], t[c][q], s);
+                dv[q] = s + b6[oc];
+            }
+            const size_t pi = ((size_t)b * NI + oc) * out_plane + opix;
+            *reinterpret_cast<float4*>(a.decoded + pi) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            const float e0 = dv[0] * mk[oc].x - xv[oc].x * mk[oc].x, e1 = dv[1] * mk[oc].y - xv[oc].y * mk[oc].y;
+            const float e2 = dv[2] * mk[oc].z - xv[oc].z * mk[oc].z, e3 = dv[3] * mk[oc].w - xv[oc].w * mk[oc].w;
+            part += ((e0 * e0) / cv[oc] + (e1 * e1) / cv[oc]) + ((e2 * e2) / cv[oc] + (e3 * e3) / cv[oc]);
         }
         acc += (double)part;
     }
@@ -362,8 +381,8 @@ int dec_tail2_forward(const DecTail2Args& d, cudaStream_t st) {
     a.items = d.B * (int64_t)d.hi * 2 * d.wi; a.hi = d.hi; a.wi = d.wi;
     for (a.lh = 0; (1 << a.lh) < d.hi; ++a.lh) {}
     for (a.lw = 0; (1 << a.lw) < d.wi; ++a.lw) {}
-    int64_t blocks = (a.items + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;       // one resident wave (4 CTAs per SM), grid-stride
+    int64_t blocks = (a.items / 2 + 255) / 256;
+    if (blocks > 148 * 3) blocks = 148 * 3;       // one resident wave (3 CTAs per SM), grid-stride
     DMB_LAUNCH((dec_tail2_forward_kernel<4, 4, 2>), (unsigned)blocks, 256, 0, st, a);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);

@@ -274,3 +274,32 @@ def test_train_step_dispatch_variants_agree_at_a_ragged_batch(monkeypatch):
                 assert float(b.abs().max()) <= 1e-6, (env, name)
                 continue
             assert float((a - b).abs().max()) <= 5e-3 * scale + 1e-7, (env, name, float((a - b).abs().max()) / scale)
+
+
+@pytest.mark.parametrize("hw", [128, 256])
+def test_fused_decoder_tail_on_other_patch_sizes(hw, monkeypatch):
+    """dec.4 + dec.6 + loss in one forward kernel (csrc/dec_tail.cu: dec_tail2_forward, two input pixels per thread, a
+    warp spans one map row or half of one) against the separate launches (DMB_DEC_TAIL2=0) on 128x128 and 256x256 patches
+    (training needs latent maps of a multiple of 128 positions), odd batch, with a one-channel mask: decoded, the five
+    losses and the flat gradient."""
+    import gpu_util as U
+    from dynamorph_b200.trainer import FusedTrainer
+    st = _state()
+    g = torch.Generator().manual_seed(hw)
+    n = 7 if hw == 128 else 3
+    x = torch.randn(n, 2, hw, hw, generator=g).cuda()
+    mask = (torch.rand(n, 1, hw, hw, generator=g) > 0.3).float().cuda()
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DMB_DEC_TAIL2", flag)
+        m = U.model_from_state(st).train()
+        tr = FusedTrainer(m, lr=0.0, use_graph=False)
+        plan = tr._plan(x, mask)
+        tr._load(plan, x, mask, None)
+        tr._fwd_bwd(plan)
+        torch.cuda.synchronize()
+        outs.append((plan.decoded.clone(), tr.losses.clone(), tr.grad.clone()))
+    (d1, l1, g1), (d0, l0, g0) = outs
+    assert float((d1 - d0).abs().max()) <= 2e-6 * float(d0.abs().max())
+    assert torch.allclose(l1[:5], l0[:5], rtol=1e-5, atol=1e-7)
+    assert float((g1 - g0).abs().max()) <= 1e-4 * float(g0.abs().max())

@@ -54,6 +54,21 @@ class VQFunction(torch.autograd.Function):
 # (the plan machinery of trainer.FusedTrainer): the inputs are copied in, the outputs cloned out, autograd still routes the
 # gradient of total_loss.  DMB_EAGER_GRAPH=0 keeps every call eager.
 # ---------------------------------------------------------------------------------------------------------------------
+class _EagerCache:
+    """Per-model cache of captured plans (lives in the module's __dict__, so it dies with the model); a pickled or
+    deep-copied model gets an EMPTY one -- CUDA graphs and their static buffers are never copied."""
+
+    def __init__(self):
+        self.seen = {}          # geometry key -> None (seen once, not captured yet) | captured plan
+        self.tr = None          # the hidden FusedTrainer that owns the static buffers
+
+    def __deepcopy__(self, memo):
+        return _EagerCache()
+
+    def __reduce__(self):
+        return (_EagerCache, ())
+
+
 def _eager_graphs_enabled() -> bool:
     import os
     return os.environ.get("DMB_EAGER_GRAPH", "1") != "0"
@@ -67,7 +82,10 @@ def _eager_plan(model, x, mask, time_matching_mat):
     eng = model._engine
     key = (tuple(x.shape), None if mask is None else tuple(mask.shape), time_matching_mat is not None,
            eng._flat.data_ptr(), x.device.index)
-    seen = model.__dict__.setdefault("_eager_seen", {})
+    cache = model.__dict__.get("_eager_cache")
+    if cache is None:
+        cache = model.__dict__["_eager_cache"] = _EagerCache()
+    seen = cache.seen
     if key not in seen:
         if len(seen) >= 8:
             seen.pop(next(iter(seen)))
@@ -75,9 +93,9 @@ def _eager_plan(model, x, mask, time_matching_mat):
         return None
     if seen[key] is None:
         from .trainer import FusedTrainer
-        tr = model.__dict__.get("_eager_tr")
-        if tr is None or tr.eng is not eng or tr.eng._flat.data_ptr() != eng._flat.data_ptr():
-            tr = model.__dict__["_eager_tr"] = FusedTrainer(model, lr=0.0, use_graph=False)
+        tr = cache.tr
+        if tr is None or tr.eng is not eng:
+            tr = cache.tr = FusedTrainer(model, lr=0.0, use_graph=False)
             tr.world, tr.sync_bn = 1, False
         with torch.cuda.device(x.device):
             st = tr._plan(x, mask, time_matching_mat)

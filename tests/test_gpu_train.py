@@ -285,7 +285,12 @@ def test_eager_api_graph_replay_is_the_eager_step(name, U, monkeypatch):
         for _ in range(5):
             m, tl = run_one_batch(m, x.clone(), tl, model_kwargs={"batch_mask": _mask(g)}, optimizer=opt, transform=None,
                                   training=True)
-        assert ("_eager_tr" in m.__dict__) == (flag == "1")           # the graphs were (not) built
+        cache = m.__dict__.get("_eager_cache")
+        assert (cache is not None and cache.tr is not None) == (flag == "1")      # the graphs were (not) built
+        if cache is not None:                          # copying / pickling a model never copies captured graphs
+            import copy, pickle
+            for c2 in (copy.deepcopy(cache), pickle.loads(pickle.dumps(cache))):
+                assert c2.tr is None and not c2.seen
         results.append((tl, {k: v.detach().clone() for k, v in m.state_dict().items()}))
     (tl1, sd1), (tl0, sd0) = results
     assert tl1["total_loss"] == tl0["total_loss"] and tl1["perplexity"] == tl0["perplexity"]

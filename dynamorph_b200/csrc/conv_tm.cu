@@ -101,6 +101,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -214,6 +218,11 @@ struct TM {
     static constexpr int CPR = CIN / CPC;                    // chunks per kernel row
     static constexpr int KC = KS * CPC;                      // K of one chunk
     static constexpr int NCH = KS * CPR;                     // chunks per tile
+    // Three chunks per tile (the 3x3 layers with 16 input channels) would leave warp group 0 with two chunks and group 1
+    // with one: there BOTH groups build every chunk, half of its channels each (24 k-values), into the same A buffer
+    static constexpr bool SPLIT = (NCH == 3) && (CPC % 2 == 0) && ((KC / 2) % 8 == 0);
+    static constexpr int CPG = SPLIT ? CPC / 2 : CPC;        // channels a group gathers per chunk
+    static constexpr int KP = KS * CPG;                      // k-values a group builds per chunk
     static constexpr int K = KS * KS * CIN;
     static constexpr int NT = (K + 31) / 32;                 // 128-byte operand tiles along K
     static constexpr int NROWS = 2 * COUT;                   // [b_hi; b_lo]
@@ -319,7 +328,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
         for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(in_full + 8u * s, 1u); mbar_init(in_empty + 8u * s, 8u); }
-        for (int s = 0; s < 2; ++s) { mbar_init(a_full + 8u * s, 4u); mbar_init(a_empty + 8u * s, 1u); }
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full + 8u * s, C::SPLIT ? 8u : 4u); mbar_init(a_empty + 8u * s, 1u); }
         mbar_init(d_full, 1u);
         mbar_init(d_empty, 8u);
         mbar_init(a2_full, 8u);
@@ -422,11 +431,11 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
         [[maybe_unused]] int acc_chan = 0;
 
         // gather + split + tensor-memory store of chunk `ch` of the tile staged at `tin` (tile = patch b, rows from row0)
-        auto produce = [&](const float* tin, int ch, int b = 0, int row0 = 0) {
+        auto produce = [&](const float* tin, int ch, int b = 0, int row0 = 0, int it = 0) {
             // gather first (shared memory only), then wait for the buffer: the MMAs of this group's previous chunk
             // overlap the loads
-            float v[KC];
-            const int ky = ch / C::CPR, ci0 = (ch % C::CPR) * C::CPC;
+            float v[C::KP];
+            const int ky = ch / C::CPR, ci0 = (ch % C::CPR) * C::CPC + (C::SPLIT ? wg * C::CPG : 0);
             const float* rp = tin + ((size_t)ci0 * C::RIN + prow * S + ky) * W + S * ox;
             // BN: affine + ReLU of the producer on every value; an input row outside the image contributes zeros (the TMA
             // zero fill would otherwise turn into `shift`), the left / right border columns are zeroed below as always
@@ -448,10 +457,10 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
             }
             if (a.dbg & 4) {
 #pragma unroll
-                for (int j = 0; j < KC; ++j) v[j] = 0.f;
+                for (int j = 0; j < C::KP; ++j) v[j] = 0.f;
             }
 #pragma unroll
-            for (int ci = 0; ci < C::CPC; ++ci) {
+            for (int ci = 0; ci < C::CPG; ++ci) {
                 if (a.dbg & 4) break;
                 [[maybe_unused]] float sc = 1.f, sh = 0.f;
                 if constexpr (C::BN) {
@@ -495,27 +504,42 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                     v[ci] = f;
                 }
             }
-            if (my_n > 0) mbar_wait(a_empty + 8u * wg, (my_n - 1) & 1u);
+            // A buffer and how often it has been used before: a group's own buffer, or (SPLIT) buffer ch & 1 shared by
+            // both groups -- buffer 0 takes chunks 0 and 2 of every tile, buffer 1 chunk 1
+            const uint32_t bufi = C::SPLIT ? (uint32_t)(ch & 1) : (uint32_t)wg;
+            const uint32_t used = C::SPLIT ? (uint32_t)(it * ((ch & 1) ? 1 : 2) + (ch >> 1)) : my_n;
+            if (used > 0) mbar_wait(a_empty + 8u * bufi, (used - 1) & 1u);
             tc_fence_after();
-            const uint32_t a_hi = lane_base + (uint32_t)wg * (uint32_t)C::A_COLS, a_lo = a_hi + (uint32_t)KC;
+            const uint32_t a_hi = lane_base + bufi * (uint32_t)C::A_COLS + (C::SPLIT ? (uint32_t)(wg * C::KP) : 0u);
+            const uint32_t a_lo = a_hi + (uint32_t)KC;
 #pragma unroll
-            for (int j0 = 0; j0 < KC; j0 += 16) {
+            for (int j0 = 0; j0 < C::KP; j0 += 16) {
                 if (a.dbg & 8) break;
                 // hi = x rounded to TF32 on the bit pattern (cvt.rna.tf32 compiles to a five-instruction sequence),
                 // lo = x - hi exactly; the tensor core drops the 13 low bits of lo
-                uint32_t hi[16], lo[16];
+                constexpr int NV16 = 16;
+                uint32_t hi[NV16], lo[NV16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    hi[j] = (__float_as_uint(v[j0 + j]) + 0x1000u) & 0xFFFFE000u;
-                    lo[j] = __float_as_uint(v[j0 + j] - __uint_as_float(hi[j]));
+                for (int j = 0; j < NV16; ++j) {
+                    if (j0 + j < C::KP) {
+                        hi[j] = (__float_as_uint(v[j0 + j]) + 0x1000u) & 0xFFFFE000u;
+                        lo[j] = __float_as_uint(v[j0 + j] - __uint_as_float(hi[j]));
+                    } else {
+                        hi[j] = 0u; lo[j] = 0u;
+                    }
                 }
-                tmem_st16(a_hi + (uint32_t)j0, hi);
-                tmem_st16(a_lo + (uint32_t)j0, lo);
+                if (j0 + 16 <= C::KP) {
+                    tmem_st16(a_hi + (uint32_t)j0, hi);
+                    tmem_st16(a_lo + (uint32_t)j0, lo);
+                } else {                                 // (KP = 24: the last eight k-values)
+                    tmem_st8(a_hi + (uint32_t)j0, hi);
+                    tmem_st8(a_lo + (uint32_t)j0, lo);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + 8u * wg);
+            if (lane == 0) mbar_arrive(a_full + 8u * bufi);
             ++my_n;
         };
 
@@ -736,7 +760,7 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmap, const TmKArgs a, const 
                 prev_tile = tile;
             } else {
 #pragma unroll 1
-                for (int ch = wg; ch < C::NCH; ch += 2) produce(tin, ch, tb, trow0);
+                for (int ch = C::SPLIT ? 0 : wg; ch < C::NCH; ch += C::SPLIT ? 1 : 2) produce(tin, ch, tb, trow0, it);
                 if constexpr (!C::FUSE) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(in_empty + 8u * stage);

@@ -360,6 +360,10 @@ struct DecTail2Args {
 };
 bool dec_tail2_supported(int ci, int cm, int ni, int hi, int wi);
 int dec_tail2_forward(const DecTail2Args& a, cudaStream_t st);
+// ConvTranspose2d(ci -> 4, 4x4 s2 p1) + bias + optional ReLU on its own, plain input (dec_tail.cu: convt_small_kernel)
+bool convt_small_supported(int ci, int co, int hi, int wi);
+int convt_small(const float* x, const float* w_packed, const float* bias, float* y, int64_t B, int ci, int co, int hi, int wi,
+                int relu, cudaStream_t st);
 bool dec_tail_supported(int cm, int ni, int hw);
 int64_t dec_tail_partial_doubles(int64_t B, int hw, int cm, int ni);
 int dec_tail_forward(const DecTailArgs& a, cudaStream_t st);

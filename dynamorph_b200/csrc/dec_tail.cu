@@ -225,6 +225,86 @@ __global__ void __launch_bounds__(256, 3) dec_tail2_forward_kernel(const Tail2Ar
     }
 }
 
+// The same transposed convolution on its own (ConvTranspose2d CI -> 4, 4x4 stride 2 padding 1, bias, optional ReLU): the
+// decoder layers with four output channels whose input has no pending transform (dec.2 of the default model: 8 -> 4 @32,
+// and dec.4 when the fused tail is off).  Same ownership as dec_tail2_forward (two input pixels x one output row parity
+// per thread, float4 stores); the input channels are walked four at a time.
+struct ConvtSmallArgs {
+    const float* x; const float* w; const float* bias; float* y;
+    int64_t items;         // B * Hi * 2 * Wi
+    int hi, wi, lh, lw, relu;
+};
+
+template <int CI>
+__global__ void __launch_bounds__(256, 3) convt_small_kernel(const ConvtSmallArgs a) {
+    static_assert(CI % 4 == 0, "input channels are walked four at a time");
+    pdl_wait();
+    __shared__ float4 ws[CI * 16];
+    for (int i = threadIdx.x; i < CI * 16; i += 256) ws[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias));
+    __syncthreads();
+    const int wi = a.wi, hi = a.hi, wo = 2 * wi, wh = wi >> 1;
+    const size_t in_plane = (size_t)hi * wi, out_plane = 4 * in_plane;
+    const int64_t items = a.items >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < items; i += (int64_t)gridDim.x * 256) {
+        const int x0 = 2 * (int)(i & (wh - 1));
+        int64_t r = i >> (a.lw - 1);
+        const int py = (int)(r & 1); r >>= 1;
+        const int y = (int)(r & (hi - 1));
+        const int64_t b = r >> a.lh;
+        const float* ip = a.x + (size_t)b * CI * in_plane;
+        float4 o[4] = {b4, b4, b4, b4};
+#pragma unroll
+        for (int cb = 0; cb < CI; cb += 4) {
+            float v[4][2][4];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int yy = y + py - 1 + d;
+                const bool rok = (unsigned)yy < (unsigned)hi;
+                const bool lok = rok && x0 > 0, hok = rok && x0 + 2 < wi;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const float* rp = ip + (cb + ci) * in_plane + (size_t)(rok ? yy : 0) * wi + x0;
+                    const float2 m = rok ? __ldg(reinterpret_cast<const float2*>(rp)) : make_float2(0.f, 0.f);
+                    v[ci][d][0] = lok ? __ldg(rp - 1) : 0.f;
+                    v[ci][d][1] = m.x; v[ci][d][2] = m.y;
+                    v[ci][d][3] = hok ? __ldg(rp + 2) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    const int ky = 3 - py - 2 * d;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float4 wa = ws[((cb + ci) * 4 + ky) * 4 + (3 - 2 * e)];
+                        const float4 wb = ws[((cb + ci) * 4 + ky) * 4 + (2 - 2 * e)];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float va = v[ci][d][j + e], vb = v[ci][d][j + e + 1];
+                            float4& oa = o[2 * j];
+                            float4& ob = o[2 * j + 1];
+                            oa.x = fmaf(va, wa.x, oa.x); oa.y = fmaf(va, wa.y, oa.y); oa.z = fmaf(va, wa.z, oa.z); oa.w = fmaf(va, wa.w, oa.w);
+                            ob.x = fmaf(vb, wb.x, ob.x); ob.y = fmaf(vb, wb.y, ob.y); ob.z = fmaf(vb, wb.z, ob.z); ob.w = fmaf(vb, wb.w, ob.w);
+                        }
+                    }
+                }
+        }
+        if (a.relu) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                o[q].x = fmaxf(o[q].x, 0.f); o[q].y = fmaxf(o[q].y, 0.f); o[q].z = fmaxf(o[q].z, 0.f); o[q].w = fmaxf(o[q].w, 0.f);
+            }
+        }
+        float* yp = a.y + (size_t)b * 4 * out_plane + (size_t)(2 * y + py) * wo + 2 * x0;
+        *reinterpret_cast<float4*>(yp) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+        *reinterpret_cast<float4*>(yp + out_plane) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
+        *reinterpret_cast<float4*>(yp + 2 * out_plane) = make_float4(o[0].z, o[1].z, o[2].z, o[3].z);
+        *reinterpret_cast<float4*>(yp + 3 * out_plane) = make_float4(o[0].w, o[1].w, o[2].w, o[3].w);
+    }
+}
+
 template <int CM, int NI>
 __global__ void __launch_bounds__(256, (CM <= 4) ? 4 : 1) dec_tail_backward_kernel(const TailArgs a) {
     pdl_wait();
@@ -384,6 +464,29 @@ int dec_tail2_forward(const DecTail2Args& d, cudaStream_t st) {
     int64_t blocks = (a.items / 2 + 255) / 256;
     if (blocks > 148 * 3) blocks = 148 * 3;       // one resident wave (3 CTAs per SM), grid-stride
     DMB_LAUNCH((dec_tail2_forward_kernel<4, 4, 2>), (unsigned)blocks, 256, 0, st, a);
+    DMB_CUDA(cudaGetLastError());
+    DMB_LAUNCHED(1);
+    return 0;
+}
+
+bool convt_small_supported(int ci, int co, int hi, int wi) {
+    return (ci == 4 || ci == 8) && co == 4 && wi >= 32 && (wi & (wi - 1)) == 0 && hi > 0 && (hi & (hi - 1)) == 0;
+}
+
+int convt_small(const float* x, const float* w_packed, const float* bias, float* y, int64_t B, int ci, int co, int hi, int wi,
+                int relu, cudaStream_t st) {
+    DMB_CHECK(convt_small_supported(ci, co, hi, wi), "convt_small: unsupported shape %d -> %d @%dx%d", ci, co, hi, wi);
+    DMB_CHECK(!(reinterpret_cast<uintptr_t>(w_packed) & 15) && !(reinterpret_cast<uintptr_t>(bias) & 15) &&
+              !(reinterpret_cast<uintptr_t>(x) & 7) && !(reinterpret_cast<uintptr_t>(y) & 15), "convt_small: alignment");
+    ConvtSmallArgs a{};
+    a.x = x; a.w = w_packed; a.bias = bias; a.y = y; a.items = B * (int64_t)hi * 2 * wi; a.hi = hi; a.wi = wi; a.relu = relu;
+    for (a.lh = 0; (1 << a.lh) < hi; ++a.lh) {}
+    for (a.lw = 0; (1 << a.lw) < wi; ++a.lw) {}
+    int64_t blocks = (a.items / 2 + 255) / 256;
+    if (blocks > 148 * 3) blocks = 148 * 3;
+    if (blocks < 1) blocks = 1;
+    if (ci == 4) DMB_LAUNCH((convt_small_kernel<4>), (unsigned)blocks, 256, 0, st, a);
+    else DMB_LAUNCH((convt_small_kernel<8>), (unsigned)blocks, 256, 0, st, a);
     DMB_CUDA(cudaGetLastError());
     DMB_LAUNCHED(1);
     return 0;

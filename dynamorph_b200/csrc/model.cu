@@ -498,6 +498,11 @@ bool tm_ct_enabled() {      // transposed form of the tensor-memory kernels (DMB
     return !(e && e[0] == '0');
 }
 
+bool convt_small_on() {      // DMB_CONVT_SMALL=0: the generic transposed-convolution kernel (convt_fwd.cu)
+    const char* e = getenv("DMB_CONVT_SMALL");
+    return !(e && e[0] == '0');
+}
+
 bool tm_fuse_enabled() {
     const char* e = getenv("DMB_TM_FUSE");
     return !(e && e[0] == '0');
@@ -521,6 +526,11 @@ int run_conv(Ctx& c, int ci, const Act& in, bool in_relu, int H, int W, float* o
         a.B = (int)c.B; a.Cin = l.cin; a.H = H; a.W = W; a.Cout = l.cout; a.ks = 4; a.stride = 2;
         a.ct = 1; a.out_relu = out_relu;
         DMB_TRY(conv_tm(a, c.st));
+        Ho = 2 * H; Wo = 2 * W;
+    } else if (l.transposed && l.ks == 4 && !bn_live && !in.s && !in_relu && convt_small_on() &&
+               convt_small_supported(l.cin, l.cout, H, W)) {
+        // four output channels, plain input: the two-pixels-per-thread streaming kernel (dec_tail.cu)
+        DMB_TRY(convt_small(in.p, c.packed + l.pw_off, c.packed + l.pb_off, out, c.B, l.cin, l.cout, H, W, out_relu ? 1 : 0, c.st));
         Ho = 2 * H; Wo = 2 * W;
     } else if (l.transposed) {
         ConvTFwdArgs a{};

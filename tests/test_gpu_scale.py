@@ -249,7 +249,7 @@ def test_train_step_dispatch_variants_agree_at_a_ragged_batch(monkeypatch):
     x = O.synthetic_patches(B, 77).cuda()
 
     def run(env):
-        for k in ("DMB_TM_BN_BATCH", "DMB_TM_DG", "DMB_TM_CT", "DMB_WG_QUEUE", "DMB_DEC_TAIL2", "DMB_TM_FIN"):
+        for k in ("DMB_TM_BN_BATCH", "DMB_TM_DG", "DMB_TM_CT", "DMB_WG_QUEUE", "DMB_DEC_TAIL2", "DMB_TM_FIN", "DMB_CONVT_SMALL"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -263,7 +263,8 @@ def test_train_step_dispatch_variants_agree_at_a_ragged_batch(monkeypatch):
         return tr.grad.clone(), tr.losses.clone(), [(names.get(id(p), "?"), o, k) for p, o, k in tr.eng._views]
 
     g0, l0, views = run({})
-    for env in ({"DMB_TM_BN_BATCH": "0", "DMB_TM_DG": "0", "DMB_TM_CT": "0", "DMB_DEC_TAIL2": "0"}, {"DMB_WG_QUEUE": "1"},
+    for env in ({"DMB_TM_BN_BATCH": "0", "DMB_TM_DG": "0", "DMB_TM_CT": "0", "DMB_DEC_TAIL2": "0", "DMB_CONVT_SMALL": "0"},
+                {"DMB_WG_QUEUE": "1"},
                 {"DMB_DEC_TAIL2": "0"}, {"DMB_TM_FIN": "1"}):
         g1, l1, _ = run(env)
         assert torch.allclose(l0[:5], l1[:5], rtol=2e-5, atol=1e-7), (env, l0, l1)

@@ -215,7 +215,7 @@ bool conv_tm_ct_supported(int cin, int cout, int H, int W, bool dg);
 int pack_tm_weights_ct(const float* w_packed, float* out, int cin, int cout, cudaStream_t st);   // image: conv_tm_weight_floats(cin, 4*cout, 3)
 int64_t conv_tm_weight_floats(int cin, int cout, int ks);
 int pack_tm_weights(const float* w_packed, float* out, int cin, int cout, int ks, cudaStream_t st);
-constexpr int TM_PACK_MAX = 16;
+constexpr int TM_PACK_MAX = 32;
 struct TmPackJob { const float* w; float* out; int cin, cout, ks; int ct; };      // ct: transposed form (w = [Cin][4][4][Cout])
 int pack_tm_weights_multi(const TmPackJob* jobs, int n, cudaStream_t st);      // all layers of a model in one launch
 int conv_tm(const ConvTmArgs& a, cudaStream_t st);

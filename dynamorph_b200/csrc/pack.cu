@@ -35,11 +35,13 @@ __device__ double bn_scale(const PackL& l, const float* params, const float* bnb
 __global__ void pack_kernel(const PackPlan p, const float* __restrict__ params,
                             const float* __restrict__ bnbuf, float* __restrict__ packed) {
     pdl_wait();      // programmatic dependent launch: everything below may read the previous kernel's output
-    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < p.total;
-         id += (int64_t)gridDim.x * blockDim.x) {
+    // (32-bit index arithmetic: the plan holds a few hundred thousand elements at most -- checked by the host -- and
+    // 64-bit div / mod by run-time values were most of this kernel's 12 us at the start of every training step)
+    const int total = (int)p.total;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
         if (id >= p.bn_start) {      // gamma / beta copies, then the zero vector
-            int64_t r = id - p.bn_start;
-            int64_t nbn_el = 0;
+            int r = id - (int)p.bn_start;
+            int nbn_el = 0;
             for (int i = 0; i < p.nbn; ++i) nbn_el += 2 * p.bc[i];
             if (r >= nbn_el) { packed[p.zero_off + (r - nbn_el)] = 0.f; continue; }
             for (int i = 0; i < p.nbn; ++i) {
@@ -55,14 +57,14 @@ __global__ void pack_kernel(const PackPlan p, const float* __restrict__ params,
         int li = 0;
         while (li + 1 < p.n && id >= p.l[li + 1].start) ++li;
         const PackL& l = p.l[li];
-        const int64_t e = id - l.start;
+        const int e = id - (int)l.start;
         const int K = l.ks;
-        if (e < l.nw) {
-            const int co = (int)(e % l.cout);
-            int64_t t = e / l.cout;
-            const int kx = (int)(t % K); t /= K;
-            const int ky = (int)(t % K);
-            const int ci = (int)(t / K);
+        if (e < (int)l.nw) {
+            const int co = e % l.cout;
+            int t = e / l.cout;
+            const int kx = t % K; t /= K;
+            const int ky = t % K;
+            const int ci = t / K;
             double mean;
             const double s = bn_scale(l, params, bnbuf, co, p.eps, &mean);
             double w;
@@ -77,23 +79,23 @@ __global__ void pack_kernel(const PackPlan p, const float* __restrict__ params,
                 w = params[l.w_off + ((int64_t)(co * l.cin + ci) * K + ky) * K + kx];
             }
             packed[l.pw_off + e] = (float)(w * s);
-        } else if (e >= l.nw + l.nb) {
+        } else if (e >= (int)(l.nw + l.nb)) {
             // data-gradient weights [cout][k][k][cin]: conv stride 1 flips the taps (correlation ->
             // convolution); stride-2 conv / ConvTranspose2d keep them (they swap kernels instead)
-            const int64_t ed = e - l.nw - l.nb;
-            const int ci = (int)(ed % l.cin);
-            int64_t t = ed / l.cin;
-            int kx = (int)(t % K); t /= K;
-            int ky = (int)(t % K);
-            const int co = (int)(t / K);
+            const int ed = e - (int)l.nw - (int)l.nb;
+            const int ci = ed % l.cin;
+            int t = ed / l.cin;
+            int kx = t % K; t /= K;
+            int ky = t % K;
+            const int co = t / K;
             if (!l.transposed && l.stride == 1) { ky = K - 1 - ky; kx = K - 1 - kx; }
             const float w = l.transposed ? params[l.w_off + ((int64_t)(ci * l.cout + co) * K + ky) * K + kx]
                                          : params[l.w_off + ((int64_t)(co * l.cin + ci) * K + ky) * K + kx];
             packed[l.pdw_off + ed] = w;
         } else {
-            const int64_t eb = e - l.nw;
-            const int co = (int)(eb % l.cout);
-            const int cls = (int)(eb / l.cout);      // 0 unless bias_classes
+            const int eb = e - (int)l.nw;
+            const int co = eb % l.cout;
+            const int cls = eb / l.cout;             // 0 unless bias_classes
             double mean;
             const double s = bn_scale(l, params, bnbuf, co, p.eps, &mean);
             double b = params[l.b_off + co];
@@ -154,6 +156,7 @@ int pack_weights(const Layout& L, const float* params, const float* bnbuf, int b
     p.nzero = L.max_c;
     start += L.max_c;
     p.total = start;
+    DMB_CHECK(p.total < (1ll << 30), "pack: plan too large for 32-bit indexing");
     const int threads = 256;
     int blocks = (int)((p.total + threads - 1) / threads);
     if (blocks > 148 * 8) blocks = 148 * 8;

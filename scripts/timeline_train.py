@@ -1,6 +1,6 @@
 """Timeline of ONE eager FusedTrainer step (torch profiler, CUDA activities): stream, start offset, duration of every
 kernel, so that the critical path / overlap of the weight-gradient side stream / gaps between launches are visible.
-    python scripts/timeline_train.py [batch]"""
+    python scripts/timeline_train.py [batch] [heavy]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,9 +11,10 @@ from dynamorph_b200.synthetic import calibrate, synthetic_patches
 from dynamorph_b200.trainer import FusedTrainer
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+heavy = len(sys.argv) > 2 and sys.argv[2] == "heavy"      # BASELINE configs[3]: num_hiddens=64, num_embeddings=512
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-m = VQ_VAE_z16().to(dev)
+m = (VQ_VAE_z16(num_hiddens=64, num_embeddings=512) if heavy else VQ_VAE_z16()).to(dev)
 calibrate(m, synthetic_patches(64, 1, dev))
 m.train()
 x = synthetic_patches(B, 7, dev)
@@ -24,10 +25,10 @@ for use_graph in (True, False):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(50):
+    for _ in range(10 if heavy else 50):
         tr.step(x)
     e1.record(); torch.cuda.synchronize()
-    print(f"B={B} graph={use_graph}: {e0.elapsed_time(e1) / 50:.3f} ms/step")
+    print(f"B={B} graph={use_graph}: {e0.elapsed_time(e1) / (10 if heavy else 50):.3f} ms/step")
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     tr.step(x); torch.cuda.synchronize()
 import json, tempfile
